@@ -1,0 +1,843 @@
+// mavg.cu -- host side of libmavg: plans, geometry, tensor maps, launches, C ABI.
+//
+// Boundary being replaced (see include/mavg.h): the XxxGpuLoad functions and the
+// DspWorkspace of the reference (basics/*.cu, gpu_utils.h:67-160) and the CUDA-event
+// phase timing of GpuTimer (benchmark.h:72-96).
+#include "../../include/mavg.h"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "mavg_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int status, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return status;
+}
+
+#define MAVG_CUDA(call)                                                                                \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess)                                                                         \
+            return fail(e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver ? MAVG_ERR_NO_DEVICE \
+                                                                                       : MAVG_ERR_CUDA, \
+                        "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__);   \
+    } while (0)
+
+#define MAVG_TRY(call)            \
+    do {                          \
+        int s_ = (call);          \
+        if (s_ != MAVG_OK) return s_; \
+    } while (0)
+
+// cuTensorMapEncodeTiled is fetched through the runtime so that libmavg.so does not link
+// libcuda.so (it must load on a box without a driver for the symbol-export tests).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int get_encoder(EncodeTiledFn* out)
+{
+    static EncodeTiledFn cached = nullptr;
+    if (!cached) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn)
+            return fail(MAVG_ERR_DRIVER, "cuTensorMapEncodeTiled unavailable: %s", cudaGetErrorString(e));
+        cached = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    *out = cached;
+    return MAVG_OK;
+}
+
+// One float signal batch as a [signals][rows][32] tensor, boxes of [1][tile_rows][32], 128B swizzle.
+int make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t signals, uint64_t signal_stride_bytes,
+             uint32_t tile_rows)
+{
+    EncodeTiledFn enc;
+    MAVG_TRY(get_encoder(&enc));
+    cuuint64_t dims[3] = {32, rows, signals};
+    cuuint64_t strides[2] = {128, signals > 1 ? signal_stride_bytes : rows * 128};
+    cuuint32_t box[3] = {32, tile_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return fail(MAVG_ERR_DRIVER, "cuTensorMapEncodeTiled failed (%d) rows=%llu signals=%llu stride=%llu", (int)r,
+                    (unsigned long long)rows, (unsigned long long)signals, (unsigned long long)signal_stride_bytes);
+    return MAVG_OK;
+}
+
+size_t elem_size(uint32_t dtype) { return dtype == MAVG_F32 ? 4 : 2; }
+
+// ---------------------------------------------------------------------------------
+// Geometry of the streaming kernel for one (k, shard) pair
+// ---------------------------------------------------------------------------------
+struct StreamGeom {
+    bool ok = false;
+    int NT = 0, R = 0, MIS = 0, mode = 0;
+    int H = 0, P = 0, S = 0;
+    int ctas_per_sm = 0;
+    uint32_t smem = 0;
+    uint32_t n_full = 0, m_part = 0, lag_chunks = 0;
+};
+
+constexpr uint32_t kMaxSmem = 232448;  // 227 KB opt-in limit per CTA on sm_100
+
+StreamGeom plan_stream(uint32_t k, const mavg_tuning& tu)
+{
+    StreamGeom g;
+    g.NT = tu.threads ? (int)tu.threads : 256;
+    g.R = tu.run ? (int)tu.run : 16;
+    if (!(g.NT == 256 || g.NT == 512) || !(g.R == 16 || g.R == 32)) return g;
+    if (g.NT * g.R > 8192) return g;  // a TMA box holds at most 256 rows of 32 floats
+    const uint32_t direct_max = tu.direct_max_k ? tu.direct_max_k : 256u;
+    g.mode = (k <= 8) ? 2 : (k <= direct_max) ? 0 : 1;
+    const uint32_t R = (uint32_t)g.R;
+    const uint32_t s = (R - k % R) % R;
+    g.m_part = R - s;
+    g.n_full = (k + s) / R - 1;
+    g.lag_chunks = (k + 3) / 4;
+    g.MIS = (g.mode == 2) ? 0 : (int)(4 * g.lag_chunks - k);
+    const uint64_t T = (uint64_t)g.NT * R;
+    const uint64_t back = (g.mode == 2) ? 8 : (uint64_t)(g.n_full + 1) * R;  // left context a tile can touch
+    g.H = (int)((back + T - 1) / T);
+    g.ctas_per_sm = tu.ctas_per_sm ? (int)tu.ctas_per_sm : 2;
+    g.P = tu.prefetch ? (int)tu.prefetch : 2;
+    // shrink the prefetch depth, then the residency, until the ring fits
+    for (;;) {
+        g.S = g.H + 1 + g.P;
+        g.smem = mavg::stream_smem_bytes(g.NT, g.R, g.S, g.H);
+        const uint32_t per_sm = 233472;  // 228 KB per SM, 1 KB reserved per resident CTA
+        if (g.smem <= kMaxSmem && (uint64_t)(g.smem + 1024) * g.ctas_per_sm <= per_sm) break;
+        if (g.P > 1) { --g.P; continue; }
+        if (g.ctas_per_sm > 1) { --g.ctas_per_sm; g.P = tu.prefetch ? (int)tu.prefetch : 2; continue; }
+        return g;  // window too long for the shared-memory history
+    }
+    g.ok = true;
+    return g;
+}
+
+typedef void (*StreamKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const mavg::StreamParams);
+
+template <int NT, int R>
+StreamKernel pick_variant(int mis, int mode, uint32_t k)
+{
+    using namespace mavg;
+    if (mode == 2) {
+        switch (k) {
+        case 1: return stream_f32_kernel<NT, R, 0, 2, 1>;
+        case 2: return stream_f32_kernel<NT, R, 0, 2, 2>;
+        case 3: return stream_f32_kernel<NT, R, 0, 2, 3>;
+        case 4: return stream_f32_kernel<NT, R, 0, 2, 4>;
+        case 5: return stream_f32_kernel<NT, R, 0, 2, 5>;
+        case 6: return stream_f32_kernel<NT, R, 0, 2, 6>;
+        case 7: return stream_f32_kernel<NT, R, 0, 2, 7>;
+        default: return stream_f32_kernel<NT, R, 0, 2, 8>;
+        }
+    }
+    if (mode == 0) {
+        switch (mis) {
+        case 0: return stream_f32_kernel<NT, R, 0, 0, 0>;
+        case 1: return stream_f32_kernel<NT, R, 1, 0, 0>;
+        case 2: return stream_f32_kernel<NT, R, 2, 0, 0>;
+        default: return stream_f32_kernel<NT, R, 3, 0, 0>;
+        }
+    }
+    switch (mis) {
+    case 0: return stream_f32_kernel<NT, R, 0, 1, 0>;
+    case 1: return stream_f32_kernel<NT, R, 1, 1, 0>;
+    case 2: return stream_f32_kernel<NT, R, 2, 1, 0>;
+    default: return stream_f32_kernel<NT, R, 3, 1, 0>;
+    }
+}
+
+StreamKernel pick_kernel(const StreamGeom& g, uint32_t k)
+{
+    if (g.NT == 256 && g.R == 16) return pick_variant<256, 16>(g.MIS, g.mode, k);
+    if (g.NT == 256 && g.R == 32) return pick_variant<256, 32>(g.MIS, g.mode, k);
+    return pick_variant<512, 16>(g.MIS, g.mode, k);
+}
+
+// ---------------------------------------------------------------------------------
+// Plan
+// ---------------------------------------------------------------------------------
+struct DevCtx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // start, h2d done, compute done, d2h done
+    // shard geometry
+    uint64_t first_frame = 0;   // interleaved/mono: first frame of the shard (plan-relative)
+    uint64_t frames = 0;        // frames in the shard
+    uint32_t first_channel = 0; // planar: first channel of the shard
+    uint32_t channels = 0;      // planar: channels in the shard; interleaved: all channels
+    // owned buffers
+    void* d_in = nullptr;
+    void* d_out = nullptr;
+    void* d_halo = nullptr;     // halo_frames * channels elements of left context (frame sharding)
+    int sm_count = 0;
+    bool timed = false;
+};
+
+}  // namespace
+
+struct mavg_plan {
+    mavg_desc desc;
+    uint32_t path = MAVG_PATH_GENERIC;
+    StreamGeom geom;
+    uint64_t halo_frames = 0;
+    std::vector<DevCtx> dev;
+    mavg_timing timing = {0, 0, 0, 0};
+    uint32_t launches_last_run = 0;
+    bool peer_ok = false;
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    DeviceGuard() { cudaGetDevice(&prev); }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+bool planar_batch(const mavg_plan* p) { return p->desc.layout == MAVG_PLANAR && p->desc.channels > 1; }
+bool frame_sharded(const mavg_plan* p) { return !planar_batch(p); }
+
+// samples per signal and signal count as the stream kernel sees one shard
+void shard_signals(const mavg_plan* p, const DevCtx& d, uint64_t* n, uint64_t* signals, uint64_t* stride_elems)
+{
+    if (planar_batch(p)) {
+        *n = p->desc.frames;
+        *signals = d.channels;
+        *stride_elems = p->desc.frames;
+    } else {
+        *n = d.frames * p->desc.channels;
+        *signals = 1;
+        *stride_elems = *n;
+    }
+}
+
+uint64_t shard_elems(const mavg_plan* p, const DevCtx& d)
+{
+    return planar_batch(p) ? (uint64_t)d.channels * p->desc.frames : d.frames * p->desc.channels;
+}
+
+int alloc_owned(mavg_plan* p, DevCtx& d)
+{
+    if (d.d_in && d.d_out) return MAVG_OK;
+    const size_t bytes = std::max<size_t>(shard_elems(p, d) * elem_size(p->desc.dtype), 256);
+    MAVG_CUDA(cudaSetDevice(d.device));
+    if (!d.d_in && cudaMalloc(&d.d_in, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(MAVG_ERR_ALLOC, "cudaMalloc of %zu input bytes failed on device %d", bytes, d.device);
+    }
+    if (!d.d_out && cudaMalloc(&d.d_out, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(MAVG_ERR_ALLOC, "cudaMalloc of %zu output bytes failed on device %d", bytes, d.device);
+    }
+    return MAVG_OK;
+}
+
+int alloc_halo(mavg_plan* p, DevCtx& d)
+{
+    if (d.d_halo || p->halo_frames == 0) return MAVG_OK;
+    const size_t bytes = p->halo_frames * p->desc.channels * elem_size(p->desc.dtype);
+    MAVG_CUDA(cudaSetDevice(d.device));
+    if (cudaMalloc(&d.d_halo, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(MAVG_ERR_ALLOC, "cudaMalloc of %zu halo bytes failed on device %d", bytes, d.device);
+    }
+    return MAVG_OK;
+}
+
+template <typename T>
+int launch_generic_t(const mavg_plan* p, DevCtx& d, const T* in, T* out, const T* halo, uint64_t out_begin,
+                     uint64_t out_end, uint32_t* launches)
+{
+    if (out_begin >= out_end) return MAVG_OK;
+    constexpr int RG = 64;
+    mavg::GenericParams gp;
+    uint32_t signals = 1;
+    if (planar_batch(p)) {
+        gp.frames = p->desc.frames;
+        gp.channels = 1;
+        gp.sig_stride = p->desc.frames;
+        signals = d.channels;
+    } else {
+        gp.frames = d.frames;
+        gp.channels = p->desc.channels;
+        gp.sig_stride = 0;
+    }
+    gp.out_begin = out_begin;
+    gp.out_end = out_end;
+    gp.halo_frames = halo ? p->halo_frames : 0;
+    gp.k = p->desc.window;
+    const uint64_t runs = (out_end - out_begin + RG - 1) / RG;
+    const uint64_t threads = runs * gp.channels;
+    const uint64_t blocks = (threads + 255) / 256;
+    if (blocks > 0x7fffffffull) return fail(MAVG_ERR_UNSUPPORTED, "generic path: signal too long");
+    // gridDim.y <= 65535: walk planar signals in slabs
+    for (uint32_t s0 = 0; s0 < signals; s0 += 65535u) {
+        const uint32_t ns = std::min<uint32_t>(65535u, signals - s0);
+        dim3 grid((unsigned)blocks, ns, 1);
+        mavg::generic_kernel<T, RG><<<grid, 256, 0, d.stream>>>(in + (uint64_t)s0 * gp.sig_stride,
+                                                               out + (uint64_t)s0 * gp.sig_stride, halo, gp);
+        MAVG_CUDA(cudaGetLastError());
+        ++*launches;
+    }
+    return MAVG_OK;
+}
+
+int launch_generic(const mavg_plan* p, DevCtx& d, const void* in, void* out, const void* halo, uint64_t out_begin,
+                   uint64_t out_end, uint32_t* launches)
+{
+    if (p->desc.dtype == MAVG_F32)
+        return launch_generic_t<float>(p, d, (const float*)in, (float*)out, (const float*)halo, out_begin, out_end,
+                                       launches);
+    return launch_generic_t<int16_t>(p, d, (const int16_t*)in, (int16_t*)out, (const int16_t*)halo, out_begin,
+                                     out_end, launches);
+}
+
+bool stream_eligible(const mavg_plan* p, const DevCtx& d, const void* in, const void* out, const void* halo)
+{
+    if (p->path != MAVG_PATH_STREAM || !p->geom.ok) return false;
+    if (((uintptr_t)in | (uintptr_t)out | (uintptr_t)halo) & 15u) return false;
+    uint64_t n, signals, stride;
+    shard_signals(p, d, &n, &signals, &stride);
+    if (n < 32) return false;
+    if (signals > 1 && (stride % 4) != 0) return false;  // tensor-map strides are multiples of 16 bytes
+    if (n / 32 > 0x7fffffffull - 65536 || signals > 0x7fffffffull) return false;
+    return true;
+}
+
+// Enqueue the kernels for one shard on its device stream.
+int launch_shard(mavg_plan* p, DevCtx& d, const void* in, void* out, const void* halo, uint32_t* launches)
+{
+    MAVG_CUDA(cudaSetDevice(d.device));
+    if (shard_elems(p, d) == 0) return MAVG_OK;
+    if (!stream_eligible(p, d, in, out, halo)) {
+        const uint64_t frames = planar_batch(p) ? p->desc.frames : d.frames;
+        return launch_generic(p, d, in, out, halo, 0, frames, launches);
+    }
+    const StreamGeom& g = p->geom;
+    uint64_t n, signals, stride;
+    shard_signals(p, d, &n, &signals, &stride);
+    const uint64_t rows = n / 32;
+    const uint32_t tile_rows = (uint32_t)(g.NT * g.R / 32);
+    const uint64_t T = (uint64_t)g.NT * g.R;
+
+    CUtensorMap in_map, out_map, halo_map;
+    MAVG_TRY(make_map(&in_map, in, rows, signals, stride * 4, tile_rows));
+    MAVG_TRY(make_map(&out_map, out, rows, signals, stride * 4, tile_rows));
+    const uint64_t halo_rows = (uint64_t)g.H * tile_rows;
+    if (halo) MAVG_TRY(make_map(&halo_map, halo, halo_rows, 1, halo_rows * 128, tile_rows));
+    else halo_map = in_map;
+
+    mavg::StreamParams sp;
+    sp.inv_k = 1.0f / (float)p->desc.window;
+    sp.k = p->desc.window;
+    sp.n_full = g.n_full;
+    sp.m_part = g.m_part;
+    sp.lag_chunks = g.lag_chunks;
+    const uint64_t tiles = (rows * 32 + T - 1) / T;
+    sp.tiles_per_signal = (int32_t)tiles;
+    const uint64_t ctas = (uint64_t)d.sm_count * g.ctas_per_sm;
+    const uint64_t want_chunks = ctas * std::max<uint32_t>(1u, p->desc.tuning.chunks_per_cta);
+    uint64_t cps = std::max<uint64_t>(1, want_chunks / signals);
+    cps = std::min<uint64_t>(cps, tiles);
+    uint64_t chunk_tiles = (tiles + cps - 1) / cps;
+    cps = (tiles + chunk_tiles - 1) / chunk_tiles;
+    sp.chunk_tiles = (int32_t)chunk_tiles;
+    sp.chunks_per_signal = (int32_t)cps;
+    if (cps * signals > 0x7fffffffull) return fail(MAVG_ERR_UNSUPPORTED, "too many tile ranges");
+    sp.total_chunks = (int32_t)(cps * signals);
+    sp.hist_tiles = g.H;
+    sp.stages = g.S;
+    sp.prefetch = g.P;
+    sp.has_halo = halo ? 1 : 0;
+
+    StreamKernel kern = pick_kernel(g, p->desc.window);
+    MAVG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+    const unsigned grid = (unsigned)std::min<uint64_t>(ctas, (uint64_t)sp.total_chunks);
+    kern<<<grid, g.NT, g.smem, d.stream>>>(in_map, out_map, halo_map, sp);
+    MAVG_CUDA(cudaGetLastError());
+    ++*launches;
+
+    // samples past the last whole 128-byte row (n % 32 of them, per signal): generic kernel
+    if (rows * 32 < n) {
+        if (signals == 1 && p->desc.channels == 1) {
+            MAVG_TRY(launch_generic(p, d, in, out, halo, rows * 32, n, launches));
+        } else {
+            // planar batch with frames % 32 != 0
+            MAVG_TRY(launch_generic(p, d, in, out, halo, rows * 32, p->desc.frames, launches));
+        }
+    }
+    return MAVG_OK;
+}
+
+int validate(const mavg_desc* d)
+{
+    if (!d) return fail(MAVG_ERR_INVALID_ARG, "desc is null");
+    if (d->struct_size != sizeof(mavg_desc))
+        return fail(MAVG_ERR_INVALID_ARG, "desc.struct_size %u != %zu", d->struct_size, sizeof(mavg_desc));
+    if (d->dtype > MAVG_I16) return fail(MAVG_ERR_INVALID_ARG, "unknown dtype %u", d->dtype);
+    if (d->layout > MAVG_PLANAR) return fail(MAVG_ERR_INVALID_ARG, "unknown layout %u", d->layout);
+    if (d->path > MAVG_PATH_GENERIC) return fail(MAVG_ERR_INVALID_ARG, "unknown path %u", d->path);
+    if (d->channels == 0) return fail(MAVG_ERR_INVALID_ARG, "channels must be >= 1");
+    if (d->window == 0) return fail(MAVG_ERR_INVALID_ARG, "window must be >= 1");
+    if (d->num_devices > MAVG_MAX_DEVICES) return fail(MAVG_ERR_INVALID_ARG, "too many devices");
+    // basics/profilable_sm_vload4.cu:231-234
+    if (d->block_size != 0 && (d->block_size < 32 || d->block_size > 1024 || d->block_size % 32 != 0))
+        return fail(MAVG_ERR_BLOCK_SIZE, "Block size must be multiple of 32 in 32..1024 (got %u)", d->block_size);
+    if (d->first_frame != 0 && d->num_devices > 1)
+        return fail(MAVG_ERR_INVALID_ARG, "first_frame > 0 is for single-device shard plans");
+    return MAVG_OK;
+}
+
+void record(DevCtx& d, int which)
+{
+    cudaEventRecord(d.ev[which], d.stream);
+}
+
+int gather_timing(mavg_plan* p)
+{
+    mavg_timing t = {0, 0, 0, 0};
+    for (DevCtx& d : p->dev) {
+        if (!d.timed) continue;
+        float a = 0, b = 0, c = 0;
+        if (cudaEventElapsedTime(&a, d.ev[0], d.ev[1]) != cudaSuccess) a = 0;
+        if (cudaEventElapsedTime(&b, d.ev[1], d.ev[2]) != cudaSuccess) b = 0;
+        if (cudaEventElapsedTime(&c, d.ev[2], d.ev[3]) != cudaSuccess) c = 0;
+        cudaGetLastError();
+        t.h2d_ms = std::max(t.h2d_ms, a);
+        t.compute_ms = std::max(t.compute_ms, b);
+        t.d2h_ms = std::max(t.d2h_ms, c);
+        t.total_ms = std::max(t.total_ms, a + b + c);
+    }
+    p->timing = t;
+    return MAVG_OK;
+}
+
+}  // namespace
+
+// =================================================================================
+// C ABI
+// =================================================================================
+extern "C" {
+
+int mavg_version(void) { return MAVG_VERSION_MAJOR * 10000 + MAVG_VERSION_MINOR * 100 + MAVG_VERSION_PATCH; }
+
+const char* mavg_strerror(int status)
+{
+    switch (status) {
+    case MAVG_OK: return "ok";
+    case MAVG_ERR_INVALID_ARG: return "invalid argument";
+    case MAVG_ERR_UNSUPPORTED: return "unsupported configuration";
+    case MAVG_ERR_CUDA: return "CUDA runtime error";
+    case MAVG_ERR_NO_DEVICE: return "no CUDA device";
+    case MAVG_ERR_ALLOC: return "allocation failed";
+    case MAVG_ERR_BLOCK_SIZE: return "block size must be a multiple of 32 in 32..1024";
+    case MAVG_ERR_DRIVER: return "CUDA driver entry point unavailable";
+    default: return "unknown status";
+    }
+}
+
+const char* mavg_last_error(void) { return g_last_error.c_str(); }
+
+int mavg_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int mavg_plan_create(const mavg_desc* desc, mavg_plan** out)
+{
+    if (!out) return fail(MAVG_ERR_INVALID_ARG, "plan out-pointer is null");
+    *out = nullptr;
+    MAVG_TRY(validate(desc));
+    int ndev_avail = mavg_device_count();
+    if (ndev_avail <= 0) return fail(MAVG_ERR_NO_DEVICE, "no CUDA device available: libmavg has no CPU fallback");
+
+    mavg_plan* p = new (std::nothrow) mavg_plan();
+    if (!p) return fail(MAVG_ERR_ALLOC, "out of host memory");
+    p->desc = *desc;
+    DeviceGuard guard;
+
+    // ---- kernel family
+    const bool stream_shape = desc->dtype == MAVG_F32 && (desc->channels == 1 || desc->layout == MAVG_PLANAR);
+    p->geom = plan_stream(desc->window, desc->tuning);
+    if (desc->path == MAVG_PATH_STREAM && !(stream_shape && p->geom.ok)) {
+        delete p;
+        return fail(MAVG_ERR_UNSUPPORTED,
+                    "stream path needs float32 mono/planar input and a window that fits the shared-memory history");
+    }
+    p->path = (desc->path != MAVG_PATH_GENERIC && stream_shape && p->geom.ok) ? MAVG_PATH_STREAM : MAVG_PATH_GENERIC;
+
+    // ---- left context a frame shard needs
+    if (p->path == MAVG_PATH_STREAM) {
+        const uint64_t T = (uint64_t)p->geom.NT * p->geom.R;
+        p->halo_frames = (uint64_t)p->geom.H * T;  // whole history tiles, so sharding keeps bit-identical sums
+    } else {
+        p->halo_frames = desc->window;
+    }
+
+    // ---- devices and shards
+    const uint32_t nd = std::max<uint32_t>(1u, desc->num_devices);
+    int cur = 0;
+    cudaGetDevice(&cur);
+    p->dev.resize(nd);
+    // frame shards start on tile boundaries (stream) so every device runs the same tile grid
+    const uint64_t align = (p->path == MAVG_PATH_STREAM && frame_sharded(p)) ? (uint64_t)p->geom.NT * p->geom.R : 1;
+    for (uint32_t r = 0; r < nd; ++r) {
+        DevCtx& d = p->dev[r];
+        d.device = desc->num_devices >= 1 ? desc->devices[r] : cur;
+        if (desc->num_devices == 0) d.device = cur;
+        if (d.device < 0 || d.device >= ndev_avail) {
+            mavg_plan_destroy(p);
+            return fail(MAVG_ERR_INVALID_ARG, "device %d out of range (have %d)", d.device, ndev_avail);
+        }
+        if (planar_batch(p)) {
+            const uint32_t c0 = (uint32_t)((uint64_t)desc->channels * r / nd);
+            const uint32_t c1 = (uint32_t)((uint64_t)desc->channels * (r + 1) / nd);
+            d.first_channel = c0;
+            d.channels = c1 - c0;
+            d.frames = desc->frames;
+        } else {
+            auto cut = [&](uint32_t i) -> uint64_t {
+                if (i == 0) return 0;
+                if (i == nd) return desc->frames;
+                uint64_t f = desc->frames / nd * i;
+                f = (f + align - 1) / align * align;
+                return std::min<uint64_t>(f, desc->frames);
+            };
+            d.first_frame = cut(r);
+            d.frames = cut(r + 1) - cut(r);
+            d.channels = desc->channels;
+            if (r > 0 && d.frames > 0 && p->dev[r - 1].frames < p->halo_frames) {
+                mavg_plan_destroy(p);
+                return fail(MAVG_ERR_UNSUPPORTED, "signal too short to shard over %u devices with window %u", nd,
+                            desc->window);
+            }
+        }
+        cudaError_t e = cudaSetDevice(d.device);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking);
+        for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&d.ev[i]);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, d.device);
+        if (e != cudaSuccess) {
+            mavg_plan_destroy(p);
+            return fail(MAVG_ERR_CUDA, "device %d setup failed: %s", d.device, cudaGetErrorString(e));
+        }
+    }
+    // peer access between neighbours (halo is read in place from the left neighbour's shard)
+    p->peer_ok = nd > 1;
+    for (uint32_t r = 1; r < nd && frame_sharded(p); ++r) {
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, p->dev[r].device, p->dev[r - 1].device);
+        if (!can) { p->peer_ok = false; continue; }
+        cudaSetDevice(p->dev[r].device);
+        cudaError_t e = cudaDeviceEnablePeerAccess(p->dev[r - 1].device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) p->peer_ok = false;
+        cudaGetLastError();
+    }
+    *out = p;
+    return MAVG_OK;
+}
+
+int mavg_plan_destroy(mavg_plan* p)
+{
+    if (!p) return MAVG_OK;
+    DeviceGuard guard;
+    for (DevCtx& d : p->dev) {
+        if (cudaSetDevice(d.device) != cudaSuccess) { cudaGetLastError(); continue; }
+        if (d.stream) cudaStreamSynchronize(d.stream);
+        if (d.d_in) cudaFree(d.d_in);
+        if (d.d_out) cudaFree(d.d_out);
+        if (d.d_halo) cudaFree(d.d_halo);
+        for (int i = 0; i < 4; ++i)
+            if (d.ev[i]) cudaEventDestroy(d.ev[i]);
+        if (d.stream && d.own_stream) cudaStreamDestroy(d.stream);
+    }
+    cudaGetLastError();
+    delete p;
+    return MAVG_OK;
+}
+
+int mavg_plan_info(const mavg_plan* p, mavg_info* info)
+{
+    if (!p || !info) return fail(MAVG_ERR_INVALID_ARG, "null argument");
+    memset(info, 0, sizeof *info);
+    info->path = p->path;
+    info->mode = p->geom.mode;
+    info->threads = p->geom.NT;
+    info->run = p->geom.R;
+    info->tile_samples = p->geom.NT * p->geom.R;
+    info->history_tiles = p->geom.H;
+    info->stages = p->geom.S;
+    info->grid = p->dev.empty() ? 0 : p->dev[0].sm_count * p->geom.ctas_per_sm;
+    info->smem_bytes = p->geom.smem;
+    info->launches_per_run = p->launches_last_run;
+    info->num_devices = (uint32_t)p->dev.size();
+    info->halo_frames = p->halo_frames;
+    for (size_t r = 0; r < p->dev.size(); ++r)
+        info->shard_frames[r] = planar_batch(p) ? p->dev[r].channels : p->dev[r].frames;
+    return MAVG_OK;
+}
+
+int mavg_set_stream(mavg_plan* p, void* cuda_stream)
+{
+    if (!p) return fail(MAVG_ERR_INVALID_ARG, "plan is null");
+    if (p->dev.size() != 1) return fail(MAVG_ERR_UNSUPPORTED, "mavg_set_stream is for single-device plans");
+    DevCtx& d = p->dev[0];
+    DeviceGuard guard;
+    MAVG_CUDA(cudaSetDevice(d.device));
+    if (d.stream && d.own_stream) {
+        cudaStreamSynchronize(d.stream);
+        cudaStreamDestroy(d.stream);
+    }
+    d.stream = (cudaStream_t)cuda_stream;
+    d.own_stream = false;
+    return MAVG_OK;
+}
+
+int mavg_plan_buffers(mavg_plan* p, uint32_t rank, void** d_in, void** d_out)
+{
+    if (!p || rank >= p->dev.size()) return fail(MAVG_ERR_INVALID_ARG, "bad plan or rank");
+    DeviceGuard guard;
+    MAVG_TRY(alloc_owned(p, p->dev[rank]));
+    if (d_in) *d_in = p->dev[rank].d_in;
+    if (d_out) *d_out = p->dev[rank].d_out;
+    return MAVG_OK;
+}
+
+int mavg_run_device_halo(mavg_plan* p, const void* d_in, void* d_out, const void* d_halo)
+{
+    if (!p || !d_in || !d_out) return fail(MAVG_ERR_INVALID_ARG, "null argument");
+    if (p->dev.size() != 1) return fail(MAVG_ERR_UNSUPPORTED, "mavg_run_device_halo is for single-device plans");
+    if (d_halo && !frame_sharded(p)) return fail(MAVG_ERR_UNSUPPORTED, "planar batches take no halo");
+    DeviceGuard guard;
+    DevCtx& d = p->dev[0];
+    MAVG_CUDA(cudaSetDevice(d.device));
+    uint32_t launches = 0;
+    record(d, 0);
+    record(d, 1);
+    int s = launch_shard(p, d, d_in, d_out, d_halo, &launches);
+    record(d, 2);
+    record(d, 3);
+    d.timed = true;
+    p->launches_last_run = launches;
+    return s;
+}
+
+int mavg_run_device(mavg_plan* p, const void* const* d_in, void* const* d_out)
+{
+    if (!p || !d_in || !d_out) return fail(MAVG_ERR_INVALID_ARG, "null argument");
+    DeviceGuard guard;
+    uint32_t launches = 0;
+    const size_t es = elem_size(p->desc.dtype);
+    for (size_t r = 0; r < p->dev.size(); ++r) {
+        DevCtx& d = p->dev[r];
+        if (!d_in[r] || !d_out[r]) return fail(MAVG_ERR_INVALID_ARG, "null shard pointer for device index %zu", r);
+        MAVG_CUDA(cudaSetDevice(d.device));
+        const void* halo = nullptr;
+        record(d, 0);
+        if (r > 0 && frame_sharded(p) && d.frames > 0) {
+            // left context = tail of the left neighbour's shard
+            const DevCtx& l = p->dev[r - 1];
+            const char* tail = (const char*)d_in[r - 1] + (l.frames - p->halo_frames) * p->desc.channels * es;
+            if (p->peer_ok) {
+                halo = tail;  // read in place over NVLink by the kernel's TMA / global loads
+            } else {
+                MAVG_TRY(alloc_halo(p, d));
+                MAVG_CUDA(cudaMemcpyPeerAsync(d.d_halo, d.device, tail, l.device,
+                                              p->halo_frames * p->desc.channels * es, d.stream));
+                halo = d.d_halo;
+            }
+        }
+        record(d, 1);
+        MAVG_TRY(launch_shard(p, d, d_in[r], d_out[r], halo, &launches));
+        record(d, 2);
+        record(d, 3);
+        d.timed = true;
+    }
+    p->launches_last_run = launches;
+    return MAVG_OK;
+}
+
+int mavg_run_owned(mavg_plan* p)
+{
+    if (!p) return fail(MAVG_ERR_INVALID_ARG, "plan is null");
+    const void* in[MAVG_MAX_DEVICES];
+    void* out[MAVG_MAX_DEVICES];
+    DeviceGuard guard;
+    for (size_t r = 0; r < p->dev.size(); ++r) {
+        MAVG_TRY(alloc_owned(p, p->dev[r]));
+        in[r] = p->dev[r].d_in;
+        out[r] = p->dev[r].d_out;
+    }
+    return mavg_run_device(p, in, out);
+}
+
+int mavg_synchronize(mavg_plan* p)
+{
+    if (!p) return fail(MAVG_ERR_INVALID_ARG, "plan is null");
+    DeviceGuard guard;
+    for (DevCtx& d : p->dev) {
+        MAVG_CUDA(cudaSetDevice(d.device));
+        MAVG_CUDA(cudaStreamSynchronize(d.stream));
+    }
+    return gather_timing(p);
+}
+
+int mavg_get_timing(mavg_plan* p, mavg_timing* t)
+{
+    if (!p || !t) return fail(MAVG_ERR_INVALID_ARG, "null argument");
+    *t = p->timing;
+    return MAVG_OK;
+}
+
+int mavg_run_host(mavg_plan* p, const void* h_in, void* h_out)
+{
+    if (!p || !h_in || !h_out) return fail(MAVG_ERR_INVALID_ARG, "null argument");
+    if (h_in == h_out) return fail(MAVG_ERR_INVALID_ARG, "output must not alias input");
+    DeviceGuard guard;
+    const size_t es = elem_size(p->desc.dtype);
+    const uint64_t C = p->desc.channels;
+    uint32_t launches = 0;
+    for (DevCtx& d : p->dev) {
+        MAVG_TRY(alloc_owned(p, d));
+        MAVG_CUDA(cudaSetDevice(d.device));
+        const uint64_t elems = shard_elems(p, d);
+        const char* src;
+        const void* halo = nullptr;
+        record(d, 0);
+        if (planar_batch(p)) {
+            src = (const char*)h_in + (uint64_t)d.first_channel * p->desc.frames * es;
+        } else {
+            src = (const char*)h_in + d.first_frame * C * es;
+            // a later shard's left context sits right before it in host memory: inside the caller's
+            // whole-signal buffer (multi-device plans) or, for a shard plan (desc.first_frame > 0), in
+            // the halo_frames frames the caller keeps in front of h_in
+            if ((d.first_frame > 0 || p->desc.first_frame > 0) && d.frames > 0) {
+                MAVG_TRY(alloc_halo(p, d));
+                const uint64_t hb = p->halo_frames * C * es;
+                MAVG_CUDA(cudaMemcpyAsync(d.d_halo, src - hb, hb, cudaMemcpyHostToDevice, d.stream));
+                halo = d.d_halo;
+            }
+        }
+        if (elems) MAVG_CUDA(cudaMemcpyAsync(d.d_in, src, elems * es, cudaMemcpyHostToDevice, d.stream));
+        record(d, 1);
+        MAVG_TRY(launch_shard(p, d, d.d_in, d.d_out, halo, &launches));
+        record(d, 2);
+        char* dst = (char*)h_out + (src - (const char*)h_in);
+        if (elems) MAVG_CUDA(cudaMemcpyAsync(dst, d.d_out, elems * es, cudaMemcpyDeviceToHost, d.stream));
+        record(d, 3);
+        d.timed = true;
+    }
+    p->launches_last_run = launches;
+    return mavg_synchronize(p);
+}
+
+int mavg_fill_synthetic_device(void* d_dst, int dtype, uint64_t n, uint64_t first_index, uint64_t seed, int dist,
+                               void* cuda_stream)
+{
+    if (!d_dst && n) return fail(MAVG_ERR_INVALID_ARG, "null destination");
+    if (dtype != MAVG_F32 && dtype != MAVG_I16) return fail(MAVG_ERR_INVALID_ARG, "unknown dtype %d", dtype);
+    if (dist < 0 || dist > MAVG_DIST_DC1E4) return fail(MAVG_ERR_INVALID_ARG, "unknown distribution %d", dist);
+    if (n == 0) return MAVG_OK;
+    const unsigned blocks = (unsigned)std::min<uint64_t>((n + 255) / 256, 148 * 16);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    if (dtype == MAVG_F32)
+        mavg::fill_f32_kernel<<<blocks, 256, 0, st>>>((float*)d_dst, n, first_index, seed, dist);
+    else
+        mavg::fill_i16_kernel<<<blocks, 256, 0, st>>>((int16_t*)d_dst, n, first_index, seed);
+    MAVG_CUDA(cudaGetLastError());
+    return MAVG_OK;
+}
+
+int mavg_fill_synthetic(mavg_plan* p, uint64_t seed, int dist)
+{
+    if (!p) return fail(MAVG_ERR_INVALID_ARG, "plan is null");
+    DeviceGuard guard;
+    for (DevCtx& d : p->dev) {
+        MAVG_TRY(alloc_owned(p, d));
+        MAVG_CUDA(cudaSetDevice(d.device));
+        uint64_t first;
+        if (planar_batch(p)) first = (uint64_t)d.first_channel * p->desc.frames;
+        else first = (p->desc.first_frame + d.first_frame) * p->desc.channels;
+        MAVG_TRY(mavg_fill_synthetic_device(d.d_in, p->desc.dtype, shard_elems(p, d), first, seed, dist, d.stream));
+    }
+    return MAVG_OK;
+}
+
+int mavg_ipc_export(const void* d_ptr, void* handle64)
+{
+    if (!d_ptr || !handle64) return fail(MAVG_ERR_INVALID_ARG, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    MAVG_CUDA(cudaIpcGetMemHandle(&h, const_cast<void*>(d_ptr)));
+    memcpy(handle64, &h, 64);
+    return MAVG_OK;
+}
+
+int mavg_ipc_open(const void* handle64, void** d_ptr)
+{
+    if (!d_ptr || !handle64) return fail(MAVG_ERR_INVALID_ARG, "null argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    MAVG_CUDA(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return MAVG_OK;
+}
+
+int mavg_ipc_close(void* d_ptr)
+{
+    if (!d_ptr) return MAVG_OK;
+    MAVG_CUDA(cudaIpcCloseMemHandle(d_ptr));
+    return MAVG_OK;
+}
+
+int mavg_device_alloc(uint64_t bytes, void** d_ptr)
+{
+    if (!d_ptr) return fail(MAVG_ERR_INVALID_ARG, "null argument");
+    if (cudaMalloc(d_ptr, bytes ? bytes : 256) != cudaSuccess) {
+        cudaError_t e = cudaGetLastError();
+        return fail(e == cudaErrorNoDevice ? MAVG_ERR_NO_DEVICE : MAVG_ERR_ALLOC, "cudaMalloc(%llu) failed: %s",
+                    (unsigned long long)bytes, cudaGetErrorString(e));
+    }
+    return MAVG_OK;
+}
+
+int mavg_device_free(void* d_ptr)
+{
+    if (d_ptr) MAVG_CUDA(cudaFree(d_ptr));
+    return MAVG_OK;
+}
+
+}  // extern "C"

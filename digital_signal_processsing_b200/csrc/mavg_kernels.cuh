@@ -1,0 +1,562 @@
+// mavg_kernels.cuh -- device code of libmavg (sm_100a only).
+//
+// Replaces every __global__ in the reference's basics/*.cu:
+//   averager_kernel (naive / smem / int2 / int4)      -> stream_f32_kernel, MODE 0
+//   hillis_steele + uniform_add + prefix-diff averager  -> stream_f32_kernel, MODE 1
+//   blelloch_scan_inclusive + blelloch_uniform_add      -> stream_f32_kernel, MODE 1
+// plus generic_kernel for every shape the streaming kernel does not take.
+//
+// Design of stream_f32_kernel (one signal = one row-major [rows][32] float tensor):
+//   * persistent CTAs; each walks contiguous ranges of tiles ("chunks") of a signal,
+//     so the k-sample left context is re-read once per chunk, not once per tile;
+//   * tiles (NT*R samples, 16-32 KB) arrive through a ring of TMA tensor loads
+//     (cp.async.bulk.tensor + mbarrier complete_tx, SWIZZLE_128B so that each
+//     thread's 64/128-byte run is read with conflict-free LDS.128); rows before
+//     sample 0 and after the end are zero-filled by the TMA unit, which IS the
+//     reference's zero halo (gpu_utils.h:112-121) without allocating one;
+//   * every thread owns a run of R consecutive outputs: window sum at the run start
+//     from group totals (MODE 0: direct sum of the <=16 totals between, no
+//     cancellation; MODE 1: difference of a tile-rebased prefix scan of the totals,
+//     warp-shuffle scan + per-tile totals), then slides w += x[i] - x[i-k];
+//   * results go to a swizzled staging tile and leave through a TMA tensor store,
+//     which also clips the rows past the end of the signal.
+// HBM traffic: 4 B read + 4 B written per sample, plus history tiles per chunk.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mavg {
+
+// ----------------------------------------------------------------------------------
+// Synthetic generator (same formula as oracle/mavg_oracle.c: oracle_mix64 / gen_f32)
+// ----------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t seed, uint64_t index)
+{
+    uint64_t z = index + seed * 0x9E3779B97F4A7C15ull + 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+__device__ __forceinline__ float synth_f32(uint64_t seed, uint64_t index, int dist)
+{
+    const uint64_t z = mix64(seed, index);
+    const float u = __fmul_rn((float)(uint32_t)(z >> 40), 1.0f / 16777216.0f);
+    switch (dist) {
+    case 0: return u;
+    case 1: return __fsub_rn(__fmul_rn(2.0f, u), 1.0f);
+    case 2: return (float)((int32_t)(z >> 48) - 32768);
+    case 3: return __fadd_rn(10000.0f, __fsub_rn(__fmul_rn(2.0f, u), 1.0f));
+    default: return 0.0f;
+    }
+}
+
+__global__ void fill_f32_kernel(float* __restrict__ dst, uint64_t n, uint64_t first, uint64_t seed, int dist)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        dst[i] = synth_f32(seed, first + i, dist);
+}
+
+__global__ void fill_i16_kernel(int16_t* __restrict__ dst, uint64_t n, uint64_t first, uint64_t seed)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        dst[i] = (int16_t)((int32_t)(mix64(seed, first + i) >> 48) - 32768);
+}
+
+// ----------------------------------------------------------------------------------
+// Generic kernel: any dtype / channel count / alignment / window.
+// One thread = one channel x RG consecutive frames; consecutive threads take
+// consecutive channels first, so many-channel interleaved signals coalesce.
+// float accumulates in fp64 (the k-term fresh sum would otherwise cost k*eps);
+// int16 accumulates exactly and divides with C truncation like the reference
+// (basics/profilable_moving_averager.cpp:23,33).
+// ----------------------------------------------------------------------------------
+struct GenericParams {
+    uint64_t frames;       // frames of this signal (per channel)
+    uint64_t out_begin;    // first frame to produce
+    uint64_t out_end;      // one past the last frame to produce
+    uint64_t halo_frames;  // frames available in `halo` (left context of frame 0)
+    uint64_t sig_stride;   // elements between consecutive planar signals (blockIdx.y)
+    uint32_t channels;     // interleave factor inside one signal
+    uint32_t k;
+};
+
+template <typename T> struct GenericAcc;
+template <> struct GenericAcc<float> {
+    typedef double type;
+    __device__ static __forceinline__ float finish(double w, uint32_t k, double inv) { (void)k; return (float)(w * inv); }
+};
+template <> struct GenericAcc<int16_t> {
+    typedef long long type;
+    __device__ static __forceinline__ int16_t finish(long long w, uint32_t k, double inv)
+    {
+        (void)inv;
+        // |w| <= k * 32768: 32-bit division whenever that fits.
+        if (k < 65536u) return (int16_t)((int)w / (int)k);
+        return (int16_t)(w / (long long)k);
+    }
+};
+
+template <typename T, int RG>
+__global__ void __launch_bounds__(256) generic_kernel(const T* __restrict__ x, T* __restrict__ y,
+                                                      const T* __restrict__ halo, const GenericParams p)
+{
+    typedef typename GenericAcc<T>::type Acc;
+    const uint32_t C = p.channels;
+    const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t c = (uint32_t)(gid % C);
+    const uint64_t run = gid / C;
+    const uint64_t f0 = p.out_begin + run * (uint64_t)RG;
+    if (f0 >= p.out_end) return;
+    const uint64_t f1 = (f0 + RG < p.out_end) ? f0 + RG : p.out_end;
+    x += (uint64_t)blockIdx.y * p.sig_stride;
+    y += (uint64_t)blockIdx.y * p.sig_stride;
+    const uint64_t k = p.k;
+    const double inv = 1.0 / (double)p.k;
+
+    // window sum over frames [f0-k, f0): negative frames come from the halo, else zero
+    Acc w = 0;
+    {
+        const long long lo = (long long)f0 - (long long)k;
+        long long j = lo;
+        if (j < 0) {
+            if (halo != nullptr) {
+                long long hlo = -(long long)p.halo_frames;
+                if (j < hlo) j = hlo;
+                const long long hend = (long long)f0 < 0 ? (long long)f0 : 0;
+                for (; j < hend; ++j) w += (Acc)halo[(uint64_t)(j + (long long)p.halo_frames) * C + c];
+            }
+            j = 0;
+        }
+        for (; j < (long long)f0; ++j) w += (Acc)x[(uint64_t)j * C + c];
+    }
+    for (uint64_t f = f0; f < f1; ++f) {
+        Acc old = 0;
+        if (f >= k) {
+            old = (Acc)x[(f - k) * C + c];
+        } else if (halo != nullptr) {
+            const uint64_t back = k - f;  // frames before frame 0
+            if (back <= p.halo_frames) old = (Acc)halo[(p.halo_frames - back) * C + c];
+        }
+        w += (Acc)x[f * C + c] - old;
+        y[f * C + c] = GenericAcc<T>::finish(w, p.k, inv);
+    }
+}
+
+// ----------------------------------------------------------------------------------
+// PTX helpers (mbarrier, TMA tensor load/store, proxy fence)
+// ----------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            uint64_t hint)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "l"(hint)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2)
+{
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(map)),
+                 "r"(src), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map)
+{
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ float4 lds128(uint32_t addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d)
+{
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ float lds32(uint32_t addr)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts32(uint32_t addr, float v)
+{
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+// SWIZZLE_128B: 16-byte chunk index bits [4:6] ^= 128-byte row index bits [7:9].
+// Valid on absolute shared addresses because every tile buffer is 1024-byte aligned.
+__device__ __forceinline__ uint32_t swz(uint32_t addr) { return addr ^ ((addr >> 3) & 0x70u); }
+
+constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;  // L2 cache hint: streaming input
+
+// ----------------------------------------------------------------------------------
+// Streaming kernel
+// ----------------------------------------------------------------------------------
+struct StreamParams {
+    float inv_k;
+    uint32_t k;
+    uint32_t n_full;       // whole thread-groups strictly between the lag group and the own group
+    uint32_t m_part;       // leading elements of the lag run that complete the window at the run start (1..R)
+    uint32_t lag_chunks;   // ceil(k / 4): 16-byte chunks from the lag run's aligned start to the own run
+    int32_t tiles_per_signal;
+    int32_t chunk_tiles;        // output tiles per chunk
+    int32_t chunks_per_signal;
+    int32_t total_chunks;       // chunks_per_signal * signals
+    int32_t hist_tiles;         // H: history tiles replayed (loaded, summarised, not written) per chunk
+    int32_t stages;             // S = H + 1 + prefetch
+    int32_t prefetch;           // P
+    int32_t has_halo;           // tiles before tile 0 come from halo_map instead of zero fill
+};
+
+// Shared-memory carve-up (bytes), shared by host (size) and device (offsets).
+__host__ __device__ inline uint32_t stream_smem_bytes(int NT, int R, int S, int H)
+{
+    const uint32_t TB = (uint32_t)NT * R * 4;
+    return 1024u                       // alignment slack
+           + (uint32_t)S * TB          // input ring
+           + 2u * TB                   // output staging (double buffered)
+           + (uint32_t)(H + 2) * NT * 4  // per-thread group totals (MODE 0) / warp-inclusive prefixes (MODE 1)
+           + (uint32_t)(H + 2) * 32 * 4  // per-tile exclusive warp offsets, [31] = tile total (MODE 1)
+           + 2u * 32 * 4               // raw warp totals, double buffered by iteration parity (MODE 1)
+           + (uint32_t)S * 8;          // mbarriers
+}
+
+// Cancellation-free window sums for compile-time K <= 8 (MODE 2): v[] holds samples
+// a-K+1 .. a+R-1; windows are assembled from power-of-two partial windows, additions only,
+// so the relative error stays ~K*2^-24 even where the window sum is nearly zero.
+template <int K, int R>
+__device__ __forceinline__ void small_window_sums(const float (&v)[R + 7], float (&w)[R])
+{
+    float w2[R + 6], w4[R + 4], w8[R];
+    if constexpr (K >= 2) {
+#pragma unroll
+        for (int i = 0; i < R + 6; ++i) w2[i] = v[i] + v[i + 1];
+    }
+    if constexpr (K >= 4) {
+#pragma unroll
+        for (int i = 0; i < R + 4; ++i) w4[i] = w2[i] + w2[i + 2];
+    }
+    if constexpr (K >= 8) {
+#pragma unroll
+        for (int i = 0; i < R; ++i) w8[i] = w4[i] + w4[i + 4];
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        float acc;
+        int off = r;
+        if constexpr (K >= 8) { acc = w8[off]; off += 8; }
+        else if constexpr (K >= 4) { acc = w4[off]; off += 4; }
+        else if constexpr (K >= 2) { acc = w2[off]; off += 2; }
+        else { acc = v[off]; off += 1; }
+        if constexpr (K < 8 && K >= 4 && (K & 2)) { acc += w2[off]; off += 2; }
+        if constexpr (K >= 2 && (K & 1)) { acc += v[off]; off += 1; }
+        w[r] = acc;
+    }
+}
+
+// MODE 0: direct group sums (9 <= k <= direct_max), MODE 1: tile-rebased prefix scan,
+// MODE 2: compile-time K <= 8, additions only (MIS unused).
+template <int NT, int R, int MIS, int MODE, int K>
+__global__ void __launch_bounds__(NT)
+    stream_f32_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map,
+                      const __grid_constant__ CUtensorMap halo_map, const StreamParams p)
+{
+    constexpr int T = NT * R;        // samples per tile
+    constexpr uint32_t TB = T * 4;   // bytes per tile
+    constexpr int ROWS = T / 32;     // 128-byte rows per tile
+    constexpr int NW = NT / 32;
+    constexpr int CH_OWN = R / 4;
+    constexpr int CH_LAG = (MODE == 2) ? 2 : CH_OWN + (MIS ? 1 : 0);
+    static_assert(MODE != 2 || (K >= 1 && K <= 8), "MODE 2 serves K in 1..8");
+    static_assert(NT % 32 == 0 && NW <= 16, "NT must be a multiple of 32, at most 512");
+    static_assert(R == 16 || R == 32, "run length");
+
+    extern __shared__ uint8_t smem_raw[];
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int S = p.stages;
+    const int H = p.hist_tiles;
+    const int P = p.prefetch;
+    const int GS = H + 2;  // summary slots
+
+    const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t ring_bytes = (uint32_t)S * TB;
+    const uint32_t outb = ring + ring_bytes;
+    const uint32_t gsum = outb + 2u * TB;                 // float [GS][NT]
+    const uint32_t wexc = gsum + (uint32_t)GS * NT * 4;   // float [GS][32]
+    const uint32_t wraw = wexc + (uint32_t)GS * 32 * 4;   // float [2][32]
+    const uint32_t bars = wraw + 2u * 32 * 4;             // u64   [S]
+
+    if (tid == 0) {
+        prefetch_tmap(&in_map);
+        prefetch_tmap(&out_map);
+        if (p.has_halo) prefetch_tmap(&halo_map);
+        for (int s = 0; s < S; ++s) mbar_init(bars + 8u * s, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    // Producer helper (thread 0 only): tensor load of tile `tile` of signal `sig` into stage `st`.
+    auto issue_load = [&](int tile, int sig, int st) {
+        const uint32_t bar = bars + 8u * st;
+        mbar_arrive_expect_tx(bar, TB);
+        if (tile < 0 && p.has_halo)
+            tma_load_3d(ring + (uint32_t)st * TB, &halo_map, bar, 0, (tile + H) * ROWS, 0, kEvictFirst);
+        else
+            tma_load_3d(ring + (uint32_t)st * TB, &in_map, bar, 0, tile * ROWS, sig, kEvictFirst);
+    };
+
+    uint32_t it = 0;   // tiles streamed so far by this CTA (history + output), never reset
+    int st = 0;        // it % S
+    int slot = 0;      // it % GS
+    uint32_t otiles = 0;   // output tiles produced so far (selects the staging buffer)
+    // deferred TMA store (thread 0): st_pending = staged but not issued, st_inflight = issued, smem read
+    // not yet confirmed
+    bool st_pending = false, st_inflight = false;
+    int st_tile = 0, st_sig = 0;
+    uint32_t st_buf = 0;
+
+    for (int chunk = blockIdx.x; chunk < p.total_chunks; chunk += gridDim.x) {
+        const int sig = chunk / p.chunks_per_signal;
+        const int t0 = (chunk - sig * p.chunks_per_signal) * p.chunk_tiles;
+        int t1 = t0 + p.chunk_tiles;
+        if (t1 > p.tiles_per_signal) t1 = p.tiles_per_signal;
+        if (t0 >= t1) continue;
+        const int first = t0 - H;
+        const int ntl = t1 - first;
+
+        if (tid == 0) {
+            int s2 = st;
+            for (int j = 0; j < P && j < ntl; ++j) {
+                issue_load(first + j, sig, s2);
+                s2 = (s2 + 1 == S) ? 0 : s2 + 1;
+            }
+        }
+
+        for (int j = 0; j < ntl; ++j) {
+            const int tile = first + j;
+            const bool is_out = (j >= H);
+            const uint32_t cur = ring + (uint32_t)st * TB;
+
+            mbar_wait(bars + 8u * st, (it / (uint32_t)S) & 1u);
+
+            // ---- own run: R consecutive samples, conflict-free swizzled LDS.128
+            float x[R];
+#pragma unroll
+            for (int c = 0; c < CH_OWN; ++c) {
+                const float4 v = lds128(swz(cur + (uint32_t)tid * (R * 4) + 16u * c));
+                x[4 * c + 0] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
+            }
+            // group total, fixed pairwise order
+            float gtot = 0.f;
+            if constexpr (MODE != 2) {
+                float q4[CH_OWN];
+#pragma unroll
+                for (int c = 0; c < CH_OWN; ++c) q4[c] = (x[4 * c] + x[4 * c + 1]) + (x[4 * c + 2] + x[4 * c + 3]);
+                gtot = (q4[0] + q4[1]) + (q4[2] + q4[3]);
+                if constexpr (R == 32) gtot += (q4[CH_OWN - 4] + q4[CH_OWN - 3]) + (q4[CH_OWN - 2] + q4[CH_OWN - 1]);
+            }
+
+            float incl = gtot;  // MODE 1: inclusive prefix of group totals inside the warp
+            if constexpr (MODE == 0) {
+                sts32(gsum + ((uint32_t)slot * NT + tid) * 4u, gtot);
+            } else if constexpr (MODE == 1) {
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const float up = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += up;
+                }
+                sts32(gsum + ((uint32_t)slot * NT + tid) * 4u, incl);
+                if (lane == 31) sts32(wraw + ((it & 1u) * 32u + warp) * 4u, incl);
+            }
+
+            if (tid == 0 && st_inflight) {  // staging buffer about to be rewritten is free again
+                tma_wait_read0();
+                st_inflight = false;
+            }
+            __syncthreads();
+
+            if (tid == 0) {
+                if (j + P < ntl) {
+                    int s2 = st + P;
+                    if (s2 >= S) s2 -= S;
+                    issue_load(first + j + P, sig, s2);
+                }
+                if (st_pending) {
+                    tma_store_3d(&out_map, st_buf, 0, st_tile * ROWS, st_sig);
+                    tma_commit();
+                    st_pending = false;
+                    st_inflight = true;
+                }
+            }
+
+            float own_off = 0.f, wex = 0.f;
+            if constexpr (MODE == 1) {
+                // exclusive offsets of the NW warp totals of this tile (every warp redundantly)
+                const float v = (lane < NW) ? lds32(wraw + ((it & 1u) * 32u + lane) * 4u) : 0.f;
+                float wi = v;
+#pragma unroll
+                for (int d = 1; d < NW; d <<= 1) {
+                    const float up = __shfl_up_sync(0xffffffffu, wi, d);
+                    if (lane >= d) wi += up;
+                }
+                wex = wi - v;
+                if (warp == 0) {
+                    if (lane < NW) sts32(wexc + ((uint32_t)slot * 32u + lane) * 4u, wex);
+                    if (lane == NW - 1) sts32(wexc + ((uint32_t)slot * 32u + 31u) * 4u, wi);  // tile total
+                }
+                own_off = __shfl_sync(0xffffffffu, wex, warp);
+            }
+
+            if (is_out) {
+                // ---- lag run: samples [a-k, a-k+R) (a = run start), loaded as aligned 16-byte chunks
+                float xl[CH_LAG * 4];
+                {
+                    const int back = (MODE == 2) ? 2 : (int)p.lag_chunks;
+                    int lin = (int)((uint32_t)st * TB) + (tid * CH_OWN - back) * 16;
+#pragma unroll
+                    for (int c = 0; c < CH_LAG; ++c) {
+                        int o = lin + 16 * c;
+                        if (o < 0) o += (int)ring_bytes;
+                        const float4 v = lds128(swz(ring + (uint32_t)o));
+                        xl[4 * c + 0] = v.x; xl[4 * c + 1] = v.y; xl[4 * c + 2] = v.z; xl[4 * c + 3] = v.w;
+                    }
+                }
+
+                const float inv = p.inv_k;
+                const uint32_t ob = outb + (otiles & 1u) * TB + (uint32_t)tid * (R * 4);
+                if constexpr (MODE == 2) {
+                    // ---- additions only: v = samples a-K+1 .. a+R-1
+                    float v[R + 7], w[R];
+#pragma unroll
+                    for (int i = 0; i < R + 7; ++i) v[i] = 0.f;
+#pragma unroll
+                    for (int i = 0; i < K - 1; ++i) v[i] = xl[8 - (K - 1) + i];
+#pragma unroll
+                    for (int i = 0; i < R; ++i) v[K - 1 + i] = x[i];
+                    small_window_sums<K, R>(v, w);
+#pragma unroll
+                    for (int c = 0; c < CH_OWN; ++c)
+                        sts128(swz(ob + 16u * c), w[4 * c] * inv, w[4 * c + 1] * inv, w[4 * c + 2] * inv,
+                               w[4 * c + 3] * inv);
+                } else {
+                    // ---- window sum over [a-k, a): whole groups between, then the tail of the lag group
+                    float acc = 0.f;
+                    if constexpr (MODE == 0) {
+                        int gi = slot * NT + tid;
+                        for (uint32_t n = 0; n < p.n_full; ++n) {
+                            gi = (gi == 0) ? GS * NT - 1 : gi - 1;
+                            acc += lds32(gsum + (uint32_t)gi * 4u);
+                        }
+                    } else {
+                        int lt = tid - (int)(p.n_full + 1u);  // thread index of the lag group, relative to this tile
+                        int h = 0;
+                        if (lt < 0) {
+                            h = (-lt + NT - 1) / NT;
+                            lt += h * NT;
+                        }
+                        int ls = slot - h;
+                        if (ls < 0) ls += GS;
+                        const float wsame = __shfl_sync(0xffffffffu, wex, lt >> 5);
+                        const float wold = lds32(wexc + ((uint32_t)ls * 32u + (uint32_t)(lt >> 5)) * 4u);
+                        const float cp_lag = lds32(gsum + ((uint32_t)ls * NT + lt) * 4u) + (h == 0 ? wsame : wold);
+                        const float e_own = own_off + (incl - gtot);
+                        if (h == 0) {
+                            acc = e_own - cp_lag;
+                        } else {
+                            float rest = lds32(wexc + ((uint32_t)ls * 32u + 31u) * 4u) - cp_lag;  // tail of the lag tile
+                            int ms = ls;
+                            for (int v2 = 1; v2 < h; ++v2) {  // whole tiles strictly between (k > tile only)
+                                ms = (ms + 1 == GS) ? 0 : ms + 1;
+                                rest += lds32(wexc + ((uint32_t)ms * 32u + 31u) * 4u);
+                            }
+                            acc = e_own + rest;
+                        }
+                    }
+#pragma unroll
+                    for (int r = 0; r < R; ++r)
+                        if ((uint32_t)r < p.m_part) acc += xl[MIS + r];
+
+                    // ---- slide and scale
+                    float w = acc;
+#pragma unroll
+                    for (int c = 0; c < CH_OWN; ++c) {
+                        float y0, y1, y2, y3;
+                        w += x[4 * c + 0] - xl[MIS + 4 * c + 0]; y0 = w * inv;
+                        w += x[4 * c + 1] - xl[MIS + 4 * c + 1]; y1 = w * inv;
+                        w += x[4 * c + 2] - xl[MIS + 4 * c + 2]; y2 = w * inv;
+                        w += x[4 * c + 3] - xl[MIS + 4 * c + 3]; y3 = w * inv;
+                        sts128(swz(ob + 16u * c), y0, y1, y2, y3);
+                    }
+                }
+                fence_proxy_async_smem();
+                if (tid == 0) {
+                    st_pending = true;
+                    st_tile = tile;
+                    st_sig = sig;
+                    st_buf = outb + (otiles & 1u) * TB;
+                }
+                ++otiles;
+            }
+
+            ++it;
+            st = (st + 1 == S) ? 0 : st + 1;
+            slot = (slot + 1 == GS) ? 0 : slot + 1;
+        }
+
+        // chunk epilogue: everyone is done reading the ring and writing the staging tile
+        __syncthreads();
+        if (tid == 0 && st_pending) {
+            tma_store_3d(&out_map, st_buf, 0, st_tile * ROWS, st_sig);
+            tma_commit();
+            st_pending = false;
+            st_inflight = true;  // the next chunk's first iteration waits for the read to finish
+        }
+    }
+    if (tid == 0) tma_wait_all0();
+}
+
+}  // namespace mavg

@@ -1,0 +1,292 @@
+"""GPU parity tests: libmavg's CUDA path, called through the C ABI, against the CPU oracle.
+
+Bars (BASELINE.json north_star): int16 bit-exact with the reference CPU function
+(basics/profilable_moving_averager.cpp:14-37); float32 max relative error <= 1e-5 against
+the fp64 oracle on U[0,1) input; zero-mean input is judged by the forward error relative to
+the mean absolute window content (elementwise relative error is ill-posed there).
+"""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _cases(npz):
+    names = sorted({k.rsplit("__", 1)[0] for k in npz.files})
+    for n in names:
+        frames, ch, k = (int(v) for v in npz[n + "__meta"])
+        yield n, npz[n + "__x"], npz[n + "__y"], frames, ch, k
+
+
+def _rel(y, e):
+    m = e != 0
+    return float(np.max(np.abs(y[m].astype(np.float64) - e[m]) / np.abs(e[m]))) if m.any() else 0.0
+
+
+def _fwd_err(y, e, x, k, oracle_mod):
+    """max |y - e| / ((1/k) * sum |x_j| over the window)"""
+    scale = oracle_mod.mavg_f64(np.abs(x), k)
+    m = scale > 0
+    return float(np.max(np.abs(y[m].astype(np.float64) - e[m]) / scale[m]))
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch
+
+
+# ------------------------------------------------------------------ golden fixtures
+def test_golden_i16_bit_exact(mavg):
+    g = np.load(os.path.join(GOLD, "golden_i16.npz"))
+    for name, x, y, frames, ch, k in _cases(g):
+        got = mavg.moving_average(x, k, channels=ch)
+        assert got.dtype == np.int16
+        assert np.array_equal(got, y), name
+
+
+def test_golden_f32(mavg, oracle_mod):
+    g = np.load(os.path.join(GOLD, "golden_f32.npz"))
+    for name, x, y, frames, ch, k in _cases(g):
+        got = mavg.moving_average(x, k, channels=ch)
+        if "usym" in name:
+            assert _fwd_err(got, y, x, k, oracle_mod) < TOL, name
+        else:
+            assert _rel(got, y) < TOL, name
+
+
+# ------------------------------------------------------------------ streaming kernel, all modes
+K_SWEEP = [1, 2, 3, 4, 5, 6, 7, 8, 9, 15, 16, 17, 31, 33, 64, 100, 255, 256, 257, 511, 1000, 1024, 2047, 4095, 4096]
+
+
+@pytest.mark.parametrize("k", K_SWEEP)
+def test_stream_path_vs_oracle(mavg, oracle_mod, k):
+    n = 5 * 4096 + 32 * 7                      # whole rows, several tiles, ragged last tile
+    x = oracle_mod.fill_f32(n, 1000 + k)
+    with mavg.Plan(n, k, path="stream") as plan:
+        assert plan.info.path == 1
+        y = plan.run_host(x)
+    assert _rel(y, oracle_mod.mavg_f64(x, k)) < TOL
+
+
+@pytest.mark.parametrize("k", [3, 16, 64, 256, 1024, 4096])
+def test_stream_path_matches_arithmetic_model_bitwise(mavg, oracle_mod, k):
+    """The CUDA kernel performs exactly the fp32 operations of tests/algo_model.py."""
+    from algo_model import stream_model
+    n = 3 * 4096
+    x = oracle_mod.fill_f32(n, 2000 + k)
+    with mavg.Plan(n, k, path="stream") as plan:
+        y = plan.run_host(x)
+    assert np.array_equal(y, stream_model(x, k, 256, 16))
+
+
+@pytest.mark.parametrize("shape", [(256, 16), (256, 32), (512, 16)])
+@pytest.mark.parametrize("k", [5, 64, 300, 4096, 9000])
+def test_stream_shapes(mavg, oracle_mod, shape, k):
+    threads, run = shape
+    n = 4 * threads * run + 64
+    x = oracle_mod.fill_f32(n, 3000 + k)
+    with mavg.Plan(n, k, path="stream", threads=threads, run=run) as plan:
+        y = plan.run_host(x)
+        assert plan.info.tile_samples == threads * run
+    assert _rel(y, oracle_mod.mavg_f64(x, k)) < TOL
+
+
+@pytest.mark.parametrize("k", [3, 100, 2000])
+def test_chunking_and_prefetch_do_not_change_bits(mavg, oracle_mod, k):
+    n = 300 * 4096
+    x = oracle_mod.fill_f32(n, 4000 + k)
+    with mavg.Plan(n, k, path="stream") as plan:
+        base = plan.run_host(x)
+    for tune in (dict(chunks_per_cta=3), dict(prefetch=1), dict(prefetch=3, ctas_per_sm=1), dict(ctas_per_sm=1, chunks_per_cta=7)):
+        with mavg.Plan(n, k, path="stream", **tune) as plan:
+            assert np.array_equal(plan.run_host(x), base), tune
+    assert _rel(base, oracle_mod.mavg_f64(x, k)) < TOL
+
+
+@pytest.mark.parametrize("dist", ["USYM", "I16", "DC1E4"])
+@pytest.mark.parametrize("k", [7, 64, 1024])
+def test_other_distributions(mavg, oracle_mod, dist, k):
+    d = getattr(oracle_mod, "DIST_" + dist)
+    n = 6 * 4096
+    x = oracle_mod.fill_f32(n, 5000 + k, d)
+    y = mavg.moving_average(x, k)
+    e = oracle_mod.mavg_f64(x, k)
+    assert _fwd_err(y, e, x, k, oracle_mod) < TOL
+    if dist == "DC1E4":
+        assert _rel(y, e) < TOL   # tile-local rebasing keeps the DC offset from eating the mantissa
+
+
+# ------------------------------------------------------------------ edge cases
+@pytest.mark.parametrize("n", [1, 2, 31, 32, 33, 100, 4095, 4096, 4097, 8191, 12345])
+@pytest.mark.parametrize("k", [1, 3, 50, 5000])
+def test_ragged_lengths_f32(mavg, oracle_mod, n, k):
+    x = oracle_mod.fill_f32(n, 6000 + n + k)
+    y = mavg.moving_average(x, k)
+    assert y.shape == x.shape
+    assert _rel(y, oracle_mod.mavg_f64(x, k)) < TOL
+
+
+def test_empty_input(mavg):
+    assert mavg.moving_average(np.zeros(0, dtype=np.float32), 5).size == 0
+    assert mavg.moving_average(np.zeros(0, dtype=np.int16), 5).size == 0
+
+
+@pytest.mark.parametrize("ch", [1, 2, 3, 8])
+@pytest.mark.parametrize("k", [1, 2, 5, 41, 64, 850, 1000, 70000])
+def test_i16_bit_exact_vs_oracle(mavg, oracle_mod, ch, k):
+    frames = 3000 if k < 70000 else 800
+    x = oracle_mod.fill_i16(frames * ch, 7000 + k + ch)
+    y = mavg.moving_average(x, k, channels=ch)
+    assert np.array_equal(y, oracle_mod.mavg_i16(x, k, ch))
+
+
+def test_i16_extremes_bit_exact(mavg, oracle_mod):
+    for val in (-32768, 32767):
+        x = np.full(5000, val, dtype=np.int16)
+        for k in (1, 3, 4096):
+            assert np.array_equal(mavg.moving_average(x, k), oracle_mod.mavg_i16(x, k))
+
+
+@pytest.mark.parametrize("ch", [2, 3, 5])
+@pytest.mark.parametrize("k", [4, 64, 700])
+def test_interleaved_f32(mavg, oracle_mod, ch, k):
+    frames = 5000
+    x = oracle_mod.fill_f32(frames * ch, 8000 + k + ch)
+    y = mavg.moving_average(x, k, channels=ch)
+    assert _rel(y, oracle_mod.mavg_f64(x, k, ch)) < TOL
+
+
+@pytest.mark.parametrize("frames", [4096 * 2, 5000, 4099])
+@pytest.mark.parametrize("k", [3, 64, 1500])
+def test_planar_batch(mavg, oracle_mod, frames, k):
+    ch = 5
+    x = oracle_mod.fill_f32(frames * ch, 9000 + k)
+    y = mavg.moving_average(x, k, channels=ch, layout="planar")
+    for c in range(ch):
+        seg = slice(c * frames, (c + 1) * frames)
+        assert _rel(y[seg], oracle_mod.mavg_f64(x[seg], k)) < TOL, c
+
+
+def test_unaligned_device_pointer_takes_generic_path(mavg, oracle_mod, torch_cuda):
+    torch = torch_cuda
+    n, k = 20000, 37
+    x = oracle_mod.fill_f32(n + 1, 11)
+    dx = torch.from_numpy(x).cuda()
+    dy = torch.zeros(n + 1, dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()   # the plan runs on its own non-blocking stream
+    with mavg.Plan(n, k) as plan:
+        plan.run_device([dx.data_ptr() + 4], [dy.data_ptr() + 4])
+        plan.synchronize()
+        assert plan.info.launches_per_run >= 1
+    y = dy.cpu().numpy()[1:]
+    assert _rel(y, oracle_mod.mavg_f64(x[1:], k)) < TOL
+
+
+def test_block_size_rule_matches_reference(mavg):
+    with pytest.raises(mavg.MavgError) as e:
+        mavg.Plan(1000, 5, block_size=100)
+    assert e.value.status == -6
+    mavg.Plan(1000, 5, block_size=256).close()
+
+
+# ------------------------------------------------------------------ device-resident runs, generator, halo
+def test_device_generator_matches_oracle(mavg, oracle_mod, torch_cuda):
+    torch = torch_cuda
+    n = 100_000
+    for dist in (0, 1, 2, 3):
+        d = torch.empty(n, dtype=torch.float32, device="cuda")
+        mavg.fill_synthetic_device(d.data_ptr(), "f32", n, 12345, 99, dist)
+        torch.cuda.synchronize()
+        assert np.array_equal(d.cpu().numpy(), oracle_mod.fill_f32(n, 99, dist, first_index=12345)), dist
+    d = torch.empty(n, dtype=torch.int16, device="cuda")
+    mavg.fill_synthetic_device(d.data_ptr(), "i16", n, 777, 5)
+    torch.cuda.synchronize()
+    assert np.array_equal(d.cpu().numpy(), oracle_mod.fill_i16(n, 5, first_index=777))
+
+
+@pytest.mark.parametrize("k", [3, 64, 1024, 4096])
+def test_shard_with_halo_is_bit_identical(mavg, oracle_mod, torch_cuda, k):
+    """Second half of a signal filtered as its own shard, left context read in place from the
+    first half's tail: the same bits as the unsharded run."""
+    torch = torch_cuda
+    T = 4096
+    n = 64 * T
+    cut = 24 * T
+    x = oracle_mod.fill_f32(n, 13)
+    dx = torch.from_numpy(x).cuda()
+    dy = torch.zeros(n, dtype=torch.float32, device="cuda")
+    dz = torch.zeros(n - cut, dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()   # the plan runs on its own non-blocking stream
+    with mavg.Plan(n, k, path="stream") as plan:
+        plan.run_device([dx.data_ptr()], [dy.data_ptr()])
+        plan.synchronize()
+    whole = dy.cpu().numpy()
+    with mavg.Plan(n - cut, k, path="stream", first_frame=cut) as plan:
+        halo = int(plan.info.halo_frames)
+        assert halo >= k and halo % T == 0
+        plan.run_device_halo(dx.data_ptr() + 4 * cut, dz.data_ptr(), dx.data_ptr() + 4 * (cut - halo))
+        plan.synchronize()
+    assert np.array_equal(dz.cpu().numpy(), whole[cut:])
+    assert _rel(whole, oracle_mod.mavg_f64(x, k)) < TOL
+
+
+def test_generic_path_with_halo(mavg, oracle_mod, torch_cuda):
+    torch = torch_cuda
+    ch, k, frames, cut = 2, 300, 9000, 4000
+    x = oracle_mod.fill_i16(frames * ch, 17)
+    dx = torch.from_numpy(x).cuda()
+    dz = torch.zeros((frames - cut) * ch, dtype=torch.int16, device="cuda")
+    torch.cuda.synchronize()
+    with mavg.Plan(frames - cut, k, channels=ch, dtype="i16", first_frame=cut) as plan:
+        halo = int(plan.info.halo_frames)
+        plan.run_device_halo(dx.data_ptr() + 2 * cut * ch, dz.data_ptr(), dx.data_ptr() + 2 * (cut - halo) * ch)
+        plan.synchronize()
+    assert np.array_equal(dz.cpu().numpy(), oracle_mod.mavg_i16(x, k, ch)[cut * ch:])
+
+
+def test_timing_and_info(mavg, oracle_mod):
+    n = 1 << 22
+    x = oracle_mod.fill_f32(n, 21)
+    with mavg.Plan(n, 64) as plan:
+        plan.run_host(x)
+        t = plan.timing()
+        assert t.compute_ms > 0 and t.h2d_ms > 0 and t.d2h_ms > 0
+        assert abs(t.total_ms - (t.h2d_ms + t.compute_ms + t.d2h_ms)) < 1e-3
+        i = plan.info
+        assert i.path == 1 and i.launches_per_run == 1 and i.grid > 0
+
+
+def test_owned_buffers_synthetic_run(mavg, oracle_mod, torch_cuda):
+    n, k = 1 << 20, 5          # BASELINE.json configs[0]: 2^20 mono, k = 5
+    with mavg.Plan(n, k) as plan:
+        plan.fill_synthetic(0x5EED0001, 0)
+        plan.run_owned()
+        plan.synchronize()
+        # read the owned output back through a host run on the same input
+        x = oracle_mod.fill_f32(n, 0x5EED0001)
+        y = plan.run_host(x)
+    assert _rel(y, oracle_mod.mavg_f64(x, k)) < TOL
+
+
+# ------------------------------------------------------------------ BASELINE.json full size
+@pytest.mark.parametrize("k", [3, 256, 4096])
+def test_full_size_2p28_vs_oracle(mavg, oracle_mod, k):
+    n = 1 << 28
+    x = oracle_mod.fill_f32(n, 0x5EED0000 + k)
+    with mavg.Plan(n, k) as plan:
+        y = plan.run_host(x)
+    e = oracle_mod.mavg_f64(x, k)
+    assert _rel(y, e) < TOL
+    del e
+    # size-independent property: constant after warm-up for a constant signal, exactly c for c = 1
+    x.fill(1.0)
+    with mavg.Plan(n, k) as plan:
+        y = plan.run_host(x)
+    assert np.all(np.abs(y[k:] - 1.0) < 1e-6)
