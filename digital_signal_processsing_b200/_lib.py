@@ -85,6 +85,7 @@ SYMBOLS = [
     ("mavg_run_device_halo", _i, [_vp, _vp, _vp, _vp]),
     ("mavg_synchronize", _i, [_vp]),
     ("mavg_get_timing", _i, [_vp, ctypes.POINTER(Timing)]),
+    ("mavg_enable_timing", _i, [_vp, _i]),
     ("mavg_set_stream", _i, [_vp, _vp]),
     ("mavg_plan_buffers", _i, [_vp, _u32, ctypes.POINTER(_vp), ctypes.POINTER(_vp)]),
     ("mavg_fill_synthetic", _i, [_vp, _u64, _i]),
@@ -95,6 +96,8 @@ SYMBOLS = [
     ("mavg_ipc_close", _i, [_vp]),
     ("mavg_device_alloc", _i, [_u64, ctypes.POINTER(_vp)]),
     ("mavg_device_free", _i, [_vp]),
+    ("mavg_host_alloc", _i, [_u64, ctypes.POINTER(_vp)]),
+    ("mavg_host_free", _i, [_vp]),
 ]
 
 

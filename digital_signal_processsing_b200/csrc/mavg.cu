@@ -107,7 +107,7 @@ constexpr uint32_t kMaxSmem = 232448;  // 227 KB opt-in limit per CTA on sm_100
 StreamGeom plan_stream(uint32_t k, const mavg_tuning& tu)
 {
     StreamGeom g;
-    g.NT = tu.threads ? (int)tu.threads : 256;
+    g.NT = tu.threads ? (int)tu.threads : 512;
     g.R = tu.run ? (int)tu.run : 16;
     if (!(g.NT == 256 || g.NT == 512) || !(g.R == 16 || g.R == 32)) return g;
     if (g.NT * g.R > 8192) return g;  // a TMA box holds at most 256 rows of 32 floats
@@ -198,6 +198,9 @@ struct DevCtx {
     void* d_halo = nullptr;     // halo_frames * channels elements of left context (frame sharding)
     int sm_count = 0;
     bool timed = false;
+    // run_host pipeline: copies on their own streams so H2D, kernels and D2H overlap
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    std::vector<cudaEvent_t> pool;  // untimed events ordering slices across the three streams
 };
 
 }  // namespace
@@ -211,6 +214,7 @@ struct mavg_plan {
     mavg_timing timing = {0, 0, 0, 0};
     uint32_t launches_last_run = 0;
     bool peer_ok = false;
+    bool timing_on = true;
 };
 
 namespace {
@@ -228,14 +232,15 @@ bool planar_batch(const mavg_plan* p) { return p->desc.layout == MAVG_PLANAR && 
 bool frame_sharded(const mavg_plan* p) { return !planar_batch(p); }
 
 // samples per signal and signal count as the stream kernel sees one shard
-void shard_signals(const mavg_plan* p, const DevCtx& d, uint64_t* n, uint64_t* signals, uint64_t* stride_elems)
+void shard_signals(const mavg_plan* p, const DevCtx& d, uint64_t frames, uint64_t* n, uint64_t* signals,
+                   uint64_t* stride_elems)
 {
     if (planar_batch(p)) {
         *n = p->desc.frames;
         *signals = d.channels;
         *stride_elems = p->desc.frames;
     } else {
-        *n = d.frames * p->desc.channels;
+        *n = frames * p->desc.channels;
         *signals = 1;
         *stride_elems = *n;
     }
@@ -275,8 +280,8 @@ int alloc_halo(mavg_plan* p, DevCtx& d)
 }
 
 template <typename T>
-int launch_generic_t(const mavg_plan* p, DevCtx& d, const T* in, T* out, const T* halo, uint64_t out_begin,
-                     uint64_t out_end, uint32_t* launches)
+int launch_generic_t(const mavg_plan* p, DevCtx& d, const T* in, T* out, const T* halo, uint64_t frames,
+                     uint64_t out_begin, uint64_t out_end, uint32_t* launches)
 {
     if (out_begin >= out_end) return MAVG_OK;
     constexpr int RG = 64;
@@ -288,7 +293,7 @@ int launch_generic_t(const mavg_plan* p, DevCtx& d, const T* in, T* out, const T
         gp.sig_stride = p->desc.frames;
         signals = d.channels;
     } else {
-        gp.frames = d.frames;
+        gp.frames = frames;
         gp.channels = p->desc.channels;
         gp.sig_stride = 0;
     }
@@ -312,40 +317,42 @@ int launch_generic_t(const mavg_plan* p, DevCtx& d, const T* in, T* out, const T
     return MAVG_OK;
 }
 
-int launch_generic(const mavg_plan* p, DevCtx& d, const void* in, void* out, const void* halo, uint64_t out_begin,
-                   uint64_t out_end, uint32_t* launches)
+int launch_generic(const mavg_plan* p, DevCtx& d, const void* in, void* out, const void* halo, uint64_t frames,
+                   uint64_t out_begin, uint64_t out_end, uint32_t* launches)
 {
     if (p->desc.dtype == MAVG_F32)
-        return launch_generic_t<float>(p, d, (const float*)in, (float*)out, (const float*)halo, out_begin, out_end,
-                                       launches);
-    return launch_generic_t<int16_t>(p, d, (const int16_t*)in, (int16_t*)out, (const int16_t*)halo, out_begin,
-                                     out_end, launches);
+        return launch_generic_t<float>(p, d, (const float*)in, (float*)out, (const float*)halo, frames, out_begin,
+                                       out_end, launches);
+    return launch_generic_t<int16_t>(p, d, (const int16_t*)in, (int16_t*)out, (const int16_t*)halo, frames,
+                                     out_begin, out_end, launches);
 }
 
-bool stream_eligible(const mavg_plan* p, const DevCtx& d, const void* in, const void* out, const void* halo)
+bool stream_eligible(const mavg_plan* p, const DevCtx& d, const void* in, const void* out, const void* halo,
+                     uint64_t frames)
 {
     if (p->path != MAVG_PATH_STREAM || !p->geom.ok) return false;
     if (((uintptr_t)in | (uintptr_t)out | (uintptr_t)halo) & 15u) return false;
     uint64_t n, signals, stride;
-    shard_signals(p, d, &n, &signals, &stride);
+    shard_signals(p, d, frames, &n, &signals, &stride);
     if (n < 32) return false;
     if (signals > 1 && (stride % 4) != 0) return false;  // tensor-map strides are multiples of 16 bytes
     if (n / 32 > 0x7fffffffull - 65536 || signals > 0x7fffffffull) return false;
     return true;
 }
 
-// Enqueue the kernels for one shard on its device stream.
-int launch_shard(mavg_plan* p, DevCtx& d, const void* in, void* out, const void* halo, uint32_t* launches)
+// Enqueue the kernels for `frames` frames (a whole shard, or one slice of it whose left context
+// is `halo`) on the device stream.  Planar batches always run whole (frames = desc.frames).
+int launch_shard(mavg_plan* p, DevCtx& d, const void* in, void* out, const void* halo, uint64_t frames,
+                 uint32_t* launches)
 {
     MAVG_CUDA(cudaSetDevice(d.device));
-    if (shard_elems(p, d) == 0) return MAVG_OK;
-    if (!stream_eligible(p, d, in, out, halo)) {
-        const uint64_t frames = planar_batch(p) ? p->desc.frames : d.frames;
-        return launch_generic(p, d, in, out, halo, 0, frames, launches);
-    }
+    if (planar_batch(p)) frames = p->desc.frames;
+    if (frames == 0 || (planar_batch(p) && d.channels == 0)) return MAVG_OK;
+    if (!stream_eligible(p, d, in, out, halo, frames))
+        return launch_generic(p, d, in, out, halo, frames, 0, frames, launches);
     const StreamGeom& g = p->geom;
     uint64_t n, signals, stride;
-    shard_signals(p, d, &n, &signals, &stride);
+    shard_signals(p, d, frames, &n, &signals, &stride);
     const uint64_t rows = n / 32;
     const uint32_t tile_rows = (uint32_t)(g.NT * g.R / 32);
     const uint64_t T = (uint64_t)g.NT * g.R;
@@ -389,12 +396,7 @@ int launch_shard(mavg_plan* p, DevCtx& d, const void* in, void* out, const void*
 
     // samples past the last whole 128-byte row (n % 32 of them, per signal): generic kernel
     if (rows * 32 < n) {
-        if (signals == 1 && p->desc.channels == 1) {
-            MAVG_TRY(launch_generic(p, d, in, out, halo, rows * 32, n, launches));
-        } else {
-            // planar batch with frames % 32 != 0
-            MAVG_TRY(launch_generic(p, d, in, out, halo, rows * 32, p->desc.frames, launches));
-        }
+        MAVG_TRY(launch_generic(p, d, in, out, halo, frames, rows * 32, frames, launches));
     }
     return MAVG_OK;
 }
@@ -418,9 +420,9 @@ int validate(const mavg_desc* d)
     return MAVG_OK;
 }
 
-void record(DevCtx& d, int which)
+void record(const mavg_plan* p, DevCtx& d, int which)
 {
-    cudaEventRecord(d.ev[which], d.stream);
+    if (p->timing_on) cudaEventRecord(d.ev[which], d.stream);
 }
 
 int gather_timing(mavg_plan* p)
@@ -581,6 +583,9 @@ int mavg_plan_destroy(mavg_plan* p)
         if (d.d_in) cudaFree(d.d_in);
         if (d.d_out) cudaFree(d.d_out);
         if (d.d_halo) cudaFree(d.d_halo);
+        if (d.s_h2d) { cudaStreamSynchronize(d.s_h2d); cudaStreamDestroy(d.s_h2d); }
+        if (d.s_d2h) { cudaStreamSynchronize(d.s_d2h); cudaStreamDestroy(d.s_d2h); }
+        for (cudaEvent_t e : d.pool) cudaEventDestroy(e);
         for (int i = 0; i < 4; ++i)
             if (d.ev[i]) cudaEventDestroy(d.ev[i]);
         if (d.stream && d.own_stream) cudaStreamDestroy(d.stream);
@@ -627,6 +632,15 @@ int mavg_set_stream(mavg_plan* p, void* cuda_stream)
     return MAVG_OK;
 }
 
+int mavg_enable_timing(mavg_plan* p, int enable)
+{
+    if (!p) return fail(MAVG_ERR_INVALID_ARG, "plan is null");
+    p->timing_on = enable != 0;
+    if (!p->timing_on)
+        for (DevCtx& d : p->dev) d.timed = false;
+    return MAVG_OK;
+}
+
 int mavg_plan_buffers(mavg_plan* p, uint32_t rank, void** d_in, void** d_out)
 {
     if (!p || rank >= p->dev.size()) return fail(MAVG_ERR_INVALID_ARG, "bad plan or rank");
@@ -646,12 +660,12 @@ int mavg_run_device_halo(mavg_plan* p, const void* d_in, void* d_out, const void
     DevCtx& d = p->dev[0];
     MAVG_CUDA(cudaSetDevice(d.device));
     uint32_t launches = 0;
-    record(d, 0);
-    record(d, 1);
-    int s = launch_shard(p, d, d_in, d_out, d_halo, &launches);
-    record(d, 2);
-    record(d, 3);
-    d.timed = true;
+    record(p, d, 0);
+    record(p, d, 1);
+    int s = launch_shard(p, d, d_in, d_out, d_halo, d.frames, &launches);
+    record(p, d, 2);
+    record(p, d, 3);
+    d.timed = p->timing_on;
     p->launches_last_run = launches;
     return s;
 }
@@ -667,7 +681,7 @@ int mavg_run_device(mavg_plan* p, const void* const* d_in, void* const* d_out)
         if (!d_in[r] || !d_out[r]) return fail(MAVG_ERR_INVALID_ARG, "null shard pointer for device index %zu", r);
         MAVG_CUDA(cudaSetDevice(d.device));
         const void* halo = nullptr;
-        record(d, 0);
+        record(p, d, 0);
         if (r > 0 && frame_sharded(p) && d.frames > 0) {
             // left context = tail of the left neighbour's shard
             const DevCtx& l = p->dev[r - 1];
@@ -681,11 +695,11 @@ int mavg_run_device(mavg_plan* p, const void* const* d_in, void* const* d_out)
                 halo = d.d_halo;
             }
         }
-        record(d, 1);
-        MAVG_TRY(launch_shard(p, d, d_in[r], d_out[r], halo, &launches));
-        record(d, 2);
-        record(d, 3);
-        d.timed = true;
+        record(p, d, 1);
+        MAVG_TRY(launch_shard(p, d, d_in[r], d_out[r], halo, d.frames, &launches));
+        record(p, d, 2);
+        record(p, d, 3);
+        d.timed = p->timing_on;
     }
     p->launches_last_run = launches;
     return MAVG_OK;
@@ -711,7 +725,9 @@ int mavg_synchronize(mavg_plan* p)
     DeviceGuard guard;
     for (DevCtx& d : p->dev) {
         MAVG_CUDA(cudaSetDevice(d.device));
+        if (d.s_h2d) MAVG_CUDA(cudaStreamSynchronize(d.s_h2d));
         MAVG_CUDA(cudaStreamSynchronize(d.stream));
+        if (d.s_d2h) MAVG_CUDA(cudaStreamSynchronize(d.s_d2h));
     }
     return gather_timing(p);
 }
@@ -734,10 +750,21 @@ int mavg_run_host(mavg_plan* p, const void* h_in, void* h_out)
     for (DevCtx& d : p->dev) {
         MAVG_TRY(alloc_owned(p, d));
         MAVG_CUDA(cudaSetDevice(d.device));
+        if (!d.s_h2d) MAVG_CUDA(cudaStreamCreateWithFlags(&d.s_h2d, cudaStreamNonBlocking));
+        if (!d.s_d2h) MAVG_CUDA(cudaStreamCreateWithFlags(&d.s_d2h, cudaStreamNonBlocking));
         const uint64_t elems = shard_elems(p, d);
         const char* src;
-        const void* halo = nullptr;
-        record(d, 0);
+        const void* halo0 = nullptr;
+        // order the copy streams behind whatever the compute stream was doing before this call
+        if (d.pool.empty()) {
+            cudaEvent_t e;
+            MAVG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            d.pool.push_back(e);
+        }
+        MAVG_CUDA(cudaEventRecord(d.pool[0], d.stream));
+        MAVG_CUDA(cudaStreamWaitEvent(d.s_h2d, d.pool[0], 0));
+        MAVG_CUDA(cudaStreamWaitEvent(d.s_d2h, d.pool[0], 0));
+        if (p->timing_on) cudaEventRecord(d.ev[0], d.s_h2d);
         if (planar_batch(p)) {
             src = (const char*)h_in + (uint64_t)d.first_channel * p->desc.frames * es;
         } else {
@@ -748,18 +775,57 @@ int mavg_run_host(mavg_plan* p, const void* h_in, void* h_out)
             if ((d.first_frame > 0 || p->desc.first_frame > 0) && d.frames > 0) {
                 MAVG_TRY(alloc_halo(p, d));
                 const uint64_t hb = p->halo_frames * C * es;
-                MAVG_CUDA(cudaMemcpyAsync(d.d_halo, src - hb, hb, cudaMemcpyHostToDevice, d.stream));
-                halo = d.d_halo;
+                MAVG_CUDA(cudaMemcpyAsync(d.d_halo, src - hb, hb, cudaMemcpyHostToDevice, d.s_h2d));
+                halo0 = d.d_halo;
             }
         }
-        if (elems) MAVG_CUDA(cudaMemcpyAsync(d.d_in, src, elems * es, cudaMemcpyHostToDevice, d.stream));
-        record(d, 1);
-        MAVG_TRY(launch_shard(p, d, d.d_in, d.d_out, halo, &launches));
-        record(d, 2);
         char* dst = (char*)h_out + (src - (const char*)h_in);
-        if (elems) MAVG_CUDA(cudaMemcpyAsync(dst, d.d_out, elems * es, cudaMemcpyDeviceToHost, d.stream));
-        record(d, 3);
-        d.timed = true;
+
+        // slices: whole tiles, at least the left context long, ~32 MiB each; planar batches and short
+        // shards go in one piece
+        uint64_t slice_frames = d.frames;
+        if (!planar_batch(p) && d.frames > 0) {
+            const uint64_t unit = (p->path == MAVG_PATH_STREAM) ? (uint64_t)p->geom.NT * p->geom.R : 1024;
+            uint64_t want = std::max<uint64_t>((32ull << 20) / (C * es), p->halo_frames);
+            want = (want + unit - 1) / unit * unit;
+            if (want * 2 <= d.frames) slice_frames = want;
+        }
+        const uint64_t nslices = (planar_batch(p) || d.frames == 0) ? 1 : (d.frames + slice_frames - 1) / slice_frames;
+        while (d.pool.size() < 1 + 2 * nslices) {
+            cudaEvent_t e;
+            MAVG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            d.pool.push_back(e);
+        }
+        for (uint64_t i = 0; i < nslices && elems > 0; ++i) {
+            uint64_t f0, fcount, off_e, cnt_e;
+            if (planar_batch(p)) {
+                f0 = 0; fcount = p->desc.frames; off_e = 0; cnt_e = elems;
+            } else {
+                f0 = i * slice_frames;
+                fcount = std::min<uint64_t>(slice_frames, d.frames - f0);
+                off_e = f0 * C; cnt_e = fcount * C;
+            }
+            cudaEvent_t e_in = d.pool[1 + 2 * i], e_k = d.pool[2 + 2 * i];
+            MAVG_CUDA(cudaMemcpyAsync((char*)d.d_in + off_e * es, src + off_e * es, cnt_e * es, cudaMemcpyHostToDevice,
+                                      d.s_h2d));
+            MAVG_CUDA(cudaEventRecord(e_in, d.s_h2d));
+            if (i + 1 == nslices && p->timing_on) cudaEventRecord(d.ev[1], d.s_h2d);
+            MAVG_CUDA(cudaStreamWaitEvent(d.stream, e_in, 0));
+            const void* halo = (i == 0) ? halo0 : (const char*)d.d_in + (off_e - p->halo_frames * C) * es;
+            MAVG_TRY(launch_shard(p, d, (const char*)d.d_in + off_e * es, (char*)d.d_out + off_e * es, halo, fcount,
+                                  &launches));
+            MAVG_CUDA(cudaEventRecord(e_k, d.stream));
+            if (i + 1 == nslices && p->timing_on) cudaEventRecord(d.ev[2], d.stream);
+            MAVG_CUDA(cudaStreamWaitEvent(d.s_d2h, e_k, 0));
+            MAVG_CUDA(cudaMemcpyAsync(dst + off_e * es, (char*)d.d_out + off_e * es, cnt_e * es, cudaMemcpyDeviceToHost,
+                                      d.s_d2h));
+        }
+        if (elems == 0 && p->timing_on) {
+            cudaEventRecord(d.ev[1], d.s_h2d);
+            cudaEventRecord(d.ev[2], d.stream);
+        }
+        if (p->timing_on) cudaEventRecord(d.ev[3], d.s_d2h);
+        d.timed = p->timing_on;
     }
     p->launches_last_run = launches;
     return mavg_synchronize(p);
@@ -837,6 +903,23 @@ int mavg_device_alloc(uint64_t bytes, void** d_ptr)
 int mavg_device_free(void* d_ptr)
 {
     if (d_ptr) MAVG_CUDA(cudaFree(d_ptr));
+    return MAVG_OK;
+}
+
+int mavg_host_alloc(uint64_t bytes, void** h_ptr)
+{
+    if (!h_ptr) return fail(MAVG_ERR_INVALID_ARG, "null argument");
+    if (cudaHostAlloc(h_ptr, bytes ? bytes : 64, cudaHostAllocPortable) != cudaSuccess) {
+        cudaError_t e = cudaGetLastError();
+        return fail(e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? MAVG_ERR_NO_DEVICE : MAVG_ERR_ALLOC,
+                    "cudaHostAlloc(%llu) failed: %s", (unsigned long long)bytes, cudaGetErrorString(e));
+    }
+    return MAVG_OK;
+}
+
+int mavg_host_free(void* h_ptr)
+{
+    if (h_ptr) MAVG_CUDA(cudaFreeHost(h_ptr));
     return MAVG_OK;
 }
 

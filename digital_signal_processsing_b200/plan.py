@@ -124,6 +124,9 @@ class Plan:
     def set_stream(self, cuda_stream: int) -> None:
         check(self._lib.mavg_set_stream(self._h, ctypes.c_void_p(cuda_stream)))
 
+    def enable_timing(self, on: bool) -> None:
+        check(self._lib.mavg_enable_timing(self._h, 1 if on else 0))
+
     def buffers(self, rank: int = 0) -> tuple[int, int]:
         a, b = ctypes.c_void_p(), ctypes.c_void_p()
         check(self._lib.mavg_plan_buffers(self._h, rank, ctypes.byref(a), ctypes.byref(b)))

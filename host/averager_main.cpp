@@ -1,0 +1,144 @@
+// averager_main.cpp -- the drop-in `averager` program on top of libmavg's C ABI.
+//
+// One program replaces the reference's eight GPU binaries (bin_parallel, bin_shared, bin_vec2,
+// bin_vec4, bin_hillis, bin_vhillis, bin_blelloch, bin_vblelloch; basics/run_benchmarks.py:8-18):
+// they differed only in the kernel, and the kernel now lives in libmavg.  The name the program is
+// invoked under (argv[0]) selects the "Algorithm" label written to the CSV.
+//
+// Same command line as the reference mains (e.g. basics/profilable_sm_vload4.cu:221-239):
+//     <bin> <wav_path> <grade> <block_size> [--gpus N] [--out out.wav] [--csv file] [--rounds M]
+//   * fewer than 3 positional arguments  -> usage on stderr, exit 1
+//   * block_size outside 32..1024 or not a multiple of 32 -> same message, exit 1 (it is only a hint now)
+//   * input: canonical 44-byte-header WAV, int16 as in the reference, or float32 (extension)
+//   * side effect: one row appended to benchmark_data.csv (reference schema + the new columns)
+//   * --out writes input header + filtered samples, the layout of writeSamples (wav_header.h:50-59)
+// Deliberate fix: the reference exits 0 when the WAV cannot be read (its `uint32_t result = -1`
+// quirk); this program exits 2 so that a sweep driver can see the failure.
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "gpu_utils.h"   // DspWorkspace, CsvLogger, MAVG_CHECK (host/mavg_workspace.h)
+#include "benchmark.h"   // ProfileResult, GpuTimer, CpuTimer, benchmark<>
+#include "wav_header.h"  // WAVHeader, mavg_wav::*
+
+namespace {
+
+struct Options {
+    std::string wav, out, csv = "benchmark_data.csv";
+    int grade = 0, block = 0, gpus = 1, rounds = measurementRounds, warmup = warmupRounds;
+};
+
+const char* algo_label(const char* argv0)
+{
+    const char* base = strrchr(argv0, '/');
+    base = base ? base + 1 : argv0;
+    struct { const char* bin; const char* label; } names[] = {
+        {"bin_parallel", "Parallel_Avg"},   {"bin_shared", "SharedMem"},      {"bin_vec2", "Vectorized_int2"},
+        {"bin_vec4", "Vectorized_int4"},    {"bin_hillis", "HillisSteele"},   {"bin_vhillis", "V_HillisSteele"},
+        {"bin_blelloch", "Blelloch"},       {"bin_vblelloch", "V_Blelloch"},
+    };
+    for (auto& n : names)
+        if (!strcmp(base, n.bin)) return n.label;
+    return "libmavg";
+}
+
+template <typename T>
+int run(const Options& o, const WAVHeader& header, const std::vector<unsigned char>& raw, const char* label)
+{
+    const size_t total = raw.size() / sizeof(T);
+    const int channels = header.numChannels ? header.numChannels : 1;
+    const char* dtype = sizeof(T) == 4 ? "float32" : "int16";
+    printf("--- libmavg averager (%s, %s) ---\n", label, dtype);
+    printf("total samples: %zu\n", total);
+    printf("point: %d\n", o.grade);
+    printf("channels: %d, GPUs: %d\n", channels, o.gpus);
+
+    // one-time cost: plan + device/pinned buffers (the reference times DspWorkspace construction the same way)
+    ProfileResult init = benchmark<CpuTimer>(3, 1, [&](CpuTimer& t) {
+        t.start();
+        DspWorkspace<T> w(total, o.grade, channels, VecMode::Int4, 0, o.block, o.gpus);
+        t.stop();
+    });
+
+    DspWorkspace<T> ws(total, o.grade, channels, VecMode::Int4, 0, o.block, o.gpus);
+    memcpy(ws.host_in(), raw.data(), total * sizeof(T));
+    ProfileResult res = benchmark<GpuTimer>(o.rounds, o.warmup, [&](GpuTimer& t) { ws.run(t); });
+    res.initialization_ms = init.compute_ms;
+    res.print_stats(total, sizeof(T));
+
+    mavg_info info;
+    MAVG_CHECK(mavg_plan_info(ws.plan(), &info));
+    printf("kernel path: %s, %u launch(es) per run\n", info.path == MAVG_PATH_STREAM ? "TMA stream" : "generic",
+           info.launches_per_run);
+
+    CsvLogger(o.csv).log(label, "Standard", total, o.grade, o.block, res, sizeof(T), sizeof(T), o.gpus, dtype,
+                         "interleaved");
+    if (!o.out.empty()) {
+        if (!mavg_wav::write_file(o.out, header, ws.host_out(), total)) {
+            fprintf(stderr, "could not open output file %s\n", o.out.c_str());
+            return 2;
+        }
+        printf(">> Filtered samples written to %s\n", o.out.c_str());
+    }
+    return 0;
+}
+
+}  // namespace
+
+int main(int argc, char* argv[])
+{
+    Options o;
+    std::vector<const char*> pos;
+    for (int i = 1; i < argc; ++i) {
+        const std::string a = argv[i];
+        auto need = [&](const char* flag) -> const char* {
+            if (i + 1 >= argc) { fprintf(stderr, "%s needs a value\n", flag); exit(1); }
+            return argv[++i];
+        };
+        if (a == "--gpus") o.gpus = atoi(need("--gpus"));
+        else if (a == "--out") o.out = need("--out");
+        else if (a == "--csv") o.csv = need("--csv");
+        else if (a == "--rounds") o.rounds = atoi(need("--rounds"));
+        else if (a == "--warmup") o.warmup = atoi(need("--warmup"));
+        else pos.push_back(argv[i]);
+    }
+    if (pos.size() < 3) {
+        fprintf(stderr, "Usage: %s <wav_path> <grade> <block_size> [--gpus N] [--out out.wav] [--csv file]\n", argv[0]);
+        return 1;
+    }
+    o.wav = pos[0];
+    o.grade = atoi(pos[1]);
+    o.block = atoi(pos[2]);
+    if (const char* e = getenv("MAVG_GPUS")) if (o.gpus == 1) o.gpus = atoi(e);
+    if (o.block < 32 || o.block > 1024 || o.block % 32 != 0) {
+        fprintf(stderr, "Error: Block size must be multiple of 32\n");
+        return 1;
+    }
+    if (o.grade < 1) {
+        fprintf(stderr, "Error: grade must be >= 1\n");
+        return 1;
+    }
+    if (o.gpus < 1 || o.gpus > MAVG_MAX_DEVICES || o.rounds < 1 || o.warmup < 0) {
+        fprintf(stderr, "Error: bad --gpus/--rounds/--warmup\n");
+        return 1;
+    }
+
+    WAVHeader header{};
+    std::vector<unsigned char> raw;
+    std::string why;
+    if (!mavg_wav::read_file(o.wav, header, raw, &why)) {
+        printf("%s\n", why.c_str());
+        return 2;
+    }
+    if (raw.empty()) {
+        printf("no samples in %s\n", o.wav.c_str());
+        return 2;
+    }
+    const char* label = algo_label(argv[0]);
+    if (mavg_wav::kind_of(header) == mavg_wav::SampleKind::Float32) return run<float>(o, header, raw, label);
+    return run<int16_t>(o, header, raw, label);
+}

@@ -1,0 +1,144 @@
+// mavg_wav.h -- canonical-header WAV reader/writer for the drop-in `averager` binaries.
+//
+// Interface twin of the reference's wav_header.h (WAVHeader :8-24, extractSamples :26-48,
+// writeSamples :50-59, extractSamples64 :62-84) so that code written against those names keeps
+// compiling, re-implemented for the new library:
+//   * one bulk read instead of one ifstream::read per sample;
+//   * float32 files (audioFormat 3, 32 bit) are accepted next to int16 -- the north-star extension;
+//   * RIFF/WAVE/data magic is validated and the sample count is clamped to the bytes present;
+//   * failures are reported through the return value, nothing is printed from library code.
+#pragma once
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <utility>
+#include <vector>
+
+#pragma pack(push, 1)
+struct WAVHeader {            // 44 bytes, little endian, exactly the on-disk layout
+    char     riff[4];         // "RIFF"
+    uint32_t sizeOfFile;      // file size - 8
+    char     wave[4];         // "WAVE"
+    char     fmt[4];          // "fmt "
+    uint32_t fmtSize;         // 16 for the canonical header
+    uint16_t audioFormat;     // 1 = integer PCM, 3 = IEEE float
+    uint16_t numChannels;
+    uint32_t sampleRate;
+    uint32_t byteRate;
+    uint16_t blockAlign;
+    uint16_t bitsPerSample;
+    char     data[4];         // "data"
+    uint32_t dataBytes;       // payload size in bytes
+};
+#pragma pack(pop)
+static_assert(sizeof(WAVHeader) == 44, "canonical WAV header is 44 bytes");
+
+namespace mavg_wav {
+
+enum class SampleKind { Unsupported, Int16, Float32 };
+
+inline SampleKind kind_of(const WAVHeader& h)
+{
+    if (h.bitsPerSample == 16) return SampleKind::Int16;  // the reference reads any 16-bit file as PCM
+    if (h.bitsPerSample == 32 && h.audioFormat == 3) return SampleKind::Float32;
+    return SampleKind::Unsupported;
+}
+
+inline bool magic_ok(const WAVHeader& h)
+{
+    return !memcmp(h.riff, "RIFF", 4) && !memcmp(h.wave, "WAVE", 4) && !memcmp(h.data, "data", 4);
+}
+
+// Reads header + payload.  Returns false (and leaves `bytes` empty) when the file cannot be read.
+inline bool read_file(const std::string& path, WAVHeader& h, std::vector<unsigned char>& bytes, std::string* why = nullptr)
+{
+    bytes.clear();
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) { if (why) *why = "could not open file"; return false; }
+    bool ok = fread(&h, sizeof h, 1, f) == 1;
+    if (!ok && why) *why = "file shorter than a WAV header";
+    if (ok && !magic_ok(h)) { ok = false; if (why) *why = "not a canonical 44-byte-header WAV file"; }
+    if (ok && kind_of(h) == SampleKind::Unsupported) {
+        ok = false;
+        if (why) *why = "unsupported bits per sample: " + std::to_string(h.bitsPerSample);
+    }
+    if (ok) {
+        bytes.resize(h.dataBytes);
+        const size_t got = h.dataBytes ? fread(bytes.data(), 1, h.dataBytes, f) : 0;
+        const size_t step = h.bitsPerSample / 8;
+        bytes.resize(got / step * step);  // clamp to whole samples actually present
+    }
+    fclose(f);
+    return ok;
+}
+
+template <typename T>
+inline bool write_file(const std::string& path, const WAVHeader& h, const T* samples, size_t count)
+{
+    FILE* f = fopen(path.c_str(), "wb");
+    if (!f) return false;
+    bool ok = fwrite(&h, sizeof h, 1, f) == 1 && (count == 0 || fwrite(samples, sizeof(T), count, f) == count);
+    return fclose(f) == 0 && ok;
+}
+
+template <typename T>
+inline WAVHeader make_header(size_t samples, uint16_t channels, uint32_t rate = 44100)
+{
+    WAVHeader h;
+    memcpy(h.riff, "RIFF", 4); memcpy(h.wave, "WAVE", 4); memcpy(h.fmt, "fmt ", 4); memcpy(h.data, "data", 4);
+    h.fmtSize = 16;
+    h.audioFormat = sizeof(T) == 4 ? 3 : 1;
+    h.numChannels = channels;
+    h.sampleRate = rate;
+    h.bitsPerSample = (uint16_t)(8 * sizeof(T));
+    h.blockAlign = (uint16_t)(channels * sizeof(T));
+    h.byteRate = rate * h.blockAlign;
+    h.dataBytes = (uint32_t)(samples * sizeof(T));
+    h.sizeOfFile = 36 + h.dataBytes;
+    return h;
+}
+
+}  // namespace mavg_wav
+
+// ---- reference-compatible names (wav_header.h:26-84)
+inline std::pair<WAVHeader, std::vector<int16_t>> extractSamples(const std::string& pathName)
+{
+    WAVHeader h{};
+    std::vector<unsigned char> raw;
+    std::string why;
+    if (!mavg_wav::read_file(pathName, h, raw, &why) || mavg_wav::kind_of(h) != mavg_wav::SampleKind::Int16) {
+        printf("%s\n", why.empty() ? "unsupported bits per sample" : why.c_str());
+        return {};
+    }
+    std::vector<int16_t> s(raw.size() / 2);
+    if (!s.empty()) memcpy(s.data(), raw.data(), s.size() * 2);
+    return {h, std::move(s)};
+}
+
+inline std::pair<WAVHeader, std::vector<int64_t>> extractSamples64(const std::string& pathName)
+{
+    auto hs = extractSamples(pathName);
+    return {hs.first, std::vector<int64_t>(hs.second.begin(), hs.second.end())};
+}
+
+inline std::pair<WAVHeader, std::vector<float>> extractSamplesF32(const std::string& pathName)
+{
+    WAVHeader h{};
+    std::vector<unsigned char> raw;
+    std::string why;
+    if (!mavg_wav::read_file(pathName, h, raw, &why) || mavg_wav::kind_of(h) != mavg_wav::SampleKind::Float32) {
+        printf("%s\n", why.empty() ? "not a float32 WAV" : why.c_str());
+        return {};
+    }
+    std::vector<float> s(raw.size() / 4);
+    if (!s.empty()) memcpy(s.data(), raw.data(), s.size() * 4);
+    return {h, std::move(s)};
+}
+
+template <typename T>
+inline void writeSamples(const std::string& name, const WAVHeader header, std::vector<T>& samples)
+{
+    if (!mavg_wav::write_file(name, header, samples.data(), samples.size())) printf("could not open output file\n");
+}

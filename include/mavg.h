@@ -194,6 +194,10 @@ int mavg_synchronize(mavg_plan *plan);
 /* Phase times of the last completed run (valid after mavg_synchronize / mavg_run_host). */
 int mavg_get_timing(mavg_plan *plan, mavg_timing *timing);
 
+/* Switches the plan's own CUDA-event phase timing off (0) or on (non-zero, the default).
+ * Off saves four event records per run when the caller times the stream itself. */
+int mavg_enable_timing(mavg_plan *plan, int enable);
+
 /* Makes the plan enqueue on a caller-owned cudaStream_t (single-device plans). */
 int mavg_set_stream(mavg_plan *plan, void *cuda_stream);
 
@@ -222,6 +226,12 @@ int mavg_ipc_close(void *d_ptr);
  * that buffers exported over IPC do not come from a caching allocator. */
 int mavg_device_alloc(uint64_t bytes, void **d_ptr);
 int mavg_device_free(void *d_ptr);
+
+/* Page-locked host memory for mavg_run_host buffers (cudaHostAlloc / cudaFreeHost): copies from
+ * pinned memory run at full PCIe speed and overlap with the kernels.  Replaces the host half
+ * of MemoryTraits (gpu_utils.h:33-65). */
+int mavg_host_alloc(uint64_t bytes, void **h_ptr);
+int mavg_host_free(void *h_ptr);
 
 #ifdef __cplusplus
 }

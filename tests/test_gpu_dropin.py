@@ -1,0 +1,132 @@
+"""GPU tests of the drop-in `averager` program (host/averager_main.cpp over the C ABI): same argv,
+same WAV in, same output layout as the reference binaries; outputs diffed against the oracle."""
+import csv
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def averager(mavg):
+    from digital_signal_processsing_b200 import build
+    bins = build.build_host()
+    assert bins, "host/averager_main.cpp missing"
+    return os.path.dirname(bins[0])
+
+
+def _run(bin_dir, name, *args, cwd):
+    return subprocess.run([os.path.join(bin_dir, name)] + [str(a) for a in args], cwd=cwd, capture_output=True, text=True)
+
+
+def test_int16_stereo_wav_bit_exact(averager, mavg, oracle_mod, tmp_path):
+    from digital_signal_processsing_b200 import wav
+    x = oracle_mod.fill_i16(2 * 50_000, 42)
+    src = tmp_path / "in.wav"
+    wav.write_samples(str(src), wav.make_header(x.size, 2, np.int16), x)
+    for name, k in (("bin_vec4", 5), ("bin_hillis", 1000), ("averager", 41)):
+        out = tmp_path / f"out_{k}.wav"
+        r = _run(averager, name, src, k, 256, "--out", out, "--rounds", 2, "--warmup", 1, cwd=tmp_path)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert "total samples: 100000" in r.stdout and f"point: {k}" in r.stdout
+        h, y = wav.extract_samples(str(out))
+        assert h.pack() == wav.make_header(x.size, 2, np.int16).pack()        # header verbatim
+        assert np.array_equal(y, oracle_mod.mavg_i16(x, k, 2))
+    rows = list(csv.DictReader(open(tmp_path / "benchmark_data.csv")))
+    assert [r["Algorithm"] for r in rows] == ["Vectorized_int4", "HillisSteele", "libmavg"]
+    first = rows[0]
+    for col in ("MemoryMode", "N_Samples", "Grade", "BlockSize", "H2D_ms", "Compute_ms", "D2H_ms", "Total_ms", "Init_ms",
+                "ColdStart_Total_ms", "Bandwidth_GBs", "Throughput_MSs", "ColdStart_MSs", "GPUs", "Dtype", "Layout",
+                "Gsamples_s", "HBM_GBs", "Pct_HBM_nominal", "Pct_HBM_measured"):
+        assert col in first
+    assert first["N_Samples"] == "100000" and first["Grade"] == "5" and first["GPUs"] == "1" and first["Dtype"] == "int16"
+    assert float(first["Compute_ms"]) > 0
+
+
+def test_float32_mono_wav(averager, mavg, oracle_mod, tmp_path):
+    from digital_signal_processsing_b200 import wav
+    n, k = 1 << 20, 5                                  # BASELINE.json configs[0]
+    x = oracle_mod.fill_f32(n, 0x5EED0001)
+    src, out = tmp_path / "in.wav", tmp_path / "out.wav"
+    wav.write_samples(str(src), wav.make_header(n, 1, np.float32), x)
+    r = _run(averager, "bin_shared", src, k, 128, "--out", out, "--rounds", 2, "--warmup", 1, cwd=tmp_path)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "TMA stream" in r.stdout
+    _, y = wav.extract_samples(str(out))
+    e = oracle_mod.mavg_f64(x, k)
+    assert np.max(np.abs(y - e) / np.abs(e)) < 1e-5
+
+
+def test_exit_codes(averager, tmp_path):
+    assert _run(averager, "bin_vec4", cwd=tmp_path).returncode == 1                       # usage
+    r = _run(averager, "bin_vec4", "x.wav", 5, 100, cwd=tmp_path)
+    assert r.returncode == 1 and "Block size must be multiple of 32" in r.stderr           # reference rule
+    assert _run(averager, "bin_vec4", "missing.wav", 5, 256, cwd=tmp_path).returncode == 2  # fixed: reference exits 0
+    bad = tmp_path / "bad.wav"
+    bad.write_bytes(b"not a wav file at all, but longer than forty-four bytes for sure......")
+    assert _run(averager, "bin_vec4", bad, 5, 256, cwd=tmp_path).returncode == 2
+
+
+def test_sweep_driver(averager, mavg, tmp_path, monkeypatch):
+    from digital_signal_processsing_b200 import run_benchmarks as rb
+    monkeypatch.chdir(tmp_path)
+    total, failures, rows = rb.run_suite([40_000], [3, 64], [64, 256], [1], [e for e in rb.EXECUTABLES if e["path"] in ("bin_vec4", "bin_blelloch")],
+                                         "int16", 2, "", verbose=False)
+    assert total == 8 and failures == 0
+    got = list(csv.DictReader(open(tmp_path / "benchmark_data.csv")))
+    assert len(got) == 8 and {r["Algorithm"] for r in got} == {"Vectorized_int4", "Blelloch"}
+
+
+def test_single_process_multi_device_plan(mavg, oracle_mod):
+    """One process driving several GPUs (the --gpus N mode of the binaries); with one GPU visible the
+    same device is listed twice, which exercises sharding + in-place peer halo on real hardware."""
+    ndev = mavg.device_count()
+    devs = [0, 1] if ndev >= 2 else [0, 0]
+    n, T = 40 * 8192 + 96, 8192
+    for k in (3, 300, 4096):
+        x = oracle_mod.fill_f32(n, 77 + k)
+        with mavg.Plan(n, k, devices=devs) as plan:
+            i = plan.info
+            assert i.num_devices == 2 and i.shard_frames[0] % T == 0 and i.shard_frames[0] + i.shard_frames[1] == n
+            y2 = plan.run_host(x)
+        with mavg.Plan(n, k) as plan:
+            y1 = plan.run_host(x)
+        assert np.array_equal(y1, y2), k                     # sharding does not change a single bit
+        e = oracle_mod.mavg_f64(x, k)
+        assert np.max(np.abs(y1 - e) / np.abs(e)) < 1e-5
+    xi = oracle_mod.fill_i16(3 * 30_000, 5)
+    with mavg.Plan(30_000, 700, channels=3, dtype="i16", devices=devs) as plan:
+        assert np.array_equal(plan.run_host(xi), oracle_mod.mavg_i16(xi, 700, 3))
+    xp = oracle_mod.fill_f32(6 * 8192 * 3, 6)
+    with mavg.Plan(8192 * 3, 64, channels=6, layout="planar", devices=devs) as plan:
+        yp = plan.run_host(xp)
+    for c in range(6):
+        seg = slice(c * 8192 * 3, (c + 1) * 8192 * 3)
+        e = oracle_mod.mavg_f64(xp[seg], 64)
+        assert np.max(np.abs(yp[seg] - e) / np.abs(e)) < 1e-5
+
+
+def test_run_host_pipeline_slices_bit_identical(mavg, oracle_mod):
+    """Large host buffers go through the sliced H2D/kernel/D2H pipeline; slices are whole tiles with
+    their left context read from the already-uploaded previous slice, so bits do not change."""
+    n = (1 << 25) + 8192 * 3 + 40           # > 2 slices of 32 MiB, ragged tail
+    for k in (5, 1024):
+        x = oracle_mod.fill_f32(n, 31 + k)
+        with mavg.Plan(n, k) as plan:
+            y = plan.run_host(x)
+            assert plan.info.launches_per_run >= 3
+            t = plan.timing()
+            assert t.total_ms > 0
+        import torch
+        dx = torch.from_numpy(x).cuda()
+        dy = torch.empty_like(dx)
+        torch.cuda.synchronize()
+        with mavg.Plan(n, k) as plan:
+            plan.run_device([dx.data_ptr()], [dy.data_ptr()])
+            plan.synchronize()
+        assert np.array_equal(y, dy.cpu().numpy())
+    xi = oracle_mod.fill_i16(2 * (1 << 24) + 2, 9)
+    assert np.array_equal(mavg.moving_average(xi, 77, channels=2), oracle_mod.mavg_i16(xi, 77, 2))

@@ -79,11 +79,12 @@ def test_stream_path_vs_oracle(mavg, oracle_mod, k):
 def test_stream_path_matches_arithmetic_model_bitwise(mavg, oracle_mod, k):
     """The CUDA kernel performs exactly the fp32 operations of tests/algo_model.py."""
     from algo_model import stream_model
-    n = 3 * 4096
+    n = 3 * 8192
     x = oracle_mod.fill_f32(n, 2000 + k)
-    with mavg.Plan(n, k, path="stream") as plan:
-        y = plan.run_host(x)
-    assert np.array_equal(y, stream_model(x, k, 256, 16))
+    for threads, run in ((256, 16), (512, 16), (256, 32)):
+        with mavg.Plan(n, k, path="stream", threads=threads, run=run) as plan:
+            y = plan.run_host(x)
+        assert np.array_equal(y, stream_model(x, k, threads, run)), (threads, run)
 
 
 @pytest.mark.parametrize("shape", [(256, 16), (256, 32), (512, 16)])
@@ -216,7 +217,7 @@ def test_shard_with_halo_is_bit_identical(mavg, oracle_mod, torch_cuda, k):
     """Second half of a signal filtered as its own shard, left context read in place from the
     first half's tail: the same bits as the unsharded run."""
     torch = torch_cuda
-    T = 4096
+    T = 8192
     n = 64 * T
     cut = 24 * T
     x = oracle_mod.fill_f32(n, 13)
