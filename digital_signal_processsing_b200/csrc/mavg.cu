@@ -69,17 +69,20 @@ int get_encoder(EncodeTiledFn* out)
     return MAVG_OK;
 }
 
-// One float signal batch as a [signals][rows][32] tensor, boxes of [1][tile_rows][32], 128B swizzle.
+// One signal batch as a [signals][rows][128 bytes] tensor (32 floats or 64 int16 per row), boxes of
+// [1][tile_rows][row], 128B swizzle.
 int make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t signals, uint64_t signal_stride_bytes,
-             uint32_t tile_rows)
+             uint32_t tile_rows, uint32_t elem_bytes)
 {
     EncodeTiledFn enc;
     MAVG_TRY(get_encoder(&enc));
-    cuuint64_t dims[3] = {32, rows, signals};
+    const uint32_t row_elems = 128 / elem_bytes;
+    cuuint64_t dims[3] = {row_elems, rows, signals};
     cuuint64_t strides[2] = {128, signals > 1 ? signal_stride_bytes : rows * 128};
-    cuuint32_t box[3] = {32, tile_rows, 1};
+    cuuint32_t box[3] = {row_elems, tile_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr,
+    CUresult r = enc(map, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT16, 3,
+                     const_cast<void*>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
@@ -100,9 +103,51 @@ struct StreamGeom {
     int ctas_per_sm = 0;
     uint32_t smem = 0;
     uint32_t n_full = 0, m_part = 0, lag_chunks = 0;
+    uint32_t elem = 4;        // bytes per sample
+    uint32_t C = 1;           // channels interleaved inside one kernel signal (int16 stereo: 2)
+    uint32_t div_mul = 0, div_shift = 0;
 };
 
 constexpr uint32_t kMaxSmem = 232448;  // 227 KB opt-in limit per CTA on sm_100
+
+// int16: 512 threads x 32 samples (64 bytes) per tile of 16384 samples; flat lag distance k * C.
+StreamGeom plan_stream_i16(uint32_t k, uint32_t C, const mavg_tuning& tu)
+{
+    StreamGeom g;
+    g.NT = 512;
+    g.R = 32;
+    g.elem = 2;
+    g.C = C;
+    if (k >= 65536u || !(C == 1 || C == 2)) return g;   // int32 window sums hold k * 32768 only below 2^16
+    const uint64_t L = (uint64_t)k * C;
+    const uint32_t R = 32;
+    const uint32_t s = (uint32_t)((R - L % R) % R);
+    g.m_part = R - s;
+    g.n_full = (uint32_t)((L + s) / R - 1);
+    g.lag_chunks = (uint32_t)((L + 7) / 8);
+    g.MIS = (int)(8ull * g.lag_chunks - L);
+    g.mode = g.n_full <= 16 ? 0 : 1;
+    const uint64_t T = (uint64_t)g.NT * R;
+    g.H = (int)(((uint64_t)(g.n_full + 1) * R + T - 1) / T);
+    g.ctas_per_sm = 1;
+    g.P = tu.prefetch ? (int)tu.prefetch : 2;
+    for (;;) {
+        g.S = g.H + 1 + g.P;
+        g.smem = mavg::stream_i16_smem_bytes(g.NT, g.S, g.H, (int)C);
+        if (g.smem <= kMaxSmem) break;
+        if (g.P > 1) { --g.P; continue; }
+        return g;
+    }
+    if (k > 1) {
+        uint32_t lg = 0;
+        while ((1u << lg) < k) ++lg;                       // ceil(log2 k)
+        const unsigned long long two_p = 1ull << (31 + lg);
+        g.div_mul = (uint32_t)((two_p + k - 1) / k);       // ceil(2^(31+lg) / k) < 2^32
+        g.div_shift = lg - 1;
+    }
+    g.ok = true;
+    return g;
+}
 
 StreamGeom plan_stream(uint32_t k, const mavg_tuning& tu)
 {
@@ -179,6 +224,33 @@ StreamKernel pick_kernel(const StreamGeom& g, uint32_t k)
     return pick_variant<512, 16>(g.MIS, g.mode, k);
 }
 
+template <int C>
+StreamKernel pick_i16(int mis, int mode)
+{
+    using namespace mavg;
+#define MAVG_I16_CASE(M)                                                        \
+    case M: return mode == 0 ? (StreamKernel)stream_i16_kernel<512, C, M, 0>    \
+                             : (StreamKernel)stream_i16_kernel<512, C, M, 1>;
+    switch (mis) {
+        MAVG_I16_CASE(0)
+        MAVG_I16_CASE(2)
+        MAVG_I16_CASE(4)
+        MAVG_I16_CASE(6)
+    default: break;
+    }
+    if constexpr (C == 1) {
+        switch (mis) {
+            MAVG_I16_CASE(1)
+            MAVG_I16_CASE(3)
+            MAVG_I16_CASE(5)
+            MAVG_I16_CASE(7)
+        default: break;
+        }
+    }
+#undef MAVG_I16_CASE
+    return nullptr;
+}
+
 // ---------------------------------------------------------------------------------
 // Plan
 // ---------------------------------------------------------------------------------
@@ -229,6 +301,8 @@ struct DeviceGuard {
 };
 
 bool planar_batch(const mavg_plan* p) { return p->desc.layout == MAVG_PLANAR && p->desc.channels > 1; }
+// frames covered by one shared-memory tile of the stream kernel
+uint64_t tile_frames(const mavg_plan* p) { return (uint64_t)p->geom.NT * p->geom.R / p->geom.C; }
 bool frame_sharded(const mavg_plan* p) { return !planar_batch(p); }
 
 // samples per signal and signal count as the stream kernel sees one shard
@@ -334,9 +408,10 @@ bool stream_eligible(const mavg_plan* p, const DevCtx& d, const void* in, const 
     if (((uintptr_t)in | (uintptr_t)out | (uintptr_t)halo) & 15u) return false;
     uint64_t n, signals, stride;
     shard_signals(p, d, frames, &n, &signals, &stride);
-    if (n < 32) return false;
-    if (signals > 1 && (stride % 4) != 0) return false;  // tensor-map strides are multiples of 16 bytes
-    if (n / 32 > 0x7fffffffull - 65536 || signals > 0x7fffffffull) return false;
+    const uint64_t row = 128 / p->geom.elem;
+    if (n < row) return false;
+    if (signals > 1 && (stride * p->geom.elem % 16) != 0) return false;  // tensor-map strides: multiples of 16 bytes
+    if (n / row > 0x7fffffffull - 65536 || signals > 0x7fffffffull) return false;
     return true;
 }
 
@@ -353,15 +428,16 @@ int launch_shard(mavg_plan* p, DevCtx& d, const void* in, void* out, const void*
     const StreamGeom& g = p->geom;
     uint64_t n, signals, stride;
     shard_signals(p, d, frames, &n, &signals, &stride);
-    const uint64_t rows = n / 32;
-    const uint32_t tile_rows = (uint32_t)(g.NT * g.R / 32);
+    const uint64_t row = 128 / g.elem;                 // samples per 128-byte row
+    const uint64_t rows = n / row;
+    const uint32_t tile_rows = (uint32_t)(g.NT * g.R / row);
     const uint64_t T = (uint64_t)g.NT * g.R;
 
     CUtensorMap in_map, out_map, halo_map;
-    MAVG_TRY(make_map(&in_map, in, rows, signals, stride * 4, tile_rows));
-    MAVG_TRY(make_map(&out_map, out, rows, signals, stride * 4, tile_rows));
+    MAVG_TRY(make_map(&in_map, in, rows, signals, stride * g.elem, tile_rows, g.elem));
+    MAVG_TRY(make_map(&out_map, out, rows, signals, stride * g.elem, tile_rows, g.elem));
     const uint64_t halo_rows = (uint64_t)g.H * tile_rows;
-    if (halo) MAVG_TRY(make_map(&halo_map, halo, halo_rows, 1, halo_rows * 128, tile_rows));
+    if (halo) MAVG_TRY(make_map(&halo_map, halo, halo_rows, 1, halo_rows * 128, tile_rows, g.elem));
     else halo_map = in_map;
 
     mavg::StreamParams sp;
@@ -370,7 +446,9 @@ int launch_shard(mavg_plan* p, DevCtx& d, const void* in, void* out, const void*
     sp.n_full = g.n_full;
     sp.m_part = g.m_part;
     sp.lag_chunks = g.lag_chunks;
-    const uint64_t tiles = (rows * 32 + T - 1) / T;
+    sp.div_mul = g.div_mul;
+    sp.div_shift = g.div_shift;
+    const uint64_t tiles = (rows * row + T - 1) / T;
     sp.tiles_per_signal = (int32_t)tiles;
     const uint64_t ctas = (uint64_t)d.sm_count * g.ctas_per_sm;
     const uint64_t want_chunks = ctas * std::max<uint32_t>(1u, p->desc.tuning.chunks_per_cta);
@@ -387,16 +465,18 @@ int launch_shard(mavg_plan* p, DevCtx& d, const void* in, void* out, const void*
     sp.prefetch = g.P;
     sp.has_halo = halo ? 1 : 0;
 
-    StreamKernel kern = pick_kernel(g, p->desc.window);
+    StreamKernel kern = g.elem == 4 ? pick_kernel(g, p->desc.window)
+                                    : (g.C == 1 ? pick_i16<1>(g.MIS, g.mode) : pick_i16<2>(g.MIS, g.mode));
+    if (!kern) return fail(MAVG_ERR_UNSUPPORTED, "no stream kernel variant for this window");
     MAVG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
     const unsigned grid = (unsigned)std::min<uint64_t>(ctas, (uint64_t)sp.total_chunks);
     kern<<<grid, g.NT, g.smem, d.stream>>>(in_map, out_map, halo_map, sp);
     MAVG_CUDA(cudaGetLastError());
     ++*launches;
 
-    // samples past the last whole 128-byte row (n % 32 of them, per signal): generic kernel
-    if (rows * 32 < n) {
-        MAVG_TRY(launch_generic(p, d, in, out, halo, frames, rows * 32, frames, launches));
+    // samples past the last whole 128-byte row (per signal): generic kernel
+    if (rows * row < n) {
+        MAVG_TRY(launch_generic(p, d, in, out, halo, frames, rows * row / g.C, frames, launches));
     }
     return MAVG_OK;
 }
@@ -494,19 +574,26 @@ int mavg_plan_create(const mavg_desc* desc, mavg_plan** out)
     DeviceGuard guard;
 
     // ---- kernel family
-    const bool stream_shape = desc->dtype == MAVG_F32 && (desc->channels == 1 || desc->layout == MAVG_PLANAR);
-    p->geom = plan_stream(desc->window, desc->tuning);
+    const bool planar = desc->layout == MAVG_PLANAR && desc->channels > 1;
+    bool stream_shape;
+    if (desc->dtype == MAVG_F32) {
+        stream_shape = desc->channels == 1 || planar;
+        p->geom = plan_stream(desc->window, desc->tuning);
+    } else {
+        stream_shape = desc->channels <= 2 || planar;
+        p->geom = plan_stream_i16(desc->window, planar ? 1u : desc->channels, desc->tuning);
+    }
     if (desc->path == MAVG_PATH_STREAM && !(stream_shape && p->geom.ok)) {
         delete p;
         return fail(MAVG_ERR_UNSUPPORTED,
-                    "stream path needs float32 mono/planar input and a window that fits the shared-memory history");
+                    "stream path needs float32 mono/planar or int16 mono/stereo/planar input and a window that fits "
+                    "the shared-memory history");
     }
     p->path = (desc->path != MAVG_PATH_GENERIC && stream_shape && p->geom.ok) ? MAVG_PATH_STREAM : MAVG_PATH_GENERIC;
 
     // ---- left context a frame shard needs
     if (p->path == MAVG_PATH_STREAM) {
-        const uint64_t T = (uint64_t)p->geom.NT * p->geom.R;
-        p->halo_frames = (uint64_t)p->geom.H * T;  // whole history tiles, so sharding keeps bit-identical sums
+        p->halo_frames = (uint64_t)p->geom.H * tile_frames(p);  // whole history tiles: sharding keeps bit-identical sums
     } else {
         p->halo_frames = desc->window;
     }
@@ -517,7 +604,7 @@ int mavg_plan_create(const mavg_desc* desc, mavg_plan** out)
     cudaGetDevice(&cur);
     p->dev.resize(nd);
     // frame shards start on tile boundaries (stream) so every device runs the same tile grid
-    const uint64_t align = (p->path == MAVG_PATH_STREAM && frame_sharded(p)) ? (uint64_t)p->geom.NT * p->geom.R : 1;
+    const uint64_t align = (p->path == MAVG_PATH_STREAM && frame_sharded(p)) ? tile_frames(p) : 1;
     for (uint32_t r = 0; r < nd; ++r) {
         DevCtx& d = p->dev[r];
         d.device = desc->num_devices >= 1 ? desc->devices[r] : cur;
@@ -785,7 +872,7 @@ int mavg_run_host(mavg_plan* p, const void* h_in, void* h_out)
         // shards go in one piece
         uint64_t slice_frames = d.frames;
         if (!planar_batch(p) && d.frames > 0) {
-            const uint64_t unit = (p->path == MAVG_PATH_STREAM) ? (uint64_t)p->geom.NT * p->geom.R : 1024;
+            const uint64_t unit = (p->path == MAVG_PATH_STREAM) ? tile_frames(p) : 1024;
             uint64_t want = std::max<uint64_t>((32ull << 20) / (C * es), p->halo_frames);
             want = (want + unit - 1) / unit * unit;
             if (want * 2 <= d.frames) slice_frames = want;

@@ -248,6 +248,8 @@ struct StreamParams {
     int32_t stages;             // S = H + 1 + prefetch
     int32_t prefetch;           // P
     int32_t has_halo;           // tiles before tile 0 come from halo_map instead of zero fill
+    uint32_t div_mul;           // int16 path: trunc(w / k) = sign(w) * (umulhi(|w|, div_mul) >> div_shift)
+    uint32_t div_shift;         //             (div_mul == 0 means k == 1)
 };
 
 // Shared-memory carve-up (bytes), shared by host (size) and device (offsets).
@@ -554,6 +556,306 @@ __global__ void __launch_bounds__(NT)
             tma_commit();
             st_pending = false;
             st_inflight = true;  // the next chunk's first iteration waits for the read to finish
+        }
+    }
+    if (tid == 0) tma_wait_all0();
+}
+
+// ----------------------------------------------------------------------------------
+// int16 streaming kernel -- the reference's own sample format (wav_header.h:26-48), mono or
+// interleaved stereo.  Same skeleton as stream_f32_kernel (persistent CTAs, TMA ring, one
+// __syncthreads per tile, TMA store); arithmetic is exact: int32 window sums (|w| <= k * 32768,
+// k < 65536) and C truncating division by multiply-high, so results are bit-identical to
+// profilable_cpu_computations (basics/profilable_moving_averager.cpp:14-37), unlike the reference
+// GPU kernels that multiply by a float reciprocal.  Interleaved channels are handled on the flat
+// sample stream: window stride C, lag distance k*C, one running sum per channel per thread.
+// HBM traffic: 2 B read + 2 B written per sample.
+// ----------------------------------------------------------------------------------
+__host__ __device__ inline uint32_t stream_i16_smem_bytes(int NT, int S, int H, int C)
+{
+    const uint32_t TB = (uint32_t)NT * 32 * 2;
+    return 1024u + (uint32_t)S * TB + 2u * TB + (uint32_t)(H + 2) * NT * C * 4 + (uint32_t)(H + 2) * 32 * C * 4 +
+           2u * 32 * C * 4 + (uint32_t)S * 8;
+}
+
+__device__ __forceinline__ uint4 lds128u(uint32_t addr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128u(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+{
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ int lds32i(uint32_t addr)
+{
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts32i(uint32_t addr, int v)
+{
+    asm volatile("st.shared.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void unpack8(const uint4 v, int* dst)
+{
+    dst[0] = (int)(v.x << 16) >> 16; dst[1] = (int)v.x >> 16;
+    dst[2] = (int)(v.y << 16) >> 16; dst[3] = (int)v.y >> 16;
+    dst[4] = (int)(v.z << 16) >> 16; dst[5] = (int)v.z >> 16;
+    dst[6] = (int)(v.w << 16) >> 16; dst[7] = (int)v.w >> 16;
+}
+// C integer division (truncation toward zero) by the plan's window
+__device__ __forceinline__ int div_trunc(int w, uint32_t mul, uint32_t sh)
+{
+    if (mul == 0u) return w;
+    const uint32_t a = (uint32_t)(w < 0 ? -w : w);
+    const int q = (int)(__umulhi(a, mul) >> sh);
+    return w < 0 ? -q : q;
+}
+
+template <int NT, int C, int MIS, int MODE>
+__global__ void __launch_bounds__(NT)
+    stream_i16_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map,
+                      const __grid_constant__ CUtensorMap halo_map, const StreamParams p)
+{
+    constexpr int R = 32;            // int16 samples per thread run = 64 bytes
+    constexpr int T = NT * R;
+    constexpr uint32_t TB = T * 2;
+    constexpr int ROWS = T / 64;     // 128-byte rows per tile
+    constexpr int NW = NT / 32;
+    constexpr int CH_OWN = 4;
+    constexpr int CH_LAG = CH_OWN + (MIS ? 1 : 0);
+    static_assert(R % C == 0 && NW <= 16 && MIS >= 0 && MIS < 8 && MIS % C == 0, "shape");
+
+    extern __shared__ uint8_t smem_raw[];
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int S = p.stages;
+    const int H = p.hist_tiles;
+    const int P = p.prefetch;
+    const int GS = H + 2;
+
+    const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t ring_bytes = (uint32_t)S * TB;
+    const uint32_t outb = ring + ring_bytes;
+    const uint32_t gsum = outb + 2u * TB;                     // int [GS][NT][C]
+    const uint32_t wexc = gsum + (uint32_t)GS * NT * C * 4;   // int [GS][32][C]  ([31] = tile total)
+    const uint32_t wraw = wexc + (uint32_t)GS * 32 * C * 4;   // int [2][32][C]
+    const uint32_t bars = wraw + 2u * 32 * C * 4;
+
+    if (tid == 0) {
+        prefetch_tmap(&in_map);
+        prefetch_tmap(&out_map);
+        if (p.has_halo) prefetch_tmap(&halo_map);
+        for (int s = 0; s < S; ++s) mbar_init(bars + 8u * s, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    auto issue_load = [&](int tile, int sig, int st) {
+        const uint32_t bar = bars + 8u * st;
+        mbar_arrive_expect_tx(bar, TB);
+        if (tile < 0 && p.has_halo)
+            tma_load_3d(ring + (uint32_t)st * TB, &halo_map, bar, 0, (tile + H) * ROWS, 0, kEvictFirst);
+        else
+            tma_load_3d(ring + (uint32_t)st * TB, &in_map, bar, 0, tile * ROWS, sig, kEvictFirst);
+    };
+
+    uint32_t it = 0;
+    int st = 0, slot = 0;
+    uint32_t otiles = 0;
+    bool st_pending = false, st_inflight = false;
+    int st_tile = 0, st_sig = 0;
+    uint32_t st_buf = 0;
+
+    for (int chunk = blockIdx.x; chunk < p.total_chunks; chunk += gridDim.x) {
+        const int sig = chunk / p.chunks_per_signal;
+        const int t0 = (chunk - sig * p.chunks_per_signal) * p.chunk_tiles;
+        int t1 = t0 + p.chunk_tiles;
+        if (t1 > p.tiles_per_signal) t1 = p.tiles_per_signal;
+        if (t0 >= t1) continue;
+        const int first = t0 - H;
+        const int ntl = t1 - first;
+
+        if (tid == 0) {
+            int s2 = st;
+            for (int j = 0; j < P && j < ntl; ++j) {
+                issue_load(first + j, sig, s2);
+                s2 = (s2 + 1 == S) ? 0 : s2 + 1;
+            }
+        }
+
+        for (int j = 0; j < ntl; ++j) {
+            const int tile = first + j;
+            const bool is_out = (j >= H);
+            const uint32_t cur = ring + (uint32_t)st * TB;
+
+            mbar_wait(bars + 8u * st, (it / (uint32_t)S) & 1u);
+
+            int x[R];
+#pragma unroll
+            for (int c = 0; c < CH_OWN; ++c) unpack8(lds128u(swz(cur + (uint32_t)tid * (R * 2) + 16u * c)), &x[8 * c]);
+            int gtot[C], incl[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) gtot[c] = 0;
+#pragma unroll
+            for (int r = 0; r < R; ++r) gtot[r % C] += x[r];
+#pragma unroll
+            for (int c = 0; c < C; ++c) incl[c] = gtot[c];
+
+            if constexpr (MODE == 0) {
+#pragma unroll
+                for (int c = 0; c < C; ++c) sts32i(gsum + (((uint32_t)slot * NT + tid) * C + c) * 4u, gtot[c]);
+            } else {
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        const int up = __shfl_up_sync(0xffffffffu, incl[c], d);
+                        if (lane >= d) incl[c] += up;
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    sts32i(gsum + (((uint32_t)slot * NT + tid) * C + c) * 4u, incl[c]);
+                    if (lane == 31) sts32i(wraw + (((it & 1u) * 32u + warp) * C + c) * 4u, incl[c]);
+                }
+            }
+
+            if (tid == 0 && st_inflight) {
+                tma_wait_read0();
+                st_inflight = false;
+            }
+            __syncthreads();
+
+            if (tid == 0) {
+                if (j + P < ntl) {
+                    int s2 = st + P;
+                    if (s2 >= S) s2 -= S;
+                    issue_load(first + j + P, sig, s2);
+                }
+                if (st_pending) {
+                    tma_store_3d(&out_map, st_buf, 0, st_tile * ROWS, st_sig);
+                    tma_commit();
+                    st_pending = false;
+                    st_inflight = true;
+                }
+            }
+
+            int own_off[C], wex[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) own_off[c] = wex[c] = 0;
+            if constexpr (MODE == 1) {
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const int v = (lane < NW) ? lds32i(wraw + (((it & 1u) * 32u + lane) * C + c) * 4u) : 0;
+                    int wi = v;
+#pragma unroll
+                    for (int d = 1; d < NW; d <<= 1) {
+                        const int up = __shfl_up_sync(0xffffffffu, wi, d);
+                        if (lane >= d) wi += up;
+                    }
+                    wex[c] = wi - v;
+                    if (warp == 0) {
+                        if (lane < NW) sts32i(wexc + (((uint32_t)slot * 32u + lane) * C + c) * 4u, wex[c]);
+                        if (lane == NW - 1) sts32i(wexc + (((uint32_t)slot * 32u + 31u) * C + c) * 4u, wi);
+                    }
+                    own_off[c] = __shfl_sync(0xffffffffu, wex[c], warp);
+                }
+            }
+
+            if (is_out) {
+                int xl[CH_LAG * 8];
+                {
+                    int lin = (int)((uint32_t)st * TB) + (tid * CH_OWN - (int)p.lag_chunks) * 16;
+#pragma unroll
+                    for (int c = 0; c < CH_LAG; ++c) {
+                        int o = lin + 16 * c;
+                        if (o < 0) o += (int)ring_bytes;
+                        unpack8(lds128u(swz(ring + (uint32_t)o)), &xl[8 * c]);
+                    }
+                }
+                int acc[C];
+#pragma unroll
+                for (int c = 0; c < C; ++c) acc[c] = 0;
+                if constexpr (MODE == 0) {
+                    int gi = slot * NT + tid;
+                    for (uint32_t n = 0; n < p.n_full; ++n) {
+                        gi = (gi == 0) ? GS * NT - 1 : gi - 1;
+#pragma unroll
+                        for (int c = 0; c < C; ++c) acc[c] += lds32i(gsum + ((uint32_t)gi * C + c) * 4u);
+                    }
+                } else {
+                    int lt = tid - (int)(p.n_full + 1u);
+                    int h = 0;
+                    if (lt < 0) {
+                        h = (-lt + NT - 1) / NT;
+                        lt += h * NT;
+                    }
+                    int ls = slot - h;
+                    if (ls < 0) ls += GS;
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        const int wsame = __shfl_sync(0xffffffffu, wex[c], lt >> 5);
+                        const int wold = lds32i(wexc + (((uint32_t)ls * 32u + (uint32_t)(lt >> 5)) * C + c) * 4u);
+                        const int cp_lag = lds32i(gsum + (((uint32_t)ls * NT + lt) * C + c) * 4u) + (h == 0 ? wsame : wold);
+                        const int e_own = own_off[c] + (incl[c] - gtot[c]);
+                        if (h == 0) {
+                            acc[c] = e_own - cp_lag;
+                        } else {
+                            int rest = lds32i(wexc + (((uint32_t)ls * 32u + 31u) * C + c) * 4u) - cp_lag;
+                            int ms = ls;
+                            for (int v2 = 1; v2 < h; ++v2) {
+                                ms = (ms + 1 == GS) ? 0 : ms + 1;
+                                rest += lds32i(wexc + (((uint32_t)ms * 32u + 31u) * C + c) * 4u);
+                            }
+                            acc[c] = e_own + rest;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                    if ((uint32_t)r < p.m_part) acc[r % C] += xl[MIS + r];
+
+                const uint32_t ob = outb + (otiles & 1u) * TB + (uint32_t)tid * (R * 2);
+                const uint32_t mul = p.div_mul, sh = p.div_shift;
+#pragma unroll
+                for (int c = 0; c < CH_OWN; ++c) {
+                    uint32_t wds[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int r0 = 8 * c + 2 * q, r1 = r0 + 1;
+                        acc[r0 % C] += x[r0] - xl[MIS + r0];
+                        const int y0 = div_trunc(acc[r0 % C], mul, sh);
+                        acc[r1 % C] += x[r1] - xl[MIS + r1];
+                        const int y1 = div_trunc(acc[r1 % C], mul, sh);
+                        wds[q] = ((uint32_t)y0 & 0xffffu) | ((uint32_t)y1 << 16);
+                    }
+                    sts128u(swz(ob + 16u * c), wds[0], wds[1], wds[2], wds[3]);
+                }
+                fence_proxy_async_smem();
+                if (tid == 0) {
+                    st_pending = true;
+                    st_tile = tile;
+                    st_sig = sig;
+                    st_buf = outb + (otiles & 1u) * TB;
+                }
+                ++otiles;
+            }
+
+            ++it;
+            st = (st + 1 == S) ? 0 : st + 1;
+            slot = (slot + 1 == GS) ? 0 : slot + 1;
+        }
+
+        __syncthreads();
+        if (tid == 0 && st_pending) {
+            tma_store_3d(&out_map, st_buf, 0, st_tile * ROWS, st_sig);
+            tma_commit();
+            st_pending = false;
+            st_inflight = true;
         }
     }
     if (tid == 0) tma_wait_all0();

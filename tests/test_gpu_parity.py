@@ -291,3 +291,57 @@ def test_full_size_2p28_vs_oracle(mavg, oracle_mod, k):
     with mavg.Plan(n, k) as plan:
         y = plan.run_host(x)
     assert np.all(np.abs(y[k:] - 1.0) < 1e-6)
+
+
+# ------------------------------------------------------------------ int16 streaming kernel (the reference's format)
+@pytest.mark.parametrize("ch", [1, 2])
+@pytest.mark.parametrize("k", [1, 2, 3, 5, 8, 16, 31, 41, 64, 255, 256, 272, 273, 544, 545, 1000, 1024, 4095, 4096, 9000, 20000])
+def test_i16_stream_kernel_bit_exact(mavg, oracle_mod, ch, k):
+    """Multi-tile int16 signals through the TMA streaming kernel: bit-identical to the reference CPU path
+    (int64-exact sums, truncating division) for every window, both arithmetic modes, mono and stereo."""
+    frames = (5 * 16384 + 64 * 3) // ch + 5          # several tiles, ragged rows, ragged tail
+    x = oracle_mod.fill_i16(frames * ch, 12000 + k + ch)
+    with mavg.Plan(frames, k, channels=ch, dtype="i16") as plan:
+        if k <= 4096:
+            assert plan.info.path == 1, "headline windows must take the streaming kernel"
+        y = plan.run_host(x)
+    assert np.array_equal(y, oracle_mod.mavg_i16(x, k, ch))
+
+
+def test_i16_stream_extremes_and_negative_truncation(mavg, oracle_mod):
+    n = 3 * 16384
+    for val in (-32768, 32767, -1, 1):
+        x = np.full(n, val, dtype=np.int16)
+        for k in (1, 3, 7, 4096, 30000):
+            assert np.array_equal(mavg.moving_average(x, k), oracle_mod.mavg_i16(x, k)), (val, k)
+    # alternating signs exercise truncation toward zero on both sides
+    x = (np.arange(n) % 7 - 3).astype(np.int16) * 1111
+    for k in (2, 5, 100):
+        assert np.array_equal(mavg.moving_average(x, k, channels=2), oracle_mod.mavg_i16(x, k, 2))
+
+
+@pytest.mark.parametrize("ch", [1, 2])
+@pytest.mark.parametrize("k", [5, 700, 4096])
+def test_i16_shard_with_halo_bit_exact(mavg, oracle_mod, torch_cuda, ch, k):
+    torch = torch_cuda
+    tile_frames = 16384 // ch
+    frames, cut = 20 * tile_frames + 333, 7 * tile_frames
+    x = oracle_mod.fill_i16(frames * ch, 13000 + k)
+    dx = torch.from_numpy(x).cuda()
+    dz = torch.zeros((frames - cut) * ch, dtype=torch.int16, device="cuda")
+    torch.cuda.synchronize()
+    with mavg.Plan(frames - cut, k, channels=ch, dtype="i16", first_frame=cut) as plan:
+        halo = int(plan.info.halo_frames)
+        assert plan.info.path == 1 and halo % tile_frames == 0 and halo >= k
+        plan.run_device_halo(dx.data_ptr() + 2 * cut * ch, dz.data_ptr(), dx.data_ptr() + 2 * (cut - halo) * ch)
+        plan.synchronize()
+    assert np.array_equal(dz.cpu().numpy(), oracle_mod.mavg_i16(x, k, ch)[cut * ch:])
+
+
+def test_i16_planar_batch(mavg, oracle_mod):
+    ch, frames, k = 3, 2 * 16384 + 8 * 5, 100
+    x = oracle_mod.fill_i16(ch * frames, 14000)
+    y = mavg.moving_average(x, k, channels=ch, layout="planar")
+    for c in range(ch):
+        seg = slice(c * frames, (c + 1) * frames)
+        assert np.array_equal(y[seg], oracle_mod.mavg_i16(x[seg], k))
