@@ -190,6 +190,11 @@ def main():
             print(json.dumps(cpu_reference_line(args, ks, max(world, args.gpus))), flush=True)
         return 0
 
+    # Everything except the final JSON line goes to stderr (NCCL prints a version banner on stdout).
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
     import digital_signal_processsing_b200 as mavg
@@ -380,8 +385,11 @@ def main():
             line.update(cpu_baseline_block(ks))
         except Exception as e:  # the CPU yardstick must never take the GPU number down with it
             line["cpu_baseline"] = {"value": None, "unit": "Gsamples/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
     if rank == 0:
         print(json.dumps(line), flush=True)
+    os.dup2(2, 1)
 
     for p in plans.values():
         p.close()
