@@ -149,30 +149,35 @@ StreamGeom plan_stream_i16(uint32_t k, uint32_t C, const mavg_tuning& tu)
     return g;
 }
 
-StreamGeom plan_stream(uint32_t k, const mavg_tuning& tu)
+// float32: C = channels interleaved in the flat stream (1 for mono / planar, 2 for stereo).
+StreamGeom plan_stream(uint32_t k, const mavg_tuning& tu, uint32_t C = 1)
 {
     StreamGeom g;
     g.NT = tu.threads ? (int)tu.threads : 512;
     g.R = tu.run ? (int)tu.run : 16;
+    g.C = C;
     if (!(g.NT == 256 || g.NT == 512) || !(g.R == 16 || g.R == 32)) return g;
     if (g.NT * g.R > 8192) return g;  // a TMA box holds at most 256 rows of 32 floats
+    if (C != 1 && !(C == 2 && g.NT == 512 && g.R == 16)) return g;  // stereo is built for the default shape only
     const uint32_t direct_max = tu.direct_max_k ? tu.direct_max_k : 256u;
-    g.mode = (k <= 8) ? 2 : (k <= direct_max) ? 0 : 1;
+    const uint64_t L = (uint64_t)k * C;                              // lag distance in flat samples
+    if (L > 0xfffffff0ull) return g;
+    g.mode = (k <= 8) ? 2 : (L <= direct_max) ? 0 : 1;
     const uint32_t R = (uint32_t)g.R;
-    const uint32_t s = (R - k % R) % R;
+    const uint32_t s = (uint32_t)((R - L % R) % R);
     g.m_part = R - s;
-    g.n_full = (k + s) / R - 1;
-    g.lag_chunks = (k + 3) / 4;
-    g.MIS = (g.mode == 2) ? 0 : (int)(4 * g.lag_chunks - k);
+    g.n_full = (uint32_t)((L + s) / R - 1);
+    g.lag_chunks = (uint32_t)((L + 3) / 4);
+    g.MIS = (g.mode == 2) ? 0 : (int)(4ull * g.lag_chunks - L);
     const uint64_t T = (uint64_t)g.NT * R;
-    const uint64_t back = (g.mode == 2) ? 8 : (uint64_t)(g.n_full + 1) * R;  // left context a tile can touch
+    const uint64_t back = (g.mode == 2) ? 4 * ((7 * C + 3) / 4) : (uint64_t)(g.n_full + 1) * R;  // left context a tile can touch
     g.H = (int)((back + T - 1) / T);
     g.ctas_per_sm = tu.ctas_per_sm ? (int)tu.ctas_per_sm : 2;
     g.P = tu.prefetch ? (int)tu.prefetch : 2;
     // shrink the prefetch depth, then the residency, until the ring fits
     for (;;) {
         g.S = g.H + 1 + g.P;
-        g.smem = mavg::stream_smem_bytes(g.NT, g.R, g.S, g.H);
+        g.smem = mavg::stream_smem_bytes(g.NT, g.R, g.S, g.H, (int)C);
         const uint32_t per_sm = 233472;  // 228 KB per SM, 1 KB reserved per resident CTA
         if (g.smem <= kMaxSmem && (uint64_t)(g.smem + 1024) * g.ctas_per_sm <= per_sm) break;
         if (g.P > 1) { --g.P; continue; }
@@ -185,40 +190,43 @@ StreamGeom plan_stream(uint32_t k, const mavg_tuning& tu)
 
 typedef void (*StreamKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const mavg::StreamParams);
 
-template <int NT, int R>
+template <int NT, int R, int C = 1>
 StreamKernel pick_variant(int mis, int mode, uint32_t k)
 {
     using namespace mavg;
     if (mode == 2) {
         switch (k) {
-        case 1: return stream_f32_kernel<NT, R, 0, 2, 1>;
-        case 2: return stream_f32_kernel<NT, R, 0, 2, 2>;
-        case 3: return stream_f32_kernel<NT, R, 0, 2, 3>;
-        case 4: return stream_f32_kernel<NT, R, 0, 2, 4>;
-        case 5: return stream_f32_kernel<NT, R, 0, 2, 5>;
-        case 6: return stream_f32_kernel<NT, R, 0, 2, 6>;
-        case 7: return stream_f32_kernel<NT, R, 0, 2, 7>;
-        default: return stream_f32_kernel<NT, R, 0, 2, 8>;
+        case 1: return stream_f32_kernel<NT, R, 0, 2, 1, C>;
+        case 2: return stream_f32_kernel<NT, R, 0, 2, 2, C>;
+        case 3: return stream_f32_kernel<NT, R, 0, 2, 3, C>;
+        case 4: return stream_f32_kernel<NT, R, 0, 2, 4, C>;
+        case 5: return stream_f32_kernel<NT, R, 0, 2, 5, C>;
+        case 6: return stream_f32_kernel<NT, R, 0, 2, 6, C>;
+        case 7: return stream_f32_kernel<NT, R, 0, 2, 7, C>;
+        default: return stream_f32_kernel<NT, R, 0, 2, 8, C>;
         }
     }
     if (mode == 0) {
-        switch (mis) {
-        case 0: return stream_f32_kernel<NT, R, 0, 0, 0>;
-        case 1: return stream_f32_kernel<NT, R, 1, 0, 0>;
-        case 2: return stream_f32_kernel<NT, R, 2, 0, 0>;
-        default: return stream_f32_kernel<NT, R, 3, 0, 0>;
+        if (mis == 0) return stream_f32_kernel<NT, R, 0, 0, 0, C>;
+        if (mis == 2) return stream_f32_kernel<NT, R, 2, 0, 0, C>;
+        if constexpr (C == 1) {
+            if (mis == 1) return stream_f32_kernel<NT, R, 1, 0, 0, C>;
+            if (mis == 3) return stream_f32_kernel<NT, R, 3, 0, 0, C>;
         }
+        return nullptr;
     }
-    switch (mis) {
-    case 0: return stream_f32_kernel<NT, R, 0, 1, 0>;
-    case 1: return stream_f32_kernel<NT, R, 1, 1, 0>;
-    case 2: return stream_f32_kernel<NT, R, 2, 1, 0>;
-    default: return stream_f32_kernel<NT, R, 3, 1, 0>;
+    if (mis == 0) return stream_f32_kernel<NT, R, 0, 1, 0, C>;
+    if (mis == 2) return stream_f32_kernel<NT, R, 2, 1, 0, C>;
+    if constexpr (C == 1) {
+        if (mis == 1) return stream_f32_kernel<NT, R, 1, 1, 0, C>;
+        if (mis == 3) return stream_f32_kernel<NT, R, 3, 1, 0, C>;
     }
+    return nullptr;
 }
 
 StreamKernel pick_kernel(const StreamGeom& g, uint32_t k)
 {
+    if (g.C == 2) return pick_variant<512, 16, 2>(g.MIS, g.mode, k);
     if (g.NT == 256 && g.R == 16) return pick_variant<256, 16>(g.MIS, g.mode, k);
     if (g.NT == 256 && g.R == 32) return pick_variant<256, 32>(g.MIS, g.mode, k);
     return pick_variant<512, 16>(g.MIS, g.mode, k);
@@ -577,8 +585,8 @@ int mavg_plan_create(const mavg_desc* desc, mavg_plan** out)
     const bool planar = desc->layout == MAVG_PLANAR && desc->channels > 1;
     bool stream_shape;
     if (desc->dtype == MAVG_F32) {
-        stream_shape = desc->channels == 1 || planar;
-        p->geom = plan_stream(desc->window, desc->tuning);
+        stream_shape = desc->channels <= 2 || planar;
+        p->geom = plan_stream(desc->window, desc->tuning, planar ? 1u : desc->channels);
     } else {
         stream_shape = desc->channels <= 2 || planar;
         p->geom = plan_stream_i16(desc->window, planar ? 1u : desc->channels, desc->tuning);
@@ -586,8 +594,7 @@ int mavg_plan_create(const mavg_desc* desc, mavg_plan** out)
     if (desc->path == MAVG_PATH_STREAM && !(stream_shape && p->geom.ok)) {
         delete p;
         return fail(MAVG_ERR_UNSUPPORTED,
-                    "stream path needs float32 mono/planar or int16 mono/stereo/planar input and a window that fits "
-                    "the shared-memory history");
+                    "stream path needs mono, stereo or planar input and a window that fits the shared-memory history");
     }
     p->path = (desc->path != MAVG_PATH_GENERIC && stream_shape && p->geom.ok) ? MAVG_PATH_STREAM : MAVG_PATH_GENERIC;
 

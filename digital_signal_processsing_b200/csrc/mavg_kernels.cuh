@@ -253,54 +253,57 @@ struct StreamParams {
 };
 
 // Shared-memory carve-up (bytes), shared by host (size) and device (offsets).
-__host__ __device__ inline uint32_t stream_smem_bytes(int NT, int R, int S, int H)
+__host__ __device__ inline uint32_t stream_smem_bytes(int NT, int R, int S, int H, int C = 1)
 {
     const uint32_t TB = (uint32_t)NT * R * 4;
-    return 1024u                       // alignment slack
-           + (uint32_t)S * TB          // input ring
-           + 2u * TB                   // output staging (double buffered)
-           + (uint32_t)(H + 2) * NT * 4  // per-thread group totals (MODE 0) / warp-inclusive prefixes (MODE 1)
-           + (uint32_t)(H + 2) * 32 * 4  // per-tile exclusive warp offsets, [31] = tile total (MODE 1)
-           + 2u * 32 * 4               // raw warp totals, double buffered by iteration parity (MODE 1)
-           + (uint32_t)S * 8;          // mbarriers
+    return 1024u                           // alignment slack
+           + (uint32_t)S * TB              // input ring
+           + 2u * TB                       // output staging (double buffered)
+           + (uint32_t)(H + 2) * NT * C * 4  // per-thread group totals (MODE 0) / warp-inclusive prefixes (MODE 1)
+           + (uint32_t)(H + 2) * 32 * C * 4  // per-tile exclusive warp offsets, [31] = tile total (MODE 1)
+           + 2u * 32 * C * 4               // raw warp totals, double buffered by iteration parity (MODE 1)
+           + (uint32_t)S * 8;              // mbarriers
 }
 
 // Cancellation-free window sums for compile-time K <= 8 (MODE 2): v[] holds samples
 // a-K+1 .. a+R-1; windows are assembled from power-of-two partial windows, additions only,
 // so the relative error stays ~K*2^-24 even where the window sum is nearly zero.
-template <int K, int R>
-__device__ __forceinline__ void small_window_sums(const float (&v)[R + 7], float (&w)[R])
+template <int K, int R, int C>
+__device__ __forceinline__ void small_window_sums(const float (&v)[R + 7 * C], float (&w)[R])
 {
-    float w2[R + 6], w4[R + 4], w8[R];
+    // v[0] is flat sample a-(K-1)*C; the window of output r is v[r + j*C], j < K (stride C = one channel)
+    float w2[R + 6 * C], w4[R + 4 * C], w8[R];
     if constexpr (K >= 2) {
 #pragma unroll
-        for (int i = 0; i < R + 6; ++i) w2[i] = v[i] + v[i + 1];
+        for (int i = 0; i < R + 6 * C; ++i) w2[i] = v[i] + v[i + C];
     }
     if constexpr (K >= 4) {
 #pragma unroll
-        for (int i = 0; i < R + 4; ++i) w4[i] = w2[i] + w2[i + 2];
+        for (int i = 0; i < R + 4 * C; ++i) w4[i] = w2[i] + w2[i + 2 * C];
     }
     if constexpr (K >= 8) {
 #pragma unroll
-        for (int i = 0; i < R; ++i) w8[i] = w4[i] + w4[i + 4];
+        for (int i = 0; i < R; ++i) w8[i] = w4[i] + w4[i + 4 * C];
     }
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         float acc;
         int off = r;
-        if constexpr (K >= 8) { acc = w8[off]; off += 8; }
-        else if constexpr (K >= 4) { acc = w4[off]; off += 4; }
-        else if constexpr (K >= 2) { acc = w2[off]; off += 2; }
-        else { acc = v[off]; off += 1; }
-        if constexpr (K < 8 && K >= 4 && (K & 2)) { acc += w2[off]; off += 2; }
-        if constexpr (K >= 2 && (K & 1)) { acc += v[off]; off += 1; }
+        if constexpr (K >= 8) { acc = w8[off]; off += 8 * C; }
+        else if constexpr (K >= 4) { acc = w4[off]; off += 4 * C; }
+        else if constexpr (K >= 2) { acc = w2[off]; off += 2 * C; }
+        else { acc = v[off]; off += C; }
+        if constexpr (K < 8 && K >= 4 && (K & 2)) { acc += w2[off]; off += 2 * C; }
+        if constexpr (K >= 2 && (K & 1)) { acc += v[off]; off += C; }
         w[r] = acc;
     }
 }
 
 // MODE 0: direct group sums (9 <= k <= direct_max), MODE 1: tile-rebased prefix scan,
 // MODE 2: compile-time K <= 8, additions only (MIS unused).
-template <int NT, int R, int MIS, int MODE, int K>
+// C = channels interleaved in the flat sample stream (1 mono/planar, 2 stereo, 4): window stride C,
+// lag distance k*C, one running sum per channel per thread.
+template <int NT, int R, int MIS, int MODE, int K, int C = 1>
 __global__ void __launch_bounds__(NT)
     stream_f32_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map,
                       const __grid_constant__ CUtensorMap halo_map, const StreamParams p)
@@ -310,8 +313,10 @@ __global__ void __launch_bounds__(NT)
     constexpr int ROWS = T / 32;     // 128-byte rows per tile
     constexpr int NW = NT / 32;
     constexpr int CH_OWN = R / 4;
-    constexpr int CH_LAG = (MODE == 2) ? 2 : CH_OWN + (MIS ? 1 : 0);
+    constexpr int PRE = (7 * C + 3) / 4;  // MODE 2: 16-byte chunks in front of the run that hold (K-1)*C samples
+    constexpr int CH_LAG = (MODE == 2) ? PRE : CH_OWN + (MIS ? 1 : 0);
     static_assert(MODE != 2 || (K >= 1 && K <= 8), "MODE 2 serves K in 1..8");
+    static_assert(R % C == 0 && MIS % C == 0, "runs hold whole frames");
     static_assert(NT % 32 == 0 && NW <= 16, "NT must be a multiple of 32, at most 512");
     static_assert(R == 16 || R == 32, "run length");
 
@@ -327,10 +332,10 @@ __global__ void __launch_bounds__(NT)
     const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t ring_bytes = (uint32_t)S * TB;
     const uint32_t outb = ring + ring_bytes;
-    const uint32_t gsum = outb + 2u * TB;                 // float [GS][NT]
-    const uint32_t wexc = gsum + (uint32_t)GS * NT * 4;   // float [GS][32]
-    const uint32_t wraw = wexc + (uint32_t)GS * 32 * 4;   // float [2][32]
-    const uint32_t bars = wraw + 2u * 32 * 4;             // u64   [S]
+    const uint32_t gsum = outb + 2u * TB;                     // float [GS][NT][C]
+    const uint32_t wexc = gsum + (uint32_t)GS * NT * C * 4;   // float [GS][32][C]
+    const uint32_t wraw = wexc + (uint32_t)GS * 32 * C * 4;   // float [2][32][C]
+    const uint32_t bars = wraw + 2u * 32 * C * 4;             // u64   [S]
 
     if (tid == 0) {
         prefetch_tmap(&in_map);
@@ -392,27 +397,42 @@ __global__ void __launch_bounds__(NT)
                 const float4 v = lds128(swz(cur + (uint32_t)tid * (R * 4) + 16u * c));
                 x[4 * c + 0] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
             }
-            // group total, fixed pairwise order
-            float gtot = 0.f;
-            if constexpr (MODE != 2) {
-                float q4[CH_OWN];
+            // per-channel group totals, fixed order
+            float gtot[C], incl[C];
 #pragma unroll
-                for (int c = 0; c < CH_OWN; ++c) q4[c] = (x[4 * c] + x[4 * c + 1]) + (x[4 * c + 2] + x[4 * c + 3]);
-                gtot = (q4[0] + q4[1]) + (q4[2] + q4[3]);
-                if constexpr (R == 32) gtot += (q4[CH_OWN - 4] + q4[CH_OWN - 3]) + (q4[CH_OWN - 2] + q4[CH_OWN - 1]);
+            for (int c = 0; c < C; ++c) gtot[c] = 0.f;
+            if constexpr (MODE != 2) {
+                if constexpr (C == 1) {  // pairwise
+                    float q4[CH_OWN];
+#pragma unroll
+                    for (int c = 0; c < CH_OWN; ++c) q4[c] = (x[4 * c] + x[4 * c + 1]) + (x[4 * c + 2] + x[4 * c + 3]);
+                    gtot[0] = (q4[0] + q4[1]) + (q4[2] + q4[3]);
+                    if constexpr (R == 32) gtot[0] += (q4[CH_OWN - 4] + q4[CH_OWN - 3]) + (q4[CH_OWN - 2] + q4[CH_OWN - 1]);
+                } else {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) gtot[r % C] += x[r];
+                }
             }
+#pragma unroll
+            for (int c = 0; c < C; ++c) incl[c] = gtot[c];  // MODE 1: inclusive prefix of group totals inside the warp
 
-            float incl = gtot;  // MODE 1: inclusive prefix of group totals inside the warp
             if constexpr (MODE == 0) {
-                sts32(gsum + ((uint32_t)slot * NT + tid) * 4u, gtot);
+#pragma unroll
+                for (int c = 0; c < C; ++c) sts32(gsum + (((uint32_t)slot * NT + tid) * C + c) * 4u, gtot[c]);
             } else if constexpr (MODE == 1) {
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
-                    const float up = __shfl_up_sync(0xffffffffu, incl, d);
-                    if (lane >= d) incl += up;
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        const float up = __shfl_up_sync(0xffffffffu, incl[c], d);
+                        if (lane >= d) incl[c] += up;
+                    }
                 }
-                sts32(gsum + ((uint32_t)slot * NT + tid) * 4u, incl);
-                if (lane == 31) sts32(wraw + ((it & 1u) * 32u + warp) * 4u, incl);
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    sts32(gsum + (((uint32_t)slot * NT + tid) * C + c) * 4u, incl[c]);
+                    if (lane == 31) sts32(wraw + (((it & 1u) * 32u + warp) * C + c) * 4u, incl[c]);
+                }
             }
 
             if (tid == 0 && st_inflight) {  // staging buffer about to be rewritten is free again
@@ -435,29 +455,34 @@ __global__ void __launch_bounds__(NT)
                 }
             }
 
-            float own_off = 0.f, wex = 0.f;
+            float own_off[C], wex[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) own_off[c] = wex[c] = 0.f;
             if constexpr (MODE == 1) {
                 // exclusive offsets of the NW warp totals of this tile (every warp redundantly)
-                const float v = (lane < NW) ? lds32(wraw + ((it & 1u) * 32u + lane) * 4u) : 0.f;
-                float wi = v;
 #pragma unroll
-                for (int d = 1; d < NW; d <<= 1) {
-                    const float up = __shfl_up_sync(0xffffffffu, wi, d);
-                    if (lane >= d) wi += up;
+                for (int c = 0; c < C; ++c) {
+                    const float v = (lane < NW) ? lds32(wraw + (((it & 1u) * 32u + lane) * C + c) * 4u) : 0.f;
+                    float wi = v;
+#pragma unroll
+                    for (int d = 1; d < NW; d <<= 1) {
+                        const float up = __shfl_up_sync(0xffffffffu, wi, d);
+                        if (lane >= d) wi += up;
+                    }
+                    wex[c] = wi - v;
+                    if (warp == 0) {
+                        if (lane < NW) sts32(wexc + (((uint32_t)slot * 32u + lane) * C + c) * 4u, wex[c]);
+                        if (lane == NW - 1) sts32(wexc + (((uint32_t)slot * 32u + 31u) * C + c) * 4u, wi);  // tile total
+                    }
+                    own_off[c] = __shfl_sync(0xffffffffu, wex[c], warp);
                 }
-                wex = wi - v;
-                if (warp == 0) {
-                    if (lane < NW) sts32(wexc + ((uint32_t)slot * 32u + lane) * 4u, wex);
-                    if (lane == NW - 1) sts32(wexc + ((uint32_t)slot * 32u + 31u) * 4u, wi);  // tile total
-                }
-                own_off = __shfl_sync(0xffffffffu, wex, warp);
             }
 
             if (is_out) {
                 // ---- lag run: samples [a-k, a-k+R) (a = run start), loaded as aligned 16-byte chunks
                 float xl[CH_LAG * 4];
                 {
-                    const int back = (MODE == 2) ? 2 : (int)p.lag_chunks;
+                    const int back = (MODE == 2) ? PRE : (int)p.lag_chunks;
                     int lin = (int)((uint32_t)st * TB) + (tid * CH_OWN - back) * 16;
 #pragma unroll
                     for (int c = 0; c < CH_LAG; ++c) {
@@ -472,26 +497,29 @@ __global__ void __launch_bounds__(NT)
                 const uint32_t ob = outb + (otiles & 1u) * TB + (uint32_t)tid * (R * 4);
                 if constexpr (MODE == 2) {
                     // ---- additions only: v = samples a-K+1 .. a+R-1
-                    float v[R + 7], w[R];
+                    float v[R + 7 * C], w[R];
 #pragma unroll
-                    for (int i = 0; i < R + 7; ++i) v[i] = 0.f;
+                    for (int i = 0; i < R + 7 * C; ++i) v[i] = 0.f;
 #pragma unroll
-                    for (int i = 0; i < K - 1; ++i) v[i] = xl[8 - (K - 1) + i];
+                    for (int i = 0; i < (K - 1) * C; ++i) v[i] = xl[4 * PRE - (K - 1) * C + i];
 #pragma unroll
-                    for (int i = 0; i < R; ++i) v[K - 1 + i] = x[i];
-                    small_window_sums<K, R>(v, w);
+                    for (int i = 0; i < R; ++i) v[(K - 1) * C + i] = x[i];
+                    small_window_sums<K, R, C>(v, w);
 #pragma unroll
                     for (int c = 0; c < CH_OWN; ++c)
                         sts128(swz(ob + 16u * c), w[4 * c] * inv, w[4 * c + 1] * inv, w[4 * c + 2] * inv,
                                w[4 * c + 3] * inv);
                 } else {
-                    // ---- window sum over [a-k, a): whole groups between, then the tail of the lag group
-                    float acc = 0.f;
+                    // ---- per-channel window sum over [a-k*C, a): whole groups between, then the tail of the lag group
+                    float acc[C];
+#pragma unroll
+                    for (int c = 0; c < C; ++c) acc[c] = 0.f;
                     if constexpr (MODE == 0) {
                         int gi = slot * NT + tid;
                         for (uint32_t n = 0; n < p.n_full; ++n) {
                             gi = (gi == 0) ? GS * NT - 1 : gi - 1;
-                            acc += lds32(gsum + (uint32_t)gi * 4u);
+#pragma unroll
+                            for (int c = 0; c < C; ++c) acc[c] += lds32(gsum + ((uint32_t)gi * C + c) * 4u);
                         }
                     } else {
                         int lt = tid - (int)(p.n_full + 1u);  // thread index of the lag group, relative to this tile
@@ -502,36 +530,41 @@ __global__ void __launch_bounds__(NT)
                         }
                         int ls = slot - h;
                         if (ls < 0) ls += GS;
-                        const float wsame = __shfl_sync(0xffffffffu, wex, lt >> 5);
-                        const float wold = lds32(wexc + ((uint32_t)ls * 32u + (uint32_t)(lt >> 5)) * 4u);
-                        const float cp_lag = lds32(gsum + ((uint32_t)ls * NT + lt) * 4u) + (h == 0 ? wsame : wold);
-                        const float e_own = own_off + (incl - gtot);
-                        if (h == 0) {
-                            acc = e_own - cp_lag;
-                        } else {
-                            float rest = lds32(wexc + ((uint32_t)ls * 32u + 31u) * 4u) - cp_lag;  // tail of the lag tile
-                            int ms = ls;
-                            for (int v2 = 1; v2 < h; ++v2) {  // whole tiles strictly between (k > tile only)
-                                ms = (ms + 1 == GS) ? 0 : ms + 1;
-                                rest += lds32(wexc + ((uint32_t)ms * 32u + 31u) * 4u);
+#pragma unroll
+                        for (int c = 0; c < C; ++c) {
+                            const float wsame = __shfl_sync(0xffffffffu, wex[c], lt >> 5);
+                            const float wold = lds32(wexc + (((uint32_t)ls * 32u + (uint32_t)(lt >> 5)) * C + c) * 4u);
+                            const float cp_lag =
+                                lds32(gsum + (((uint32_t)ls * NT + lt) * C + c) * 4u) + (h == 0 ? wsame : wold);
+                            const float e_own = own_off[c] + (incl[c] - gtot[c]);
+                            if (h == 0) {
+                                acc[c] = e_own - cp_lag;
+                            } else {
+                                float rest = lds32(wexc + (((uint32_t)ls * 32u + 31u) * C + c) * 4u) - cp_lag;  // lag-tile tail
+                                int ms = ls;
+                                for (int v2 = 1; v2 < h; ++v2) {  // whole tiles strictly between (k*C > tile only)
+                                    ms = (ms + 1 == GS) ? 0 : ms + 1;
+                                    rest += lds32(wexc + (((uint32_t)ms * 32u + 31u) * C + c) * 4u);
+                                }
+                                acc[c] = e_own + rest;
                             }
-                            acc = e_own + rest;
                         }
                     }
 #pragma unroll
                     for (int r = 0; r < R; ++r)
-                        if ((uint32_t)r < p.m_part) acc += xl[MIS + r];
+                        if ((uint32_t)r < p.m_part) acc[r % C] += xl[MIS + r];
 
-                    // ---- slide and scale
-                    float w = acc;
+                    // ---- slide and scale (acc[c] is the running window sum of channel c)
 #pragma unroll
-                    for (int c = 0; c < CH_OWN; ++c) {
-                        float y0, y1, y2, y3;
-                        w += x[4 * c + 0] - xl[MIS + 4 * c + 0]; y0 = w * inv;
-                        w += x[4 * c + 1] - xl[MIS + 4 * c + 1]; y1 = w * inv;
-                        w += x[4 * c + 2] - xl[MIS + 4 * c + 2]; y2 = w * inv;
-                        w += x[4 * c + 3] - xl[MIS + 4 * c + 3]; y3 = w * inv;
-                        sts128(swz(ob + 16u * c), y0, y1, y2, y3);
+                    for (int c4 = 0; c4 < CH_OWN; ++c4) {
+                        float y[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int r = 4 * c4 + q;
+                            acc[r % C] += x[r] - xl[MIS + r];
+                            y[q] = acc[r % C] * inv;
+                        }
+                        sts128(swz(ob + 16u * c4), y[0], y[1], y[2], y[3]);
                     }
                 }
                 fence_proxy_async_smem();

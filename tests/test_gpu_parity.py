@@ -345,3 +345,41 @@ def test_i16_planar_batch(mavg, oracle_mod):
     for c in range(ch):
         seg = slice(c * frames, (c + 1) * frames)
         assert np.array_equal(y[seg], oracle_mod.mavg_i16(x[seg], k))
+
+
+# ------------------------------------------------------------------ stereo float32 through the streaming kernel
+@pytest.mark.parametrize("k", [1, 2, 3, 5, 7, 8, 9, 16, 17, 64, 128, 129, 255, 256, 1000, 1024, 2048, 4096, 5000])
+def test_stereo_f32_stream_kernel(mavg, oracle_mod, k):
+    frames = 3 * 4096 + 37 * 16 + 3            # several stereo tiles (4096 frames each), ragged rows and tail
+    x = oracle_mod.fill_f32(2 * frames, 15000 + k)
+    with mavg.Plan(frames, k, channels=2) as plan:
+        assert plan.info.path == 1
+        y = plan.run_host(x)
+    assert _rel(y, oracle_mod.mavg_f64(x, k, 2)) < TOL
+    # channel independence: the left channel equals the mono filter of the left samples
+    if k in (3, 64, 1024):
+        left = np.ascontiguousarray(x[0::2])
+        np.testing.assert_allclose(y[0::2], mavg.moving_average(left, k), rtol=2e-6, atol=0)
+
+
+@pytest.mark.parametrize("k", [3, 300, 4096])
+def test_stereo_f32_shard_with_halo_bit_identical(mavg, oracle_mod, torch_cuda, k):
+    torch = torch_cuda
+    tf = 4096                                   # frames per stereo tile
+    frames, cut = 30 * tf + 100, 11 * tf
+    x = oracle_mod.fill_f32(2 * frames, 16000 + k)
+    dx = torch.from_numpy(x).cuda()
+    dy = torch.zeros(2 * frames, dtype=torch.float32, device="cuda")
+    dz = torch.zeros(2 * (frames - cut), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    with mavg.Plan(frames, k, channels=2) as plan:
+        plan.run_device([dx.data_ptr()], [dy.data_ptr()])
+        plan.synchronize()
+    with mavg.Plan(frames - cut, k, channels=2, first_frame=cut) as plan:
+        halo = int(plan.info.halo_frames)
+        assert halo % tf == 0 and halo >= k
+        plan.run_device_halo(dx.data_ptr() + 8 * cut, dz.data_ptr(), dx.data_ptr() + 8 * (cut - halo))
+        plan.synchronize()
+    whole = dy.cpu().numpy()
+    assert np.array_equal(dz.cpu().numpy(), whole[2 * cut:])
+    assert _rel(whole, oracle_mod.mavg_f64(x, k, 2)) < TOL
