@@ -273,12 +273,12 @@ def main():
     def step(record=None):
         nonlocal launches_per_step
         cnt = 0
+        if record is not None:
+            record[0].record(stream)
         for i, k in enumerate(ks):
-            if record is not None:
-                record[i][0].record(stream)
             plans[k].run_device_halo(d_in.value, d_out.value, halo_ptr[k] or None)
             if record is not None:
-                record[i][1].record(stream)
+                record[i + 1].record(stream)   # one event per boundary: launch i is timed from event i to i+1
             cnt += int(plans[k].info.launches_per_run)
         launches_per_step = cnt
 
@@ -288,8 +288,7 @@ def main():
     stream.synchronize()
 
     # ---------------- timed region: K steps, events on the launching stream
-    ev = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in ks]
-          for _ in range(args.steps)]
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(len(ks) + 1)] for _ in range(args.steps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler = ClockSampler(local_rank)
     barrier()
@@ -304,7 +303,7 @@ def main():
     clocks = sampler.stop()
     barrier()
     elapsed_ms = e0.elapsed_time(e1)
-    per_k_ms = [sum(ev[s][i][0].elapsed_time(ev[s][i][1]) for s in range(args.steps)) / args.steps for i in range(len(ks))]
+    per_k_ms = [sum(ev[s][i].elapsed_time(ev[s][i + 1]) for s in range(args.steps)) / args.steps for i in range(len(ks))]
     if world > 1:
         t = torch.tensor([elapsed_ms] + per_k_ms, device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -14,6 +14,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "mavg_kernels.cuh"
@@ -188,6 +189,34 @@ StreamGeom plan_stream(uint32_t k, const mavg_tuning& tu, uint32_t C = 1)
     return g;
 }
 
+// many-channel interleaved float32: 16 warps x 16 frames per tile of [256 frames][32 channels]
+constexpr int kColsNW = 16, kColsRF = 16;
+StreamGeom plan_cols(uint32_t k, uint32_t C, const mavg_tuning& tu)
+{
+    StreamGeom g;
+    g.NT = kColsNW * 32;
+    g.R = kColsRF;
+    g.C = C;
+    g.mode = 3;
+    if (k < 9 || C < 32 || C % 4 != 0) return g;   // tiny windows keep the fp64 generic kernel
+    const uint32_t R = kColsRF, FT = kColsNW * kColsRF;
+    const uint32_t s = (R - k % R) % R;
+    g.m_part = R - s;
+    g.n_full = (k + s) / R - 1;
+    g.H = (int)(((uint64_t)(g.n_full + 1) * R + FT - 1) / FT);
+    g.ctas_per_sm = 1;
+    g.P = tu.prefetch ? (int)tu.prefetch : 2;
+    for (;;) {
+        g.S = g.H + 1 + g.P;
+        g.smem = mavg::cols_smem_bytes(kColsNW, kColsRF, g.S, g.H);
+        if (g.smem <= kMaxSmem) break;
+        if (g.P > 1) { --g.P; continue; }
+        return g;
+    }
+    g.ok = true;
+    return g;
+}
+
 typedef void (*StreamKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const mavg::StreamParams);
 
 template <int NT, int R, int C = 1>
@@ -310,7 +339,11 @@ struct DeviceGuard {
 
 bool planar_batch(const mavg_plan* p) { return p->desc.layout == MAVG_PLANAR && p->desc.channels > 1; }
 // frames covered by one shared-memory tile of the stream kernel
-uint64_t tile_frames(const mavg_plan* p) { return (uint64_t)p->geom.NT * p->geom.R / p->geom.C; }
+uint64_t tile_frames(const mavg_plan* p)
+{
+    if (p->geom.mode == 3) return (uint64_t)kColsNW * kColsRF;
+    return (uint64_t)p->geom.NT * p->geom.R / p->geom.C;
+}
 bool frame_sharded(const mavg_plan* p) { return !planar_batch(p); }
 
 // samples per signal and signal count as the stream kernel sees one shard
@@ -391,8 +424,12 @@ int launch_generic_t(const mavg_plan* p, DevCtx& d, const T* in, T* out, const T
     for (uint32_t s0 = 0; s0 < signals; s0 += 65535u) {
         const uint32_t ns = std::min<uint32_t>(65535u, signals - s0);
         dim3 grid((unsigned)blocks, ns, 1);
-        mavg::generic_kernel<T, RG><<<grid, 256, 0, d.stream>>>(in + (uint64_t)s0 * gp.sig_stride,
-                                                               out + (uint64_t)s0 * gp.sig_stride, halo, gp);
+        const T* in_s = in + (uint64_t)s0 * gp.sig_stride;
+        T* out_s = out + (uint64_t)s0 * gp.sig_stride;
+        if (std::is_same<T, float>::value && gp.k >= 9)
+            mavg::generic_kernel<T, RG, std::is_same<T, float>::value><<<grid, 256, 0, d.stream>>>(in_s, out_s, halo, gp);
+        else
+            mavg::generic_kernel<T, RG, false><<<grid, 256, 0, d.stream>>>(in_s, out_s, halo, gp);
         MAVG_CUDA(cudaGetLastError());
         ++*launches;
     }
@@ -423,6 +460,67 @@ bool stream_eligible(const mavg_plan* p, const DevCtx& d, const void* in, const 
     return true;
 }
 
+int make_map_2d(CUtensorMap* map, const void* base, uint64_t channels, uint64_t frames, uint32_t tile_frames_)
+{
+    EncodeTiledFn enc;
+    MAVG_TRY(get_encoder(&enc));
+    cuuint64_t dims[2] = {channels, frames};
+    cuuint64_t strides[1] = {channels * 4};
+    cuuint32_t box[2] = {32, tile_frames_};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return fail(MAVG_ERR_DRIVER, "cuTensorMapEncodeTiled (2-D) failed (%d) channels=%llu frames=%llu", (int)r,
+                    (unsigned long long)channels, (unsigned long long)frames);
+    return MAVG_OK;
+}
+
+// many-channel interleaved float32 through the column kernel
+int launch_cols(mavg_plan* p, DevCtx& d, const void* in, void* out, const void* halo, uint64_t frames,
+                uint32_t* launches)
+{
+    const StreamGeom& g = p->geom;
+    const uint32_t C = p->desc.channels;
+    const uint32_t FT = kColsNW * kColsRF;
+    CUtensorMap in_map, halo_map;
+    MAVG_TRY(make_map_2d(&in_map, in, C, frames, FT));
+    if (halo) MAVG_TRY(make_map_2d(&halo_map, halo, C, (uint64_t)g.H * FT, FT));
+    else halo_map = in_map;
+    mavg::ColsParams cp;
+    cp.inv_k = 1.0f / (float)p->desc.window;
+    cp.k = p->desc.window;
+    cp.n_full = g.n_full;
+    cp.m_part = g.m_part;
+    cp.channels = C;
+    cp.frames = frames;
+    cp.col_blocks = (int32_t)((C + 31) / 32);
+    const uint64_t tiles = (frames + FT - 1) / FT;
+    cp.tiles_per_col = (int32_t)tiles;
+    const uint64_t ctas = (uint64_t)d.sm_count;
+    const uint64_t per_cta = std::max<uint32_t>(8u, p->desc.tuning.chunks_per_cta);
+    uint64_t cps = std::min<uint64_t>(tiles, (ctas * per_cta + cp.col_blocks - 1) / cp.col_blocks);
+    uint64_t chunk_tiles = (tiles + cps - 1) / cps;
+    cps = (tiles + chunk_tiles - 1) / chunk_tiles;
+    if (cps * cp.col_blocks > 0x7fffffffull || tiles > 0x7fffffffull / FT)
+        return fail(MAVG_ERR_UNSUPPORTED, "signal too long for the column kernel");
+    cp.chunk_tiles = (int32_t)chunk_tiles;
+    cp.chunks_per_col = (int32_t)cps;
+    cp.total_chunks = (int32_t)(cps * cp.col_blocks);
+    cp.hist_tiles = g.H;
+    cp.stages = g.S;
+    cp.prefetch = g.P;
+    cp.has_halo = halo ? 1 : 0;
+    auto kern = mavg::stream_cols_f32_kernel<kColsNW, kColsRF>;
+    MAVG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+    const unsigned grid = (unsigned)std::min<uint64_t>(ctas, (uint64_t)cp.total_chunks);
+    kern<<<grid, kColsNW * 32, g.smem, d.stream>>>(in_map, halo_map, (float*)out, cp);
+    MAVG_CUDA(cudaGetLastError());
+    ++*launches;
+    return MAVG_OK;
+}
+
 // Enqueue the kernels for `frames` frames (a whole shard, or one slice of it whose left context
 // is `halo`) on the device stream.  Planar batches always run whole (frames = desc.frames).
 int launch_shard(mavg_plan* p, DevCtx& d, const void* in, void* out, const void* halo, uint64_t frames,
@@ -431,6 +529,11 @@ int launch_shard(mavg_plan* p, DevCtx& d, const void* in, void* out, const void*
     MAVG_CUDA(cudaSetDevice(d.device));
     if (planar_batch(p)) frames = p->desc.frames;
     if (frames == 0 || (planar_batch(p) && d.channels == 0)) return MAVG_OK;
+    if (p->path == MAVG_PATH_STREAM && p->geom.ok && p->geom.mode == 3) {
+        if ((((uintptr_t)in | (uintptr_t)out | (uintptr_t)halo) & 15u) == 0 && frames < (1ull << 31))
+            return launch_cols(p, d, in, out, halo, frames, launches);
+        return launch_generic(p, d, in, out, halo, frames, 0, frames, launches);
+    }
     if (!stream_eligible(p, d, in, out, halo, frames))
         return launch_generic(p, d, in, out, halo, frames, 0, frames, launches);
     const StreamGeom& g = p->geom;
@@ -587,6 +690,10 @@ int mavg_plan_create(const mavg_desc* desc, mavg_plan** out)
     if (desc->dtype == MAVG_F32) {
         stream_shape = desc->channels <= 2 || planar;
         p->geom = plan_stream(desc->window, desc->tuning, planar ? 1u : desc->channels);
+        if (!planar && desc->channels >= 32) {
+            p->geom = plan_cols(desc->window, desc->channels, desc->tuning);
+            stream_shape = p->geom.ok;
+        }
     } else {
         stream_shape = desc->channels <= 2 || planar;
         p->geom = plan_stream_i16(desc->window, planar ? 1u : desc->channels, desc->tuning);

@@ -101,7 +101,10 @@ template <> struct GenericAcc<int16_t> {
     }
 };
 
-template <typename T, int RG>
+// F32SLIDE (float only, k >= 9): the k-term start sum is still formed in fp64, but the RG sliding
+// updates run in fp32 (error <= RG * 2^-24 relative to the window sum), which removes three
+// fp32<->fp64 conversions per sample.  Tiny windows keep the fp64 update: their sums can be ~0.
+template <typename T, int RG, bool F32SLIDE>
 __global__ void __launch_bounds__(256) generic_kernel(const T* __restrict__ x, T* __restrict__ y,
                                                       const T* __restrict__ halo, const GenericParams p)
 {
@@ -134,6 +137,33 @@ __global__ void __launch_bounds__(256) generic_kernel(const T* __restrict__ x, T
         }
         for (; j < (long long)f0; ++j) w += (Acc)x[(uint64_t)j * C + c];
     }
+    if constexpr (F32SLIDE) {
+        float wf = (float)w;
+        const float invf = 1.0f / (float)p.k;
+        if (f0 >= k) {  // steady state: no halo / zero-padding cases inside the run
+            const T* xo = x + (f0 - k) * C + c;
+            const T* xn = x + f0 * C + c;
+            T* yo = y + f0 * C + c;
+            const uint32_t cnt = (uint32_t)(f1 - f0);
+#pragma unroll 8
+            for (uint32_t i = 0; i < cnt; ++i) {
+                wf += (float)xn[(uint64_t)i * C] - (float)xo[(uint64_t)i * C];
+                yo[(uint64_t)i * C] = (T)(wf * invf);
+            }
+            return;
+        }
+        for (uint64_t f = f0; f < f1; ++f) {
+            float old = 0.f;
+            if (f >= k) {
+                old = (float)x[(f - k) * C + c];
+            } else if (halo != nullptr) {
+                const uint64_t back = k - f;
+                if (back <= p.halo_frames) old = (float)halo[(p.halo_frames - back) * C + c];
+            }
+            wf += (float)x[f * C + c] - old;
+            y[f * C + c] = (T)(wf * invf);
+        }
+    } else {
     for (uint64_t f = f0; f < f1; ++f) {
         Acc old = 0;
         if (f >= k) {
@@ -144,6 +174,7 @@ __global__ void __launch_bounds__(256) generic_kernel(const T* __restrict__ x, T
         }
         w += (Acc)x[f * C + c] - old;
         y[f * C + c] = GenericAcc<T>::finish(w, p.k, inv);
+    }
     }
 }
 
@@ -892,6 +923,202 @@ __global__ void __launch_bounds__(NT)
         }
     }
     if (tid == 0) tma_wait_all0();
+}
+
+// ----------------------------------------------------------------------------------
+// Column kernel -- many-channel interleaved float32 ([frame][channel], C >= 32), e.g.
+// BASELINE config 5's 256-channel batch in the reference layout.
+// One CTA streams [FT frames x 32 channels] tiles of one 32-channel column block down the
+// frames (2-D TMA boxes, no swizzle: lane = channel, so every shared-memory access is one
+// conflict-free 128-byte row).  Warp w owns frames [w*RF, (w+1)*RF) of the tile, lane l one
+// channel.  Window sum at the run start = direct additions of whole-group totals (groups ->
+// tile totals, no subtraction anywhere) + head of the lag run; then w += x[f] - x[f-k].
+// Outputs are stored straight from registers: each warp store is one full 128-byte row segment.
+// ----------------------------------------------------------------------------------
+struct ColsParams {
+    float inv_k;
+    uint32_t k;
+    uint32_t n_full;       // whole RF-frame groups strictly between the lag group and the own group
+    uint32_t m_part;       // leading frames of the lag run that complete the window at the run start
+    uint32_t channels;
+    uint64_t frames;       // frames of this shard
+    int32_t col_blocks;    // ceil(channels / 32)
+    int32_t tiles_per_col;
+    int32_t chunk_tiles;
+    int32_t chunks_per_col;
+    int32_t total_chunks;  // col_blocks * chunks_per_col
+    int32_t hist_tiles;
+    int32_t stages;
+    int32_t prefetch;
+    int32_t has_halo;
+};
+
+__host__ __device__ inline uint32_t cols_smem_bytes(int NW, int RF, int S, int H)
+{
+    return 1024u + (uint32_t)S * NW * RF * 128u + (uint32_t)(H + 2) * NW * 32 * 4 + (uint32_t)(H + 2) * 32 * 4 +
+           (uint32_t)S * 8;
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                            uint64_t hint)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "l"(hint)
+        : "memory");
+}
+
+template <int NW, int RF>
+__global__ void __launch_bounds__(NW * 32)
+    stream_cols_f32_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap halo_map,
+                           float* __restrict__ out, const ColsParams p)
+{
+    constexpr int FT = NW * RF;          // frames per tile
+    constexpr uint32_t TB = FT * 128u;   // bytes per tile (32 channels x 4 bytes per frame)
+    static_assert(FT <= 256, "a TMA box holds at most 256 rows");
+
+    extern __shared__ uint8_t smem_raw[];
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int S = p.stages;
+    const int H = p.hist_tiles;
+    const int P = p.prefetch;
+    const int GS = H + 2;
+
+    const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t ring_bytes = (uint32_t)S * TB;
+    const uint32_t gsum = ring + ring_bytes;                    // float [GS][NW][32]
+    const uint32_t ttot = gsum + (uint32_t)GS * NW * 32 * 4;    // float [GS][32]
+    const uint32_t bars = ttot + (uint32_t)GS * 32 * 4;
+
+    if (tid == 0) {
+        prefetch_tmap(&in_map);
+        if (p.has_halo) prefetch_tmap(&halo_map);
+        for (int s = 0; s < S; ++s) mbar_init(bars + 8u * s, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    auto issue_load = [&](int tile, int cb, int st) {
+        const uint32_t bar = bars + 8u * st;
+        mbar_arrive_expect_tx(bar, TB);
+        if (tile < 0 && p.has_halo)
+            tma_load_2d(ring + (uint32_t)st * TB, &halo_map, bar, cb * 32, (tile + H) * FT, kEvictFirst);
+        else
+            tma_load_2d(ring + (uint32_t)st * TB, &in_map, bar, cb * 32, tile * FT, kEvictFirst);
+    };
+
+    uint32_t it = 0;
+    int st = 0, slot = 0;
+
+    for (int chunk = blockIdx.x; chunk < p.total_chunks; chunk += gridDim.x) {
+        // consecutive chunk ids sweep the column blocks of one frame range, so neighbouring CTAs
+        // read neighbouring 128-byte segments of the same rows at about the same time
+        const int rng = chunk / p.col_blocks;
+        const int cb = chunk - rng * p.col_blocks;
+        const int t0 = rng * p.chunk_tiles;
+        int t1 = t0 + p.chunk_tiles;
+        if (t1 > p.tiles_per_col) t1 = p.tiles_per_col;
+        if (t0 >= t1) continue;
+        const int first = t0 - H;
+        const int ntl = t1 - first;
+        const uint32_t ch = (uint32_t)cb * 32u + lane;
+        const bool ch_ok = ch < p.channels;
+
+        if (tid == 0) {
+            int s2 = st;
+            for (int j = 0; j < P && j < ntl; ++j) {
+                issue_load(first + j, cb, s2);
+                s2 = (s2 + 1 == S) ? 0 : s2 + 1;
+            }
+        }
+
+        for (int j = 0; j < ntl; ++j) {
+            const int tile = first + j;
+            const bool is_out = (j >= H);
+            const uint32_t cur = ring + (uint32_t)st * TB;
+
+            mbar_wait(bars + 8u * st, (it / (uint32_t)S) & 1u);
+
+            float x[RF];
+#pragma unroll
+            for (int r = 0; r < RF; ++r) x[r] = lds32(cur + ((uint32_t)(warp * RF + r) * 32u + lane) * 4u);
+            float gtot;
+            {
+                float q[RF / 4];
+#pragma unroll
+                for (int c = 0; c < RF / 4; ++c) q[c] = (x[4 * c] + x[4 * c + 1]) + (x[4 * c + 2] + x[4 * c + 3]);
+                gtot = (q[0] + q[1]) + (q[2] + q[3]);
+                if constexpr (RF == 32) gtot += (q[RF / 4 - 4] + q[RF / 4 - 3]) + (q[RF / 4 - 2] + q[RF / 4 - 1]);
+            }
+            sts32(gsum + (((uint32_t)slot * NW + warp) * 32u + lane) * 4u, gtot);
+
+            __syncthreads();
+
+            if (tid == 0 && j + P < ntl) {
+                int s2 = st + P;
+                if (s2 >= S) s2 -= S;
+                issue_load(first + j + P, cb, s2);
+            }
+
+            // groups of this tile in front of the own group (warp-uniform trip count)
+            float e_own = 0.f;
+            for (int w2 = 0; w2 < warp; ++w2) e_own += lds32(gsum + (((uint32_t)slot * NW + w2) * 32u + lane) * 4u);
+            if (warp == NW - 1) sts32(ttot + ((uint32_t)slot * 32u + lane) * 4u, e_own + gtot);
+
+            if (is_out) {
+                float xl[RF];
+                {
+                    const int base = (int)((uint32_t)st * TB) + (warp * RF - (int)p.k) * 128 + lane * 4;
+#pragma unroll
+                    for (int r = 0; r < RF; ++r) {
+                        int o = base + 128 * r;
+                        if (o < 0) o += (int)ring_bytes;
+                        xl[r] = lds32(ring + (uint32_t)o);
+                    }
+                }
+                int lw = warp - (int)(p.n_full + 1u);   // group (warp slot) that holds the lag run's first frame
+                int h = 0;
+                if (lw < 0) {
+                    h = (-lw + NW - 1) / NW;
+                    lw += h * NW;
+                }
+                float acc = 0.f;
+                if (h == 0) {
+                    for (int w2 = lw + 1; w2 < warp; ++w2) acc += lds32(gsum + (((uint32_t)slot * NW + w2) * 32u + lane) * 4u);
+                } else {
+                    int ls = slot - h;
+                    if (ls < 0) ls += GS;
+                    for (int w2 = lw + 1; w2 < NW; ++w2) acc += lds32(gsum + (((uint32_t)ls * NW + w2) * 32u + lane) * 4u);
+                    int ms = ls;
+                    for (int v = 1; v < h; ++v) {
+                        ms = (ms + 1 == GS) ? 0 : ms + 1;
+                        acc += lds32(ttot + ((uint32_t)ms * 32u + lane) * 4u);
+                    }
+                    acc += e_own;
+                }
+#pragma unroll
+                for (int r = 0; r < RF; ++r)
+                    if ((uint32_t)r < p.m_part) acc += xl[r];
+
+                const float inv = p.inv_k;
+                const uint64_t f_base = (uint64_t)tile * FT + (uint64_t)warp * RF;
+                float* dst = out + f_base * p.channels + ch;
+#pragma unroll
+                for (int r = 0; r < RF; ++r) {
+                    acc += x[r] - xl[r];
+                    if (ch_ok && f_base + r < p.frames) dst[(uint64_t)r * p.channels] = acc * inv;
+                }
+            }
+
+            ++it;
+            st = (st + 1 == S) ? 0 : st + 1;
+            slot = (slot + 1 == GS) ? 0 : slot + 1;
+        }
+        __syncthreads();   // ring stages may be refilled by the next chunk's prologue
+    }
 }
 
 }  // namespace mavg

@@ -245,11 +245,23 @@ def test_generic_path_with_halo(mavg, oracle_mod, torch_cuda):
     dx = torch.from_numpy(x).cuda()
     dz = torch.zeros((frames - cut) * ch, dtype=torch.int16, device="cuda")
     torch.cuda.synchronize()
-    with mavg.Plan(frames - cut, k, channels=ch, dtype="i16", first_frame=cut) as plan:
+    with mavg.Plan(frames - cut, k, channels=ch, dtype="i16", first_frame=cut, path="generic") as plan:
         halo = int(plan.info.halo_frames)
+        assert halo == k and plan.info.path == 2      # the generic kernel asks for exactly k frames of context
         plan.run_device_halo(dx.data_ptr() + 2 * cut * ch, dz.data_ptr(), dx.data_ptr() + 2 * (cut - halo) * ch)
         plan.synchronize()
     assert np.array_equal(dz.cpu().numpy(), oracle_mod.mavg_i16(x, k, ch)[cut * ch:])
+    # three-channel float32 takes the generic kernel by itself
+    xf = oracle_mod.fill_f32(frames * 3, 18)
+    dxf = torch.from_numpy(xf).cuda()
+    dzf = torch.zeros((frames - cut) * 3, dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    with mavg.Plan(frames - cut, k, channels=3, first_frame=cut) as plan:
+        halo = int(plan.info.halo_frames)
+        assert halo == k and plan.info.path == 2
+        plan.run_device_halo(dxf.data_ptr() + 4 * cut * 3, dzf.data_ptr(), dxf.data_ptr() + 4 * (cut - halo) * 3)
+        plan.synchronize()
+    assert _rel(dzf.cpu().numpy(), oracle_mod.mavg_f64(xf, k, 3)[cut * 3:]) < TOL
 
 
 def test_timing_and_info(mavg, oracle_mod):
@@ -383,3 +395,42 @@ def test_stereo_f32_shard_with_halo_bit_identical(mavg, oracle_mod, torch_cuda, 
     whole = dy.cpu().numpy()
     assert np.array_equal(dz.cpu().numpy(), whole[2 * cut:])
     assert _rel(whole, oracle_mod.mavg_f64(x, k, 2)) < TOL
+
+
+# ------------------------------------------------------------------ many-channel interleaved float32 (column kernel)
+@pytest.mark.parametrize("ch", [32, 36, 64, 100, 256])
+@pytest.mark.parametrize("k", [9, 16, 17, 64, 255, 256, 700, 1024, 1500, 5])
+def test_many_channel_interleaved_f32(mavg, oracle_mod, ch, k):
+    frames = 3 * 256 + 77 if ch >= 100 else 9 * 256 + 13
+    x = oracle_mod.fill_f32(frames * ch, 17000 + k + ch)
+    with mavg.Plan(frames, k, channels=ch) as plan:
+        y = plan.run_host(x)
+        i = plan.info
+        if 9 <= k <= 1024:
+            assert i.path == 1 and i.mode == 3, "expected the column kernel"
+        else:
+            assert i.path == 2
+    assert _rel(y, oracle_mod.mavg_f64(x, k, ch)) < TOL
+
+
+@pytest.mark.parametrize("k", [64, 1000])
+def test_many_channel_shard_with_halo_bit_identical(mavg, oracle_mod, torch_cuda, k):
+    torch = torch_cuda
+    ch, tf = 64, 256
+    frames, cut = 40 * tf + 50, 13 * tf
+    x = oracle_mod.fill_f32(frames * ch, 18000 + k)
+    dx = torch.from_numpy(x).cuda()
+    dy = torch.zeros(frames * ch, dtype=torch.float32, device="cuda")
+    dz = torch.zeros((frames - cut) * ch, dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    with mavg.Plan(frames, k, channels=ch) as plan:
+        plan.run_device([dx.data_ptr()], [dy.data_ptr()])
+        plan.synchronize()
+    with mavg.Plan(frames - cut, k, channels=ch, first_frame=cut) as plan:
+        halo = int(plan.info.halo_frames)
+        assert halo % tf == 0 and halo >= k
+        plan.run_device_halo(dx.data_ptr() + 4 * cut * ch, dz.data_ptr(), dx.data_ptr() + 4 * (cut - halo) * ch)
+        plan.synchronize()
+    whole = dy.cpu().numpy()
+    assert np.array_equal(dz.cpu().numpy(), whole[cut * ch:])
+    assert _rel(whole, oracle_mod.mavg_f64(x, k, ch)) < TOL
