@@ -67,6 +67,7 @@ def main():
     ap.add_argument("--log2", type=int, default=32, help="total samples (log2) for configs 4/5")
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--tune", default="", help="comma list key=value forwarded to mavg_tuning")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -76,6 +77,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     stream = torch.cuda.Stream()
     lib = _lib.load()
+    tune = {kv.split("=")[0]: int(kv.split("=")[1]) for kv in args.tune.split(",") if kv}
     out = {"config": args.config, "n_gpus": world}
 
     if args.config == "4":
@@ -140,7 +142,7 @@ def main():
             d_in, d_out = alloc(4 * n), alloc(4 * n)
             mavg.fill_synthetic_device(d_in.value, "f32", n, first_frame * C, SEED, 0, stream.cuda_stream)
             stream.synchronize()
-            plan = mavg.Plan(f_per, k, channels=C, layout="interleaved", first_frame=first_frame)
+            plan = mavg.Plan(f_per, k, channels=C, layout="interleaved", first_frame=first_frame, **tune)
             plan.set_stream(stream.cuda_stream)
             plan.enable_timing(False)
             halo = int(plan.info.halo_frames)
@@ -164,7 +166,7 @@ def main():
             if peer:
                 peer.close()
         total = C * F
-        out.update(workload=f"256 ch x 2^{args.log2 - 8} frames f32, k=64, {layout}, {world} GPU(s)", ms=ms,
+        out.update(workload=f"256 ch x 2^{args.log2 - 8} frames f32, k=64, {layout}, {world} GPU(s)", ms=ms, tune=tune,
                    gsamples_s=total / ms / 1e6, hbm_gbs_per_gpu=8 * n / ms / 1e6, max_rel_err_spot=worst,
                    path="stream" if info.path == 1 else "generic")
         plan.close()
