@@ -305,6 +305,8 @@ struct DevCtx {
     void* d_in = nullptr;
     void* d_out = nullptr;
     void* d_halo = nullptr;     // halo_frames * channels elements of left context (frame sharding)
+    void* d_bsum = nullptr;     // generic path, long windows: 64-frame block sums
+    size_t bsum_bytes = 0;
     int sm_count = 0;
     bool timed = false;
     // run_host pipeline: copies on their own streams so H2D, kernels and D2H overlap
@@ -416,6 +418,35 @@ int launch_generic_t(const mavg_plan* p, DevCtx& d, const T* in, T* out, const T
     gp.out_end = out_end;
     gp.halo_frames = halo ? p->halo_frames : 0;
     gp.k = p->desc.window;
+    gp.bsum = nullptr;
+    gp.nblk = 0;
+    // long windows: one extra pass builds RG-frame block sums so each run starts from k/RG table entries
+    if (gp.k >= 256 && out_begin == 0 && gp.frames >= 4 * (uint64_t)RG) {
+        typedef typename mavg::GenericAcc<T>::type Acc;
+        const uint64_t nblk = (gp.frames + RG - 1) / RG;
+        const size_t need = (size_t)nblk * gp.channels * signals * sizeof(Acc);
+        if (d.bsum_bytes < need) {
+            if (d.d_bsum) MAVG_CUDA(cudaFree(d.d_bsum));
+            d.d_bsum = nullptr;
+            d.bsum_bytes = 0;
+            if (cudaMalloc(&d.d_bsum, need) != cudaSuccess) {
+                cudaGetLastError();
+                return fail(MAVG_ERR_ALLOC, "cudaMalloc of %zu block-sum bytes failed", need);
+            }
+            d.bsum_bytes = need;
+        }
+        const uint64_t bthreads = nblk * gp.channels;
+        const uint64_t bblocks = (bthreads + 255) / 256;
+        if (bblocks <= 0x7fffffffull && signals <= 65535u) {
+            dim3 bgrid((unsigned)bblocks, signals, 1);
+            mavg::block_sums_kernel<T, RG><<<bgrid, 256, 0, d.stream>>>(in, (Acc*)d.d_bsum, gp.frames, gp.sig_stride,
+                                                                      gp.channels, nblk);
+            MAVG_CUDA(cudaGetLastError());
+            ++*launches;
+            gp.bsum = d.d_bsum;
+            gp.nblk = nblk;
+        }
+    }
     const uint64_t runs = (out_end - out_begin + RG - 1) / RG;
     const uint64_t threads = runs * gp.channels;
     const uint64_t blocks = (threads + 255) / 256;
@@ -784,6 +815,7 @@ int mavg_plan_destroy(mavg_plan* p)
         if (d.d_in) cudaFree(d.d_in);
         if (d.d_out) cudaFree(d.d_out);
         if (d.d_halo) cudaFree(d.d_halo);
+        if (d.d_bsum) cudaFree(d.d_bsum);
         if (d.s_h2d) { cudaStreamSynchronize(d.s_h2d); cudaStreamDestroy(d.s_h2d); }
         if (d.s_d2h) { cudaStreamSynchronize(d.s_d2h); cudaStreamDestroy(d.s_d2h); }
         for (cudaEvent_t e : d.pool) cudaEventDestroy(e);

@@ -83,6 +83,8 @@ struct GenericParams {
     uint64_t sig_stride;   // elements between consecutive planar signals (blockIdx.y)
     uint32_t channels;     // interleave factor inside one signal
     uint32_t k;
+    const void* bsum;      // optional: per-channel sums of 64-frame blocks [signal][block][channel] (Acc type)
+    uint64_t nblk;         // blocks per signal in bsum
 };
 
 template <typename T> struct GenericAcc;
@@ -100,6 +102,25 @@ template <> struct GenericAcc<int16_t> {
         return (int16_t)(w / (long long)k);
     }
 };
+
+// Sums of RG-frame blocks per channel, so that long windows start from k/RG block sums instead of k
+// samples.  Same thread mapping as generic_kernel: consecutive threads = consecutive channels.
+template <typename T, int RG>
+__global__ void __launch_bounds__(256) block_sums_kernel(const T* __restrict__ x, typename GenericAcc<T>::type* __restrict__ bs,
+                                                         uint64_t frames, uint64_t sig_stride, uint32_t C, uint64_t nblk)
+{
+    typedef typename GenericAcc<T>::type Acc;
+    const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t c = (uint32_t)(gid % C);
+    const uint64_t b = gid / C;
+    if (b >= nblk) return;
+    x += (uint64_t)blockIdx.y * sig_stride;
+    const uint64_t f0 = b * RG;
+    const uint64_t f1 = (f0 + RG < frames) ? f0 + RG : frames;
+    Acc a = 0;
+    for (uint64_t f = f0; f < f1; ++f) a += (Acc)x[f * C + c];
+    bs[((uint64_t)blockIdx.y * nblk + b) * C + c] = a;
+}
 
 // F32SLIDE (float only, k >= 9): the k-term start sum is still formed in fp64, but the RG sliding
 // updates run in fp32 (error <= RG * 2^-24 relative to the window sum), which removes three
@@ -123,7 +144,14 @@ __global__ void __launch_bounds__(256) generic_kernel(const T* __restrict__ x, T
 
     // window sum over frames [f0-k, f0): negative frames come from the halo, else zero
     Acc w = 0;
-    {
+    if (p.bsum != nullptr && f0 >= k && f0 % RG == 0) {
+        // whole RG-frame blocks from the block-sum table, the ragged head from the samples
+        const Acc* bs = (const Acc*)p.bsum + (uint64_t)blockIdx.y * p.nblk * C;
+        const uint64_t lo = f0 - k;
+        const uint64_t jb = (lo + RG - 1) / RG;
+        for (uint64_t f = lo; f < jb * RG; ++f) w += (Acc)x[f * C + c];
+        for (uint64_t j = jb; j < f0 / RG; ++j) w += bs[j * C + c];
+    } else {
         const long long lo = (long long)f0 - (long long)k;
         long long j = lo;
         if (j < 0) {

@@ -434,3 +434,18 @@ def test_many_channel_shard_with_halo_bit_identical(mavg, oracle_mod, torch_cuda
     whole = dy.cpu().numpy()
     assert np.array_equal(dz.cpu().numpy(), whole[cut * ch:])
     assert _rel(whole, oracle_mod.mavg_f64(x, k, ch)) < TOL
+
+
+# ------------------------------------------------------------------ generic kernel, long windows (block-sum start)
+@pytest.mark.parametrize("case", [("f32", 3, 4096), ("f32", 6, 1000), ("i16", 5, 3000), ("i16", 3, 257), ("f32", 1, 60000)])
+def test_generic_long_windows(mavg, oracle_mod, case):
+    dtype, ch, k = case
+    frames = 150_001
+    if dtype == "f32":
+        x = oracle_mod.fill_f32(frames * ch, 19000 + k)
+        y = mavg.moving_average(x, k, channels=ch, path="generic")
+        assert _rel(y, oracle_mod.mavg_f64(x, k, ch)) < TOL
+    else:
+        x = oracle_mod.fill_i16(frames * ch, 19000 + k)
+        y = mavg.moving_average(x, k, channels=ch, path="generic")
+        assert np.array_equal(y, oracle_mod.mavg_i16(x, k, ch))

@@ -63,7 +63,7 @@ def timed(fn, stream, iters, warmup, world):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--config", required=True, choices=["4", "5p", "5i", "i16"])
+    ap.add_argument("--config", required=True, choices=["4", "5p", "5i", "i16", "g3"])
     ap.add_argument("--log2", type=int, default=32, help="total samples (log2) for configs 4/5")
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
@@ -170,6 +170,23 @@ def main():
                    gsamples_s=total / ms / 1e6, hbm_gbs_per_gpu=8 * n / ms / 1e6, max_rel_err_spot=worst,
                    path="stream" if info.path == 1 else "generic")
         plan.close()
+
+    elif args.config == "g3":  # shapes only the generic kernel takes: 3-channel interleaved float32
+        n_frames, C = 1 << 25, 3
+        n = n_frames * C
+        d_in, d_out = alloc(4 * n), alloc(4 * n)
+        mavg.fill_synthetic_device(d_in.value, "f32", n, 0, SEED, 0, stream.cuda_stream)
+        stream.synchronize()
+        res = {}
+        for k in (3, 64, 256, 1024, 4096):
+            plan = mavg.Plan(n_frames, k, channels=C)
+            plan.set_stream(stream.cuda_stream)
+            plan.enable_timing(False)
+            ms = timed(lambda: plan.run_device([d_in.value], [d_out.value]), stream, 3, 1, world)
+            res[str(k)] = {"ms": round(ms, 4), "gsamples_s": round(n / ms / 1e6, 1), "hbm_gbs": round(8 * n / ms / 1e6, 1),
+                           "path": "stream" if plan.info.path == 1 else "generic", "launches": int(plan.info.launches_per_run)}
+            plan.close()
+        out.update(workload="3-channel interleaved float32, 3 x 2^25 samples, k sweep (generic kernel)", per_k=res)
 
     else:  # i16: the reference's own input format
         n_frames, C = 1 << 27, 2

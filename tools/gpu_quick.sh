@@ -1,9 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for t in "prefetch=1" "prefetch=3" "prefetch=4" "prefetch=2,chunks_per_cta=2" "prefetch=4,chunks_per_cta=32" "prefetch=3,chunks_per_cta=16"; do
-echo "== cfg 5i $t"; timeout 600 python tools/bench_configs.py --config 5i --log2 30 --tune "$t" 2>/dev/null | python -c "
-import sys,json
-for l in sys.stdin:
-    if l.startswith('{'):
-        d=json.loads(l); print(d['tune'], round(d['ms'],4), round(d['hbm_gbs_per_gpu'],1))"
-done
+echo "== pytest subset"; timeout 1200 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "generic or interleaved or i16_bit_exact or ragged or golden" > gpurun_out/pytest_quick.log 2>&1; echo "rc=$?"; tail -5 gpurun_out/pytest_quick.log
+echo "== g3"; timeout 600 python tools/bench_configs.py --config g3 > gpurun_out/cfg_g3.json 2> gpurun_out/cfg_g3.err; echo "rc=$?"; cat gpurun_out/cfg_g3.json; tail -3 gpurun_out/cfg_g3.err
