@@ -107,6 +107,7 @@ struct StreamGeom {
     uint32_t elem = 4;        // bytes per sample
     uint32_t C = 1;           // channels interleaved inside one kernel signal (int16 stereo: 2)
     uint32_t div_mul = 0, div_shift = 0;
+    int cww = 1;              // column kernel: 32-channel column-warps side by side in one tile
 };
 
 constexpr uint32_t kMaxSmem = 232448;  // 227 KB opt-in limit per CTA on sm_100
@@ -199,21 +200,28 @@ StreamGeom plan_cols(uint32_t k, uint32_t C, const mavg_tuning& tu)
     g.C = C;
     g.mode = 3;
     if (k < 9 || C < 32 || C % 4 != 0) return g;   // tiny windows keep the fp64 generic kernel
-    const uint32_t R = kColsRF, FT = kColsNW * kColsRF;
+    const uint32_t R = kColsRF;
     const uint32_t s = (R - k % R) % R;
     g.m_part = R - s;
     g.n_full = (k + s) / R - 1;
-    g.H = (int)(((uint64_t)(g.n_full + 1) * R + FT - 1) / FT);
     g.ctas_per_sm = 1;
-    g.P = tu.prefetch ? (int)tu.prefetch : 2;
-    for (;;) {
-        g.S = g.H + 1 + g.P;
-        g.smem = mavg::cols_smem_bytes(kColsNW, kColsRF, g.S, g.H);
-        if (g.smem <= kMaxSmem) break;
-        if (g.P > 1) { --g.P; continue; }
-        return g;
+    // widest tile (most contiguous bytes per row) whose history still leaves two tiles of prefetch
+    for (int cww = 8; cww >= 1; cww >>= 1) {
+        if (32u * cww > C && cww > 1) continue;
+        const uint32_t FT = (kColsNW / cww) * kColsRF;
+        g.cww = cww;
+        g.H = (int)(((uint64_t)(g.n_full + 1) * R + FT - 1) / FT);
+        g.P = tu.prefetch ? (int)tu.prefetch : 2;
+        bool fits = false;
+        for (;;) {
+            g.S = g.H + 1 + g.P;
+            g.smem = mavg::cols_smem_bytes(kColsNW, kColsRF, g.S, g.H);
+            if (g.smem <= kMaxSmem) { fits = true; break; }
+            if (cww == 1 && g.P > 1) { --g.P; continue; }   // only the narrowest shape trades prefetch for history
+            break;
+        }
+        if (fits) { g.ok = true; return g; }
     }
-    g.ok = true;
     return g;
 }
 
@@ -343,7 +351,7 @@ bool planar_batch(const mavg_plan* p) { return p->desc.layout == MAVG_PLANAR && 
 // frames covered by one shared-memory tile of the stream kernel
 uint64_t tile_frames(const mavg_plan* p)
 {
-    if (p->geom.mode == 3) return (uint64_t)kColsNW * kColsRF;
+    if (p->geom.mode == 3) return (uint64_t)(kColsNW / p->geom.cww) * kColsRF;
     return (uint64_t)p->geom.NT * p->geom.R / p->geom.C;
 }
 bool frame_sharded(const mavg_plan* p) { return !planar_batch(p); }
@@ -491,13 +499,14 @@ bool stream_eligible(const mavg_plan* p, const DevCtx& d, const void* in, const 
     return true;
 }
 
-int make_map_2d(CUtensorMap* map, const void* base, uint64_t channels, uint64_t frames, uint32_t tile_frames_)
+int make_map_2d(CUtensorMap* map, const void* base, uint64_t channels, uint64_t frames, uint32_t tile_frames_,
+                uint32_t tile_channels)
 {
     EncodeTiledFn enc;
     MAVG_TRY(get_encoder(&enc));
     cuuint64_t dims[2] = {channels, frames};
     cuuint64_t strides[1] = {channels * 4};
-    cuuint32_t box[2] = {32, tile_frames_};
+    cuuint32_t box[2] = {tile_channels, tile_frames_};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -514,10 +523,11 @@ int launch_cols(mavg_plan* p, DevCtx& d, const void* in, void* out, const void* 
 {
     const StreamGeom& g = p->geom;
     const uint32_t C = p->desc.channels;
-    const uint32_t FT = kColsNW * kColsRF;
+    const uint32_t FT = (kColsNW / g.cww) * kColsRF;
+    const uint32_t CW = 32u * g.cww;
     CUtensorMap in_map, halo_map;
-    MAVG_TRY(make_map_2d(&in_map, in, C, frames, FT));
-    if (halo) MAVG_TRY(make_map_2d(&halo_map, halo, C, (uint64_t)g.H * FT, FT));
+    MAVG_TRY(make_map_2d(&in_map, in, C, frames, FT, CW));
+    if (halo) MAVG_TRY(make_map_2d(&halo_map, halo, C, (uint64_t)g.H * FT, FT, CW));
     else halo_map = in_map;
     mavg::ColsParams cp;
     cp.inv_k = 1.0f / (float)p->desc.window;
@@ -526,7 +536,7 @@ int launch_cols(mavg_plan* p, DevCtx& d, const void* in, void* out, const void* 
     cp.m_part = g.m_part;
     cp.channels = C;
     cp.frames = frames;
-    cp.col_blocks = (int32_t)((C + 31) / 32);
+    cp.col_blocks = (int32_t)((C + CW - 1) / CW);
     const uint64_t tiles = (frames + FT - 1) / FT;
     cp.tiles_per_col = (int32_t)tiles;
     const uint64_t ctas = (uint64_t)d.sm_count;
@@ -543,7 +553,11 @@ int launch_cols(mavg_plan* p, DevCtx& d, const void* in, void* out, const void* 
     cp.stages = g.S;
     cp.prefetch = g.P;
     cp.has_halo = halo ? 1 : 0;
-    auto kern = mavg::stream_cols_f32_kernel<kColsNW, kColsRF>;
+    void (*kern)(const CUtensorMap, const CUtensorMap, float*, const mavg::ColsParams) =
+        g.cww == 8   ? mavg::stream_cols_f32_kernel<kColsNW, kColsRF, 8>
+        : g.cww == 4 ? mavg::stream_cols_f32_kernel<kColsNW, kColsRF, 4>
+        : g.cww == 2 ? mavg::stream_cols_f32_kernel<kColsNW, kColsRF, 2>
+                     : mavg::stream_cols_f32_kernel<kColsNW, kColsRF, 1>;
     MAVG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
     const unsigned grid = (unsigned)std::min<uint64_t>(ctas, (uint64_t)cp.total_chunks);
     kern<<<grid, kColsNW * 32, g.smem, d.stream>>>(in_map, halo_map, (float*)out, cp);

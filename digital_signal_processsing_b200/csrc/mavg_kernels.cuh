@@ -970,7 +970,7 @@ struct ColsParams {
     uint32_t m_part;       // leading frames of the lag run that complete the window at the run start
     uint32_t channels;
     uint64_t frames;       // frames of this shard
-    int32_t col_blocks;    // ceil(channels / 32)
+    int32_t col_blocks;    // ceil(channels / channels-per-tile)
     int32_t tiles_per_col;
     int32_t chunk_tiles;
     int32_t chunks_per_col;
@@ -981,9 +981,10 @@ struct ColsParams {
     int32_t has_halo;
 };
 
-__host__ __device__ inline uint32_t cols_smem_bytes(int NW, int RF, int S, int H)
+// NWT warps in total; tile bytes and summary sizes do not depend on how they are split into columns
+__host__ __device__ inline uint32_t cols_smem_bytes(int NWT, int RF, int S, int H)
 {
-    return 1024u + (uint32_t)S * NW * RF * 128u + (uint32_t)(H + 2) * NW * 32 * 4 + (uint32_t)(H + 2) * 32 * 4 +
+    return 1024u + (uint32_t)S * NWT * RF * 128u + (uint32_t)(H + 2) * NWT * 32 * 4 + (uint32_t)(H + 2) * 256 * 4 +
            (uint32_t)S * 8;
 }
 
@@ -997,19 +998,25 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         : "memory");
 }
 
-template <int NW, int RF>
-__global__ void __launch_bounds__(NW * 32)
+// NWT warps per CTA arranged as CWW column-warps (32 channels each, side by side) x NW = NWT / CWW
+// frame-warps (RF frames each).  Wider tiles (CWW > 1) read longer contiguous row pieces from HBM but
+// hold fewer frames of history, so the host picks the widest shape whose window still fits.
+template <int NWT, int RF, int CWW>
+__global__ void __launch_bounds__(NWT * 32)
     stream_cols_f32_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap halo_map,
                            float* __restrict__ out, const ColsParams p)
 {
-    constexpr int FT = NW * RF;          // frames per tile
-    constexpr uint32_t TB = FT * 128u;   // bytes per tile (32 channels x 4 bytes per frame)
-    static_assert(FT <= 256, "a TMA box holds at most 256 rows");
+    constexpr int NW = NWT / CWW;            // frame-warps
+    constexpr int CW = 32 * CWW;             // channels per tile
+    constexpr uint32_t ROWB = CW * 4u;       // bytes per tile row (one frame)
+    constexpr int FT = NW * RF;              // frames per tile
+    constexpr uint32_t TB = FT * ROWB;       // bytes per tile
+    static_assert(NWT % CWW == 0 && FT <= 256 && CW <= 256, "a TMA box holds at most 256 x 256 elements");
 
     extern __shared__ uint8_t smem_raw[];
     const int tid = threadIdx.x;
-    const int lane = tid & 31;
-    const int warp = tid >> 5;
+    const int lane = (tid & 31) + 32 * ((tid >> 5) % CWW);   // channel inside the tile
+    const int warp = (tid >> 5) / CWW;                       // frame-warp
     const int S = p.stages;
     const int H = p.hist_tiles;
     const int P = p.prefetch;
@@ -1017,9 +1024,9 @@ __global__ void __launch_bounds__(NW * 32)
 
     const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t ring_bytes = (uint32_t)S * TB;
-    const uint32_t gsum = ring + ring_bytes;                    // float [GS][NW][32]
-    const uint32_t ttot = gsum + (uint32_t)GS * NW * 32 * 4;    // float [GS][32]
-    const uint32_t bars = ttot + (uint32_t)GS * 32 * 4;
+    const uint32_t gsum = ring + ring_bytes;                    // float [GS][NW][CW]
+    const uint32_t ttot = gsum + (uint32_t)GS * NW * CW * 4;    // float [GS][CW]
+    const uint32_t bars = ttot + (uint32_t)GS * CW * 4;
 
     if (tid == 0) {
         prefetch_tmap(&in_map);
@@ -1033,9 +1040,9 @@ __global__ void __launch_bounds__(NW * 32)
         const uint32_t bar = bars + 8u * st;
         mbar_arrive_expect_tx(bar, TB);
         if (tile < 0 && p.has_halo)
-            tma_load_2d(ring + (uint32_t)st * TB, &halo_map, bar, cb * 32, (tile + H) * FT, kEvictFirst);
+            tma_load_2d(ring + (uint32_t)st * TB, &halo_map, bar, cb * CW, (tile + H) * FT, kEvictFirst);
         else
-            tma_load_2d(ring + (uint32_t)st * TB, &in_map, bar, cb * 32, tile * FT, kEvictFirst);
+            tma_load_2d(ring + (uint32_t)st * TB, &in_map, bar, cb * CW, tile * FT, kEvictFirst);
     };
 
     uint32_t it = 0;
@@ -1052,7 +1059,7 @@ __global__ void __launch_bounds__(NW * 32)
         if (t0 >= t1) continue;
         const int first = t0 - H;
         const int ntl = t1 - first;
-        const uint32_t ch = (uint32_t)cb * 32u + lane;
+        const uint32_t ch = (uint32_t)cb * CW + lane;
         const bool ch_ok = ch < p.channels;
 
         if (tid == 0) {
@@ -1072,7 +1079,7 @@ __global__ void __launch_bounds__(NW * 32)
 
             float x[RF];
 #pragma unroll
-            for (int r = 0; r < RF; ++r) x[r] = lds32(cur + ((uint32_t)(warp * RF + r) * 32u + lane) * 4u);
+            for (int r = 0; r < RF; ++r) x[r] = lds32(cur + ((uint32_t)(warp * RF + r) * CW + lane) * 4u);
             float gtot;
             {
                 float q[RF / 4];
@@ -1081,7 +1088,7 @@ __global__ void __launch_bounds__(NW * 32)
                 gtot = (q[0] + q[1]) + (q[2] + q[3]);
                 if constexpr (RF == 32) gtot += (q[RF / 4 - 4] + q[RF / 4 - 3]) + (q[RF / 4 - 2] + q[RF / 4 - 1]);
             }
-            sts32(gsum + (((uint32_t)slot * NW + warp) * 32u + lane) * 4u, gtot);
+            sts32(gsum + (((uint32_t)slot * NW + warp) * CW + lane) * 4u, gtot);
 
             __syncthreads();
 
@@ -1091,39 +1098,59 @@ __global__ void __launch_bounds__(NW * 32)
                 issue_load(first + j + P, cb, s2);
             }
 
-            // groups of this tile in front of the own group (warp-uniform trip count)
+            // where the lag run starts: `lw` = group (warp slot), `h` = tiles back (both warp-uniform)
+            int lw = warp - (int)(p.n_full + 1u);
+            int h = 0;
+            if (lw < 0) {
+                h = (-lw + NW - 1) / NW;
+                lw += h * NW;
+            }
+            // groups of this tile in front of the own group: needed when the window reaches into an earlier
+            // tile, and by the last warp for the tile total (which only windows longer than a tile consume)
             float e_own = 0.f;
-            for (int w2 = 0; w2 < warp; ++w2) e_own += lds32(gsum + (((uint32_t)slot * NW + w2) * 32u + lane) * 4u);
-            if (warp == NW - 1) sts32(ttot + ((uint32_t)slot * 32u + lane) * 4u, e_own + gtot);
+            if (h > 0 || (H > 1 && warp == NW - 1)) {
+                const uint32_t g0 = gsum + ((uint32_t)slot * NW * CW + lane) * 4u;
+#pragma unroll 4
+                for (int w2 = 0; w2 < warp; ++w2) e_own += lds32(g0 + (uint32_t)w2 * ROWB);
+            }
+            if (H > 1 && warp == NW - 1) sts32(ttot + ((uint32_t)slot * CW + lane) * 4u, e_own + gtot);
 
             if (is_out) {
                 float xl[RF];
                 {
-                    const int base = (int)((uint32_t)st * TB) + (warp * RF - (int)p.k) * 128 + lane * 4;
+                    // 16 consecutive ring rows starting k frames above the own run; the ring wraps at most
+                    // once inside the run, and where it does is warp-uniform (lane offsets stay inside a row)
+                    int row0 = (int)((uint32_t)st * (uint32_t)FT) + warp * RF - (int)p.k;   // ring row of the first lag frame
+                    const int ring_rows = S * FT;
+                    if (row0 + RF <= 0) row0 += ring_rows;
+                    if (row0 >= 0) {
+                        const uint32_t a0 = ring + (uint32_t)row0 * ROWB + (uint32_t)lane * 4u;
 #pragma unroll
-                    for (int r = 0; r < RF; ++r) {
-                        int o = base + 128 * r;
-                        if (o < 0) o += (int)ring_bytes;
-                        xl[r] = lds32(ring + (uint32_t)o);
+                        for (int r = 0; r < RF; ++r) xl[r] = lds32(a0 + ROWB * r);
+                    } else {  // rows row0..-1 live at the end of the ring
+                        const uint32_t a0 = ring + (uint32_t)lane * 4u;
+#pragma unroll
+                        for (int r = 0; r < RF; ++r) {
+                            const int rr = row0 + r;
+                            xl[r] = lds32(a0 + (uint32_t)(rr < 0 ? rr + ring_rows : rr) * ROWB);
+                        }
                     }
-                }
-                int lw = warp - (int)(p.n_full + 1u);   // group (warp slot) that holds the lag run's first frame
-                int h = 0;
-                if (lw < 0) {
-                    h = (-lw + NW - 1) / NW;
-                    lw += h * NW;
                 }
                 float acc = 0.f;
                 if (h == 0) {
-                    for (int w2 = lw + 1; w2 < warp; ++w2) acc += lds32(gsum + (((uint32_t)slot * NW + w2) * 32u + lane) * 4u);
+                    const uint32_t g0 = gsum + ((uint32_t)slot * NW * CW + lane) * 4u;
+#pragma unroll 4
+                    for (int w2 = lw + 1; w2 < warp; ++w2) acc += lds32(g0 + (uint32_t)w2 * ROWB);
                 } else {
                     int ls = slot - h;
                     if (ls < 0) ls += GS;
-                    for (int w2 = lw + 1; w2 < NW; ++w2) acc += lds32(gsum + (((uint32_t)ls * NW + w2) * 32u + lane) * 4u);
+                    const uint32_t g0 = gsum + ((uint32_t)ls * NW * CW + lane) * 4u;
+#pragma unroll 4
+                    for (int w2 = lw + 1; w2 < NW; ++w2) acc += lds32(g0 + (uint32_t)w2 * ROWB);
                     int ms = ls;
                     for (int v = 1; v < h; ++v) {
                         ms = (ms + 1 == GS) ? 0 : ms + 1;
-                        acc += lds32(ttot + ((uint32_t)ms * 32u + lane) * 4u);
+                        acc += lds32(ttot + ((uint32_t)ms * CW + lane) * 4u);
                     }
                     acc += e_own;
                 }
@@ -1134,10 +1161,22 @@ __global__ void __launch_bounds__(NW * 32)
                 const float inv = p.inv_k;
                 const uint64_t f_base = (uint64_t)tile * FT + (uint64_t)warp * RF;
                 float* dst = out + f_base * p.channels + ch;
+                // frames of this run inside the signal (warp-uniform); channels past C store nothing
+                int nvalid = 0;
+                if (ch_ok && f_base < p.frames) nvalid = (p.frames - f_base < (uint64_t)RF) ? (int)(p.frames - f_base) : RF;
+                const uint32_t cstride = p.channels;
+                if (nvalid == RF) {
 #pragma unroll
-                for (int r = 0; r < RF; ++r) {
-                    acc += x[r] - xl[r];
-                    if (ch_ok && f_base + r < p.frames) dst[(uint64_t)r * p.channels] = acc * inv;
+                    for (int r = 0; r < RF; ++r) {
+                        acc += x[r] - xl[r];
+                        dst[(uint32_t)r * cstride] = acc * inv;
+                    }
+                } else {
+#pragma unroll
+                    for (int r = 0; r < RF; ++r) {
+                        acc += x[r] - xl[r];
+                        if (r < nvalid) dst[(uint32_t)r * cstride] = acc * inv;
+                    }
                 }
             }
 
