@@ -117,12 +117,12 @@ StreamGeom plan_stream_i16(uint32_t k, uint32_t C, const mavg_tuning& tu)
 {
     StreamGeom g;
     g.NT = 512;
-    g.R = 32;
+    g.R = 32;   // 16-sample runs with two CTAs per SM were measured 10-20 % slower (per-run overheads dominate)
     g.elem = 2;
     g.C = C;
     if (k >= 65536u || !(C == 1 || C == 2)) return g;   // int32 window sums hold k * 32768 only below 2^16
     const uint64_t L = (uint64_t)k * C;
-    const uint32_t R = 32;
+    const uint32_t R = (uint32_t)g.R;
     const uint32_t s = (uint32_t)((R - L % R) % R);
     g.m_part = R - s;
     g.n_full = (uint32_t)((L + s) / R - 1);
@@ -131,13 +131,15 @@ StreamGeom plan_stream_i16(uint32_t k, uint32_t C, const mavg_tuning& tu)
     g.mode = g.n_full <= 16 ? 0 : 1;
     const uint64_t T = (uint64_t)g.NT * R;
     g.H = (int)(((uint64_t)(g.n_full + 1) * R + T - 1) / T);
-    g.ctas_per_sm = 1;
+    g.ctas_per_sm = tu.ctas_per_sm ? (int)tu.ctas_per_sm : (g.R == 16 ? 2 : 1);
     g.P = tu.prefetch ? (int)tu.prefetch : 2;
     for (;;) {
         g.S = g.H + 1 + g.P;
-        g.smem = mavg::stream_i16_smem_bytes(g.NT, g.S, g.H, (int)C);
-        if (g.smem <= kMaxSmem) break;
+        g.smem = mavg::stream_i16_smem_bytes(g.NT, g.R, g.S, g.H, (int)C);
+        const uint32_t per_sm = 233472;
+        if (g.smem <= kMaxSmem && (uint64_t)(g.smem + 1024) * g.ctas_per_sm <= per_sm) break;
         if (g.P > 1) { --g.P; continue; }
+        if (g.ctas_per_sm > 1) { --g.ctas_per_sm; g.P = tu.prefetch ? (int)tu.prefetch : 2; continue; }
         return g;
     }
     if (k > 1) {
@@ -269,13 +271,13 @@ StreamKernel pick_kernel(const StreamGeom& g, uint32_t k)
     return pick_variant<512, 16>(g.MIS, g.mode, k);
 }
 
-template <int C>
+template <int R, int C>
 StreamKernel pick_i16(int mis, int mode)
 {
     using namespace mavg;
-#define MAVG_I16_CASE(M)                                                        \
-    case M: return mode == 0 ? (StreamKernel)stream_i16_kernel<512, C, M, 0>    \
-                             : (StreamKernel)stream_i16_kernel<512, C, M, 1>;
+#define MAVG_I16_CASE(M)                                                           \
+    case M: return mode == 0 ? (StreamKernel)stream_i16_kernel<512, R, C, M, 0>    \
+                             : (StreamKernel)stream_i16_kernel<512, R, C, M, 1>;
     switch (mis) {
         MAVG_I16_CASE(0)
         MAVG_I16_CASE(2)
@@ -622,7 +624,7 @@ int launch_shard(mavg_plan* p, DevCtx& d, const void* in, void* out, const void*
     sp.has_halo = halo ? 1 : 0;
 
     StreamKernel kern = g.elem == 4 ? pick_kernel(g, p->desc.window)
-                                    : (g.C == 1 ? pick_i16<1>(g.MIS, g.mode) : pick_i16<2>(g.MIS, g.mode));
+                                    : (g.C == 1 ? pick_i16<32, 1>(g.MIS, g.mode) : pick_i16<32, 2>(g.MIS, g.mode));
     if (!kern) return fail(MAVG_ERR_UNSUPPORTED, "no stream kernel variant for this window");
     MAVG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
     const unsigned grid = (unsigned)std::min<uint64_t>(ctas, (uint64_t)sp.total_chunks);

@@ -663,9 +663,9 @@ __global__ void __launch_bounds__(NT)
 // sample stream: window stride C, lag distance k*C, one running sum per channel per thread.
 // HBM traffic: 2 B read + 2 B written per sample.
 // ----------------------------------------------------------------------------------
-__host__ __device__ inline uint32_t stream_i16_smem_bytes(int NT, int S, int H, int C)
+__host__ __device__ inline uint32_t stream_i16_smem_bytes(int NT, int R, int S, int H, int C)
 {
-    const uint32_t TB = (uint32_t)NT * 32 * 2;
+    const uint32_t TB = (uint32_t)NT * R * 2;
     return 1024u + (uint32_t)S * TB + 2u * TB + (uint32_t)(H + 2) * NT * C * 4 + (uint32_t)(H + 2) * 32 * C * 4 +
            2u * 32 * C * 4 + (uint32_t)S * 8;
 }
@@ -706,17 +706,17 @@ __device__ __forceinline__ int div_trunc(int w, uint32_t mul, uint32_t sh)
     return w < 0 ? -q : q;
 }
 
-template <int NT, int C, int MIS, int MODE>
-__global__ void __launch_bounds__(NT)
+template <int NT, int R, int C, int MIS, int MODE>
+__global__ void __launch_bounds__(NT, (R == 16 ? 2 : 1))
     stream_i16_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map,
                       const __grid_constant__ CUtensorMap halo_map, const StreamParams p)
 {
-    constexpr int R = 32;            // int16 samples per thread run = 64 bytes
+    // R int16 samples per thread run (32 = 64 bytes, 16 = 32 bytes)
     constexpr int T = NT * R;
     constexpr uint32_t TB = T * 2;
     constexpr int ROWS = T / 64;     // 128-byte rows per tile
     constexpr int NW = NT / 32;
-    constexpr int CH_OWN = 4;
+    constexpr int CH_OWN = R / 8;
     constexpr int CH_LAG = CH_OWN + (MIS ? 1 : 0);
     static_assert(R % C == 0 && NW <= 16 && MIS >= 0 && MIS < 8 && MIS % C == 0, "shape");
 

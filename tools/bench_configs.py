@@ -196,7 +196,7 @@ def main():
         stream.synchronize()
         res = {}
         for k in (3, 16, 64, 256, 1024, 4096):
-            plan = mavg.Plan(n_frames, k, channels=C, dtype="i16")
+            plan = mavg.Plan(n_frames, k, channels=C, dtype="i16", **tune)
             plan.set_stream(stream.cuda_stream)
             plan.enable_timing(False)
             ms = timed(lambda: plan.run_device([d_in.value], [d_out.value]), stream, 3, 1, world)
@@ -207,7 +207,7 @@ def main():
             res[str(k)] = {"ms": round(ms, 4), "gsamples_s": round(n / ms / 1e6, 1), "hbm_gbs": round(4 * n / ms / 1e6, 1),
                            "bit_exact_head": ok, "path": "stream" if plan.info.path == 1 else "generic"}
             plan.close()
-        out.update(workload="stereo int16, 2^28 samples, k sweep, device resident", per_k=res)
+        out.update(workload="stereo int16, 2^28 samples, k sweep, device resident", per_k=res, tune=tune)
 
     if rank == 0:
         print(json.dumps(out), flush=True)
