@@ -1030,12 +1030,12 @@ int mavg_run_host(mavg_plan* p, const void* h_in, void* h_out)
         }
         char* dst = (char*)h_out + (src - (const char*)h_in);
 
-        // slices: whole tiles, at least the left context long, ~32 MiB each; planar batches and short
+        // slices: whole tiles, at least the left context long, ~16 MiB each; planar batches and short
         // shards go in one piece
         uint64_t slice_frames = d.frames;
         if (!planar_batch(p) && d.frames > 0) {
             const uint64_t unit = (p->path == MAVG_PATH_STREAM) ? tile_frames(p) : 1024;
-            uint64_t want = std::max<uint64_t>((32ull << 20) / (C * es), p->halo_frames);
+            uint64_t want = std::max<uint64_t>((16ull << 20) / (C * es), p->halo_frames);
             want = (want + unit - 1) / unit * unit;
             if (want * 2 <= d.frames) slice_frames = want;
         }
