@@ -91,6 +91,7 @@ SYMBOLS = [
     ("mavg_fill_synthetic", _i, [_vp, _u64, _i]),
     ("mavg_fill_synthetic_device", _i, [_vp, _i, _u64, _u64, _u64, _i, _vp]),
     ("mavg_run_owned", _i, [_vp]),
+    ("mavg_prefix_sum", _i, [_i, _vp, _vp, _u64, _u32, _vp]),
     ("mavg_ipc_export", _i, [_vp, _vp]),
     ("mavg_ipc_open", _i, [_vp, ctypes.POINTER(_vp)]),
     ("mavg_ipc_close", _i, [_vp]),

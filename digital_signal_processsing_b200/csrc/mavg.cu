@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "mavg_kernels.cuh"
+#include "mavg_scan.cuh"
 
 namespace {
 
@@ -684,6 +685,40 @@ int gather_timing(mavg_plan* p)
 
 }  // namespace
 
+namespace {
+template <typename TIn, typename TAcc>
+int launch_scan(const void* d_in, void* d_out, uint64_t n, uint32_t C, cudaStream_t st)
+{
+    const uint64_t tiles = (n + 4095) / 4096;
+    if (tiles > 0x7fffffffull) return fail(MAVG_ERR_UNSUPPORTED, "signal too long for mavg_prefix_sum");
+    // scratch: ticket (padded), status[tiles], aggregates[tiles][C], prefixes[tiles][C]
+    const size_t status_off = 256, aggr_off = status_off + ((tiles * 4 + 255) / 256) * 256;
+    const size_t pref_off = aggr_off + tiles * C * sizeof(TAcc);
+    const size_t total = pref_off + tiles * C * sizeof(TAcc);
+    char* scratch = nullptr;
+    MAVG_CUDA(cudaMallocAsync((void**)&scratch, total, st));
+    MAVG_CUDA(cudaMemsetAsync(scratch, 0, aggr_off, st));
+    uint32_t* ticket = (uint32_t*)scratch;
+    uint32_t* status = (uint32_t*)(scratch + status_off);
+    TAcc* aggr = (TAcc*)(scratch + aggr_off);
+    TAcc* pref = (TAcc*)(scratch + pref_off);
+    const TIn* in = (const TIn*)d_in;
+    TAcc* out = (TAcc*)d_out;
+    const unsigned grid = (unsigned)tiles;
+    switch (C) {
+    case 1: mavg::scan_lookback_kernel<TIn, TAcc, 1><<<grid, 256, 0, st>>>(in, out, n, ticket, status, aggr, pref); break;
+    case 2: mavg::scan_lookback_kernel<TIn, TAcc, 2><<<grid, 256, 0, st>>>(in, out, n, ticket, status, aggr, pref); break;
+    case 4: mavg::scan_lookback_kernel<TIn, TAcc, 4><<<grid, 256, 0, st>>>(in, out, n, ticket, status, aggr, pref); break;
+    default: mavg::scan_lookback_kernel<TIn, TAcc, 8><<<grid, 256, 0, st>>>(in, out, n, ticket, status, aggr, pref); break;
+    }
+    cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(scratch, st);
+    if (e != cudaSuccess) return fail(MAVG_ERR_CUDA, "scan launch failed: %s", cudaGetErrorString(e));
+    return MAVG_OK;
+}
+}  // namespace
+
+
 // =================================================================================
 // C ABI
 // =================================================================================
@@ -903,6 +938,7 @@ int mavg_plan_buffers(mavg_plan* p, uint32_t rank, void** d_in, void** d_out)
 int mavg_run_device_halo(mavg_plan* p, const void* d_in, void* d_out, const void* d_halo)
 {
     if (!p || !d_in || !d_out) return fail(MAVG_ERR_INVALID_ARG, "null argument");
+    if (d_in == d_out) return fail(MAVG_ERR_INVALID_ARG, "output must not alias input (windows re-read samples behind the write front)");
     if (p->dev.size() != 1) return fail(MAVG_ERR_UNSUPPORTED, "mavg_run_device_halo is for single-device plans");
     if (d_halo && !frame_sharded(p)) return fail(MAVG_ERR_UNSUPPORTED, "planar batches take no halo");
     DeviceGuard guard;
@@ -928,6 +964,7 @@ int mavg_run_device(mavg_plan* p, const void* const* d_in, void* const* d_out)
     for (size_t r = 0; r < p->dev.size(); ++r) {
         DevCtx& d = p->dev[r];
         if (!d_in[r] || !d_out[r]) return fail(MAVG_ERR_INVALID_ARG, "null shard pointer for device index %zu", r);
+        if (d_in[r] == d_out[r]) return fail(MAVG_ERR_INVALID_ARG, "output must not alias input");
         MAVG_CUDA(cudaSetDevice(d.device));
         const void* halo = nullptr;
         record(p, d, 0);
@@ -1153,6 +1190,20 @@ int mavg_device_free(void* d_ptr)
 {
     if (d_ptr) MAVG_CUDA(cudaFree(d_ptr));
     return MAVG_OK;
+}
+
+int mavg_prefix_sum(int dtype, const void* d_in, void* d_out, uint64_t frames, uint32_t channels, void* cuda_stream)
+{
+    if (dtype != MAVG_F32 && dtype != MAVG_I16) return fail(MAVG_ERR_INVALID_ARG, "unknown dtype %d", dtype);
+    if (!(channels == 1 || channels == 2 || channels == 4 || channels == 8))
+        return fail(MAVG_ERR_UNSUPPORTED, "mavg_prefix_sum takes 1, 2, 4 or 8 interleaved channels (got %u)", channels);
+    if (frames == 0) return MAVG_OK;
+    if (!d_in || !d_out) return fail(MAVG_ERR_INVALID_ARG, "null argument");
+    if (mavg_device_count() <= 0) return fail(MAVG_ERR_NO_DEVICE, "no CUDA device available: libmavg has no CPU fallback");
+    const uint64_t n = frames * channels;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    if (dtype == MAVG_I16) return launch_scan<int16_t, long long>(d_in, d_out, n, channels, st);
+    return launch_scan<float, double>(d_in, d_out, n, channels, st);
 }
 
 int mavg_host_alloc(uint64_t bytes, void** h_ptr)

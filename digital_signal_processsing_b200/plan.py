@@ -142,6 +142,12 @@ def fill_synthetic_device(ptr: int, dtype: str, n: int, first_index: int, seed: 
                                                  ctypes.c_void_p(stream)))
 
 
+def prefix_sum_device(in_ptr: int, out_ptr: int, dtype: str, frames: int, channels: int = 1, stream: int = 0) -> None:
+    """Per-channel inclusive prefix sum on device buffers (int16 -> int64, float32 -> float64), one pass."""
+    check(_lib.load().mavg_prefix_sum(_DTYPES[dtype], ctypes.c_void_p(in_ptr), ctypes.c_void_p(out_ptr), frames,
+                                      channels, ctypes.c_void_p(stream)))
+
+
 def moving_average(x: np.ndarray, window: int, channels: int = 1, layout: str = "interleaved",
                    block_size: int = 0, path: str = "auto") -> np.ndarray:
     """One-shot convenience: moving average of a host array on the GPU (int16 or float32)."""

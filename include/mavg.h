@@ -217,6 +217,16 @@ int mavg_fill_synthetic_device(void *d_dst, int dtype, uint64_t n, uint64_t firs
 /* Runs plan-owned input -> plan-owned output (after mavg_fill_synthetic). */
 int mavg_run_owned(mavg_plan *plan);
 
+/* Reusable primitive: per-channel inclusive prefix sum of an interleaved device signal in ONE pass
+ * (decoupled look-back), what recursive_hillis_steele / recursive_blelloch compute with multi-level
+ * recursion (basics/hillis_steele_averager.cu:69-84, basics/blelloch_scan_averager.cu:134-167):
+ *   out[f*C + c] = sum_{j <= f} in[j*C + c]
+ * dtype MAVG_I16 -> int64 output (exact), MAVG_F32 -> float64 output.  channels must be 1, 2, 4 or 8.
+ * Asynchronous on `cuda_stream`; scratch is taken from and returned to the stream-ordered allocator.
+ * The moving-average kernels do not call it (they never need a prefix over the whole signal). */
+int mavg_prefix_sum(int dtype, const void *d_in, void *d_out, uint64_t frames, uint32_t channels,
+                    void *cuda_stream);
+
 /* CUDA IPC helpers for one-process-per-GPU sharding: export a 64-byte handle of a
  * cudaMalloc'ed buffer, open it in the neighbour process, close it. */
 int mavg_ipc_export(const void *d_ptr, void *handle64);
