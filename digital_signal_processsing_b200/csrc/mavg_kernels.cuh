@@ -324,6 +324,159 @@ __host__ __device__ inline uint32_t stream_smem_bytes(int NT, int R, int S, int 
            + (uint32_t)S * 8;              // mbarriers
 }
 
+// ----------------------------------------------------------------------------------
+// TileRing -- the producer/consumer protocol every flat streaming kernel shares:
+//   * an S-stage ring of TMA tiles (S = history H + 1 + prefetch P) filled by thread 0, one mbarrier per
+//     stage, stages recycled by the single __syncthreads each tile costs;
+//   * persistent walking of contiguous tile ranges ("chunks"): H history tiles are replayed per chunk;
+//   * a double-buffered output staging tile whose TMA store is issued one iteration late (after the next
+//     __syncthreads) and whose reuse waits on cp.async.bulk.wait_group.read.
+// Shared-memory carve-up: [ring S*TB][staging 2*TB][kernel-specific summaries ...][S mbarriers].
+// ----------------------------------------------------------------------------------
+template <uint32_t TB, int ROWS>
+struct TileRing {
+    uint32_t ring, ring_bytes, outb, bars;
+    int S, H, P, GS;
+    uint32_t it;       // tiles streamed so far by this CTA (history + output), never reset
+    int st;            // it % S
+    int slot;          // it % GS, the summary slot of the current tile
+    uint32_t otiles;   // output tiles produced so far (selects the staging buffer)
+    // deferred TMA store (thread 0): st_pending = staged but not issued, st_inflight = issued, read not confirmed
+    bool st_pending, st_inflight;
+    int st_tile, st_sig;
+    uint32_t st_buf;
+    const CUtensorMap *in_map, *out_map, *halo_map;
+    bool has_halo;
+
+    // returns the first shared address after the staging tiles (where the kernel puts its summaries)
+    __device__ __forceinline__ uint32_t setup(uint32_t smem_base, const StreamParams& p, const CUtensorMap* in,
+                                              const CUtensorMap* out, const CUtensorMap* halo)
+    {
+        ring = (smem_base + 1023u) & ~1023u;
+        S = p.stages; H = p.hist_tiles; P = p.prefetch; GS = H + 2;
+        ring_bytes = (uint32_t)S * TB;
+        outb = ring + ring_bytes;
+        it = 0; st = 0; slot = 0; otiles = 0;
+        st_pending = st_inflight = false; st_tile = st_sig = 0; st_buf = 0;
+        in_map = in; out_map = out; halo_map = halo; has_halo = p.has_halo != 0;
+        return outb + 2u * TB;
+    }
+    __device__ __forceinline__ void init_barriers(uint32_t bars_addr)
+    {
+        bars = bars_addr;
+        if (threadIdx.x == 0) {
+            prefetch_tmap(in_map);
+            prefetch_tmap(out_map);
+            if (has_halo) prefetch_tmap(halo_map);
+            for (int s = 0; s < S; ++s) mbar_init(bars + 8u * s, 1);
+            fence_mbar_init();
+        }
+        __syncthreads();
+    }
+    // thread 0: tensor load of tile `tile` of signal `sig` into stage `stage`; tiles before tile 0 come from
+    // the halo map (sharded signals) or are zero-filled by the TMA unit
+    __device__ __forceinline__ void issue_load(int tile, int sig, int stage) const
+    {
+        const uint32_t bar = bars + 8u * stage;
+        mbar_arrive_expect_tx(bar, TB);
+        if (tile < 0 && has_halo)
+            tma_load_3d(ring + (uint32_t)stage * TB, halo_map, bar, 0, (tile + H) * ROWS, 0, kEvictFirst);
+        else
+            tma_load_3d(ring + (uint32_t)stage * TB, in_map, bar, 0, tile * ROWS, sig, kEvictFirst);
+    }
+    __device__ __forceinline__ void prologue(int first, int ntl, int sig) const
+    {
+        if (threadIdx.x == 0) {
+            int s2 = st;
+            for (int j = 0; j < P && j < ntl; ++j) {
+                issue_load(first + j, sig, s2);
+                s2 = (s2 + 1 == S) ? 0 : s2 + 1;
+            }
+        }
+    }
+    // all threads: wait for the current tile; returns its shared address
+    __device__ __forceinline__ uint32_t wait_tile() const
+    {
+        mbar_wait(bars + 8u * st, (it / (uint32_t)S) & 1u);
+        return ring + (uint32_t)st * TB;
+    }
+    __device__ __forceinline__ void before_sync()
+    {
+        if (threadIdx.x == 0 && st_inflight) {  // the staging buffer about to be rewritten is free again
+            tma_wait_read0();
+            st_inflight = false;
+        }
+    }
+    // thread 0, right after the tile's __syncthreads: refill the stage nobody reads any more, issue the
+    // store of the previous output tile
+    __device__ __forceinline__ void after_sync(int j, int ntl, int first, int sig)
+    {
+        if (threadIdx.x == 0) {
+            if (j + P < ntl) {
+                int s2 = st + P;
+                if (s2 >= S) s2 -= S;
+                issue_load(first + j + P, sig, s2);
+            }
+            flush_store();
+        }
+    }
+    __device__ __forceinline__ void flush_store()
+    {
+        if (st_pending) {
+            tma_store_3d(out_map, st_buf, 0, st_tile * ROWS, st_sig);
+            tma_commit();
+            st_pending = false;
+            st_inflight = true;
+        }
+    }
+    __device__ __forceinline__ uint32_t out_tile() const { return outb + (otiles & 1u) * TB; }
+    // all threads, after writing their part of the staging tile
+    __device__ __forceinline__ void staged(int tile, int sig)
+    {
+        fence_proxy_async_smem();
+        if (threadIdx.x == 0) {
+            st_pending = true;
+            st_tile = tile;
+            st_sig = sig;
+            st_buf = out_tile();
+        }
+        ++otiles;
+    }
+    __device__ __forceinline__ void advance()
+    {
+        ++it;
+        st = (st + 1 == S) ? 0 : st + 1;
+        slot = (slot + 1 == GS) ? 0 : slot + 1;
+    }
+    // everyone is done reading the ring and writing the staging tile of this chunk
+    __device__ __forceinline__ void epilogue()
+    {
+        __syncthreads();
+        if (threadIdx.x == 0) flush_store();
+    }
+    __device__ __forceinline__ void finish() const
+    {
+        if (threadIdx.x == 0) tma_wait_all0();
+    }
+    // shared address of byte offset `off` relative to the current tile (negative = history tiles)
+    __device__ __forceinline__ uint32_t rel(int off) const
+    {
+        int o = (int)((uint32_t)st * TB) + off;
+        if (o < 0) o += (int)ring_bytes;
+        return ring + (uint32_t)o;
+    }
+};
+
+// decodes chunk -> (signal, tile range); false when the range is empty
+__device__ __forceinline__ bool chunk_range(const StreamParams& p, int chunk, int& sig, int& t0, int& t1)
+{
+    sig = chunk / p.chunks_per_signal;
+    t0 = (chunk - sig * p.chunks_per_signal) * p.chunk_tiles;
+    t1 = t0 + p.chunk_tiles;
+    if (t1 > p.tiles_per_signal) t1 = p.tiles_per_signal;
+    return t0 < t1;
+}
+
 // Cancellation-free window sums for compile-time K <= 8 (MODE 2): v[] holds samples
 // a-K+1 .. a+R-1; windows are assembled from power-of-two partial windows, additions only,
 // so the relative error stays ~K*2^-24 even where the window sum is nearly zero.
@@ -383,71 +536,26 @@ __global__ void __launch_bounds__(NT)
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    const int S = p.stages;
-    const int H = p.hist_tiles;
-    const int P = p.prefetch;
-    const int GS = H + 2;  // summary slots
-
-    const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t ring_bytes = (uint32_t)S * TB;
-    const uint32_t outb = ring + ring_bytes;
-    const uint32_t gsum = outb + 2u * TB;                     // float [GS][NT][C]
+    TileRing<TB, ROWS> tr;
+    const uint32_t gsum = tr.setup(smem_u32(smem_raw), p, &in_map, &out_map, &halo_map);   // float [GS][NT][C]
+    const int H = tr.H, GS = tr.GS;
     const uint32_t wexc = gsum + (uint32_t)GS * NT * C * 4;   // float [GS][32][C]
     const uint32_t wraw = wexc + (uint32_t)GS * 32 * C * 4;   // float [2][32][C]
-    const uint32_t bars = wraw + 2u * 32 * C * 4;             // u64   [S]
-
-    if (tid == 0) {
-        prefetch_tmap(&in_map);
-        prefetch_tmap(&out_map);
-        if (p.has_halo) prefetch_tmap(&halo_map);
-        for (int s = 0; s < S; ++s) mbar_init(bars + 8u * s, 1);
-        fence_mbar_init();
-    }
-    __syncthreads();
-
-    // Producer helper (thread 0 only): tensor load of tile `tile` of signal `sig` into stage `st`.
-    auto issue_load = [&](int tile, int sig, int st) {
-        const uint32_t bar = bars + 8u * st;
-        mbar_arrive_expect_tx(bar, TB);
-        if (tile < 0 && p.has_halo)
-            tma_load_3d(ring + (uint32_t)st * TB, &halo_map, bar, 0, (tile + H) * ROWS, 0, kEvictFirst);
-        else
-            tma_load_3d(ring + (uint32_t)st * TB, &in_map, bar, 0, tile * ROWS, sig, kEvictFirst);
-    };
-
-    uint32_t it = 0;   // tiles streamed so far by this CTA (history + output), never reset
-    int st = 0;        // it % S
-    int slot = 0;      // it % GS
-    uint32_t otiles = 0;   // output tiles produced so far (selects the staging buffer)
-    // deferred TMA store (thread 0): st_pending = staged but not issued, st_inflight = issued, smem read
-    // not yet confirmed
-    bool st_pending = false, st_inflight = false;
-    int st_tile = 0, st_sig = 0;
-    uint32_t st_buf = 0;
+    tr.init_barriers(wraw + 2u * 32 * C * 4);                 // u64   [S]
 
     for (int chunk = blockIdx.x; chunk < p.total_chunks; chunk += gridDim.x) {
-        const int sig = chunk / p.chunks_per_signal;
-        const int t0 = (chunk - sig * p.chunks_per_signal) * p.chunk_tiles;
-        int t1 = t0 + p.chunk_tiles;
-        if (t1 > p.tiles_per_signal) t1 = p.tiles_per_signal;
-        if (t0 >= t1) continue;
+        int sig, t0, t1;
+        if (!chunk_range(p, chunk, sig, t0, t1)) continue;
         const int first = t0 - H;
         const int ntl = t1 - first;
-
-        if (tid == 0) {
-            int s2 = st;
-            for (int j = 0; j < P && j < ntl; ++j) {
-                issue_load(first + j, sig, s2);
-                s2 = (s2 + 1 == S) ? 0 : s2 + 1;
-            }
-        }
+        tr.prologue(first, ntl, sig);
 
         for (int j = 0; j < ntl; ++j) {
             const int tile = first + j;
             const bool is_out = (j >= H);
-            const uint32_t cur = ring + (uint32_t)st * TB;
-
-            mbar_wait(bars + 8u * st, (it / (uint32_t)S) & 1u);
+            const uint32_t cur = tr.wait_tile();
+            const int slot = tr.slot;
+            const uint32_t it = tr.it;
 
             // ---- own run: R consecutive samples, conflict-free swizzled LDS.128
             float x[R];
@@ -494,25 +602,9 @@ __global__ void __launch_bounds__(NT)
                 }
             }
 
-            if (tid == 0 && st_inflight) {  // staging buffer about to be rewritten is free again
-                tma_wait_read0();
-                st_inflight = false;
-            }
+            tr.before_sync();
             __syncthreads();
-
-            if (tid == 0) {
-                if (j + P < ntl) {
-                    int s2 = st + P;
-                    if (s2 >= S) s2 -= S;
-                    issue_load(first + j + P, sig, s2);
-                }
-                if (st_pending) {
-                    tma_store_3d(&out_map, st_buf, 0, st_tile * ROWS, st_sig);
-                    tma_commit();
-                    st_pending = false;
-                    st_inflight = true;
-                }
-            }
+            tr.after_sync(j, ntl, first, sig);
 
             float own_off[C], wex[C];
 #pragma unroll
@@ -542,18 +634,16 @@ __global__ void __launch_bounds__(NT)
                 float xl[CH_LAG * 4];
                 {
                     const int back = (MODE == 2) ? PRE : (int)p.lag_chunks;
-                    int lin = (int)((uint32_t)st * TB) + (tid * CH_OWN - back) * 16;
+                    const int lin = (tid * CH_OWN - back) * 16;
 #pragma unroll
                     for (int c = 0; c < CH_LAG; ++c) {
-                        int o = lin + 16 * c;
-                        if (o < 0) o += (int)ring_bytes;
-                        const float4 v = lds128(swz(ring + (uint32_t)o));
+                        const float4 v = lds128(swz(tr.rel(lin + 16 * c)));
                         xl[4 * c + 0] = v.x; xl[4 * c + 1] = v.y; xl[4 * c + 2] = v.z; xl[4 * c + 3] = v.w;
                     }
                 }
 
                 const float inv = p.inv_k;
-                const uint32_t ob = outb + (otiles & 1u) * TB + (uint32_t)tid * (R * 4);
+                const uint32_t ob = tr.out_tile() + (uint32_t)tid * (R * 4);
                 if constexpr (MODE == 2) {
                     // ---- additions only: v = samples a-K+1 .. a+R-1
                     float v[R + 7 * C], w[R];
@@ -626,31 +716,14 @@ __global__ void __launch_bounds__(NT)
                         sts128(swz(ob + 16u * c4), y[0], y[1], y[2], y[3]);
                     }
                 }
-                fence_proxy_async_smem();
-                if (tid == 0) {
-                    st_pending = true;
-                    st_tile = tile;
-                    st_sig = sig;
-                    st_buf = outb + (otiles & 1u) * TB;
-                }
-                ++otiles;
+                tr.staged(tile, sig);
             }
-
-            ++it;
-            st = (st + 1 == S) ? 0 : st + 1;
-            slot = (slot + 1 == GS) ? 0 : slot + 1;
+            tr.advance();
         }
 
-        // chunk epilogue: everyone is done reading the ring and writing the staging tile
-        __syncthreads();
-        if (tid == 0 && st_pending) {
-            tma_store_3d(&out_map, st_buf, 0, st_tile * ROWS, st_sig);
-            tma_commit();
-            st_pending = false;
-            st_inflight = true;  // the next chunk's first iteration waits for the read to finish
-        }
+        tr.epilogue();
     }
-    if (tid == 0) tma_wait_all0();
+    tr.finish();
 }
 
 // ----------------------------------------------------------------------------------
@@ -724,67 +797,26 @@ __global__ void __launch_bounds__(NT, (R == 16 ? 2 : 1))
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    const int S = p.stages;
-    const int H = p.hist_tiles;
-    const int P = p.prefetch;
-    const int GS = H + 2;
-
-    const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t ring_bytes = (uint32_t)S * TB;
-    const uint32_t outb = ring + ring_bytes;
-    const uint32_t gsum = outb + 2u * TB;                     // int [GS][NT][C]
+    TileRing<TB, ROWS> tr;
+    const uint32_t gsum = tr.setup(smem_u32(smem_raw), p, &in_map, &out_map, &halo_map);   // int [GS][NT][C]
+    const int H = tr.H, GS = tr.GS;
     const uint32_t wexc = gsum + (uint32_t)GS * NT * C * 4;   // int [GS][32][C]  ([31] = tile total)
     const uint32_t wraw = wexc + (uint32_t)GS * 32 * C * 4;   // int [2][32][C]
-    const uint32_t bars = wraw + 2u * 32 * C * 4;
-
-    if (tid == 0) {
-        prefetch_tmap(&in_map);
-        prefetch_tmap(&out_map);
-        if (p.has_halo) prefetch_tmap(&halo_map);
-        for (int s = 0; s < S; ++s) mbar_init(bars + 8u * s, 1);
-        fence_mbar_init();
-    }
-    __syncthreads();
-
-    auto issue_load = [&](int tile, int sig, int st) {
-        const uint32_t bar = bars + 8u * st;
-        mbar_arrive_expect_tx(bar, TB);
-        if (tile < 0 && p.has_halo)
-            tma_load_3d(ring + (uint32_t)st * TB, &halo_map, bar, 0, (tile + H) * ROWS, 0, kEvictFirst);
-        else
-            tma_load_3d(ring + (uint32_t)st * TB, &in_map, bar, 0, tile * ROWS, sig, kEvictFirst);
-    };
-
-    uint32_t it = 0;
-    int st = 0, slot = 0;
-    uint32_t otiles = 0;
-    bool st_pending = false, st_inflight = false;
-    int st_tile = 0, st_sig = 0;
-    uint32_t st_buf = 0;
+    tr.init_barriers(wraw + 2u * 32 * C * 4);
 
     for (int chunk = blockIdx.x; chunk < p.total_chunks; chunk += gridDim.x) {
-        const int sig = chunk / p.chunks_per_signal;
-        const int t0 = (chunk - sig * p.chunks_per_signal) * p.chunk_tiles;
-        int t1 = t0 + p.chunk_tiles;
-        if (t1 > p.tiles_per_signal) t1 = p.tiles_per_signal;
-        if (t0 >= t1) continue;
+        int sig, t0, t1;
+        if (!chunk_range(p, chunk, sig, t0, t1)) continue;
         const int first = t0 - H;
         const int ntl = t1 - first;
-
-        if (tid == 0) {
-            int s2 = st;
-            for (int j = 0; j < P && j < ntl; ++j) {
-                issue_load(first + j, sig, s2);
-                s2 = (s2 + 1 == S) ? 0 : s2 + 1;
-            }
-        }
+        tr.prologue(first, ntl, sig);
 
         for (int j = 0; j < ntl; ++j) {
             const int tile = first + j;
             const bool is_out = (j >= H);
-            const uint32_t cur = ring + (uint32_t)st * TB;
-
-            mbar_wait(bars + 8u * st, (it / (uint32_t)S) & 1u);
+            const uint32_t cur = tr.wait_tile();
+            const int slot = tr.slot;
+            const uint32_t it = tr.it;
 
             int x[R];
 #pragma unroll
@@ -816,25 +848,9 @@ __global__ void __launch_bounds__(NT, (R == 16 ? 2 : 1))
                 }
             }
 
-            if (tid == 0 && st_inflight) {
-                tma_wait_read0();
-                st_inflight = false;
-            }
+            tr.before_sync();
             __syncthreads();
-
-            if (tid == 0) {
-                if (j + P < ntl) {
-                    int s2 = st + P;
-                    if (s2 >= S) s2 -= S;
-                    issue_load(first + j + P, sig, s2);
-                }
-                if (st_pending) {
-                    tma_store_3d(&out_map, st_buf, 0, st_tile * ROWS, st_sig);
-                    tma_commit();
-                    st_pending = false;
-                    st_inflight = true;
-                }
-            }
+            tr.after_sync(j, ntl, first, sig);
 
             int own_off[C], wex[C];
 #pragma unroll
@@ -861,13 +877,9 @@ __global__ void __launch_bounds__(NT, (R == 16 ? 2 : 1))
             if (is_out) {
                 int xl[CH_LAG * 8];
                 {
-                    int lin = (int)((uint32_t)st * TB) + (tid * CH_OWN - (int)p.lag_chunks) * 16;
+                    const int lin = (tid * CH_OWN - (int)p.lag_chunks) * 16;
 #pragma unroll
-                    for (int c = 0; c < CH_LAG; ++c) {
-                        int o = lin + 16 * c;
-                        if (o < 0) o += (int)ring_bytes;
-                        unpack8(lds128u(swz(ring + (uint32_t)o)), &xl[8 * c]);
-                    }
+                    for (int c = 0; c < CH_LAG; ++c) unpack8(lds128u(swz(tr.rel(lin + 16 * c))), &xl[8 * c]);
                 }
                 int acc[C];
 #pragma unroll
@@ -911,7 +923,7 @@ __global__ void __launch_bounds__(NT, (R == 16 ? 2 : 1))
                 for (int r = 0; r < R; ++r)
                     if ((uint32_t)r < p.m_part) acc[r % C] += xl[MIS + r];
 
-                const uint32_t ob = outb + (otiles & 1u) * TB + (uint32_t)tid * (R * 2);
+                const uint32_t ob = tr.out_tile() + (uint32_t)tid * (R * 2);
                 const uint32_t mul = p.div_mul, sh = p.div_shift;
 #pragma unroll
                 for (int c = 0; c < CH_OWN; ++c) {
@@ -927,30 +939,14 @@ __global__ void __launch_bounds__(NT, (R == 16 ? 2 : 1))
                     }
                     sts128u(swz(ob + 16u * c), wds[0], wds[1], wds[2], wds[3]);
                 }
-                fence_proxy_async_smem();
-                if (tid == 0) {
-                    st_pending = true;
-                    st_tile = tile;
-                    st_sig = sig;
-                    st_buf = outb + (otiles & 1u) * TB;
-                }
-                ++otiles;
+                tr.staged(tile, sig);
             }
-
-            ++it;
-            st = (st + 1 == S) ? 0 : st + 1;
-            slot = (slot + 1 == GS) ? 0 : slot + 1;
+            tr.advance();
         }
 
-        __syncthreads();
-        if (tid == 0 && st_pending) {
-            tma_store_3d(&out_map, st_buf, 0, st_tile * ROWS, st_sig);
-            tma_commit();
-            st_pending = false;
-            st_inflight = true;
-        }
+        tr.epilogue();
     }
-    if (tid == 0) tma_wait_all0();
+    tr.finish();
 }
 
 // ----------------------------------------------------------------------------------

@@ -72,14 +72,14 @@ int run(const Options& o, const WAVHeader& header, const std::vector<unsigned ch
     // CSV's Compute_ms keeps the reference's meaning (kernels only, benchmark.h:88-96): it is measured on the
     // device-resident buffers the last run left behind.  Total_ms stays the wall time of the overlapped call.
     {
-        const float total = res.total_ms;
+        const float wall_ms = res.total_ms;
         ProfileResult dev = benchmark<GpuTimer>(o.rounds, 2, [&](GpuTimer& t) {
             MAVG_CHECK(mavg_run_owned(ws.plan()));
             MAVG_CHECK(mavg_synchronize(ws.plan()));
             t.capture(ws.plan());
         });
         res.compute_ms = dev.compute_ms;
-        res.total_ms = total;
+        res.total_ms = wall_ms;
     }
     res.print_stats(total, sizeof(T));
 
