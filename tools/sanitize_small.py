@@ -1,0 +1,38 @@
+#!/usr/bin/env python
+"""Small end-to-end pass over every kernel family, meant to run under compute-sanitizer (memcheck)."""
+import os, sys
+sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..")))
+import numpy as np
+import torch
+import digital_signal_processsing_b200 as mavg
+import oracle
+
+def rel(y, e):
+    return float(np.max(np.abs(y - e) / np.abs(e)))
+
+n = 3 * 8192 + 100
+x = oracle.fill_f32(n, 1)
+for k in (3, 64, 300, 4096, 9000):
+    assert rel(mavg.moving_average(x, k), oracle.mavg_f64(x, k)) < 1e-5, k
+xs = oracle.fill_f32(2 * n, 2)
+for k in (5, 100, 2000):
+    assert rel(mavg.moving_average(xs, k, channels=2), oracle.mavg_f64(xs, k, 2)) < 1e-5, k
+xi = oracle.fill_i16(2 * (2 * 16384 + 77), 3)
+for k in (3, 41, 1000, 4096):
+    assert np.array_equal(mavg.moving_average(xi, k, channels=2), oracle.mavg_i16(xi, k, 2)), k
+xc = oracle.fill_f32(64 * (3 * 256 + 9), 4)
+for k in (16, 300, 1000):
+    assert rel(mavg.moving_average(xc, k, channels=64), oracle.mavg_f64(xc, k, 64)) < 1e-5, k
+xg = oracle.fill_f32(3 * 20001, 5)
+for k in (4, 700):
+    assert rel(mavg.moving_average(xg, k, channels=3), oracle.mavg_f64(xg, k, 3)) < 1e-5, k
+xp = oracle.fill_f32(4 * 8192 * 2, 6)
+yp = mavg.moving_average(xp, 64, channels=4, layout="planar")
+assert rel(yp[:16384], oracle.mavg_f64(xp[:16384], 64)) < 1e-5
+d = torch.from_numpy(oracle.fill_i16(2 * 50001, 7)).cuda()
+o = torch.zeros(2 * 50001, dtype=torch.int64, device="cuda")
+torch.cuda.synchronize()
+mavg.prefix_sum_device(d.data_ptr(), o.data_ptr(), "i16", 50001, 2)
+torch.cuda.synchronize()
+assert torch.equal(o, torch.cumsum(d.view(-1, 2).to(torch.int64), 0).view(-1))
+print("sanitize_small: all kernel families ok")
