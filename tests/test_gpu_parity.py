@@ -449,3 +449,28 @@ def test_generic_long_windows(mavg, oracle_mod, case):
         x = oracle_mod.fill_i16(frames * ch, 19000 + k)
         y = mavg.moving_average(x, k, channels=ch, path="generic")
         assert np.array_equal(y, oracle_mod.mavg_i16(x, k, ch))
+
+
+# ------------------------------------------------------------------ full size, the other fast paths
+def test_full_size_i16_stereo_2p28_bit_exact(mavg, oracle_mod):
+    """2^28 stereo int16 samples (the reference's format at the benchmark size): every output bit-identical
+    to the CPU oracle, for a direct-mode and a scan-mode window."""
+    n = 1 << 28
+    x = oracle_mod.fill_i16(n, 0x5EED0100)
+    for k in (5, 1000):
+        with mavg.Plan(n // 2, k, channels=2, dtype="i16") as plan:
+            assert plan.info.path == 1
+            y = plan.run_host(x)
+        e = oracle_mod.mavg_i16_mt(x, k, 2, 8)
+        assert np.array_equal(y, e), k
+        del y, e
+
+
+def test_full_size_f32_stereo_2p27_frames(mavg, oracle_mod):
+    n = 1 << 28                                   # 2^27 stereo frames
+    x = oracle_mod.fill_f32(n, 0x5EED0200)
+    with mavg.Plan(n // 2, 64, channels=2) as plan:
+        assert plan.info.path == 1
+        y = plan.run_host(x)
+    e = oracle_mod.mavg_f64(x, 64, 2)
+    assert _rel(y, e) < TOL
