@@ -117,8 +117,8 @@ constexpr uint32_t kMaxSmem = 232448;  // 227 KB opt-in limit per CTA on sm_100
 StreamGeom plan_stream_i16(uint32_t k, uint32_t C, const mavg_tuning& tu)
 {
     StreamGeom g;
-    g.NT = 512;
-    g.R = 32;   // 16-sample runs with two CTAs per SM were measured 10-20 % slower (per-run overheads dominate)
+    g.NT = 512;  // 256 threads x 2 CTAs per SM measured no faster: the kernel is bound by instruction issue
+    g.R = 32;    // 16-sample runs with two CTAs per SM were measured 10-20 % slower (per-run overheads dominate)
     g.elem = 2;
     g.C = C;
     if (k >= 65536u || !(C == 1 || C == 2)) return g;   // int32 window sums hold k * 32768 only below 2^16
@@ -132,7 +132,7 @@ StreamGeom plan_stream_i16(uint32_t k, uint32_t C, const mavg_tuning& tu)
     g.mode = g.n_full <= 16 ? 0 : 1;
     const uint64_t T = (uint64_t)g.NT * R;
     g.H = (int)(((uint64_t)(g.n_full + 1) * R + T - 1) / T);
-    g.ctas_per_sm = tu.ctas_per_sm ? (int)tu.ctas_per_sm : (g.R == 16 ? 2 : 1);
+    g.ctas_per_sm = tu.ctas_per_sm ? (int)tu.ctas_per_sm : (g.NT == 256 ? 2 : 1);
     g.P = tu.prefetch ? (int)tu.prefetch : 2;
     for (;;) {
         g.S = g.H + 1 + g.P;
@@ -272,13 +272,13 @@ StreamKernel pick_kernel(const StreamGeom& g, uint32_t k)
     return pick_variant<512, 16>(g.MIS, g.mode, k);
 }
 
-template <int R, int C>
+template <int NT, int R, int C>
 StreamKernel pick_i16(int mis, int mode)
 {
     using namespace mavg;
-#define MAVG_I16_CASE(M)                                                           \
-    case M: return mode == 0 ? (StreamKernel)stream_i16_kernel<512, R, C, M, 0>    \
-                             : (StreamKernel)stream_i16_kernel<512, R, C, M, 1>;
+#define MAVG_I16_CASE(M)                                                          \
+    case M: return mode == 0 ? (StreamKernel)stream_i16_kernel<NT, R, C, M, 0>    \
+                             : (StreamKernel)stream_i16_kernel<NT, R, C, M, 1>;
     switch (mis) {
         MAVG_I16_CASE(0)
         MAVG_I16_CASE(2)
@@ -625,7 +625,7 @@ int launch_shard(mavg_plan* p, DevCtx& d, const void* in, void* out, const void*
     sp.has_halo = halo ? 1 : 0;
 
     StreamKernel kern = g.elem == 4 ? pick_kernel(g, p->desc.window)
-                                    : (g.C == 1 ? pick_i16<32, 1>(g.MIS, g.mode) : pick_i16<32, 2>(g.MIS, g.mode));
+                                    : (g.C == 1 ? pick_i16<512, 32, 1>(g.MIS, g.mode) : pick_i16<512, 32, 2>(g.MIS, g.mode));
     if (!kern) return fail(MAVG_ERR_UNSUPPORTED, "no stream kernel variant for this window");
     MAVG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
     const unsigned grid = (unsigned)std::min<uint64_t>(ctas, (uint64_t)sp.total_chunks);

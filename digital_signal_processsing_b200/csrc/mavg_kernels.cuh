@@ -780,7 +780,7 @@ __device__ __forceinline__ int div_trunc(int w, uint32_t mul, uint32_t sh)
 }
 
 template <int NT, int R, int C, int MIS, int MODE>
-__global__ void __launch_bounds__(NT, (R == 16 ? 2 : 1))
+__global__ void __launch_bounds__(NT, (NT == 256 ? 2 : 1))
     stream_i16_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map,
                       const __grid_constant__ CUtensorMap halo_map, const StreamParams p)
 {

@@ -1,3 +1,9 @@
 #!/bin/bash
 mkdir -p gpurun_out
-echo "== pytest scan"; timeout 1200 python -m pytest tests/test_gpu_scan.py -m gpu -q -x > gpurun_out/pytest_scan.log 2>&1; echo "rc=$?"; tail -15 gpurun_out/pytest_scan.log
+for t in "" "threads=256" "threads=256,prefetch=3" "threads=256,prefetch=4"; do
+echo "== i16 tune=[$t]"; timeout 600 python tools/bench_configs.py --config i16 --tune "$t" 2>/dev/null | python -c "
+import sys,json
+for l in sys.stdin:
+    if l.startswith('{'):
+        d=json.loads(l); print({k:(v['ms'],v['bit_exact_head']) for k,v in d['per_k'].items()})"
+done
