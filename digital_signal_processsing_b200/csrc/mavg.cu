@@ -121,7 +121,11 @@ StreamGeom plan_stream_i16(uint32_t k, uint32_t C, const mavg_tuning& tu)
     g.R = 32;    // 16-sample runs with two CTAs per SM were measured 10-20 % slower (per-run overheads dominate)
     g.elem = 2;
     g.C = C;
-    if (k >= 65536u || !(C == 1 || C == 2)) return g;   // int32 window sums hold k * 32768 only below 2^16
+    // Biased window sums w' = w + 32768 k <= 65535 k must stay below 2^32 and the 32-bit magic division must be
+    // exact for every dividend u < k * 2^16: with L = ceil(log2 k), M = ceil(2^(31+L) / k), e = M k - 2^(31+L) < k,
+    // floor(u M / 2^(31+L)) = floor(u / k) needs u e < 2^(31+L), i.e. 2^(2L+16) <= 2^(31+L), i.e. k <= 32768.
+    // k == 1 (identity) and longer windows are left to the generic kernel.
+    if (k < 2 || k > 32768u || !(C == 1 || C == 2)) return g;
     const uint64_t L = (uint64_t)k * C;
     const uint32_t R = (uint32_t)g.R;
     const uint32_t s = (uint32_t)((R - L % R) % R);
@@ -143,7 +147,7 @@ StreamGeom plan_stream_i16(uint32_t k, uint32_t C, const mavg_tuning& tu)
         if (g.ctas_per_sm > 1) { --g.ctas_per_sm; g.P = tu.prefetch ? (int)tu.prefetch : 2; continue; }
         return g;
     }
-    if (k > 1) {
+    {
         uint32_t lg = 0;
         while ((1u << lg) < k) ++lg;                       // ceil(log2 k)
         const unsigned long long two_p = 1ull << (31 + lg);
@@ -607,6 +611,18 @@ int launch_shard(mavg_plan* p, DevCtx& d, const void* in, void* out, const void*
     sp.lag_chunks = g.lag_chunks;
     sp.div_mul = g.div_mul;
     sp.div_shift = g.div_shift;
+    sp.bias_k = 32768u * p->desc.window;
+    sp.c65536 = 65536u;
+    memset(sp.wtab, 0, sizeof sp.wtab);
+    if (g.elem == 2) {
+        // dp2a byte weights: element e of the aligned lag words is run element r = e - MIS; it belongs to the
+        // head of the lag run when r < m_part, and to channel r % C
+        for (uint32_t wi = 0; wi < 20; ++wi)
+            for (uint32_t hh = 0; hh < 2; ++hh) {
+                const int r = (int)(2 * wi + hh) - g.MIS;
+                if (r >= 0 && (uint32_t)r < g.m_part) sp.wtab[(uint32_t)r % g.C][wi] |= 1u << (8 * hh);
+            }
+    }
     const uint64_t tiles = (rows * row + T - 1) / T;
     sp.tiles_per_signal = (int32_t)tiles;
     const uint64_t ctas = (uint64_t)d.sm_count * g.ctas_per_sm;

@@ -307,8 +307,14 @@ struct StreamParams {
     int32_t stages;             // S = H + 1 + prefetch
     int32_t prefetch;           // P
     int32_t has_halo;           // tiles before tile 0 come from halo_map instead of zero fill
-    uint32_t div_mul;           // int16 path: trunc(w / k) = sign(w) * (umulhi(|w|, div_mul) >> div_shift)
-    uint32_t div_shift;         //             (div_mul == 0 means k == 1)
+    // int16 path (biased domain, every sample carries +32768): with w' = w + 32768*k in [0, 65535*k],
+    //   trunc(w / k) + 32768 = umulhi(w' + (w' < bias_k ? k-1 : 0), div_mul) >> div_shift
+    uint32_t div_mul;
+    uint32_t div_shift;
+    uint32_t bias_k;            // 32768 * k
+    uint32_t c65536;            // 65536 as a run-time value, so mul.hi/mad stay on the FMA pipe
+    uint32_t wtab[2][20];       // dp2a byte weights selecting, per 32-bit lag word, the halves that belong to the
+                                // head of the lag run (first m_part elements) for channel 0 / channel 1
 };
 
 // Shared-memory carve-up (bytes), shared by host (size) and device (offsets).
@@ -763,20 +769,37 @@ __device__ __forceinline__ void sts32i(uint32_t addr, int v)
 {
     asm volatile("st.shared.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
-__device__ __forceinline__ void unpack8(const uint4 v, int* dst)
+// Instruction-pipe balance (ncu on the first version: ALU pipe 77 %, FMA pipe 16 %, kernel issue-bound at
+// 62-75 % of the HBM roofline): everything runs in a BIASED unsigned domain (sample + 32768), which makes the
+// window sum non-negative, so the truncating division needs no abs/negate, and lets the unpack / pack / head
+// sum run on the FMA pipe: hi = mul.hi(v, 65536), lo = mad(hi, -65536, v), pack = mad(hi, 65536, lo),
+// head sum = dp2a with constant byte weights.  TMA zero fill (signal padding) becomes 32768 after the bias
+// flip, i.e. a biased zero, so padding stays consistent.
+__device__ __forceinline__ void unpack2u(uint32_t v, uint32_t c16, uint32_t nc16, uint32_t& lo, uint32_t& hi)
 {
-    dst[0] = (int)(v.x << 16) >> 16; dst[1] = (int)v.x >> 16;
-    dst[2] = (int)(v.y << 16) >> 16; dst[3] = (int)v.y >> 16;
-    dst[4] = (int)(v.z << 16) >> 16; dst[5] = (int)v.z >> 16;
-    dst[6] = (int)(v.w << 16) >> 16; dst[7] = (int)v.w >> 16;
+    const uint32_t vb = v ^ 0x80008000u;
+    asm("mul.hi.u32 %0, %1, %2;" : "=r"(hi) : "r"(vb), "r"(c16));
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(lo) : "r"(hi), "r"(nc16), "r"(vb));
 }
-// C integer division (truncation toward zero) by the plan's window
-__device__ __forceinline__ int div_trunc(int w, uint32_t mul, uint32_t sh)
+__device__ __forceinline__ void unpack8u(const uint4 v, uint32_t c16, uint32_t nc16, uint32_t* dst)
 {
-    if (mul == 0u) return w;
-    const uint32_t a = (uint32_t)(w < 0 ? -w : w);
-    const int q = (int)(__umulhi(a, mul) >> sh);
-    return w < 0 ? -q : q;
+    unpack2u(v.x, c16, nc16, dst[0], dst[1]);
+    unpack2u(v.y, c16, nc16, dst[2], dst[3]);
+    unpack2u(v.z, c16, nc16, dst[4], dst[5]);
+    unpack2u(v.w, c16, nc16, dst[6], dst[7]);
+}
+// two biased 16-bit results -> one output word of two int16
+__device__ __forceinline__ uint32_t pack2u(uint32_t lo, uint32_t hi, uint32_t c16)
+{
+    uint32_t w;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(w) : "r"(hi), "r"(c16), "r"(lo));
+    return w ^ 0x80008000u;
+}
+// trunc((wb - bias_k) / k) + 32768 for wb in [0, 65535 k], k <= 32768 (exactness: plan_stream_i16)
+__device__ __forceinline__ uint32_t div_biased(uint32_t wb, uint32_t bias_k, uint32_t km1, uint32_t mul, uint32_t sh)
+{
+    const uint32_t u = wb + ((wb < bias_k) ? km1 : 0u);
+    return __umulhi(u, mul) >> sh;
 }
 
 template <int NT, int R, int C, int MIS, int MODE>
@@ -803,6 +826,7 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : 1))
     const uint32_t wexc = gsum + (uint32_t)GS * NT * C * 4;   // int [GS][32][C]  ([31] = tile total)
     const uint32_t wraw = wexc + (uint32_t)GS * 32 * C * 4;   // int [2][32][C]
     tr.init_barriers(wraw + 2u * 32 * C * 4);
+    const uint32_t c16 = p.c65536, nc16 = 0u - p.c65536;
 
     for (int chunk = blockIdx.x; chunk < p.total_chunks; chunk += gridDim.x) {
         int sig, t0, t1;
@@ -818,12 +842,13 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : 1))
             const int slot = tr.slot;
             const uint32_t it = tr.it;
 
-            int x[R];
+            uint32_t x[R];
 #pragma unroll
-            for (int c = 0; c < CH_OWN; ++c) unpack8(lds128u(swz(cur + (uint32_t)tid * (R * 2) + 16u * c)), &x[8 * c]);
-            int gtot[C], incl[C];
+            for (int c = 0; c < CH_OWN; ++c)
+                unpack8u(lds128u(swz(cur + (uint32_t)tid * (R * 2) + 16u * c)), c16, nc16, &x[8 * c]);
+            uint32_t gtot[C], incl[C];
 #pragma unroll
-            for (int c = 0; c < C; ++c) gtot[c] = 0;
+            for (int c = 0; c < C; ++c) gtot[c] = 0u;
 #pragma unroll
             for (int r = 0; r < R; ++r) gtot[r % C] += x[r];
 #pragma unroll
@@ -831,20 +856,20 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : 1))
 
             if constexpr (MODE == 0) {
 #pragma unroll
-                for (int c = 0; c < C; ++c) sts32i(gsum + (((uint32_t)slot * NT + tid) * C + c) * 4u, gtot[c]);
+                for (int c = 0; c < C; ++c) sts32i(gsum + (((uint32_t)slot * NT + tid) * C + c) * 4u, (int)gtot[c]);
             } else {
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
 #pragma unroll
                     for (int c = 0; c < C; ++c) {
-                        const int up = __shfl_up_sync(0xffffffffu, incl[c], d);
+                        const uint32_t up = __shfl_up_sync(0xffffffffu, incl[c], d);
                         if (lane >= d) incl[c] += up;
                     }
                 }
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
-                    sts32i(gsum + (((uint32_t)slot * NT + tid) * C + c) * 4u, incl[c]);
-                    if (lane == 31) sts32i(wraw + (((it & 1u) * 32u + warp) * C + c) * 4u, incl[c]);
+                    sts32i(gsum + (((uint32_t)slot * NT + tid) * C + c) * 4u, (int)incl[c]);
+                    if (lane == 31) sts32i(wraw + (((it & 1u) * 32u + warp) * C + c) * 4u, (int)incl[c]);
                 }
             }
 
@@ -852,44 +877,55 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : 1))
             __syncthreads();
             tr.after_sync(j, ntl, first, sig);
 
-            int own_off[C], wex[C];
+            uint32_t own_off[C], wex[C];
 #pragma unroll
-            for (int c = 0; c < C; ++c) own_off[c] = wex[c] = 0;
+            for (int c = 0; c < C; ++c) own_off[c] = wex[c] = 0u;
             if constexpr (MODE == 1) {
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
-                    const int v = (lane < NW) ? lds32i(wraw + (((it & 1u) * 32u + lane) * C + c) * 4u) : 0;
-                    int wi = v;
+                    const uint32_t v = (lane < NW) ? (uint32_t)lds32i(wraw + (((it & 1u) * 32u + lane) * C + c) * 4u) : 0u;
+                    uint32_t wi = v;
 #pragma unroll
                     for (int d = 1; d < NW; d <<= 1) {
-                        const int up = __shfl_up_sync(0xffffffffu, wi, d);
+                        const uint32_t up = __shfl_up_sync(0xffffffffu, wi, d);
                         if (lane >= d) wi += up;
                     }
                     wex[c] = wi - v;
                     if (warp == 0) {
-                        if (lane < NW) sts32i(wexc + (((uint32_t)slot * 32u + lane) * C + c) * 4u, wex[c]);
-                        if (lane == NW - 1) sts32i(wexc + (((uint32_t)slot * 32u + 31u) * C + c) * 4u, wi);
+                        if (lane < NW) sts32i(wexc + (((uint32_t)slot * 32u + lane) * C + c) * 4u, (int)wex[c]);
+                        if (lane == NW - 1) sts32i(wexc + (((uint32_t)slot * 32u + 31u) * C + c) * 4u, (int)wi);
                     }
                     own_off[c] = __shfl_sync(0xffffffffu, wex[c], warp);
                 }
             }
 
             if (is_out) {
-                int xl[CH_LAG * 8];
+                uint32_t xl[CH_LAG * 8];
+                uint32_t acc[C];
+#pragma unroll
+                for (int c = 0; c < C; ++c) acc[c] = 0u;
                 {
+                    // lag run as aligned 16-byte chunks; the head of the run (first m_part elements) is summed
+                    // straight from the packed words with dp2a and the plan's constant byte weights
                     const int lin = (tid * CH_OWN - (int)p.lag_chunks) * 16;
 #pragma unroll
-                    for (int c = 0; c < CH_LAG; ++c) unpack8(lds128u(swz(tr.rel(lin + 16 * c))), &xl[8 * c]);
-                }
-                int acc[C];
+                    for (int c = 0; c < CH_LAG; ++c) {
+                        const uint4 v = lds128u(swz(tr.rel(lin + 16 * c)));
+                        const uint32_t w4[4] = {v.x ^ 0x80008000u, v.y ^ 0x80008000u, v.z ^ 0x80008000u, v.w ^ 0x80008000u};
 #pragma unroll
-                for (int c = 0; c < C; ++c) acc[c] = 0;
+                        for (int q = 0; q < 4; ++q) {
+#pragma unroll
+                            for (int ch = 0; ch < C; ++ch) acc[ch] = __dp2a_lo(w4[q], p.wtab[ch][4 * c + q], acc[ch]);
+                        }
+                        unpack8u(v, c16, nc16, &xl[8 * c]);
+                    }
+                }
                 if constexpr (MODE == 0) {
                     int gi = slot * NT + tid;
                     for (uint32_t n = 0; n < p.n_full; ++n) {
                         gi = (gi == 0) ? GS * NT - 1 : gi - 1;
 #pragma unroll
-                        for (int c = 0; c < C; ++c) acc[c] += lds32i(gsum + ((uint32_t)gi * C + c) * 4u);
+                        for (int c = 0; c < C; ++c) acc[c] += (uint32_t)lds32i(gsum + ((uint32_t)gi * C + c) * 4u);
                     }
                 } else {
                     int lt = tid - (int)(p.n_full + 1u);
@@ -902,29 +938,26 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : 1))
                     if (ls < 0) ls += GS;
 #pragma unroll
                     for (int c = 0; c < C; ++c) {
-                        const int wsame = __shfl_sync(0xffffffffu, wex[c], lt >> 5);
-                        const int wold = lds32i(wexc + (((uint32_t)ls * 32u + (uint32_t)(lt >> 5)) * C + c) * 4u);
-                        const int cp_lag = lds32i(gsum + (((uint32_t)ls * NT + lt) * C + c) * 4u) + (h == 0 ? wsame : wold);
-                        const int e_own = own_off[c] + (incl[c] - gtot[c]);
+                        const uint32_t wsame = __shfl_sync(0xffffffffu, wex[c], lt >> 5);
+                        const uint32_t wold = (uint32_t)lds32i(wexc + (((uint32_t)ls * 32u + (uint32_t)(lt >> 5)) * C + c) * 4u);
+                        const uint32_t cp_lag =
+                            (uint32_t)lds32i(gsum + (((uint32_t)ls * NT + lt) * C + c) * 4u) + (h == 0 ? wsame : wold);
+                        const uint32_t e_own = own_off[c] + (incl[c] - gtot[c]);
                         if (h == 0) {
-                            acc[c] = e_own - cp_lag;
+                            acc[c] += e_own - cp_lag;
                         } else {
-                            int rest = lds32i(wexc + (((uint32_t)ls * 32u + 31u) * C + c) * 4u) - cp_lag;
+                            uint32_t rest = (uint32_t)lds32i(wexc + (((uint32_t)ls * 32u + 31u) * C + c) * 4u) - cp_lag;
                             int ms = ls;
                             for (int v2 = 1; v2 < h; ++v2) {
                                 ms = (ms + 1 == GS) ? 0 : ms + 1;
-                                rest += lds32i(wexc + (((uint32_t)ms * 32u + 31u) * C + c) * 4u);
+                                rest += (uint32_t)lds32i(wexc + (((uint32_t)ms * 32u + 31u) * C + c) * 4u);
                             }
-                            acc[c] = e_own + rest;
+                            acc[c] += e_own + rest;
                         }
                     }
                 }
-#pragma unroll
-                for (int r = 0; r < R; ++r)
-                    if ((uint32_t)r < p.m_part) acc[r % C] += xl[MIS + r];
-
                 const uint32_t ob = tr.out_tile() + (uint32_t)tid * (R * 2);
-                const uint32_t mul = p.div_mul, sh = p.div_shift;
+                const uint32_t mul = p.div_mul, sh = p.div_shift, bias_k = p.bias_k, km1 = p.k - 1u;
 #pragma unroll
                 for (int c = 0; c < CH_OWN; ++c) {
                     uint32_t wds[4];
@@ -932,10 +965,10 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : 1))
                     for (int q = 0; q < 4; ++q) {
                         const int r0 = 8 * c + 2 * q, r1 = r0 + 1;
                         acc[r0 % C] += x[r0] - xl[MIS + r0];
-                        const int y0 = div_trunc(acc[r0 % C], mul, sh);
+                        const uint32_t y0 = div_biased(acc[r0 % C], bias_k, km1, mul, sh);
                         acc[r1 % C] += x[r1] - xl[MIS + r1];
-                        const int y1 = div_trunc(acc[r1 % C], mul, sh);
-                        wds[q] = ((uint32_t)y0 & 0xffffu) | ((uint32_t)y1 << 16);
+                        const uint32_t y1 = div_biased(acc[r1 % C], bias_k, km1, mul, sh);
+                        wds[q] = pack2u(y0, y1, c16);
                     }
                     sts128u(swz(ob + 16u * c), wds[0], wds[1], wds[2], wds[3]);
                 }
