@@ -670,11 +670,21 @@ __global__ void __launch_bounds__(NT)
 #pragma unroll
                     for (int c = 0; c < C; ++c) acc[c] = 0.f;
                     if constexpr (MODE == 0) {
-                        int gi = slot * NT + tid;
-                        for (uint32_t n = 0; n < p.n_full; ++n) {
-                            gi = (gi == 0) ? GS * NT - 1 : gi - 1;
+                        // the n_full groups in front of the own one, nearest first; the summary ring wraps at
+                        // most once, so the walk is two straight runs without a per-step wrap test
+                        const int gi = slot * NT + tid;
+                        const int n1 = ((int)p.n_full < gi) ? (int)p.n_full : gi;
+                        uint32_t ga = gsum + (uint32_t)gi * (C * 4u);
+                        for (int n = 0; n < n1; ++n) {
+                            ga -= C * 4u;
 #pragma unroll
-                            for (int c = 0; c < C; ++c) acc[c] += lds32(gsum + ((uint32_t)gi * C + c) * 4u);
+                            for (int c = 0; c < C; ++c) acc[c] += lds32(ga + 4u * c);
+                        }
+                        ga = gsum + (uint32_t)(GS * NT) * (C * 4u);
+                        for (int n = n1; n < (int)p.n_full; ++n) {
+                            ga -= C * 4u;
+#pragma unroll
+                            for (int c = 0; c < C; ++c) acc[c] += lds32(ga + 4u * c);
                         }
                     } else {
                         int lt = tid - (int)(p.n_full + 1u);  // thread index of the lag group, relative to this tile
@@ -921,11 +931,19 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : 1))
                     }
                 }
                 if constexpr (MODE == 0) {
-                    int gi = slot * NT + tid;
-                    for (uint32_t n = 0; n < p.n_full; ++n) {
-                        gi = (gi == 0) ? GS * NT - 1 : gi - 1;
+                    const int gi = slot * NT + tid;
+                    const int n1 = ((int)p.n_full < gi) ? (int)p.n_full : gi;
+                    uint32_t ga = gsum + (uint32_t)gi * (C * 4u);
+                    for (int n = 0; n < n1; ++n) {
+                        ga -= C * 4u;
 #pragma unroll
-                        for (int c = 0; c < C; ++c) acc[c] += (uint32_t)lds32i(gsum + ((uint32_t)gi * C + c) * 4u);
+                        for (int c = 0; c < C; ++c) acc[c] += (uint32_t)lds32i(ga + 4u * c);
+                    }
+                    ga = gsum + (uint32_t)(GS * NT) * (C * 4u);
+                    for (int n = n1; n < (int)p.n_full; ++n) {
+                        ga -= C * 4u;
+#pragma unroll
+                        for (int c = 0; c < C; ++c) acc[c] += (uint32_t)lds32i(ga + 4u * c);
                     }
                 } else {
                     int lt = tid - (int)(p.n_full + 1u);
