@@ -60,6 +60,25 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic_bytes():
+    """DRAM bytes per launch of the dominant kernel (dram__bytes_read.sum + dram__bytes_write.sum) from the
+    committed `ncu --set full` capture of this same workload (profiles/r01/ncu_stream_full.csv, three launches:
+    k = 3, 64, 4096); None when the summary is missing.  Never measured under the profiler at bench time."""
+    p = os.path.join(ROOT, "profiles", "r01", "ncu_stream_full.csv")
+    try:
+        import csv
+        rows = {r[0]: r for r in csv.reader(open(p))}
+        scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+        total = 0.0
+        for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            r = rows[key]
+            vals = [float(v) for v in r[2:]]
+            total += scale[r[1]] * sum(vals) / len(vals)
+        return total
+    except Exception:
+        return None
+
+
 # ---------------------------------------------------------------------------- reference arm
 def cpu_reference_line(args, ks, world):
     """The reference's own CPU implementation (oracle/_ref, built from /root/reference) timed on the
@@ -374,7 +393,8 @@ def main():
         "e2e": e2e,
         "gpu_launches": launches_per_step * args.steps * world,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "frac_of_nominal_8tbs": achieved / 8000.0,
+                     "traffic": ncu_traffic_bytes(), "traffic_unit": "DRAM bytes per launch, ncu --set full, 2^28 samples "
+                     "(profiles/r01/ncu_stream_full.csv)", "peak_source": peak_src, "frac_of_nominal_8tbs": achieved / 8000.0,
                      "kernel": "mavg::stream_f32_kernel (mean over the k sweep)",
                      "algorithmic_bytes_per_launch": BYTES_PER_SAMPLE * n},
         "per_k": per_k,

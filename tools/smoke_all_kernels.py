@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Small end-to-end pass over every kernel family, meant to run under compute-sanitizer (memcheck)."""
+"""Small end-to-end pass over every kernel family, a quick correctness smoke of each path (compute-sanitizer is closed on this pool)."""
 import os, sys
 sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..")))
 import numpy as np
@@ -35,4 +35,4 @@ torch.cuda.synchronize()
 mavg.prefix_sum_device(d.data_ptr(), o.data_ptr(), "i16", 50001, 2)
 torch.cuda.synchronize()
 assert torch.equal(o, torch.cumsum(d.view(-1, 2).to(torch.int64), 0).view(-1))
-print("sanitize_small: all kernel families ok")
+print("smoke_all_kernels: all kernel families ok")
