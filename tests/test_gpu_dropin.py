@@ -100,6 +100,24 @@ def test_single_process_multi_device_plan(mavg, oracle_mod):
     xi = oracle_mod.fill_i16(3 * 30_000, 5)
     with mavg.Plan(30_000, 700, channels=3, dtype="i16", devices=devs) as plan:
         assert np.array_equal(plan.run_host(xi), oracle_mod.mavg_i16(xi, 700, 3))
+    # every frame-sharded fast path: stereo float32, stereo int16 (stream), 64-channel interleaved (column kernel)
+    xs = oracle_mod.fill_f32(2 * (20 * 4096 + 77), 8)
+    with mavg.Plan(20 * 4096 + 77, 300, channels=2, devices=devs) as plan:
+        ys2 = plan.run_host(xs)
+    with mavg.Plan(20 * 4096 + 77, 300, channels=2) as plan:
+        assert np.array_equal(plan.run_host(xs), ys2)
+    xi2 = oracle_mod.fill_i16(2 * (9 * 8192 + 33), 9)
+    with mavg.Plan(9 * 8192 + 33, 1000, channels=2, dtype="i16", devices=devs) as plan:
+        assert plan.info.path == 1
+        assert np.array_equal(plan.run_host(xi2), oracle_mod.mavg_i16(xi2, 1000, 2))
+    xc = oracle_mod.fill_f32(64 * (30 * 128 + 5), 10)
+    with mavg.Plan(30 * 128 + 5, 64, channels=64, devices=devs) as plan:
+        assert plan.info.mode == 3
+        yc2 = plan.run_host(xc)
+    with mavg.Plan(30 * 128 + 5, 64, channels=64) as plan:
+        assert np.array_equal(plan.run_host(xc), yc2)
+    e = oracle_mod.mavg_f64(xc, 64, 64)
+    assert np.max(np.abs(yc2 - e) / np.abs(e)) < 1e-5
     xp = oracle_mod.fill_f32(6 * 8192 * 3, 6)
     with mavg.Plan(8192 * 3, 64, channels=6, layout="planar", devices=devs) as plan:
         yp = plan.run_host(xp)
