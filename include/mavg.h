@@ -67,8 +67,10 @@ typedef enum mavg_layout {
 /* Kernel family.  AUTO picks STREAM whenever its preconditions hold. */
 typedef enum mavg_path {
     MAVG_PATH_AUTO = 0,
-    MAVG_PATH_STREAM = 1,  /* TMA-staged shared-memory streaming kernel (direct window
-                              sums for k <= 256, tile-rebased prefix scan above)          */
+    MAVG_PATH_STREAM = 1,  /* TMA-staged shared-memory streaming kernels: float32 mono /
+                              stereo / planar, int16 mono / stereo / planar, float32 with
+                              >= 32 interleaved channels (direct window sums for small k,
+                              tile-rebased prefix scan above)                              */
     MAVG_PATH_GENERIC = 2  /* register sliding-window kernel on global memory; any shape  */
 } mavg_path;
 
@@ -85,12 +87,12 @@ typedef enum mavg_dist {
 
 /* Optional tuning overrides; 0 = library default. */
 typedef struct mavg_tuning {
-    uint32_t threads;        /* threads per CTA of the stream kernel: 128, 256 or 512      */
+    uint32_t threads;        /* threads per CTA of the float32 stream kernel: 256 or 512   */
     uint32_t run;            /* samples per thread run: 16 or 32                           */
     uint32_t prefetch;       /* tiles in flight ahead of the one being filtered            */
     uint32_t ctas_per_sm;    /* resident CTAs per SM the grid is sized for                 */
     uint32_t chunks_per_cta; /* contiguous tile ranges each CTA walks (>=1)                */
-    uint32_t direct_max_k;   /* largest k served by direct window sums (default 256)       */
+    uint32_t direct_max_k;   /* largest k*channels served by direct group sums (default 256) */
     uint32_t reserved[2];
 } mavg_tuning;
 
