@@ -63,7 +63,7 @@ def timed(fn, stream, iters, warmup, world):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--config", required=True, choices=["4", "5p", "5i", "i16", "g3"])
+    ap.add_argument("--config", required=True, choices=["4", "5p", "5i", "i16", "g3", "s2", "scan"])
     ap.add_argument("--log2", type=int, default=32, help="total samples (log2) for configs 4/5")
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
@@ -170,6 +170,44 @@ def main():
                    gsamples_s=total / ms / 1e6, hbm_gbs_per_gpu=8 * n / ms / 1e6, max_rel_err_spot=worst,
                    path="stream" if info.path == 1 else "generic")
         plan.close()
+
+    elif args.config == "s2":  # stereo float32 through the flat streaming kernel (C = 2)
+        n_frames, C = 1 << 27, 2
+        n = n_frames * C
+        d_in, d_out = alloc(4 * n), alloc(4 * n)
+        mavg.fill_synthetic_device(d_in.value, "f32", n, 0, SEED, 0, stream.cuda_stream)
+        stream.synchronize()
+        res = {}
+        for k in (3, 16, 64, 256, 1024, 4096):
+            plan = mavg.Plan(n_frames, k, channels=C, **tune)
+            plan.set_stream(stream.cuda_stream)
+            plan.enable_timing(False)
+            ms = timed(lambda: plan.run_device([d_in.value], [d_out.value]), stream, 5, 2, world)
+            y = torch.as_tensor(_Arr(d_out.value, n), device="cuda")
+            m = 1 << 16
+            x = oracle.fill_f32(m, SEED)
+            e = oracle.mavg_f64(x, k, C)
+            err = float(np.max(np.abs(y[:m].cpu().numpy() - e) / np.abs(e)))
+            res[str(k)] = {"ms": round(ms, 4), "gsamples_s": round(n / ms / 1e6, 1), "hbm_gbs": round(8 * n / ms / 1e6, 1),
+                           "max_rel_err_head": err, "path": "stream" if plan.info.path == 1 else "generic"}
+            plan.close()
+        out.update(workload="stereo float32, 2^28 samples (2^27 frames), k sweep, device resident", per_k=res)
+
+    elif args.config == "scan":  # mavg_prefix_sum, the look-back scan primitive
+        res = {}
+        for dtype, C, esz, tstr in (("i16", 1, 2, "<i2"), ("i16", 2, 2, "<i2"), ("f32", 1, 4, "<f4")):
+            n_frames = (1 << 28) // C
+            n = n_frames * C
+            d_in, d_out = alloc(esz * n), alloc(8 * n)
+            mavg.fill_synthetic_device(d_in.value, dtype, n, 0, SEED, 0, stream.cuda_stream)
+            stream.synchronize()
+            ms = timed(lambda: mavg.prefix_sum_device(d_in.value, d_out.value, dtype, n_frames, C, stream.cuda_stream),
+                       stream, 5, 2, world)
+            res[f"{dtype}_c{C}"] = {"ms": round(ms, 4), "gsamples_s": round(n / ms / 1e6, 1),
+                                    "hbm_gbs": round((esz + 8) * n / ms / 1e6, 1)}
+            lib.mavg_device_free(d_in)
+            lib.mavg_device_free(d_out)
+        out.update(workload="mavg_prefix_sum on 2^28 samples (bytes = input + 8-byte output per sample)", per_k=res)
 
     elif args.config == "g3":  # shapes only the generic kernel takes: 3-channel interleaved float32
         n_frames, C = 1 << 25, 3
