@@ -41,8 +41,9 @@ def _stale(target: str, sources: list[str]) -> bool:
 
 
 def lib_sources() -> list[str]:
-    return [os.path.join(CSRC, "mavg.cu"), os.path.join(CSRC, "mavg_kernels.cuh"),
-            os.path.join(ROOT, "include", "mavg.h")]
+    """mavg.cu first (the translation unit), then every header it includes."""
+    headers = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h")))
+    return [os.path.join(CSRC, "mavg.cu")] + headers + [os.path.join(ROOT, "include", "mavg.h")]
 
 
 def build_lib(force: bool = False, verbose: bool = False) -> str:

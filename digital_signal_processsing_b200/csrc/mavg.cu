@@ -702,15 +702,43 @@ int gather_timing(mavg_plan* p)
 }  // namespace
 
 namespace {
-template <typename TIn, typename TAcc>
+template <typename TIn, typename TLoc, typename TAcc, int C>
+int launch_scan_c(const TIn* in, TAcc* out, uint64_t n, cudaStream_t st, uint32_t* ticket, uint32_t* status, TAcc* aggr,
+                  TAcc* pref, unsigned grid)
+{
+    auto kern = mavg::scan_lookback_kernel<TIn, TLoc, TAcc, C>;
+    const uint32_t smem = mavg::scan_smem_bytes<TLoc, C>();
+    MAVG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, 256, smem, st>>>(in, out, n, ticket, status, aggr, pref);
+    return MAVG_OK;
+}
+
+template <typename TIn, typename TLoc, typename TAcc>
 int launch_scan(const void* d_in, void* d_out, uint64_t n, uint32_t C, cudaStream_t st)
 {
-    const uint64_t tiles = (n + 4095) / 4096;
+    const uint64_t chunk = mavg::kScanChunkBytes / sizeof(TLoc);
+    const uint64_t tiles = (n + chunk - 1) / chunk;
     if (tiles > 0x7fffffffull) return fail(MAVG_ERR_UNSUPPORTED, "signal too long for mavg_prefix_sum");
-    // scratch: ticket (padded), status[tiles], aggregates[tiles][C], prefixes[tiles][C]
+    // scratch: ticket (padded), status[chunks], aggregates[chunks][C], prefixes[chunks][C]
     const size_t status_off = 256, aggr_off = status_off + ((tiles * 4 + 255) / 256) * 256;
     const size_t pref_off = aggr_off + tiles * C * sizeof(TAcc);
     const size_t total = pref_off + tiles * C * sizeof(TAcc);
+    // keep freed scratch cached in the device's default pool: with the default release threshold (0) every
+    // synchronisation hands the memory back to the OS and the next call pays a millisecond-scale allocation
+    {
+        int dev = 0;
+        MAVG_CUDA(cudaGetDevice(&dev));
+        static bool pool_tuned[64] = {false};
+        if (dev >= 0 && dev < 64 && !pool_tuned[dev]) {
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+                unsigned long long keep = ~0ull;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+            cudaGetLastError();
+            pool_tuned[dev] = true;
+        }
+    }
     char* scratch = nullptr;
     MAVG_CUDA(cudaMallocAsync((void**)&scratch, total, st));
     MAVG_CUDA(cudaMemsetAsync(scratch, 0, aggr_off, st));
@@ -721,14 +749,16 @@ int launch_scan(const void* d_in, void* d_out, uint64_t n, uint32_t C, cudaStrea
     const TIn* in = (const TIn*)d_in;
     TAcc* out = (TAcc*)d_out;
     const unsigned grid = (unsigned)tiles;
+    int rc;
     switch (C) {
-    case 1: mavg::scan_lookback_kernel<TIn, TAcc, 1><<<grid, 256, 0, st>>>(in, out, n, ticket, status, aggr, pref); break;
-    case 2: mavg::scan_lookback_kernel<TIn, TAcc, 2><<<grid, 256, 0, st>>>(in, out, n, ticket, status, aggr, pref); break;
-    case 4: mavg::scan_lookback_kernel<TIn, TAcc, 4><<<grid, 256, 0, st>>>(in, out, n, ticket, status, aggr, pref); break;
-    default: mavg::scan_lookback_kernel<TIn, TAcc, 8><<<grid, 256, 0, st>>>(in, out, n, ticket, status, aggr, pref); break;
+    case 1: rc = launch_scan_c<TIn, TLoc, TAcc, 1>(in, out, n, st, ticket, status, aggr, pref, grid); break;
+    case 2: rc = launch_scan_c<TIn, TLoc, TAcc, 2>(in, out, n, st, ticket, status, aggr, pref, grid); break;
+    case 4: rc = launch_scan_c<TIn, TLoc, TAcc, 4>(in, out, n, st, ticket, status, aggr, pref, grid); break;
+    default: rc = launch_scan_c<TIn, TLoc, TAcc, 8>(in, out, n, st, ticket, status, aggr, pref, grid); break;
     }
     cudaError_t e = cudaGetLastError();
     cudaFreeAsync(scratch, st);
+    if (rc != MAVG_OK) return rc;
     if (e != cudaSuccess) return fail(MAVG_ERR_CUDA, "scan launch failed: %s", cudaGetErrorString(e));
     return MAVG_OK;
 }
@@ -1218,8 +1248,8 @@ int mavg_prefix_sum(int dtype, const void* d_in, void* d_out, uint64_t frames, u
     if (mavg_device_count() <= 0) return fail(MAVG_ERR_NO_DEVICE, "no CUDA device available: libmavg has no CPU fallback");
     const uint64_t n = frames * channels;
     cudaStream_t st = (cudaStream_t)cuda_stream;
-    if (dtype == MAVG_I16) return launch_scan<int16_t, long long>(d_in, d_out, n, channels, st);
-    return launch_scan<float, double>(d_in, d_out, n, channels, st);
+    if (dtype == MAVG_I16) return launch_scan<int16_t, int, long long>(d_in, d_out, n, channels, st);
+    return launch_scan<float, double, double>(d_in, d_out, n, channels, st);
 }
 
 int mavg_host_alloc(uint64_t bytes, void** h_ptr)
