@@ -206,7 +206,7 @@ StreamGeom plan_cols(uint32_t k, uint32_t C, const mavg_tuning& tu)
     g.R = kColsRF;
     g.C = C;
     g.mode = 3;
-    if (k < 9 || C < 32 || C % 4 != 0) return g;   // tiny windows keep the fp64 generic kernel
+    if (C < 32 || C % 4 != 0) return g;
     const uint32_t R = kColsRF;
     const uint32_t s = (R - k % R) % R;
     g.m_part = R - s;

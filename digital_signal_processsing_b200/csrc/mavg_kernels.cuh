@@ -1164,7 +1164,37 @@ __global__ void __launch_bounds__(NWT * 32)
             }
             if (H > 1 && warp == NW - 1) sts32(ttot + ((uint32_t)slot * CW + lane) * 4u, e_own + gtot);
 
-            if (is_out) {
+            if (is_out && p.k <= 8u) {
+                // Tiny windows: additions only, straight from the ring (a subtractive update could exceed 1e-5
+                // relative error where a 3-term window sum is nearly zero).  Row r of the own run needs the k-1
+                // rows above it; they sit in this tile or at the end of the previous one.
+                const int row_base = (int)((uint32_t)st * (uint32_t)FT) + warp * RF;
+                const int ring_rows = S * FT;
+                const float inv = p.inv_k;
+                const uint64_t f_base = (uint64_t)tile * FT + (uint64_t)warp * RF;
+                float* dst = out + f_base * p.channels + ch;
+                int nvalid = 0;
+                if (ch_ok && f_base < p.frames) nvalid = (p.frames - f_base < (uint64_t)RF) ? (int)(p.frames - f_base) : RF;
+                const uint32_t a0 = ring + (uint32_t)lane * 4u;
+                float prev[7];   // rows row_base-7 .. row_base-1 (oldest first)
+#pragma unroll
+                for (int j = 0; j < 7; ++j) {
+                    int rr = row_base - 7 + j;
+                    if (rr < 0) rr += ring_rows;
+                    prev[j] = lds32(a0 + (uint32_t)rr * ROWB);
+                }
+#pragma unroll
+                for (int r = 0; r < RF; ++r) {
+                    // window = x[r], x[r-1], ..., k terms, oldest terms added first in a fixed order
+                    float acc = 0.f;
+#pragma unroll
+                    for (int j = 7; j >= 1; --j) {
+                        if ((uint32_t)j < p.k) acc += (r - j >= 0) ? x[(r - j) < 0 ? 0 : (r - j)] : prev[7 + (r - j)];
+                    }
+                    acc += x[r];
+                    if (r < nvalid) dst[(uint32_t)r * p.channels] = acc * inv;
+                }
+            } else if (is_out) {
                 float xl[RF];
                 {
                     // 16 consecutive ring rows starting k frames above the own run; the ring wraps at most

@@ -400,14 +400,14 @@ def test_stereo_f32_shard_with_halo_bit_identical(mavg, oracle_mod, torch_cuda, 
 
 # ------------------------------------------------------------------ many-channel interleaved float32 (column kernel)
 @pytest.mark.parametrize("ch", [32, 36, 64, 100, 256])
-@pytest.mark.parametrize("k", [9, 16, 17, 64, 255, 256, 700, 1024, 1500, 5])
+@pytest.mark.parametrize("k", [9, 16, 17, 64, 255, 256, 700, 1024, 1500, 5, 1, 2, 3, 8])
 def test_many_channel_interleaved_f32(mavg, oracle_mod, ch, k):
     frames = 3 * 256 + 77 if ch >= 100 else 9 * 256 + 13
     x = oracle_mod.fill_f32(frames * ch, 17000 + k + ch)
     with mavg.Plan(frames, k, channels=ch) as plan:
         y = plan.run_host(x)
         i = plan.info
-        if 9 <= k <= 1024:
+        if k <= 1024:
             assert i.path == 1 and i.mode == 3, "expected the column kernel"
         else:
             assert i.path == 2
