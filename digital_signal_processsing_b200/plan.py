@@ -142,6 +142,38 @@ def fill_synthetic_device(ptr: int, dtype: str, n: int, first_index: int, seed: 
                                                  ctypes.c_void_p(stream)))
 
 
+class PinnedArray:
+    """Page-locked host buffer (mavg_host_alloc) viewed as a NumPy array: copies to and from it run at full
+    PCIe speed and overlap with the kernels inside `Plan.run_host`.  Replaces the host half of the reference's
+    `MemoryTraits` (gpu_utils.h:33-65).  Keep the object alive while `.array` is in use."""
+
+    def __init__(self, count: int, dtype):
+        self._lib = _lib.load()
+        dt = np.dtype(dtype)
+        self._ptr = ctypes.c_void_p()
+        check(self._lib.mavg_host_alloc(max(1, count) * dt.itemsize, ctypes.byref(self._ptr)))
+        buf = (ctypes.c_uint8 * (count * dt.itemsize)).from_address(self._ptr.value)
+        self.array = np.frombuffer(buf, dtype=dt, count=count)
+
+    def close(self) -> None:
+        if self._ptr:
+            self.array = None
+            self._lib.mavg_host_free(self._ptr)
+            self._ptr = ctypes.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def prefix_sum_device(in_ptr: int, out_ptr: int, dtype: str, frames: int, channels: int = 1, stream: int = 0) -> None:
     """Per-channel inclusive prefix sum on device buffers (int16 -> int64, float32 -> float64), one pass."""
     check(_lib.load().mavg_prefix_sum(_DTYPES[dtype], ctypes.c_void_p(in_ptr), ctypes.c_void_p(out_ptr), frames,

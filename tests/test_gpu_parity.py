@@ -475,3 +475,15 @@ def test_full_size_f32_stereo_2p27_frames(mavg, oracle_mod):
         y = plan.run_host(x)
     e = oracle_mod.mavg_f64(x, 64, 2)
     assert _rel(y, e) < TOL
+
+
+def test_pinned_host_buffers(mavg, oracle_mod):
+    """run_host on page-locked buffers from the library (the drop-in binaries use the same allocator)."""
+    n, k = 3 * (1 << 22) + 7, 100
+    with mavg.PinnedArray(n, np.float32) as hin, mavg.PinnedArray(n, np.float32) as hout:
+        hin.array[:] = oracle_mod.fill_f32(n, 23000)
+        with mavg.Plan(n, k) as plan:
+            y = plan.run_host(hin.array, out=hout.array)
+            assert y is hout.array
+            assert plan.timing().total_ms > 0
+        assert _rel(hout.array, oracle_mod.mavg_f64(hin.array, k)) < TOL
