@@ -6,7 +6,7 @@
   config 5i: same, interleaved [F][C] (the reference layout), frames partitioned over N GPUs with a halo
   i16      : stereo int16 (the reference's own input format), 2^28 samples per GPU, k sweep
 
-Run with `python tools/bench_configs.py --config 4` (1 GPU) or under torch.distributed.run for N > 1.
+Run with `python tests/perf/bench_configs.py --config 4` (1 GPU) or under torch.distributed.run for N > 1.
 Every run spot-checks its output against the fp64 oracle recomputed from the generator.
 """
 import argparse
@@ -15,7 +15,7 @@ import json
 import os
 import sys
 
-ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), "..", ".."))
 sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402

@@ -3,7 +3,7 @@
 (oracle/Makefile refgpu -> oracle/_ref/gpu/), run on the B200 next to libmavg's drop-in program on the
 same stereo int16 WAV.  Reads each program's benchmark_data.csv row (Compute_ms = kernels only).
 
-  python tools/ref_gpu_yardstick.py [--log2 27] [--grades 3,64,1024] [--out gpurun_out/ref_gpu_yardstick.csv]
+  python tests/perf/ref_gpu_yardstick.py [--log2 27] [--grades 3,64,1024] [--out gpurun_out/ref_gpu_yardstick.csv]
 """
 import argparse
 import csv
@@ -13,7 +13,7 @@ import subprocess
 import sys
 import tempfile
 
-ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), "..", ".."))
 sys.path.insert(0, ROOT)
 from digital_signal_processsing_b200 import build, run_benchmarks  # noqa: E402
 

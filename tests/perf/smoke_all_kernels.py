@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Small end-to-end pass over every kernel family, a quick correctness smoke of each path (compute-sanitizer is closed on this pool)."""
 import os, sys
-sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..")))
+sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..", "..")))
 import numpy as np
 import torch
 import digital_signal_processsing_b200 as mavg

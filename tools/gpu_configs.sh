@@ -3,8 +3,8 @@
 N=${1:-1}
 mkdir -p gpurun_out
 run() {
-  if [ "$N" = "1" ]; then timeout 900 python tools/bench_configs.py "$@";
-  else timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29520 tools/bench_configs.py "$@"; fi
+  if [ "$N" = "1" ]; then timeout 900 python tests/perf/bench_configs.py "$@";
+  else timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29520 tests/perf/bench_configs.py "$@"; fi
 }
 for c in 4 5p 5i; do
   echo "== config $c N=$N"; run --config $c > gpurun_out/cfg${c}_n$N.json 2> gpurun_out/cfg${c}_n$N.err; echo "rc=$?"; cat gpurun_out/cfg${c}_n$N.json; grep -v "OMP_NUM_THREADS\|^\*\*\*\|^$" gpurun_out/cfg${c}_n$N.err | tail -5
