@@ -68,13 +68,47 @@ def make_header(num_samples: int, channels: int, dtype, sample_rate: int = 44100
                      bitsPerSample=bits, dataBytes=data_bytes)
 
 
+def _walk_chunks(f) -> WAVHeader:
+    """General RIFF walk for files that are not in the canonical 44-byte form (18/40-byte fmt chunks,
+    WAVE_FORMAT_EXTENSIBLE, `fact`/`LIST` chunks before the data -- what scipy writes for float32).  Leaves the
+    file positioned at the payload and returns a synthesised canonical header."""
+    f.seek(12)
+    fmt = None
+    while True:
+        head = f.read(8)
+        if len(head) < 8:
+            raise ValueError("no fmt/data chunk found")
+        cid, size = head[:4], struct.unpack("<I", head[4:])[0]
+        if cid == b"fmt ":
+            body = f.read(size + (size & 1))
+            if size < 16:
+                raise ValueError("truncated fmt chunk")
+            tag, ch, rate, brate, align, bits = struct.unpack("<HHIIHH", body[:16])
+            if tag == 0xFFFE and size >= 26:
+                tag = struct.unpack("<H", body[24:26])[0]     # sub-format GUID starts with the format tag
+            fmt = (tag, ch, rate, brate, align, bits)
+        elif cid == b"data":
+            if fmt is None:
+                raise ValueError("data chunk before fmt chunk")
+            tag, ch, rate, brate, align, bits = fmt
+            return WAVHeader(sizeOfFile=36 + size, audioFormat=tag, numChannels=ch, sampleRate=rate, byteRate=brate,
+                             blockAlign=align, bitsPerSample=bits, dataBytes=size)
+        else:
+            f.seek(size + (size & 1), 1)
+
+
 def extract_samples(path: str) -> Tuple[WAVHeader, np.ndarray]:
-    """(header, interleaved samples).  Raises on unreadable/unsupported files."""
+    """(header, interleaved samples).  Raises on unreadable/unsupported files.  Canonical files are read as they
+    are; other RIFF/WAVE layouts are walked chunk by chunk and come back with a canonical header."""
     with open(path, "rb") as f:
         raw = f.read(HEADER_BYTES)
         if len(raw) < HEADER_BYTES:
             raise ValueError("file shorter than a canonical WAV header")
         h = WAVHeader.unpack(raw)
+        if h.riff != b"RIFF" or h.wave != b"WAVE":
+            raise ValueError("not a RIFF/WAVE file")
+        if not (h.fmt == b"fmt " and h.fmtSize == 16 and h.data == b"data"):
+            h = _walk_chunks(f)
         if h.bitsPerSample == 16:
             dtype = np.int16
         elif h.bitsPerSample == 32 and h.audioFormat == IEEE_FLOAT:

@@ -5,7 +5,8 @@
 // compiling, re-implemented for the new library:
 //   * one bulk read instead of one ifstream::read per sample;
 //   * float32 files (audioFormat 3, 32 bit) are accepted next to int16 -- the north-star extension;
-//   * RIFF/WAVE/data magic is validated and the sample count is clamped to the bytes present;
+//   * RIFF/WAVE magic is validated, non-canonical layouts (fact/LIST chunks, 18/40-byte fmt, extensible format)
+//     are walked chunk by chunk, and the sample count is clamped to the bytes present;
 //   * failures are reported through the return value, nothing is printed from library code.
 #pragma once
 
@@ -52,26 +53,67 @@ inline bool magic_ok(const WAVHeader& h)
 }
 
 // Reads header + payload.  Returns false (and leaves `bytes` empty) when the file cannot be read.
+// Canonical files (44-byte header, the only thing the reference parses) are taken as they are.  Other RIFF/WAVE
+// files -- an 18- or 40-byte fmt chunk, WAVE_FORMAT_EXTENSIBLE, `fact` / `LIST` chunks in front of the data (what
+// scipy writes for float32) -- are walked chunk by chunk and returned with a synthesised canonical header, so the
+// rest of the program (and the output file) only ever sees the 44-byte form.
 inline bool read_file(const std::string& path, WAVHeader& h, std::vector<unsigned char>& bytes, std::string* why = nullptr)
 {
     bytes.clear();
     FILE* f = fopen(path.c_str(), "rb");
     if (!f) { if (why) *why = "could not open file"; return false; }
-    bool ok = fread(&h, sizeof h, 1, f) == 1;
-    if (!ok && why) *why = "file shorter than a WAV header";
-    if (ok && !magic_ok(h)) { ok = false; if (why) *why = "not a canonical 44-byte-header WAV file"; }
-    if (ok && kind_of(h) == SampleKind::Unsupported) {
-        ok = false;
+    auto fail = [&](const char* msg) { if (why) *why = msg; fclose(f); return false; };
+    if (fread(&h, sizeof h, 1, f) != 1) return fail("file shorter than a WAV header");
+    if (memcmp(h.riff, "RIFF", 4) || memcmp(h.wave, "WAVE", 4)) return fail("not a RIFF/WAVE file");
+    uint64_t data_bytes = 0;
+    if (magic_ok(h) && h.fmtSize == 16) {
+        data_bytes = h.dataBytes;                              // canonical: payload follows directly
+    } else {
+        // general RIFF walk from the first chunk (offset 12)
+        if (fseek(f, 12, SEEK_SET) != 0) return fail("seek failed");
+        bool have_fmt = false, have_data = false;
+        uint16_t tag = 0, channels = 0, bits = 0, align = 0;
+        uint32_t rate = 0, brate = 0;
+        for (;;) {
+            char id[4];
+            uint32_t size = 0;
+            if (fread(id, 4, 1, f) != 1 || fread(&size, 4, 1, f) != 1) break;
+            if (!memcmp(id, "fmt ", 4)) {
+                unsigned char buf[40] = {0};
+                const uint32_t take = size < 40 ? size : 40;
+                if (size < 16 || fread(buf, 1, take, f) != take) return fail("truncated fmt chunk");
+                memcpy(&tag, buf, 2); memcpy(&channels, buf + 2, 2); memcpy(&rate, buf + 4, 4);
+                memcpy(&brate, buf + 8, 4); memcpy(&align, buf + 12, 2); memcpy(&bits, buf + 14, 2);
+                if (tag == 0xFFFE && take >= 26) memcpy(&tag, buf + 24, 2);   // extensible: sub-format GUID starts with the tag
+                have_fmt = true;
+                if (fseek(f, (long)(size - take) + (size & 1), SEEK_CUR) != 0) break;
+            } else if (!memcmp(id, "data", 4)) {
+                data_bytes = size;
+                have_data = true;
+                break;                                           // payload starts here
+            } else if (fseek(f, (long)size + (size & 1), SEEK_CUR) != 0) {
+                break;
+            }
+        }
+        if (!have_fmt || !have_data) return fail("no fmt/data chunk found");
+        memcpy(h.fmt, "fmt ", 4); memcpy(h.data, "data", 4);
+        h.fmtSize = 16; h.audioFormat = tag; h.numChannels = channels; h.sampleRate = rate; h.byteRate = brate;
+        h.blockAlign = align; h.bitsPerSample = bits;
+        h.dataBytes = (uint32_t)data_bytes;
+        h.sizeOfFile = 36 + h.dataBytes;
+    }
+    if (kind_of(h) == SampleKind::Unsupported) {
         if (why) *why = "unsupported bits per sample: " + std::to_string(h.bitsPerSample);
+        fclose(f);
+        return false;
     }
-    if (ok) {
-        bytes.resize(h.dataBytes);
-        const size_t got = h.dataBytes ? fread(bytes.data(), 1, h.dataBytes, f) : 0;
-        const size_t step = h.bitsPerSample / 8;
-        bytes.resize(got / step * step);  // clamp to whole samples actually present
-    }
+    bytes.resize(data_bytes);
+    const size_t got = data_bytes ? fread(bytes.data(), 1, data_bytes, f) : 0;
+    const size_t step = h.bitsPerSample / 8;
+    bytes.resize(got / step * step);  // clamp to whole samples actually present
+    if (bytes.size() != data_bytes) { h.dataBytes = (uint32_t)bytes.size(); h.sizeOfFile = 36 + h.dataBytes; }
     fclose(f);
-    return ok;
+    return true;
 }
 
 template <typename T>

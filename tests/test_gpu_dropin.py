@@ -60,6 +60,24 @@ def test_float32_mono_wav(averager, mavg, oracle_mod, tmp_path):
     assert np.max(np.abs(y - e) / np.abs(e)) < 1e-5
 
 
+def test_scipy_float32_stereo_wav(averager, mavg, oracle_mod, tmp_path):
+    """A float32 WAV as scipy writes it (18-byte fmt + fact chunk: 58-byte header) goes straight through the
+    drop-in program; the output file carries a canonical 44-byte header."""
+    sciwav = pytest.importorskip("scipy.io.wavfile")
+    from digital_signal_processsing_b200 import wav
+    frames, k = 70_001, 64
+    x = oracle_mod.fill_f32(2 * frames, 4242)
+    src, out = tmp_path / "sci.wav", tmp_path / "out.wav"
+    sciwav.write(str(src), 44100, x.reshape(-1, 2))
+    r = _run(averager, "bin_vec2", src, k, 64, "--out", out, "--rounds", 2, "--warmup", 1, cwd=tmp_path)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "channels: 2" in r.stdout and "TMA stream" in r.stdout
+    h, y = wav.extract_samples(str(out))
+    assert (h.fmtSize, h.audioFormat, h.numChannels, h.bitsPerSample) == (16, 3, 2, 32)
+    e = oracle_mod.mavg_f64(x, k, 2)
+    assert np.max(np.abs(y - e) / np.abs(e)) < 1e-5
+
+
 def test_exit_codes(averager, tmp_path):
     assert _run(averager, "bin_vec4", cwd=tmp_path).returncode == 1                       # usage
     r = _run(averager, "bin_vec4", "x.wav", 5, 100, cwd=tmp_path)

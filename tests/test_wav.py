@@ -45,3 +45,81 @@ def test_rejects_unsupported(tmp_path):
         wav.extract_samples(str(p))
     with pytest.raises(ValueError):
         wav.make_header(2**31, 1, np.float32)   # dataBytes is a uint32
+
+
+def test_non_canonical_layouts(tmp_path):
+    """scipy writes float32 with an 18-byte fmt chunk and a `fact` chunk (58-byte header); other tools put a LIST
+    chunk in front of the data or use WAVE_FORMAT_EXTENSIBLE.  The reference's 44-byte struct mis-parses all of
+    them; the new reader walks the chunks and hands back a canonical header."""
+    sciwav = pytest.importorskip("scipy.io.wavfile")
+    x = (np.arange(600, dtype=np.float32) / 600.0).reshape(-1, 2)
+    p = str(tmp_path / "f32.wav")
+    sciwav.write(p, 48000, x)
+    h, y = wav.extract_samples(p)
+    assert (h.audioFormat, h.numChannels, h.bitsPerSample, h.sampleRate) == (3, 2, 32, 48000)
+    assert h.fmtSize == 16 and h.dataBytes == x.size * 4 and np.array_equal(y, x.reshape(-1))
+    # hand-made: 16-byte fmt, a LIST chunk of odd size (padded), then data
+    import struct
+    s = np.arange(-50, 50, dtype=np.int16)
+    fmt = struct.pack("<HHIIHH", 1, 1, 8000, 16000, 2, 16)
+    lst = b"INFOabcde"                                  # 9 bytes -> one pad byte
+    body = b"WAVE" + b"fmt " + struct.pack("<I", 16) + fmt + b"LIST" + struct.pack("<I", len(lst)) + lst + b"\0" \
+        + b"data" + struct.pack("<I", s.nbytes) + s.tobytes()
+    q = tmp_path / "list.wav"
+    q.write_bytes(b"RIFF" + struct.pack("<I", len(body)) + body)
+    h, y = wav.extract_samples(str(q))
+    assert h.numChannels == 1 and h.bitsPerSample == 16 and np.array_equal(y, s)
+    # WAVE_FORMAT_EXTENSIBLE float32
+    ext = struct.pack("<HHIIHH", 0xFFFE, 2, 44100, 44100 * 8, 8, 32) + struct.pack("<HHI", 22, 32, 3) \
+        + struct.pack("<H", 3) + bytes(14)
+    z = np.linspace(-1, 1, 64, dtype=np.float32)
+    body = b"WAVE" + b"fmt " + struct.pack("<I", len(ext)) + ext + b"data" + struct.pack("<I", z.nbytes) + z.tobytes()
+    r = tmp_path / "ext.wav"
+    r.write_bytes(b"RIFF" + struct.pack("<I", len(body)) + body)
+    h, y = wav.extract_samples(str(r))
+    assert h.audioFormat == 3 and h.numChannels == 2 and np.array_equal(y, z)
+
+
+def test_cpp_reader_matches_python_reader(tmp_path):
+    """host/mavg_wav.h (the reader of the drop-in binaries) parses the same files the same way -- checked on the
+    CPU with a tiny harness that needs neither libmavg nor a GPU."""
+    import os
+    import subprocess
+    sciwav = pytest.importorskip("scipy.io.wavfile")
+    root = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+    src = tmp_path / "wavdump.cpp"
+    src.write_text('''
+#include "mavg_wav.h"
+int main(int argc, char** argv) {
+    WAVHeader h{}; std::vector<unsigned char> b; std::string why;
+    if (!mavg_wav::read_file(argv[1], h, b, &why)) { printf("ERR %s\\n", why.c_str()); return 2; }
+    unsigned long long sum = 0; for (unsigned char c : b) sum = sum * 131 + c;
+    printf("%u %u %u %u %zu %llu\\n", h.audioFormat, h.numChannels, h.bitsPerSample, h.sampleRate, b.size(), sum);
+    return 0;
+}''')
+    exe = tmp_path / "wavdump"
+    subprocess.run(["g++", "-O1", "-std=c++17", "-I", os.path.join(root, "host"), str(src), "-o", str(exe)], check=True)
+
+    def digest(raw: bytes) -> int:
+        s = 0
+        for c in raw:
+            s = (s * 131 + c) % (1 << 64)
+        return s
+
+    files = []
+    a = tmp_path / "canon.wav"
+    xi = np.arange(-300, 300, dtype=np.int16)
+    wav.write_samples(str(a), wav.make_header(xi.size, 2, np.int16), xi)
+    files.append(a)
+    b = tmp_path / "scipy_f32.wav"
+    sciwav.write(str(b), 22050, (np.arange(500, dtype=np.float32) / 7).reshape(-1, 1))
+    files.append(b)
+    for f in files:
+        h, y = wav.extract_samples(str(f))
+        out = subprocess.run([str(exe), str(f)], capture_output=True, text=True, check=True).stdout.split()
+        assert [int(v) for v in out[:5]] == [h.audioFormat, h.numChannels, h.bitsPerSample, h.sampleRate, y.nbytes]
+        assert int(out[5]) == digest(y.tobytes())
+    bad = tmp_path / "bad.wav"
+    bad.write_bytes(b"RIFFxxxxWAVEjunk" + bytes(64))
+    r = subprocess.run([str(exe), str(bad)], capture_output=True, text=True)
+    assert r.returncode == 2 and "ERR" in r.stdout
