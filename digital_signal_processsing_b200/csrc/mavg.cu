@@ -74,7 +74,7 @@ int get_encoder(EncodeTiledFn* out)
 // One signal batch as a [signals][rows][128 bytes] tensor (32 floats or 64 int16 per row), boxes of
 // [1][tile_rows][row], 128B swizzle.
 int make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t signals, uint64_t signal_stride_bytes,
-             uint32_t tile_rows, uint32_t elem_bytes)
+             uint32_t tile_rows, uint32_t elem_bytes, bool swizzle = true)
 {
     EncodeTiledFn enc;
     MAVG_TRY(get_encoder(&enc));
@@ -85,8 +85,8 @@ int make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t signals
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(map, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT16, 3,
                      const_cast<void*>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
         return fail(MAVG_ERR_DRIVER, "cuTensorMapEncodeTiled failed (%d) rows=%llu signals=%llu stride=%llu", (int)r,
                     (unsigned long long)rows, (unsigned long long)signals, (unsigned long long)signal_stride_bytes);
@@ -109,6 +109,7 @@ struct StreamGeom {
     uint32_t C = 1;           // channels interleaved inside one kernel signal (int16 stereo: 2)
     uint32_t div_mul = 0, div_shift = 0;
     int cww = 1;              // column kernel: 32-channel column-warps side by side in one tile
+    int runs = 0;             // few-channel kernel: 16-frame runs per tile
 };
 
 constexpr uint32_t kMaxSmem = 232448;  // 227 KB opt-in limit per CTA on sm_100
@@ -229,6 +230,39 @@ StreamGeom plan_cols(uint32_t k, uint32_t C, const mavg_tuning& tu)
         }
         if (fits) { g.ok = true; return g; }
     }
+    return g;
+}
+
+// 3..31 interleaved float32 channels, k <= 256: thread = (16-frame run, channel), flat TMA tiles
+StreamGeom plan_fewc(uint32_t k, uint32_t C, const mavg_tuning& tu)
+{
+    StreamGeom g;
+    g.NT = 512;
+    g.R = 16;
+    g.C = C;
+    g.mode = 4;
+    if (C < 3 || C > 31 || k > 256) return g;
+    const uint32_t R = 16;
+    const uint32_t s = (R - k % R) % R;
+    g.m_part = R - s;
+    g.n_full = (k + s) / R - 1;
+    uint32_t NR = 512 / C;
+    while (NR > 0 && (NR * C) % 16 != 0) --NR;       // tile = whole 1024-byte swizzle atoms
+    if (NR == 0) return g;
+    if (g.n_full + 1 > NR) return g;                 // the window must fit in this tile plus the previous one
+    g.runs = (int)NR;
+    g.H = 1;
+    g.ctas_per_sm = 1;
+    g.P = tu.prefetch ? (int)tu.prefetch : 2;
+    const uint32_t tile_bytes = NR * C * R * 4;
+    for (;;) {
+        g.S = g.H + 1 + g.P;
+        g.smem = mavg::fewc_smem_bytes(tile_bytes, g.S, g.H, NR * C);
+        if (g.smem <= kMaxSmem) break;
+        if (g.P > 1) { --g.P; continue; }
+        return g;
+    }
+    g.ok = true;
     return g;
 }
 
@@ -359,6 +393,7 @@ bool planar_batch(const mavg_plan* p) { return p->desc.layout == MAVG_PLANAR && 
 uint64_t tile_frames(const mavg_plan* p)
 {
     if (p->geom.mode == 3) return (uint64_t)(kColsNW / p->geom.cww) * kColsRF;
+    if (p->geom.mode == 4) return (uint64_t)p->geom.runs * 16;
     return (uint64_t)p->geom.NT * p->geom.R / p->geom.C;
 }
 bool frame_sharded(const mavg_plan* p) { return !planar_batch(p); }
@@ -573,6 +608,54 @@ int launch_cols(mavg_plan* p, DevCtx& d, const void* in, void* out, const void* 
     return MAVG_OK;
 }
 
+// 3..31 interleaved float32 channels through the few-channel kernel
+int launch_fewc(mavg_plan* p, DevCtx& d, const void* in, void* out, const void* halo, uint64_t frames,
+                uint32_t* launches)
+{
+    const StreamGeom& g = p->geom;
+    const uint32_t C = p->desc.channels;
+    const uint64_t n = frames * C;                       // flat samples
+    const uint64_t rows = n / 32;
+    const uint64_t tile_floats = (uint64_t)g.runs * C * 16;
+    const uint32_t tile_rows = (uint32_t)(tile_floats / 32);
+    CUtensorMap in_map, out_map, halo_map;
+    MAVG_TRY(make_map(&in_map, in, rows, 1, rows * 128, tile_rows, 4));
+    MAVG_TRY(make_map(&out_map, out, rows, 1, rows * 128, tile_rows, 4));
+    if (halo) MAVG_TRY(make_map(&halo_map, halo, (uint64_t)g.H * tile_rows, 1, (uint64_t)g.H * tile_rows * 128, tile_rows, 4));
+    else halo_map = in_map;
+    mavg::FewcParams fp;
+    memset(&fp, 0, sizeof fp);
+    mavg::StreamParams& sp = fp.sp;
+    sp.inv_k = 1.0f / (float)p->desc.window;
+    sp.k = p->desc.window;
+    sp.n_full = g.n_full;
+    sp.m_part = g.m_part;
+    const uint64_t tiles = (rows * 32 + tile_floats - 1) / tile_floats;
+    sp.tiles_per_signal = (int32_t)tiles;
+    const uint64_t ctas = (uint64_t)d.sm_count;
+    uint64_t cps = std::min<uint64_t>(tiles, ctas * std::max<uint32_t>(1u, p->desc.tuning.chunks_per_cta));
+    uint64_t chunk_tiles = (tiles + cps - 1) / cps;
+    cps = (tiles + chunk_tiles - 1) / chunk_tiles;
+    sp.chunk_tiles = (int32_t)chunk_tiles;
+    sp.chunks_per_signal = (int32_t)cps;
+    sp.total_chunks = (int32_t)cps;
+    sp.hist_tiles = g.H;
+    sp.stages = g.S;
+    sp.prefetch = g.P;
+    sp.has_halo = halo ? 1 : 0;
+    fp.channels = C;
+    fp.runs = (uint32_t)g.runs;
+    auto kern = mavg::stream_fewc_f32_kernel<16>;
+    MAVG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+    const unsigned grid = (unsigned)std::min<uint64_t>(ctas, cps);
+    kern<<<grid, 512, g.smem, d.stream>>>(in_map, out_map, halo_map, fp);
+    MAVG_CUDA(cudaGetLastError());
+    ++*launches;
+    // flat samples past the last whole 128-byte row: the frames that touch them go to the generic kernel
+    if (rows * 32 < n) MAVG_TRY(launch_generic(p, d, in, out, halo, frames, rows * 32 / C, frames, launches));
+    return MAVG_OK;
+}
+
 // Enqueue the kernels for `frames` frames (a whole shard, or one slice of it whose left context
 // is `halo`) on the device stream.  Planar batches always run whole (frames = desc.frames).
 int launch_shard(mavg_plan* p, DevCtx& d, const void* in, void* out, const void* halo, uint64_t frames,
@@ -581,6 +664,12 @@ int launch_shard(mavg_plan* p, DevCtx& d, const void* in, void* out, const void*
     MAVG_CUDA(cudaSetDevice(d.device));
     if (planar_batch(p)) frames = p->desc.frames;
     if (frames == 0 || (planar_batch(p) && d.channels == 0)) return MAVG_OK;
+    if (p->path == MAVG_PATH_STREAM && p->geom.ok && p->geom.mode == 4) {
+        const uint64_t nflat = frames * p->desc.channels;
+        if ((((uintptr_t)in | (uintptr_t)out | (uintptr_t)halo) & 15u) == 0 && nflat >= 32 && nflat / 32 < (1ull << 31) - 65536)
+            return launch_fewc(p, d, in, out, halo, frames, launches);
+        return launch_generic(p, d, in, out, halo, frames, 0, frames, launches);
+    }
     if (p->path == MAVG_PATH_STREAM && p->geom.ok && p->geom.mode == 3) {
         if ((((uintptr_t)in | (uintptr_t)out | (uintptr_t)halo) & 15u) == 0 && frames < (1ull << 31))
             return launch_cols(p, d, in, out, halo, frames, launches);
@@ -820,6 +909,9 @@ int mavg_plan_create(const mavg_desc* desc, mavg_plan** out)
         p->geom = plan_stream(desc->window, desc->tuning, planar ? 1u : desc->channels);
         if (!planar && desc->channels >= 32) {
             p->geom = plan_cols(desc->window, desc->channels, desc->tuning);
+            stream_shape = p->geom.ok;
+        } else if (!planar && desc->channels >= 3) {
+            p->geom = plan_fewc(desc->window, desc->channels, desc->tuning);
             stream_shape = p->geom.ok;
         }
     } else {

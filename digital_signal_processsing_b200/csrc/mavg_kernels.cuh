@@ -339,8 +339,14 @@ __host__ __device__ inline uint32_t stream_smem_bytes(int NT, int R, int S, int 
 //     __syncthreads) and whose reuse waits on cp.async.bulk.wait_group.read.
 // Shared-memory carve-up: [ring S*TB][staging 2*TB][kernel-specific summaries ...][S mbarriers].
 // ----------------------------------------------------------------------------------
-template <uint32_t TB, int ROWS>
+// TB_ / ROWS_ = tile bytes / 128-byte rows per tile as compile-time constants, or 0 for run-time values passed to
+// setup() (the few-channel kernel's tile depends on the channel count).
+template <uint32_t TB_, int ROWS_>
 struct TileRing {
+    uint32_t tb_rt;
+    int rows_rt;
+    __device__ __forceinline__ uint32_t tbv() const { return TB_ ? TB_ : tb_rt; }
+    __device__ __forceinline__ int rowsv() const { return ROWS_ ? ROWS_ : rows_rt; }
     uint32_t ring, ring_bytes, outb, bars;
     int S, H, P, GS;
     uint32_t it;       // tiles streamed so far by this CTA (history + output), never reset
@@ -356,16 +362,19 @@ struct TileRing {
 
     // returns the first shared address after the staging tiles (where the kernel puts its summaries)
     __device__ __forceinline__ uint32_t setup(uint32_t smem_base, const StreamParams& p, const CUtensorMap* in,
-                                              const CUtensorMap* out, const CUtensorMap* halo)
+                                              const CUtensorMap* out, const CUtensorMap* halo, uint32_t tb_runtime = 0,
+                                              int rows_runtime = 0)
     {
+        tb_rt = tb_runtime;
+        rows_rt = rows_runtime;
         ring = (smem_base + 1023u) & ~1023u;
         S = p.stages; H = p.hist_tiles; P = p.prefetch; GS = H + 2;
-        ring_bytes = (uint32_t)S * TB;
+        ring_bytes = (uint32_t)S * tbv();
         outb = ring + ring_bytes;
         it = 0; st = 0; slot = 0; otiles = 0;
         st_pending = st_inflight = false; st_tile = st_sig = 0; st_buf = 0;
         in_map = in; out_map = out; halo_map = halo; has_halo = p.has_halo != 0;
-        return outb + 2u * TB;
+        return outb + 2u * tbv();
     }
     __device__ __forceinline__ void init_barriers(uint32_t bars_addr)
     {
@@ -384,11 +393,11 @@ struct TileRing {
     __device__ __forceinline__ void issue_load(int tile, int sig, int stage) const
     {
         const uint32_t bar = bars + 8u * stage;
-        mbar_arrive_expect_tx(bar, TB);
+        mbar_arrive_expect_tx(bar, tbv());
         if (tile < 0 && has_halo)
-            tma_load_3d(ring + (uint32_t)stage * TB, halo_map, bar, 0, (tile + H) * ROWS, 0, kEvictFirst);
+            tma_load_3d(ring + (uint32_t)stage * tbv(), halo_map, bar, 0, (tile + H) * rowsv(), 0, kEvictFirst);
         else
-            tma_load_3d(ring + (uint32_t)stage * TB, in_map, bar, 0, tile * ROWS, sig, kEvictFirst);
+            tma_load_3d(ring + (uint32_t)stage * tbv(), in_map, bar, 0, tile * rowsv(), sig, kEvictFirst);
     }
     __device__ __forceinline__ void prologue(int first, int ntl, int sig) const
     {
@@ -404,7 +413,7 @@ struct TileRing {
     __device__ __forceinline__ uint32_t wait_tile() const
     {
         mbar_wait(bars + 8u * st, (it / (uint32_t)S) & 1u);
-        return ring + (uint32_t)st * TB;
+        return ring + (uint32_t)st * tbv();
     }
     __device__ __forceinline__ void before_sync()
     {
@@ -429,13 +438,13 @@ struct TileRing {
     __device__ __forceinline__ void flush_store()
     {
         if (st_pending) {
-            tma_store_3d(out_map, st_buf, 0, st_tile * ROWS, st_sig);
+            tma_store_3d(out_map, st_buf, 0, st_tile * rowsv(), st_sig);
             tma_commit();
             st_pending = false;
             st_inflight = true;
         }
     }
-    __device__ __forceinline__ uint32_t out_tile() const { return outb + (otiles & 1u) * TB; }
+    __device__ __forceinline__ uint32_t out_tile() const { return outb + (otiles & 1u) * tbv(); }
     // all threads, after writing their part of the staging tile
     __device__ __forceinline__ void staged(int tile, int sig)
     {
@@ -467,7 +476,7 @@ struct TileRing {
     // shared address of byte offset `off` relative to the current tile (negative = history tiles)
     __device__ __forceinline__ uint32_t rel(int off) const
     {
-        int o = (int)((uint32_t)st * TB) + off;
+        int o = (int)((uint32_t)st * tbv()) + off;
         if (o < 0) o += (int)ring_bytes;
         return ring + (uint32_t)o;
     }
@@ -1265,6 +1274,133 @@ __global__ void __launch_bounds__(NWT * 32)
         }
         __syncthreads();   // ring stages may be refilled by the next chunk's prologue
     }
+}
+
+// ----------------------------------------------------------------------------------
+// Few-channel kernel -- interleaved float32 with 3..32 channels (5.1 / 7.1 audio, ...), windows up to 256 frames.
+// Flat TMA tiles of the interleaved stream exactly like the mono kernel (TileRing, TMA store), but the work is
+// split the way the column kernel does it: thread = (run of RF frames, channel), neighbouring threads take
+// neighbouring channels of the same run.  NR = floor(512 / C) runs per tile, rounded down so that NR * C is a
+// multiple of 16 (tile = whole 1024-byte swizzle atoms), tile = NR * RF frames.  Tiles use SWIZZLE_128B: with a
+// dense layout the runs of one warp start 16*C words apart and collide on one or two banks (5-way conflicts for
+// C = 3 or 6); the XOR with the 128-byte row index spreads them.  Window start sum = direct additions of the <= 16 preceding
+// run totals of the same channel (this tile or the previous one) + head of the lag run; k <= 8 takes the
+// additions-only path.  8 B/sample.
+// ----------------------------------------------------------------------------------
+struct FewcParams {
+    StreamParams sp;       // ring geometry, k, inv_k, n_full, m_part (in frames)
+    uint32_t channels;
+    uint32_t runs;         // NR
+};
+
+__host__ __device__ inline uint32_t fewc_smem_bytes(uint32_t tile_bytes, int S, int H, uint32_t active_threads)
+{
+    return 1024u + (uint32_t)S * tile_bytes + 2u * tile_bytes + (uint32_t)(H + 2) * active_threads * 4 + (uint32_t)S * 8 + 64;
+}
+
+template <int RF>
+__global__ void __launch_bounds__(512)
+    stream_fewc_f32_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map,
+                           const __grid_constant__ CUtensorMap halo_map, const FewcParams fp)
+{
+    const StreamParams& p = fp.sp;
+    const uint32_t C = fp.channels;
+    const int NR = (int)fp.runs;
+    const uint32_t NRC = (uint32_t)NR * C;                 // active threads
+    const uint32_t tile_bytes = NRC * RF * 4u;
+    extern __shared__ uint8_t smem_raw[];
+    const int tid = threadIdx.x;
+    const bool active = (uint32_t)tid < NRC;
+    const int run = active ? (int)((uint32_t)tid / C) : 0;
+    const uint32_t c = active ? (uint32_t)tid - (uint32_t)run * C : 0u;
+
+    TileRing<0, 0> tr;
+    const uint32_t gsum = tr.setup(smem_u32(smem_raw), p, &in_map, &out_map, &halo_map, tile_bytes, (int)(tile_bytes / 128u));
+    const int H = p.hist_tiles, GS = p.hist_tiles + 2;      // float [GS][NRC] run totals
+    tr.init_barriers((gsum + (uint32_t)GS * NRC * 4u + 7u) & ~7u);
+    const uint32_t row_stride = C * 4u;                     // bytes between consecutive frames of one channel
+
+    for (int chunk = blockIdx.x; chunk < p.total_chunks; chunk += gridDim.x) {
+        int sig, t0, t1;
+        if (!chunk_range(p, chunk, sig, t0, t1)) continue;
+        const int first = t0 - H;
+        const int ntl = t1 - first;
+        tr.prologue(first, ntl, sig);
+
+        for (int j = 0; j < ntl; ++j) {
+            const int tile = first + j;
+            const bool is_out = (j >= H);
+            const uint32_t cur = tr.wait_tile();
+            const int slot = tr.slot;
+
+            float x[RF];
+            const uint32_t own = ((uint32_t)run * RF * C + c) * 4u;     // byte offset of the run's first sample in the tile
+#pragma unroll
+            for (int r = 0; r < RF; ++r) x[r] = active ? lds32(swz(cur + own + (uint32_t)r * row_stride)) : 0.f;
+            float gtot;
+            {
+                float q[RF / 4];
+#pragma unroll
+                for (int i = 0; i < RF / 4; ++i) q[i] = (x[4 * i] + x[4 * i + 1]) + (x[4 * i + 2] + x[4 * i + 3]);
+                gtot = (q[0] + q[1]) + (q[2] + q[3]);
+            }
+            if (active) sts32(gsum + ((uint32_t)slot * NRC + tid) * 4u, gtot);
+
+            tr.before_sync();
+            __syncthreads();
+            tr.after_sync(j, ntl, first, sig);
+
+            if (is_out) {
+                const float inv = p.inv_k;
+                const uint32_t ob = tr.out_tile() + own;
+                if (active && p.k <= 8u) {
+                    // additions only: the k-1 frames above the run come from this tile or the end of the previous one
+                    float prev[7];
+#pragma unroll
+                    for (int i = 0; i < 7; ++i) prev[i] = lds32(swz(tr.rel((int)own - (7 - i) * (int)row_stride)));
+#pragma unroll
+                    for (int r = 0; r < RF; ++r) {
+                        float acc = 0.f;
+#pragma unroll
+                        for (int i = 7; i >= 1; --i) {
+                            if ((uint32_t)i < p.k) acc += (r - i >= 0) ? x[(r - i) < 0 ? 0 : (r - i)] : prev[7 + (r - i)];
+                        }
+                        acc += x[r];
+                        sts32(swz(ob + (uint32_t)r * row_stride), acc * inv);
+                    }
+                } else if (active) {
+                    float xl[RF];
+                    const int lag0 = (int)own - (int)(p.k * row_stride);      // first lag sample, relative to the tile
+#pragma unroll
+                    for (int r = 0; r < RF; ++r) xl[r] = lds32(swz(tr.rel(lag0 + r * (int)row_stride)));
+                    // run totals of the same channel between the lag run's group and the own run: D - 1 of them,
+                    // nearest first; they sit in this tile and, for the first runs, at the end of the previous one
+                    const int D = (int)p.n_full + 1;
+                    float acc = 0.f;
+                    const uint32_t g_cur = gsum + ((uint32_t)slot * NRC + c) * 4u;
+                    const int in_cur = (run < D - 1) ? run : D - 1;           // how many of them are in this tile
+                    for (int w2 = 1; w2 <= in_cur; ++w2) acc += lds32(g_cur + (uint32_t)(run - w2) * row_stride);
+                    if (in_cur < D - 1) {
+                        const int ps = (slot == 0) ? GS - 1 : slot - 1;
+                        const uint32_t g_prev = gsum + ((uint32_t)ps * NRC + c) * 4u;
+                        for (int w2 = 1; w2 <= D - 1 - in_cur; ++w2) acc += lds32(g_prev + (uint32_t)(NR - w2) * row_stride);
+                    }
+#pragma unroll
+                    for (int r = 0; r < RF; ++r)
+                        if ((uint32_t)r < p.m_part) acc += xl[r];
+#pragma unroll
+                    for (int r = 0; r < RF; ++r) {
+                        acc += x[r] - xl[r];
+                        sts32(swz(ob + (uint32_t)r * row_stride), acc * inv);
+                    }
+                }
+                tr.staged(tile, sig);
+            }
+            tr.advance();
+        }
+        tr.epilogue();
+    }
+    tr.finish();
 }
 
 }  // namespace mavg

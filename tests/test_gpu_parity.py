@@ -487,3 +487,47 @@ def test_pinned_host_buffers(mavg, oracle_mod):
             assert y is hout.array
             assert plan.timing().total_ms > 0
         assert _rel(hout.array, oracle_mod.mavg_f64(hin.array, k)) < TOL
+
+
+# ------------------------------------------------------------------ 3..31 interleaved float32 channels (few-channel kernel)
+@pytest.mark.parametrize("ch", [3, 5, 6, 7, 8, 12, 24, 31])
+@pytest.mark.parametrize("k", [1, 2, 3, 8, 9, 16, 17, 64, 100, 255, 256, 300])
+def test_few_channel_interleaved_f32(mavg, oracle_mod, ch, k):
+    frames = 3 * (512 // ch) * 16 + 41           # several tiles, ragged tail (flat length not a multiple of 32)
+    x = oracle_mod.fill_f32(frames * ch, 24000 + k + ch)
+    runs = 512 // ch
+    while runs * ch % 16:
+        runs -= 1
+    with mavg.Plan(frames, k, channels=ch) as plan:
+        y = plan.run_host(x)
+        i = plan.info
+        if k <= 256 and (k + 15) // 16 <= runs:
+            assert i.path == 1 and i.mode == 4, "expected the few-channel kernel"
+    assert _rel(y, oracle_mod.mavg_f64(x, k, ch)) < TOL
+
+
+@pytest.mark.parametrize("case", [(6, 64), (3, 5), (7, 200)])
+def test_few_channel_shard_with_halo_bit_identical(mavg, oracle_mod, torch_cuda, case):
+    torch = torch_cuda
+    ch, k = case
+    with mavg.Plan(100_000, k, channels=ch) as probe:
+        tf = int(probe.info.halo_frames)            # one history tile
+        assert probe.info.mode == 4 and tf >= k
+    frames, cut = 37 * tf + 123, 9 * tf
+    x = oracle_mod.fill_f32(frames * ch, 25000 + k)
+    dx = torch.from_numpy(x).cuda()
+    dy = torch.zeros(frames * ch, dtype=torch.float32, device="cuda")
+    dz = torch.zeros((frames - cut) * ch, dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    with mavg.Plan(frames, k, channels=ch) as plan:
+        plan.run_device([dx.data_ptr()], [dy.data_ptr()])
+        plan.synchronize()
+    with mavg.Plan(frames - cut, k, channels=ch, first_frame=cut) as plan:
+        halo = int(plan.info.halo_frames)
+        plan.run_device_halo(dx.data_ptr() + 4 * cut * ch, dz.data_ptr(), dx.data_ptr() + 4 * (cut - halo) * ch)
+        plan.synchronize()
+    whole = dy.cpu().numpy()
+    tail_frames = ((frames - cut) * ch // 32) * 32 // ch      # frames produced by the streaming kernel in the shard run
+    assert np.array_equal(dz.cpu().numpy()[:tail_frames * ch], whole[cut * ch:(cut + tail_frames) * ch])
+    assert _rel(dz.cpu().numpy(), oracle_mod.mavg_f64(x, k, ch)[cut * ch:]) < TOL
+    assert _rel(whole, oracle_mod.mavg_f64(x, k, ch)) < TOL
