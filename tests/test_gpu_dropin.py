@@ -78,6 +78,20 @@ def test_scipy_float32_stereo_wav(averager, mavg, oracle_mod, tmp_path):
     assert np.max(np.abs(y - e) / np.abs(e)) < 1e-5
 
 
+def test_six_channel_float32_wav(averager, mavg, oracle_mod, tmp_path):
+    from digital_signal_processsing_b200 import wav
+    frames, k = 40_000, 33
+    x = oracle_mod.fill_f32(6 * frames, 777)
+    src, out = tmp_path / "six.wav", tmp_path / "six_out.wav"
+    wav.write_samples(str(src), wav.make_header(x.size, 6, np.float32), x)
+    r = _run(averager, "averager", src, k, 256, "--out", out, "--rounds", 2, "--warmup", 1, cwd=tmp_path)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "channels: 6" in r.stdout and "TMA stream" in r.stdout
+    _, y = wav.extract_samples(str(out))
+    e = oracle_mod.mavg_f64(x, k, 6)
+    assert np.max(np.abs(y - e) / np.abs(e)) < 1e-5
+
+
 def test_exit_codes(averager, tmp_path):
     assert _run(averager, "bin_vec4", cwd=tmp_path).returncode == 1                       # usage
     r = _run(averager, "bin_vec4", "x.wav", 5, 100, cwd=tmp_path)
@@ -136,6 +150,12 @@ def test_single_process_multi_device_plan(mavg, oracle_mod):
         assert np.array_equal(plan.run_host(xc), yc2)
     e = oracle_mod.mavg_f64(xc, 64, 64)
     assert np.max(np.abs(yc2 - e) / np.abs(e)) < 1e-5
+    x6 = oracle_mod.fill_f32(6 * (50 * 1280 + 17), 12)        # 5.1 audio: six interleaved channels (few-channel kernel)
+    with mavg.Plan(50 * 1280 + 17, 100, channels=6, devices=devs) as plan:
+        assert plan.info.mode == 4
+        y6 = plan.run_host(x6)
+    e6 = oracle_mod.mavg_f64(x6, 100, 6)
+    assert np.max(np.abs(y6 - e6) / np.abs(e6)) < 1e-5
     xp = oracle_mod.fill_f32(6 * 8192 * 3, 6)
     with mavg.Plan(8192 * 3, 64, channels=6, layout="planar", devices=devs) as plan:
         yp = plan.run_host(xp)
