@@ -107,7 +107,7 @@ struct StreamGeom {
     uint32_t n_full = 0, m_part = 0, lag_chunks = 0;
     uint32_t elem = 4;        // bytes per sample
     uint32_t C = 1;           // channels interleaved inside one kernel signal (int16 stereo: 2)
-    uint32_t div_mul = 0, div_shift = 0;
+    uint32_t div_mul = 0, div_shift = 0, wscale = 1;
     int cww = 1;              // column kernel: 32-channel column-warps side by side in one tile
     int runs = 0;             // few-channel kernel: 16-frame runs per tile
 };
@@ -122,10 +122,13 @@ StreamGeom plan_stream_i16(uint32_t k, uint32_t C, const mavg_tuning& tu)
     g.R = 32;    // 16-sample runs with two CTAs per SM were measured 10-20 % slower (per-run overheads dominate)
     g.elem = 2;
     g.C = C;
-    // Biased window sums w' = w + 32768 k <= 65535 k must stay below 2^32 and the 32-bit magic division must be
-    // exact for every dividend u < k * 2^16: with L = ceil(log2 k), M = ceil(2^(31+L) / k), e = M k - 2^(31+L) < k,
-    // floor(u M / 2^(31+L)) = floor(u / k) needs u e < 2^(31+L), i.e. 2^(2L+16) <= 2^(31+L), i.e. k <= 32768.
-    // k == 1 (identity) and longer windows are left to the generic kernel.
+    // Window sums |w| <= 32768 k fit int32 for k <= 32768, and C's truncating w / k is computed exactly as
+    //   t = mulhi_s32(w, M);  y = (t >> s) + (t >>> 31)      with L = ceil(log2 k), M = floor(2^(30+L) / k) + 1, s = L - 2:
+    // e = M k - 2^(30+L) is in (0, k], so for 0 <= w: floor(w M / 2^(30+L)) = floor(w / k) because w e < 2^(30+L)
+    // (2^15 k * k <= 2^(15+2L) <= 2^(30+L)); for w < 0 the product lies strictly below w / k by less than 1 / k,
+    // so its floor is trunc(w / k) - 1 and the sign bit adds the 1 back.  M < 2^31 needs k >= 3; k == 2 runs with
+    // every dp2a weight doubled (sums 2 w) and the constants of k = 4.  k == 1 (identity) and longer windows are
+    // left to the generic kernel.
     if (k < 2 || k > 32768u || !(C == 1 || C == 2)) return g;
     const uint64_t L = (uint64_t)k * C;
     const uint32_t R = (uint32_t)g.R;
@@ -149,11 +152,12 @@ StreamGeom plan_stream_i16(uint32_t k, uint32_t C, const mavg_tuning& tu)
         return g;
     }
     {
+        const uint32_t kd = k == 2 ? 4u : k;               // divisor seen by the kernel (weights doubled for k == 2)
+        g.wscale = k == 2 ? 2u : 1u;
         uint32_t lg = 0;
-        while ((1u << lg) < k) ++lg;                       // ceil(log2 k)
-        const unsigned long long two_p = 1ull << (31 + lg);
-        g.div_mul = (uint32_t)((two_p + k - 1) / k);       // ceil(2^(31+lg) / k) < 2^32
-        g.div_shift = lg - 1;
+        while ((1u << lg) < kd) ++lg;                      // ceil(log2 kd) >= 2
+        g.div_mul = (uint32_t)((1ull << (30 + lg)) / kd + 1);   // < 2^31
+        g.div_shift = lg - 2;
     }
     g.ok = true;
     return g;
@@ -233,16 +237,19 @@ StreamGeom plan_cols(uint32_t k, uint32_t C, const mavg_tuning& tu)
     return g;
 }
 
-// 3..31 interleaved float32 channels, k <= 256: thread = (16-frame run, channel), flat TMA tiles
-StreamGeom plan_fewc(uint32_t k, uint32_t C, const mavg_tuning& tu)
+// 3..31 interleaved channels, k <= 256: thread = (run of R frames, channel), flat TMA tiles.
+// float32: 16-frame runs; int16: 32-frame runs (both 64 bytes of one channel... per frame stride), 2 <= k.
+StreamGeom plan_fewc(uint32_t k, uint32_t C, const mavg_tuning& tu, uint32_t elem = 4)
 {
     StreamGeom g;
     g.NT = 512;
-    g.R = 16;
+    g.R = elem == 4 ? 16 : 32;
     g.C = C;
+    g.elem = elem;
     g.mode = 4;
     if (C < 3 || C > 31 || k > 256) return g;
-    const uint32_t R = 16;
+    if (elem == 2 && k < 2) return g;                // k == 1 (identity) stays on the generic kernel
+    const uint32_t R = (uint32_t)g.R;
     const uint32_t s = (R - k % R) % R;
     g.m_part = R - s;
     g.n_full = (k + s) / R - 1;
@@ -254,13 +261,19 @@ StreamGeom plan_fewc(uint32_t k, uint32_t C, const mavg_tuning& tu)
     g.H = 1;
     g.ctas_per_sm = 1;
     g.P = tu.prefetch ? (int)tu.prefetch : 2;
-    const uint32_t tile_bytes = NR * C * R * 4;
+    const uint32_t tile_bytes = NR * C * R * elem;
     for (;;) {
         g.S = g.H + 1 + g.P;
         g.smem = mavg::fewc_smem_bytes(tile_bytes, g.S, g.H, NR * C);
         if (g.smem <= kMaxSmem) break;
         if (g.P > 1) { --g.P; continue; }
         return g;
+    }
+    if (elem == 2) {                                  // same magic as plan_stream_i16, exact for |w| < 2^31
+        uint32_t lg = 0;
+        while ((1u << lg) < k) ++lg;
+        g.div_mul = (uint32_t)(((1ull << (31 + lg)) + k - 1) / k);
+        g.div_shift = lg - 1;
     }
     g.ok = true;
     return g;
@@ -393,7 +406,7 @@ bool planar_batch(const mavg_plan* p) { return p->desc.layout == MAVG_PLANAR && 
 uint64_t tile_frames(const mavg_plan* p)
 {
     if (p->geom.mode == 3) return (uint64_t)(kColsNW / p->geom.cww) * kColsRF;
-    if (p->geom.mode == 4) return (uint64_t)p->geom.runs * 16;
+    if (p->geom.mode == 4) return (uint64_t)p->geom.runs * p->geom.R;
     return (uint64_t)p->geom.NT * p->geom.R / p->geom.C;
 }
 bool frame_sharded(const mavg_plan* p) { return !planar_batch(p); }
@@ -615,13 +628,14 @@ int launch_fewc(mavg_plan* p, DevCtx& d, const void* in, void* out, const void* 
     const StreamGeom& g = p->geom;
     const uint32_t C = p->desc.channels;
     const uint64_t n = frames * C;                       // flat samples
-    const uint64_t rows = n / 32;
-    const uint64_t tile_floats = (uint64_t)g.runs * C * 16;
-    const uint32_t tile_rows = (uint32_t)(tile_floats / 32);
+    const uint64_t row = 128 / g.elem;                   // samples per 128-byte row
+    const uint64_t rows = n / row;
+    const uint64_t tile_floats = (uint64_t)g.runs * C * g.R;   // samples per tile
+    const uint32_t tile_rows = (uint32_t)(tile_floats / row);
     CUtensorMap in_map, out_map, halo_map;
-    MAVG_TRY(make_map(&in_map, in, rows, 1, rows * 128, tile_rows, 4));
-    MAVG_TRY(make_map(&out_map, out, rows, 1, rows * 128, tile_rows, 4));
-    if (halo) MAVG_TRY(make_map(&halo_map, halo, (uint64_t)g.H * tile_rows, 1, (uint64_t)g.H * tile_rows * 128, tile_rows, 4));
+    MAVG_TRY(make_map(&in_map, in, rows, 1, rows * 128, tile_rows, g.elem));
+    MAVG_TRY(make_map(&out_map, out, rows, 1, rows * 128, tile_rows, g.elem));
+    if (halo) MAVG_TRY(make_map(&halo_map, halo, (uint64_t)g.H * tile_rows, 1, (uint64_t)g.H * tile_rows * 128, tile_rows, g.elem));
     else halo_map = in_map;
     mavg::FewcParams fp;
     memset(&fp, 0, sizeof fp);
@@ -630,7 +644,9 @@ int launch_fewc(mavg_plan* p, DevCtx& d, const void* in, void* out, const void* 
     sp.k = p->desc.window;
     sp.n_full = g.n_full;
     sp.m_part = g.m_part;
-    const uint64_t tiles = (rows * 32 + tile_floats - 1) / tile_floats;
+    sp.div_mul = g.div_mul;
+    sp.div_shift = g.div_shift;
+    const uint64_t tiles = (rows * row + tile_floats - 1) / tile_floats;
     sp.tiles_per_signal = (int32_t)tiles;
     const uint64_t ctas = (uint64_t)d.sm_count;
     uint64_t cps = std::min<uint64_t>(tiles, ctas * std::max<uint32_t>(1u, p->desc.tuning.chunks_per_cta));
@@ -645,14 +661,15 @@ int launch_fewc(mavg_plan* p, DevCtx& d, const void* in, void* out, const void* 
     sp.has_halo = halo ? 1 : 0;
     fp.channels = C;
     fp.runs = (uint32_t)g.runs;
-    auto kern = mavg::stream_fewc_f32_kernel<16>;
+    void (*kern)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const mavg::FewcParams) =
+        g.elem == 4 ? mavg::stream_fewc_f32_kernel<16> : mavg::stream_fewc_i16_kernel<32>;
     MAVG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
     const unsigned grid = (unsigned)std::min<uint64_t>(ctas, cps);
     kern<<<grid, 512, g.smem, d.stream>>>(in_map, out_map, halo_map, fp);
     MAVG_CUDA(cudaGetLastError());
     ++*launches;
     // flat samples past the last whole 128-byte row: the frames that touch them go to the generic kernel
-    if (rows * 32 < n) MAVG_TRY(launch_generic(p, d, in, out, halo, frames, rows * 32 / C, frames, launches));
+    if (rows * row < n) MAVG_TRY(launch_generic(p, d, in, out, halo, frames, rows * row / C, frames, launches));
     return MAVG_OK;
 }
 
@@ -666,7 +683,7 @@ int launch_shard(mavg_plan* p, DevCtx& d, const void* in, void* out, const void*
     if (frames == 0 || (planar_batch(p) && d.channels == 0)) return MAVG_OK;
     if (p->path == MAVG_PATH_STREAM && p->geom.ok && p->geom.mode == 4) {
         const uint64_t nflat = frames * p->desc.channels;
-        if ((((uintptr_t)in | (uintptr_t)out | (uintptr_t)halo) & 15u) == 0 && nflat >= 32 && nflat / 32 < (1ull << 31) - 65536)
+        if ((((uintptr_t)in | (uintptr_t)out | (uintptr_t)halo) & 15u) == 0 && nflat >= 64 && nflat / 32 < (1ull << 31) - 65536)
             return launch_fewc(p, d, in, out, halo, frames, launches);
         return launch_generic(p, d, in, out, halo, frames, 0, frames, launches);
     }
@@ -700,8 +717,7 @@ int launch_shard(mavg_plan* p, DevCtx& d, const void* in, void* out, const void*
     sp.lag_chunks = g.lag_chunks;
     sp.div_mul = g.div_mul;
     sp.div_shift = g.div_shift;
-    sp.bias_k = 32768u * p->desc.window;
-    sp.c65536 = 65536u;
+    sp.wscale = g.wscale;
     memset(sp.wtab, 0, sizeof sp.wtab);
     if (g.elem == 2) {
         // dp2a byte weights: element e of the aligned lag words is run element r = e - MIS; it belongs to the
@@ -709,7 +725,7 @@ int launch_shard(mavg_plan* p, DevCtx& d, const void* in, void* out, const void*
         for (uint32_t wi = 0; wi < 20; ++wi)
             for (uint32_t hh = 0; hh < 2; ++hh) {
                 const int r = (int)(2 * wi + hh) - g.MIS;
-                if (r >= 0 && (uint32_t)r < g.m_part) sp.wtab[(uint32_t)r % g.C][wi] |= 1u << (8 * hh);
+                if (r >= 0 && (uint32_t)r < g.m_part) sp.wtab[(uint32_t)r % g.C][wi] |= g.wscale << (8 * hh);
             }
     }
     const uint64_t tiles = (rows * row + T - 1) / T;
@@ -917,6 +933,10 @@ int mavg_plan_create(const mavg_desc* desc, mavg_plan** out)
     } else {
         stream_shape = desc->channels <= 2 || planar;
         p->geom = plan_stream_i16(desc->window, planar ? 1u : desc->channels, desc->tuning);
+        if (!planar && desc->channels >= 3) {
+            p->geom = plan_fewc(desc->window, desc->channels, desc->tuning, 2);
+            stream_shape = p->geom.ok;
+        }
     }
     if (desc->path == MAVG_PATH_STREAM && !(stream_shape && p->geom.ok)) {
         delete p;

@@ -307,12 +307,10 @@ struct StreamParams {
     int32_t stages;             // S = H + 1 + prefetch
     int32_t prefetch;           // P
     int32_t has_halo;           // tiles before tile 0 come from halo_map instead of zero fill
-    // int16 path (biased domain, every sample carries +32768): with w' = w + 32768*k in [0, 65535*k],
-    //   trunc(w / k) + 32768 = umulhi(w' + (w' < bias_k ? k-1 : 0), div_mul) >> div_shift
+    // int16 paths: multiply-high constants of the exact truncating division (plan_stream_i16 / plan_fewc)
     uint32_t div_mul;
     uint32_t div_shift;
-    uint32_t bias_k;            // 32768 * k
-    uint32_t c65536;            // 65536 as a run-time value, so mul.hi/mad stay on the FMA pipe
+    uint32_t wscale;            // stream_i16_kernel: dp2a weight magnitude (1; 2 when k == 2, divisor then 4)
     uint32_t wtab[2][20];       // dp2a byte weights selecting, per 32-bit lag word, the halves that belong to the
                                 // head of the lag run (first m_part elements) for channel 0 / channel 1
 };
@@ -788,39 +786,28 @@ __device__ __forceinline__ void sts32i(uint32_t addr, int v)
 {
     asm volatile("st.shared.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
-// Instruction-pipe balance (ncu on the first version: ALU pipe 77 %, FMA pipe 16 %, kernel issue-bound at
-// 62-75 % of the HBM roofline): everything runs in a BIASED unsigned domain (sample + 32768), which makes the
-// window sum non-negative, so the truncating division needs no abs/negate, and lets part of the unpack, the
-// pack and the head sum run on the FMA pipe: hi = v >> 16 (ALU), lo = mad(hi, -65536, v), pack =
-// mad(hi, 65536, lo), head sum = dp2a with constant byte weights.  (mul.hi for `hi` was measured 4 % slower:
-// IMAD.HI issues at a lower rate than IMAD, and the exact division already needs one per sample.)  TMA zero fill (signal padding) becomes 32768 after the bias
-// flip, i.e. a biased zero, so padding stays consistent.
-__device__ __forceinline__ void unpack2u(uint32_t v, uint32_t c16, uint32_t nc16, uint32_t& lo, uint32_t& hi)
+// Instruction budget (ncu: the first version was issue-bound at 62-75 % of the HBM roofline, ALU pipe 77 %; a
+// biased-unsigned rework reached 67-80 % at 17 instructions per sample).  This version never unpacks a sample:
+// every sum is a dp2a on the PACKED words -- d = c + a.lo16 * b.byte0 + a.hi16 * b.byte1, signed -- with byte
+// weights that pick a half (+w), drop it (0) or subtract it (-w):
+//   run totals    gtot[ch] = dp2a(x_word, own weights of ch)          1 (mono) or 2 (stereo) per word
+//   head of lag   acc[ch]  = dp2a(lag_word, plan's table)             1 or 2 per lag word
+//   slide         acc     += x[r] - x[r-k]  = two dp2a with +w / -w   2 per sample
+// and C's truncating division is the signed multiply-high form  t = mulhi(acc, M); y = (t >> s) + (t >>> 31)
+// (exactness: plan_stream_i16).  Two results are merged with one byte permute.  About 8 instructions per
+// sample, most of them on the FMA pipe (dp2a, mulhi), the shifts and the permute on the ALU pipe.
+// TMA zero fill is the signal's zero padding as it is.
+__device__ __forceinline__ int dp2a_s(uint32_t a, uint32_t b, int c)
 {
-    const uint32_t vb = v ^ 0x80008000u;
-    (void)c16;
-    hi = vb >> 16;                                                                       // ALU pipe
-    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(lo) : "r"(hi), "r"(nc16), "r"(vb));          // FMA pipe: vb - hi * 65536
+    int d;
+    asm("dp2a.lo.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
 }
-__device__ __forceinline__ void unpack8u(const uint4 v, uint32_t c16, uint32_t nc16, uint32_t* dst)
+// trunc(w / k) for |w| <= 32768 k (times the weight scale), k <= 32768
+__device__ __forceinline__ uint32_t div_trunc_mulhi(int w, int mul, uint32_t sh)
 {
-    unpack2u(v.x, c16, nc16, dst[0], dst[1]);
-    unpack2u(v.y, c16, nc16, dst[2], dst[3]);
-    unpack2u(v.z, c16, nc16, dst[4], dst[5]);
-    unpack2u(v.w, c16, nc16, dst[6], dst[7]);
-}
-// two biased 16-bit results -> one output word of two int16
-__device__ __forceinline__ uint32_t pack2u(uint32_t lo, uint32_t hi, uint32_t c16)
-{
-    uint32_t w;
-    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(w) : "r"(hi), "r"(c16), "r"(lo));
-    return w ^ 0x80008000u;
-}
-// trunc((wb - bias_k) / k) + 32768 for wb in [0, 65535 k], k <= 32768 (exactness: plan_stream_i16)
-__device__ __forceinline__ uint32_t div_biased(uint32_t wb, uint32_t bias_k, uint32_t km1, uint32_t mul, uint32_t sh)
-{
-    const uint32_t u = wb + ((wb < bias_k) ? km1 : 0u);
-    return __umulhi(u, mul) >> sh;
+    const int t = __mulhi(w, mul);
+    return (uint32_t)((t >> sh) + (int)((uint32_t)t >> 31));
 }
 
 template <int NT, int R, int C, int MIS, int MODE>
@@ -847,7 +834,9 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : 1))
     const uint32_t wexc = gsum + (uint32_t)GS * NT * C * 4;   // int [GS][32][C]  ([31] = tile total)
     const uint32_t wraw = wexc + (uint32_t)GS * 32 * C * 4;   // int [2][32][C]
     tr.init_barriers(wraw + 2u * 32 * C * 4);
-    const uint32_t c16 = p.c65536, nc16 = 0u - p.c65536;
+    // dp2a byte weights (+w / -w on the low or the high half; w = 2 when k == 2, see plan_stream_i16)
+    const uint32_t w_lo = p.wscale, w_hi = p.wscale << 8;
+    const uint32_t n_lo = (0u - p.wscale) & 0xffu, n_hi = n_lo << 8;
 
     for (int chunk = blockIdx.x; chunk < p.total_chunks; chunk += gridDim.x) {
         int sig, t0, t1;
@@ -863,17 +852,29 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : 1))
             const int slot = tr.slot;
             const uint32_t it = tr.it;
 
-            uint32_t x[R];
+            uint32_t xw[R / 2];                              // own run, packed
 #pragma unroll
-            for (int c = 0; c < CH_OWN; ++c)
-                unpack8u(lds128u(swz(cur + (uint32_t)tid * (R * 2) + 16u * c)), c16, nc16, &x[8 * c]);
+            for (int c = 0; c < CH_OWN; ++c) {
+                const uint4 v = lds128u(swz(cur + (uint32_t)tid * (R * 2) + 16u * c));
+                xw[4 * c] = v.x, xw[4 * c + 1] = v.y, xw[4 * c + 2] = v.z, xw[4 * c + 3] = v.w;
+            }
             uint32_t gtot[C], incl[C];
+            {
+                int gt[C];
 #pragma unroll
-            for (int c = 0; c < C; ++c) gtot[c] = 0u;
+                for (int c = 0; c < C; ++c) gt[c] = 0;
 #pragma unroll
-            for (int r = 0; r < R; ++r) gtot[r % C] += x[r];
+                for (int q = 0; q < R / 2; ++q) {
+                    if constexpr (C == 1) {
+                        gt[0] = dp2a_s(xw[q], w_lo | w_hi, gt[0]);
+                    } else {
+                        gt[0] = dp2a_s(xw[q], w_lo, gt[0]);
+                        gt[1] = dp2a_s(xw[q], w_hi, gt[1]);
+                    }
+                }
 #pragma unroll
-            for (int c = 0; c < C; ++c) incl[c] = gtot[c];
+                for (int c = 0; c < C; ++c) incl[c] = gtot[c] = (uint32_t)gt[c];
+            }
 
             if constexpr (MODE == 0) {
 #pragma unroll
@@ -921,24 +922,24 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : 1))
             }
 
             if (is_out) {
-                uint32_t xl[CH_LAG * 8];
+                uint32_t xlw[CH_LAG * 4];                    // lag run, packed
                 uint32_t acc[C];
 #pragma unroll
                 for (int c = 0; c < C; ++c) acc[c] = 0u;
                 {
                     // lag run as aligned 16-byte chunks; the head of the run (first m_part elements) is summed
-                    // straight from the packed words with dp2a and the plan's constant byte weights
+                    // straight from the packed words with the plan's byte-weight table
                     const int lin = (tid * CH_OWN - (int)p.lag_chunks) * 16;
 #pragma unroll
                     for (int c = 0; c < CH_LAG; ++c) {
                         const uint4 v = lds128u(swz(tr.rel(lin + 16 * c)));
-                        const uint32_t w4[4] = {v.x ^ 0x80008000u, v.y ^ 0x80008000u, v.z ^ 0x80008000u, v.w ^ 0x80008000u};
+                        xlw[4 * c] = v.x, xlw[4 * c + 1] = v.y, xlw[4 * c + 2] = v.z, xlw[4 * c + 3] = v.w;
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
 #pragma unroll
-                            for (int ch = 0; ch < C; ++ch) acc[ch] = __dp2a_lo(w4[q], p.wtab[ch][4 * c + q], acc[ch]);
+                            for (int ch = 0; ch < C; ++ch)
+                                acc[ch] = (uint32_t)dp2a_s(xlw[4 * c + q], p.wtab[ch][4 * c + q], (int)acc[ch]);
                         }
-                        unpack8u(v, c16, nc16, &xl[8 * c]);
                     }
                 }
                 if constexpr (MODE == 0) {
@@ -986,18 +987,24 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : 1))
                     }
                 }
                 const uint32_t ob = tr.out_tile() + (uint32_t)tid * (R * 2);
-                const uint32_t mul = p.div_mul, sh = p.div_shift, bias_k = p.bias_k, km1 = p.k - 1u;
+                const int mul = (int)p.div_mul;
+                const uint32_t sh = p.div_shift;
 #pragma unroll
                 for (int c = 0; c < CH_OWN; ++c) {
                     uint32_t wds[4];
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        const int r0 = 8 * c + 2 * q, r1 = r0 + 1;
-                        acc[r0 % C] += x[r0] - xl[MIS + r0];
-                        const uint32_t y0 = div_biased(acc[r0 % C], bias_k, km1, mul, sh);
-                        acc[r1 % C] += x[r1] - xl[MIS + r1];
-                        const uint32_t y1 = div_biased(acc[r1 % C], bias_k, km1, mul, sh);
-                        wds[q] = pack2u(y0, y1, c16);
+                        uint32_t y[2];
+#pragma unroll
+                        for (int hh = 0; hh < 2; ++hh) {
+                            const int r = 8 * c + 2 * q + hh;       // run element; its lag partner is element MIS + r
+                            const int e = MIS + r;                  // of the aligned lag words
+                            int a2 = dp2a_s(xw[r >> 1], hh ? w_hi : w_lo, (int)acc[r % C]);
+                            a2 = dp2a_s(xlw[e >> 1], (e & 1) ? n_hi : n_lo, a2);
+                            acc[r % C] = (uint32_t)a2;
+                            y[hh] = div_trunc_mulhi(a2, mul, sh);
+                        }
+                        wds[q] = __byte_perm(y[0], y[1], 0x5410);
                     }
                     sts128u(swz(ob + 16u * c), wds[0], wds[1], wds[2], wds[3]);
                 }
@@ -1392,6 +1399,116 @@ __global__ void __launch_bounds__(512)
                     for (int r = 0; r < RF; ++r) {
                         acc += x[r] - xl[r];
                         sts32(swz(ob + (uint32_t)r * row_stride), acc * inv);
+                    }
+                }
+                tr.staged(tile, sig);
+            }
+            tr.advance();
+        }
+        tr.epilogue();
+    }
+    tr.finish();
+}
+
+// ----------------------------------------------------------------------------------
+// Few-channel int16 twin: 3..31 interleaved int16 channels (multichannel PCM WAV), 2 <= k <= 256.  Same layout
+// and work split as stream_fewc_f32_kernel with 32-frame runs; int32-exact window sums and the multiply-high
+// truncating division, so results stay bit-identical to profilable_cpu_computations.  4 B/sample.
+// ----------------------------------------------------------------------------------
+__device__ __forceinline__ int lds16s(uint32_t addr)
+{
+    int v;
+    asm volatile("ld.shared.s16 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts16(uint32_t addr, int v)
+{
+    asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"((short)v) : "memory");
+}
+// C integer division (truncation toward zero) for |w| < 2^31: sign-mask abs, multiply-high, sign restore
+__device__ __forceinline__ int div_trunc_i32(int w, uint32_t mul, uint32_t sh)
+{
+    const int sg = w >> 31;
+    const uint32_t a = (uint32_t)((w ^ sg) - sg);
+    const int q = (int)(__umulhi(a, mul) >> sh);
+    return (q ^ sg) - sg;
+}
+
+template <int RF>
+__global__ void __launch_bounds__(512)
+    stream_fewc_i16_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map,
+                           const __grid_constant__ CUtensorMap halo_map, const FewcParams fp)
+{
+    const StreamParams& p = fp.sp;
+    const uint32_t C = fp.channels;
+    const int NR = (int)fp.runs;
+    const uint32_t NRC = (uint32_t)NR * C;
+    const uint32_t tile_bytes = NRC * RF * 2u;
+    extern __shared__ uint8_t smem_raw[];
+    const int tid = threadIdx.x;
+    const bool active = (uint32_t)tid < NRC;
+    const int run = active ? (int)((uint32_t)tid / C) : 0;
+    const uint32_t c = active ? (uint32_t)tid - (uint32_t)run * C : 0u;
+
+    TileRing<0, 0> tr;
+    const uint32_t gsum = tr.setup(smem_u32(smem_raw), p, &in_map, &out_map, &halo_map, tile_bytes, (int)(tile_bytes / 128u));
+    const int H = p.hist_tiles, GS = p.hist_tiles + 2;      // int [GS][NRC] run totals
+    tr.init_barriers((gsum + (uint32_t)GS * NRC * 4u + 7u) & ~7u);
+    const uint32_t row_stride = C * 2u;                     // bytes between consecutive frames of one channel
+    const uint32_t g_stride = C * 4u;                       // bytes between consecutive runs' totals of one channel
+
+    for (int chunk = blockIdx.x; chunk < p.total_chunks; chunk += gridDim.x) {
+        int sig, t0, t1;
+        if (!chunk_range(p, chunk, sig, t0, t1)) continue;
+        const int first = t0 - H;
+        const int ntl = t1 - first;
+        tr.prologue(first, ntl, sig);
+
+        for (int j = 0; j < ntl; ++j) {
+            const int tile = first + j;
+            const bool is_out = (j >= H);
+            const uint32_t cur = tr.wait_tile();
+            const int slot = tr.slot;
+
+            int x[RF];
+            const uint32_t own = ((uint32_t)run * RF * C + c) * 2u;
+            int gtot = 0;
+#pragma unroll
+            for (int r = 0; r < RF; ++r) {
+                x[r] = active ? lds16s(swz(cur + own + (uint32_t)r * row_stride)) : 0;
+                gtot += x[r];
+            }
+            if (active) sts32i(gsum + ((uint32_t)slot * NRC + tid) * 4u, gtot);
+
+            tr.before_sync();
+            __syncthreads();
+            tr.after_sync(j, ntl, first, sig);
+
+            if (is_out) {
+                if (active) {
+                    const uint32_t ob = tr.out_tile() + own;
+                    const int lag0 = (int)own - (int)(p.k * row_stride);
+                    int xl[RF];
+#pragma unroll
+                    for (int r = 0; r < RF; ++r) xl[r] = lds16s(swz(tr.rel(lag0 + r * (int)row_stride)));
+                    const int D = (int)p.n_full + 1;
+                    int acc = 0;
+                    const uint32_t g_cur = gsum + ((uint32_t)slot * NRC + c) * 4u;
+                    const int in_cur = (run < D - 1) ? run : D - 1;
+                    for (int w2 = 1; w2 <= in_cur; ++w2) acc += lds32i(g_cur + (uint32_t)(run - w2) * g_stride);
+                    if (in_cur < D - 1) {
+                        const int ps = (slot == 0) ? GS - 1 : slot - 1;
+                        const uint32_t g_prev = gsum + ((uint32_t)ps * NRC + c) * 4u;
+                        for (int w2 = 1; w2 <= D - 1 - in_cur; ++w2) acc += lds32i(g_prev + (uint32_t)(NR - w2) * g_stride);
+                    }
+#pragma unroll
+                    for (int r = 0; r < RF; ++r)
+                        if ((uint32_t)r < p.m_part) acc += xl[r];
+                    const uint32_t mul = p.div_mul, sh = p.div_shift;
+#pragma unroll
+                    for (int r = 0; r < RF; ++r) {
+                        acc += x[r] - xl[r];
+                        sts16(swz(ob + (uint32_t)r * row_stride), div_trunc_i32(acc, mul, sh));
                     }
                 }
                 tr.staged(tile, sig);

@@ -43,27 +43,39 @@ def test_geometry_identities():
             assert g["H"] * g["T"] >= k
 
 
-def test_int16_biased_division_is_exact():
-    """Host restatement of the int16 kernel's division (plan_stream_i16 / div_biased in csrc): with every sample
-    biased by +32768 the window sum is w' = w + 32768 k, and
-        trunc(w / k) + 32768 == umulhi(w' + (w' < 32768 k ? k - 1 : 0), M) >> (L - 1)
-    with L = ceil(log2 k), M = ceil(2^(31+L) / k), for every k in 2..32768 and every reachable w'."""
+def _mulhi_s32(a, m):
+    return (a * m) >> 32            # numpy int64 / Python ints: arithmetic shift = floor, like mul.hi.s32
+
+
+def test_int16_mulhi_division_is_exact():
+    """Host restatement of the int16 kernel's division (plan_stream_i16 / div_trunc_mulhi in csrc):
+        trunc(w / k) == (t >> s) + (t >>> 31),  t = mulhi_s32(w, M),  M = floor(2^(30+L) / k) + 1,  s = L - 2
+    with L = ceil(log2 k), for every k in 3..32768 and every reachable window sum |w| <= 32768 k.  The quotient
+    only changes at multiples of k, so every multiple and both neighbours are checked for the k listed, plus
+    random sums.  k == 2 runs with doubled weights (w -> 2 w) and the constants of k = 4."""
     rng = np.random.default_rng(5)
-    ks = list(range(2, 300)) + [511, 512, 513, 1000, 1024, 4095, 4096, 4097, 16384, 30000, 32767, 32768]
-    for k in ks:
-        L = (k - 1).bit_length()
-        M = ((1 << (31 + L)) + k - 1) // k
-        assert M < 2**32 and L >= 1
-        B = 32768 * k
-        wb = np.concatenate([np.array([0, 1, k - 1, k, B - 1, B, B + 1, B - k, B + k, 65535 * k, 65535 * k - 1], dtype=np.int64),
-                             rng.integers(0, 65535 * k + 1, size=400)])
-        w = wb - B
-        want = np.sign(w) * (np.abs(w) // k) + 32768          # truncation toward zero, biased
-        u = wb + np.where(wb < B, k - 1, 0)
-        assert u.max() < 2**32
-        got = np.array([((int(v) * M) >> 32) >> (L - 1) for v in u], dtype=np.int64)
+    ks = list(range(3, 300)) + [511, 512, 513, 1000, 1023, 1024, 1025, 4095, 4096, 4097, 16383, 16384, 16385,
+                                30000, 32767, 32768]
+
+    def check(k, w, scale=1):
+        kd = k * scale
+        L = (kd - 1).bit_length()
+        M = (1 << (30 + L)) // kd + 1
+        assert L >= 2 and M < 2**31
+        ws = w * scale
+        assert np.abs(ws).max() < 2**31
+        t = _mulhi_s32(ws, M)
+        got = (t >> (L - 2)) + ((t >> 31) & 1)
+        want = np.sign(w) * (np.abs(w) // k)
         assert np.array_equal(got, want), k
-        assert got.min() >= 0 and got.max() <= 65535
+
+    for k in ks:
+        q = np.arange(-32768, 32768, dtype=np.int64) * k
+        w = np.concatenate([q, q - 1, q + 1, q + k - 1, np.array([-32768 * k, 32767 * k]),
+                            rng.integers(-32768 * k, 32767 * k + 1, size=2000)])
+        w = w[(w >= -32768 * k) & (w <= 32767 * k)]
+        check(k, w)
+    check(2, np.arange(-65536, 65535, dtype=np.int64), scale=2)
 
 
 def test_int16_head_weights_cover_exactly_the_head():

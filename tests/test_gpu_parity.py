@@ -531,3 +531,60 @@ def test_few_channel_shard_with_halo_bit_identical(mavg, oracle_mod, torch_cuda,
     assert np.array_equal(dz.cpu().numpy()[:tail_frames * ch], whole[cut * ch:(cut + tail_frames) * ch])
     assert _rel(dz.cpu().numpy(), oracle_mod.mavg_f64(x, k, ch)[cut * ch:]) < TOL
     assert _rel(whole, oracle_mod.mavg_f64(x, k, ch)) < TOL
+
+
+# ------------------------------------------------------------------ 3..31 interleaved int16 channels (multichannel PCM)
+def _fewc_runs(ch):
+    runs = 512 // ch
+    while runs * ch % 16:
+        runs -= 1
+    return runs
+
+
+@pytest.mark.parametrize("ch", [3, 5, 6, 7, 8, 12, 24, 31])
+@pytest.mark.parametrize("k", [1, 2, 3, 7, 8, 31, 32, 33, 64, 100, 255, 256, 300])
+def test_few_channel_interleaved_i16_bit_exact(mavg, oracle_mod, ch, k):
+    runs = _fewc_runs(ch)
+    frames = 3 * runs * 32 + 41                    # several tiles, ragged tail (flat length not a multiple of 64)
+    x = oracle_mod.fill_i16(frames * ch, 26000 + k + ch)
+    with mavg.Plan(frames, k, channels=ch, dtype="i16") as plan:
+        y = plan.run_host(x)
+        i = plan.info
+        if 2 <= k <= 256 and (k + 31) // 32 <= runs:
+            assert i.path == 1 and i.mode == 4 and i.run == 32, "expected the few-channel int16 kernel"
+    assert np.array_equal(y, oracle_mod.mavg_i16(x, k, ch))
+
+
+def test_few_channel_i16_extremes_and_negative_truncation(mavg, oracle_mod):
+    """Saturated inputs (window sums up to 256 * 32768 in magnitude) and sign-alternating ramps whose sums straddle
+    zero: the multiply-high division has to truncate toward zero exactly as C's `/` does."""
+    ch = 6
+    frames = 4 * 80 * 32 + 5
+    for val in (-32768, 32767, -1, 1):
+        x = np.full(frames * ch, val, dtype=np.int16)
+        for k in (2, 3, 7, 100, 255, 256):
+            with mavg.Plan(frames, k, channels=ch, dtype="i16") as plan:
+                assert plan.info.mode == 4
+                assert np.array_equal(plan.run_host(x), oracle_mod.mavg_i16(x, k, ch)), (val, k)
+    x = ((np.arange(frames * ch) % 11 - 5) * 997).astype(np.int16)
+    for k in (2, 3, 5, 6, 7, 9, 10, 11, 12, 13, 100):
+        assert np.array_equal(mavg.moving_average(x, k, channels=ch), oracle_mod.mavg_i16(x, k, ch)), k
+
+
+@pytest.mark.parametrize("case", [(6, 64), (3, 5), (7, 200)])
+def test_few_channel_i16_shard_with_halo_bit_exact(mavg, oracle_mod, torch_cuda, case):
+    torch = torch_cuda
+    ch, k = case
+    with mavg.Plan(100_000, k, channels=ch, dtype="i16") as probe:
+        tf = int(probe.info.halo_frames)
+        assert probe.info.mode == 4 and tf >= k
+    frames, cut = 37 * tf + 123, 9 * tf
+    x = oracle_mod.fill_i16(frames * ch, 27000 + k)
+    dx = torch.from_numpy(x).cuda()
+    dz = torch.zeros((frames - cut) * ch, dtype=torch.int16, device="cuda")
+    torch.cuda.synchronize()
+    with mavg.Plan(frames - cut, k, channels=ch, dtype="i16", first_frame=cut) as plan:
+        halo = int(plan.info.halo_frames)
+        plan.run_device_halo(dx.data_ptr() + 2 * cut * ch, dz.data_ptr(), dx.data_ptr() + 2 * (cut - halo) * ch)
+        plan.synchronize()
+    assert np.array_equal(dz.cpu().numpy(), oracle_mod.mavg_i16(x, k, ch)[cut * ch:])
