@@ -31,7 +31,8 @@ class Tuning(ctypes.Structure):
         ("ctas_per_sm", ctypes.c_uint32),
         ("chunks_per_cta", ctypes.c_uint32),
         ("direct_max_k", ctypes.c_uint32),
-        ("reserved", ctypes.c_uint32 * 2),
+        ("slice_bytes", ctypes.c_uint32),
+        ("reserved", ctypes.c_uint32 * 1),
     ]
 
 

@@ -1225,12 +1225,21 @@ int mavg_run_host(mavg_plan* p, const void* h_in, void* h_out)
         }
         char* dst = (char*)h_out + (src - (const char*)h_in);
 
-        // slices: whole tiles, at least the left context long, ~16 MiB each; planar batches and short
-        // shards go in one piece
+        // slices: whole tiles, at least the left context long; planar batches and short shards go in one piece.
+        // The H2D stream is the critical path: N slices of s bytes take N (s / B + o) + s / B with a fixed cost
+        // o per slice (measured 21 us at B = 49.5 GB/s each way, PCIe 5 x16), which is least at s = sqrt(total o B)
+        // ~ sqrt(total * 1 MiB): 32 MiB slices for a 1 GiB shard, 8 MiB for 64 MiB (profiles/r01/pcie_probe.json).
+        // Reading and writing the pinned host buffers straight from the kernel (no copies, one launch) was
+        // measured at 38.5 GB/s each way against 47 for the sliced copies, so it is not used.
         uint64_t slice_frames = d.frames;
         if (!planar_batch(p) && d.frames > 0) {
             const uint64_t unit = (p->path == MAVG_PATH_STREAM) ? tile_frames(p) : 1024;
-            uint64_t want = std::max<uint64_t>((16ull << 20) / (C * es), p->halo_frames);
+            uint64_t slice_bytes = p->desc.tuning.slice_bytes;
+            if (!slice_bytes) {
+                slice_bytes = 4ull << 20;
+                while (slice_bytes < (64ull << 20) && slice_bytes * slice_bytes < ((d.frames * C * es) << 20)) slice_bytes <<= 1;
+            }
+            uint64_t want = std::max<uint64_t>(slice_bytes / (C * es), p->halo_frames);
             want = (want + unit - 1) / unit * unit;
             if (want * 2 <= d.frames) slice_frames = want;
         }

@@ -93,7 +93,8 @@ typedef struct mavg_tuning {
     uint32_t ctas_per_sm;    /* resident CTAs per SM the grid is sized for                 */
     uint32_t chunks_per_cta; /* contiguous tile ranges each CTA walks (>=1)                */
     uint32_t direct_max_k;   /* largest k*channels served by direct group sums (default 256) */
-    uint32_t reserved[2];
+    uint32_t slice_bytes;    /* mavg_run_host: bytes per pipelined H2D/kernel/D2H slice (default 16 MiB) */
+    uint32_t reserved[1];
 } mavg_tuning;
 
 /* Plan description.  Replaces the DspWorkspace constructor arguments
