@@ -108,6 +108,8 @@ struct StreamGeom {
     uint32_t elem = 4;        // bytes per sample
     uint32_t C = 1;           // channels interleaved inside one kernel signal (int16 stereo: 2)
     uint32_t div_mul = 0, div_shift = 0, wscale = 1;
+    bool long_mode = false;     // few-channel kernels: prefix mode
+    bool pair = false;          // few-channel int16 with an even channel count: the kernel works on channel-pair words
     int cww = 1;              // column kernel: 32-channel column-warps side by side in one tile
     int runs = 0;             // few-channel kernel: 16-frame runs per tile
 };
@@ -115,6 +117,17 @@ struct StreamGeom {
 constexpr uint32_t kMaxSmem = 232448;  // 227 KB opt-in limit per CTA on sm_100
 
 // int16: 512 threads x 32 samples (64 bytes) per tile of 16384 samples; flat lag distance k * C.
+// Constants of the signed multiply-high division (proof: plan_stream_i16), 2 <= k <= 32768
+void i16_mulhi_consts(uint32_t k, uint32_t* mul, uint32_t* shift, uint32_t* wscale)
+{
+    const uint32_t kd = k == 2 ? 4u : k;               // divisor seen by the kernel (weights doubled for k == 2)
+    *wscale = k == 2 ? 2u : 1u;
+    uint32_t lg = 0;
+    while ((1u << lg) < kd) ++lg;                      // ceil(log2 kd) >= 2
+    *mul = (uint32_t)((1ull << (30 + lg)) / kd + 1);   // < 2^31
+    *shift = lg - 2;
+}
+
 StreamGeom plan_stream_i16(uint32_t k, uint32_t C, const mavg_tuning& tu)
 {
     StreamGeom g;
@@ -151,14 +164,7 @@ StreamGeom plan_stream_i16(uint32_t k, uint32_t C, const mavg_tuning& tu)
         if (g.ctas_per_sm > 1) { --g.ctas_per_sm; g.P = tu.prefetch ? (int)tu.prefetch : 2; continue; }
         return g;
     }
-    {
-        const uint32_t kd = k == 2 ? 4u : k;               // divisor seen by the kernel (weights doubled for k == 2)
-        g.wscale = k == 2 ? 2u : 1u;
-        uint32_t lg = 0;
-        while ((1u << lg) < kd) ++lg;                      // ceil(log2 kd) >= 2
-        g.div_mul = (uint32_t)((1ull << (30 + lg)) / kd + 1);   // < 2^31
-        g.div_shift = lg - 2;
-    }
+    i16_mulhi_consts(k, &g.div_mul, &g.div_shift, &g.wscale);
     g.ok = true;
     return g;
 }
@@ -238,17 +244,26 @@ StreamGeom plan_cols(uint32_t k, uint32_t C, const mavg_tuning& tu)
 }
 
 // 3..31 interleaved channels, k <= 256: thread = (run of R frames, channel), flat TMA tiles.
-// float32: 16-frame runs; int16: 32-frame runs (both 64 bytes of one channel... per frame stride), 2 <= k.
+// float32: 16-frame runs.  int16, odd channel counts: 32-frame runs of 2-byte samples.  int16, even channel
+// counts: the kernel sees C/2 "channels" of 32-bit words (channel pairs), 16-frame runs (g.pair, g.C = C/2,
+// g.elem = 4).  int16 needs k >= 2 (k == 1, the identity, stays on the generic kernel).
 StreamGeom plan_fewc(uint32_t k, uint32_t C, const mavg_tuning& tu, uint32_t elem = 4)
 {
     StreamGeom g;
     g.NT = 512;
+    g.mode = 4;
+    g.C = C;
+    if (C < 3 || C > 31 || k > 32768u) return g;     // int32 sums and the int16 divisions are exact up to here
+    if (elem == 2 && k < 2) return g;
+    const bool i16 = elem == 2;
+    if (i16 && C % 2 == 0) {
+        g.pair = true;
+        C /= 2;
+        elem = 4;
+    }
     g.R = elem == 4 ? 16 : 32;
     g.C = C;
     g.elem = elem;
-    g.mode = 4;
-    if (C < 3 || C > 31 || k > 256) return g;
-    if (elem == 2 && k < 2) return g;                // k == 1 (identity) stays on the generic kernel
     const uint32_t R = (uint32_t)g.R;
     const uint32_t s = (R - k % R) % R;
     g.m_part = R - s;
@@ -256,20 +271,26 @@ StreamGeom plan_fewc(uint32_t k, uint32_t C, const mavg_tuning& tu, uint32_t ele
     uint32_t NR = 512 / C;
     while (NR > 0 && (NR * C) % 16 != 0) --NR;       // tile = whole 1024-byte swizzle atoms
     if (NR == 0) return g;
-    if (g.n_full + 1 > NR) return g;                 // the window must fit in this tile plus the previous one
     g.runs = (int)NR;
-    g.H = 1;
+    g.H = (int)((g.n_full + 1 + NR - 1) / NR);       // history tiles: the lag run lies at most H tiles back
+    // whole runs of the window: summed one by one up to direct_max_k frames (at most 16 runs, this tile and the
+    // previous one), through per-tile prefixes beyond
+    g.long_mode = k > (tu.direct_max_k ? tu.direct_max_k : 256u) || g.n_full > 16 || g.H > 1;
+    if (g.long_mode && k <= 8) g.long_mode = false;
+    if (!g.long_mode && g.H > 1) return g;
     g.ctas_per_sm = 1;
     g.P = tu.prefetch ? (int)tu.prefetch : 2;
     const uint32_t tile_bytes = NR * C * R * elem;
     for (;;) {
         g.S = g.H + 1 + g.P;
-        g.smem = mavg::fewc_smem_bytes(tile_bytes, g.S, g.H, NR * C);
+        g.smem = mavg::fewc_smem_bytes(tile_bytes, g.S, g.H, NR * C, g.pair ? 8u : 4u);
         if (g.smem <= kMaxSmem) break;
         if (g.P > 1) { --g.P; continue; }
         return g;
     }
-    if (elem == 2) {                                  // same magic as plan_stream_i16, exact for |w| < 2^31
+    if (g.pair) {
+        i16_mulhi_consts(k, &g.div_mul, &g.div_shift, &g.wscale);
+    } else if (i16) {                                 // unsigned form on |w| (div_trunc_i32), exact for |w| < 2^31
         uint32_t lg = 0;
         while ((1u << lg) < k) ++lg;
         g.div_mul = (uint32_t)(((1ull << (31 + lg)) + k - 1) / k);
@@ -626,9 +647,9 @@ int launch_fewc(mavg_plan* p, DevCtx& d, const void* in, void* out, const void* 
                 uint32_t* launches)
 {
     const StreamGeom& g = p->geom;
-    const uint32_t C = p->desc.channels;
-    const uint64_t n = frames * C;                       // flat samples
-    const uint64_t row = 128 / g.elem;                   // samples per 128-byte row
+    const uint32_t C = g.C;                              // channels as the kernel sees them (pairs for g.pair)
+    const uint64_t n = frames * C;                       // flat kernel elements (samples, or words for g.pair)
+    const uint64_t row = 128 / g.elem;                   // elements per 128-byte row
     const uint64_t rows = n / row;
     const uint64_t tile_floats = (uint64_t)g.runs * C * g.R;   // samples per tile
     const uint32_t tile_rows = (uint32_t)(tile_floats / row);
@@ -646,6 +667,7 @@ int launch_fewc(mavg_plan* p, DevCtx& d, const void* in, void* out, const void* 
     sp.m_part = g.m_part;
     sp.div_mul = g.div_mul;
     sp.div_shift = g.div_shift;
+    sp.wscale = g.wscale;
     const uint64_t tiles = (rows * row + tile_floats - 1) / tile_floats;
     sp.tiles_per_signal = (int32_t)tiles;
     const uint64_t ctas = (uint64_t)d.sm_count;
@@ -661,8 +683,10 @@ int launch_fewc(mavg_plan* p, DevCtx& d, const void* in, void* out, const void* 
     sp.has_halo = halo ? 1 : 0;
     fp.channels = C;
     fp.runs = (uint32_t)g.runs;
+    fp.long_mode = g.long_mode ? 1u : 0u;
     void (*kern)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const mavg::FewcParams) =
-        g.elem == 4 ? mavg::stream_fewc_f32_kernel<16> : mavg::stream_fewc_i16_kernel<32>;
+        g.pair ? mavg::stream_fewc_i16x2_kernel<16>
+               : g.elem == 4 ? mavg::stream_fewc_f32_kernel<16> : mavg::stream_fewc_i16_kernel<32>;
     MAVG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
     const unsigned grid = (unsigned)std::min<uint64_t>(ctas, cps);
     kern<<<grid, 512, g.smem, d.stream>>>(in_map, out_map, halo_map, fp);

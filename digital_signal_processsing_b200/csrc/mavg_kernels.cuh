@@ -786,6 +786,26 @@ __device__ __forceinline__ void sts32i(uint32_t addr, int v)
 {
     asm volatile("st.shared.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
+__device__ __forceinline__ uint32_t lds32u(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts32u(uint32_t addr, uint32_t v)
+{
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ int2 lds64i(uint32_t addr)
+{
+    int2 v;
+    asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts64i(uint32_t addr, int a, int b)
+{
+    asm volatile("st.shared.v2.s32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
 // Instruction budget (ncu: the first version was issue-bound at 62-75 % of the HBM roofline, ALU pipe 77 %; a
 // biased-unsigned rework reached 67-80 % at 17 instructions per sample).  This version never unpacks a sample:
 // every sum is a dp2a on the PACKED words -- d = c + a.lo16 * b.byte0 + a.hi16 * b.byte1, signed -- with byte
@@ -1298,11 +1318,104 @@ struct FewcParams {
     StreamParams sp;       // ring geometry, k, inv_k, n_full, m_part (in frames)
     uint32_t channels;
     uint32_t runs;         // NR
+    uint32_t long_mode;    // whole runs of the window summed through per-tile prefixes instead of one by one
 };
 
-__host__ __device__ inline uint32_t fewc_smem_bytes(uint32_t tile_bytes, int S, int H, uint32_t active_threads)
+__host__ __device__ inline uint32_t fewc_smem_bytes(uint32_t tile_bytes, int S, int H, uint32_t active_threads,
+                                                    uint32_t total_bytes = 4)
 {
-    return 1024u + (uint32_t)S * tile_bytes + 2u * tile_bytes + (uint32_t)(H + 2) * active_threads * 4 + (uint32_t)S * 8 + 64;
+    return 1024u + (uint32_t)S * tile_bytes + 2u * tile_bytes + (uint32_t)(H + 2) * active_threads * total_bytes +
+           (uint32_t)S * 8 + 64;
+}
+
+// ---- long windows in the few-channel kernels (more than 16 whole runs between the lag run and the own run) ----
+// After the tile's barrier every warp turns the run totals of "its" channels (warp, warp + 16, ...) of the
+// current slot into inclusive prefixes over the tile's runs, IN PLACE; a second barrier publishes them.  The sum
+// of the n_full runs in front of the own run is then a difference of two prefixes of this tile, or prefix +
+// whole-tile totals + (tile total - prefix) of the oldest tile.  Every difference stays inside one tile, so the
+// float32 cancellation error is bounded by eps * (tile sum), as in the mono kernel's MODE 1; the tile grid is
+// anchored at global frame 0, so shards and slices reproduce the unsharded sums bit for bit.
+template <typename T>
+__device__ __forceinline__ T lds_t(uint32_t addr);
+template <>
+__device__ __forceinline__ float lds_t<float>(uint32_t addr) { return lds32(addr); }
+template <>
+__device__ __forceinline__ int lds_t<int>(uint32_t addr) { return lds32i(addr); }
+__device__ __forceinline__ void sts_t(uint32_t addr, float v) { sts32(addr, v); }
+__device__ __forceinline__ void sts_t(uint32_t addr, int v) { sts32i(addr, v); }
+
+// slot_base: totals of the current tile, entry (run * C + c) holds NV values of type T
+template <typename T, int NV>
+__device__ __forceinline__ void fewc_scan_slot(uint32_t slot_base, int NR, uint32_t C)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int q = (NR + 31) >> 5;                          // runs per lane, <= 8 (NR <= 256)
+    for (uint32_t c = (uint32_t)warp; c < C; c += (uint32_t)nwarps) {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            T loc[8];
+            T run_sum = T(0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int r = lane * q + i;
+                loc[i] = T(0);
+                if (i < q && r < NR) {
+                    run_sum += lds_t<T>(slot_base + (((uint32_t)r * C + c) * NV + v) * 4u);
+                    loc[i] = run_sum;
+                }
+            }
+            T incl = run_sum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const T up = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += up;
+            }
+            const T excl = incl - run_sum;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int r = lane * q + i;
+                if (i < q && r < NR) sts_t(slot_base + (((uint32_t)r * C + c) * NV + v) * 4u, loc[i] + excl);
+            }
+        }
+    }
+}
+
+// sum of the n_full runs in front of run `run` of channel c (prefixes as left by fewc_scan_slot)
+template <typename T, int NV>
+__device__ __forceinline__ void fewc_window_long(T (&acc)[NV], uint32_t gsum, int slot, int GS, int NR, uint32_t C,
+                                                 uint32_t c, int run, int n_full)
+{
+    const uint32_t slot_bytes = (uint32_t)NR * C * NV * 4u;
+    auto at = [&](int s, int r, int v) -> T {
+        return lds_t<T>(gsum + (uint32_t)s * slot_bytes + (((uint32_t)r * C + c) * NV + v) * 4u);
+    };
+    const int q0 = run - n_full;                           // first run of the sum, in this tile's numbering
+    if (q0 >= 0) {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            T t = at(slot, run - 1, v);
+            if (q0 > 0) t -= at(slot, q0 - 1, v);
+            acc[v] = t;
+        }
+    } else {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) acc[v] = run > 0 ? at(slot, run - 1, v) : T(0);
+        int m = -q0;                                       // runs still to take from older tiles
+        int s2 = slot;
+        while (m > NR) {
+            s2 = (s2 == 0) ? GS - 1 : s2 - 1;
+#pragma unroll
+            for (int v = 0; v < NV; ++v) acc[v] += at(s2, NR - 1, v);
+            m -= NR;
+        }
+        s2 = (s2 == 0) ? GS - 1 : s2 - 1;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {                     // the last m runs of the oldest tile, 1 <= m <= NR
+            T t = at(s2, NR - 1, v);
+            if (m < NR) t -= at(s2, NR - 1 - m, v);
+            acc[v] += t;
+        }
+    }
 }
 
 template <int RF>
@@ -1326,6 +1439,7 @@ __global__ void __launch_bounds__(512)
     const int H = p.hist_tiles, GS = p.hist_tiles + 2;      // float [GS][NRC] run totals
     tr.init_barriers((gsum + (uint32_t)GS * NRC * 4u + 7u) & ~7u);
     const uint32_t row_stride = C * 4u;                     // bytes between consecutive frames of one channel
+    const bool long_mode = fp.long_mode != 0;
 
     for (int chunk = blockIdx.x; chunk < p.total_chunks; chunk += gridDim.x) {
         int sig, t0, t1;
@@ -1356,6 +1470,10 @@ __global__ void __launch_bounds__(512)
             tr.before_sync();
             __syncthreads();
             tr.after_sync(j, ntl, first, sig);
+            if (long_mode) {
+                fewc_scan_slot<float, 1>(gsum + (uint32_t)slot * NRC * 4u, NR, C);
+                __syncthreads();
+            }
 
             if (is_out) {
                 const float inv = p.inv_k;
@@ -1384,13 +1502,19 @@ __global__ void __launch_bounds__(512)
                     // nearest first; they sit in this tile and, for the first runs, at the end of the previous one
                     const int D = (int)p.n_full + 1;
                     float acc = 0.f;
-                    const uint32_t g_cur = gsum + ((uint32_t)slot * NRC + c) * 4u;
-                    const int in_cur = (run < D - 1) ? run : D - 1;           // how many of them are in this tile
-                    for (int w2 = 1; w2 <= in_cur; ++w2) acc += lds32(g_cur + (uint32_t)(run - w2) * row_stride);
-                    if (in_cur < D - 1) {
-                        const int ps = (slot == 0) ? GS - 1 : slot - 1;
-                        const uint32_t g_prev = gsum + ((uint32_t)ps * NRC + c) * 4u;
-                        for (int w2 = 1; w2 <= D - 1 - in_cur; ++w2) acc += lds32(g_prev + (uint32_t)(NR - w2) * row_stride);
+                    if (long_mode) {
+                        float a1[1];
+                        fewc_window_long<float, 1>(a1, gsum, slot, GS, NR, C, c, run, D - 1);
+                        acc = a1[0];
+                    } else {
+                        const uint32_t g_cur = gsum + ((uint32_t)slot * NRC + c) * 4u;
+                        const int in_cur = (run < D - 1) ? run : D - 1;       // how many of them are in this tile
+                        for (int w2 = 1; w2 <= in_cur; ++w2) acc += lds32(g_cur + (uint32_t)(run - w2) * row_stride);
+                        if (in_cur < D - 1) {
+                            const int ps = (slot == 0) ? GS - 1 : slot - 1;
+                            const uint32_t g_prev = gsum + ((uint32_t)ps * NRC + c) * 4u;
+                            for (int w2 = 1; w2 <= D - 1 - in_cur; ++w2) acc += lds32(g_prev + (uint32_t)(NR - w2) * row_stride);
+                        }
                     }
 #pragma unroll
                     for (int r = 0; r < RF; ++r)
@@ -1455,6 +1579,7 @@ __global__ void __launch_bounds__(512)
     const int H = p.hist_tiles, GS = p.hist_tiles + 2;      // int [GS][NRC] run totals
     tr.init_barriers((gsum + (uint32_t)GS * NRC * 4u + 7u) & ~7u);
     const uint32_t row_stride = C * 2u;                     // bytes between consecutive frames of one channel
+    const bool long_mode = fp.long_mode != 0;
     const uint32_t g_stride = C * 4u;                       // bytes between consecutive runs' totals of one channel
 
     for (int chunk = blockIdx.x; chunk < p.total_chunks; chunk += gridDim.x) {
@@ -1483,6 +1608,10 @@ __global__ void __launch_bounds__(512)
             tr.before_sync();
             __syncthreads();
             tr.after_sync(j, ntl, first, sig);
+            if (long_mode) {
+                fewc_scan_slot<int, 1>(gsum + (uint32_t)slot * NRC * 4u, NR, C);
+                __syncthreads();
+            }
 
             if (is_out) {
                 if (active) {
@@ -1493,13 +1622,19 @@ __global__ void __launch_bounds__(512)
                     for (int r = 0; r < RF; ++r) xl[r] = lds16s(swz(tr.rel(lag0 + r * (int)row_stride)));
                     const int D = (int)p.n_full + 1;
                     int acc = 0;
-                    const uint32_t g_cur = gsum + ((uint32_t)slot * NRC + c) * 4u;
-                    const int in_cur = (run < D - 1) ? run : D - 1;
-                    for (int w2 = 1; w2 <= in_cur; ++w2) acc += lds32i(g_cur + (uint32_t)(run - w2) * g_stride);
-                    if (in_cur < D - 1) {
-                        const int ps = (slot == 0) ? GS - 1 : slot - 1;
-                        const uint32_t g_prev = gsum + ((uint32_t)ps * NRC + c) * 4u;
-                        for (int w2 = 1; w2 <= D - 1 - in_cur; ++w2) acc += lds32i(g_prev + (uint32_t)(NR - w2) * g_stride);
+                    if (long_mode) {
+                        int a1[1];
+                        fewc_window_long<int, 1>(a1, gsum, slot, GS, NR, C, c, run, D - 1);
+                        acc = a1[0];
+                    } else {
+                        const uint32_t g_cur = gsum + ((uint32_t)slot * NRC + c) * 4u;
+                        const int in_cur = (run < D - 1) ? run : D - 1;
+                        for (int w2 = 1; w2 <= in_cur; ++w2) acc += lds32i(g_cur + (uint32_t)(run - w2) * g_stride);
+                        if (in_cur < D - 1) {
+                            const int ps = (slot == 0) ? GS - 1 : slot - 1;
+                            const uint32_t g_prev = gsum + ((uint32_t)ps * NRC + c) * 4u;
+                            for (int w2 = 1; w2 <= D - 1 - in_cur; ++w2) acc += lds32i(g_prev + (uint32_t)(NR - w2) * g_stride);
+                        }
                     }
 #pragma unroll
                     for (int r = 0; r < RF; ++r)
@@ -1509,6 +1644,125 @@ __global__ void __launch_bounds__(512)
                     for (int r = 0; r < RF; ++r) {
                         acc += x[r] - xl[r];
                         sts16(swz(ob + (uint32_t)r * row_stride), div_trunc_i32(acc, mul, sh));
+                    }
+                }
+                tr.staged(tile, sig);
+            }
+            tr.advance();
+        }
+        tr.epilogue();
+    }
+    tr.finish();
+}
+
+// ----------------------------------------------------------------------------------
+// Even channel counts (4, 6 = 5.1, 8 = 7.1, ... 30) of interleaved int16: the frame is C/2 32-bit words, each a
+// pair of neighbouring channels, so the kernel is stream_fewc_f32_kernel's layout over WORDS (thread = 16-frame
+// run of one channel pair, 32-bit shared-memory accesses instead of three 2-byte ones per sample) with
+// stream_i16_kernel's arithmetic: dp2a on the packed words for run totals, head and slide, signed multiply-high
+// division, one byte permute per output word.  fp.channels = C/2 here.
+// ----------------------------------------------------------------------------------
+template <int RF>
+__global__ void __launch_bounds__(512)
+    stream_fewc_i16x2_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map,
+                             const __grid_constant__ CUtensorMap halo_map, const FewcParams fp)
+{
+    const StreamParams& p = fp.sp;
+    const uint32_t C = fp.channels;                        // channel PAIRS
+    const int NR = (int)fp.runs;
+    const uint32_t NRC = (uint32_t)NR * C;
+    const uint32_t tile_bytes = NRC * RF * 4u;
+    extern __shared__ uint8_t smem_raw[];
+    const int tid = threadIdx.x;
+    const bool active = (uint32_t)tid < NRC;
+    const int run = active ? (int)((uint32_t)tid / C) : 0;
+    const uint32_t c = active ? (uint32_t)tid - (uint32_t)run * C : 0u;
+
+    TileRing<0, 0> tr;
+    const uint32_t gsum = tr.setup(smem_u32(smem_raw), p, &in_map, &out_map, &halo_map, tile_bytes, (int)(tile_bytes / 128u));
+    const int H = p.hist_tiles, GS = p.hist_tiles + 2;      // int [GS][NRC][2] run totals (low / high channel)
+    tr.init_barriers((gsum + (uint32_t)GS * NRC * 8u + 7u) & ~7u);
+    const uint32_t row_stride = C * 4u;                     // bytes between consecutive frames of one pair
+    const bool long_mode = fp.long_mode != 0;
+    const uint32_t g_stride = C * 8u;                       // bytes between consecutive runs' totals of one pair
+    const uint32_t w_lo = p.wscale, w_hi = p.wscale << 8;
+    const uint32_t n_lo = (0u - p.wscale) & 0xffu, n_hi = n_lo << 8;
+
+    for (int chunk = blockIdx.x; chunk < p.total_chunks; chunk += gridDim.x) {
+        int sig, t0, t1;
+        if (!chunk_range(p, chunk, sig, t0, t1)) continue;
+        const int first = t0 - H;
+        const int ntl = t1 - first;
+        tr.prologue(first, ntl, sig);
+
+        for (int j = 0; j < ntl; ++j) {
+            const int tile = first + j;
+            const bool is_out = (j >= H);
+            const uint32_t cur = tr.wait_tile();
+            const int slot = tr.slot;
+
+            uint32_t x[RF];
+            const uint32_t own = ((uint32_t)run * RF * C + c) * 4u;
+            int g0 = 0, g1 = 0;
+#pragma unroll
+            for (int r = 0; r < RF; ++r) {
+                x[r] = active ? lds32u(swz(cur + own + (uint32_t)r * row_stride)) : 0u;
+                g0 = dp2a_s(x[r], w_lo, g0);
+                g1 = dp2a_s(x[r], w_hi, g1);
+            }
+            if (active) sts64i(gsum + ((uint32_t)slot * NRC + tid) * 8u, g0, g1);
+
+            tr.before_sync();
+            __syncthreads();
+            tr.after_sync(j, ntl, first, sig);
+            if (long_mode) {
+                fewc_scan_slot<int, 2>(gsum + (uint32_t)slot * NRC * 8u, NR, C);
+                __syncthreads();
+            }
+
+            if (is_out) {
+                if (active) {
+                    const uint32_t ob = tr.out_tile() + own;
+                    const int lag0 = (int)own - (int)(p.k * row_stride);
+                    uint32_t xl[RF];
+#pragma unroll
+                    for (int r = 0; r < RF; ++r) xl[r] = lds32u(swz(tr.rel(lag0 + r * (int)row_stride)));
+                    const int D = (int)p.n_full + 1;
+                    int a0 = 0, a1 = 0;
+                    if (long_mode) {
+                        int a2[2];
+                        fewc_window_long<int, 2>(a2, gsum, slot, GS, NR, C, c, run, D - 1);
+                        a0 = a2[0], a1 = a2[1];
+                    } else {
+                        const uint32_t g_cur = gsum + ((uint32_t)slot * NRC + c) * 8u;
+                        const int in_cur = (run < D - 1) ? run : D - 1;
+                        for (int w2 = 1; w2 <= in_cur; ++w2) {
+                            const int2 t = lds64i(g_cur + (uint32_t)(run - w2) * g_stride);
+                            a0 += t.x, a1 += t.y;
+                        }
+                        if (in_cur < D - 1) {
+                            const int ps = (slot == 0) ? GS - 1 : slot - 1;
+                            const uint32_t g_prev = gsum + ((uint32_t)ps * NRC + c) * 8u;
+                            for (int w2 = 1; w2 <= D - 1 - in_cur; ++w2) {
+                                const int2 t = lds64i(g_prev + (uint32_t)(NR - w2) * g_stride);
+                                a0 += t.x, a1 += t.y;
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int r = 0; r < RF; ++r)
+                        if ((uint32_t)r < p.m_part) {
+                            a0 = dp2a_s(xl[r], w_lo, a0);
+                            a1 = dp2a_s(xl[r], w_hi, a1);
+                        }
+                    const int mul = (int)p.div_mul;
+                    const uint32_t sh = p.div_shift;
+#pragma unroll
+                    for (int r = 0; r < RF; ++r) {
+                        a0 = dp2a_s(xl[r], n_lo, dp2a_s(x[r], w_lo, a0));
+                        a1 = dp2a_s(xl[r], n_hi, dp2a_s(x[r], w_hi, a1));
+                        sts32u(swz(ob + (uint32_t)r * row_stride),
+                               __byte_perm(div_trunc_mulhi(a0, mul, sh), div_trunc_mulhi(a1, mul, sh), 0x5410));
                     }
                 }
                 tr.staged(tile, sig);

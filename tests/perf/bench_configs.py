@@ -216,7 +216,7 @@ def main():
         mavg.fill_synthetic_device(d_in.value, "f32", n, 0, SEED, 0, stream.cuda_stream)
         stream.synchronize()
         res = {}
-        for k in (3, 64, 256, 1024, 4096):
+        for k in (3, 32, 64, 128, 256, 1024, 4096):
             plan = mavg.Plan(n_frames, k, channels=C, **tune)
             plan.set_stream(stream.cuda_stream)
             plan.enable_timing(False)
@@ -234,7 +234,7 @@ def main():
         mavg.fill_synthetic_device(d_in.value, "i16", n, 0, SEED, 0, stream.cuda_stream)
         stream.synchronize()
         res = {}
-        for k in (3, 64, 256, 1024):
+        for k in (3, 32, 64, 128, 256, 1024):
             plan = mavg.Plan(n_frames, k, channels=C, dtype="i16", **tune)
             plan.set_stream(stream.cuda_stream)
             plan.enable_timing(False)

@@ -544,34 +544,37 @@ def _fewc_runs(ch):
 @pytest.mark.parametrize("ch", [3, 5, 6, 7, 8, 12, 24, 31])
 @pytest.mark.parametrize("k", [1, 2, 3, 7, 8, 31, 32, 33, 64, 100, 255, 256, 300])
 def test_few_channel_interleaved_i16_bit_exact(mavg, oracle_mod, ch, k):
-    runs = _fewc_runs(ch)
-    frames = 3 * runs * 32 + 41                    # several tiles, ragged tail (flat length not a multiple of 64)
+    """Odd channel counts: 2-byte accesses, 32-frame runs.  Even counts: channel pairs as 32-bit words, 16-frame runs."""
+    pair = ch % 2 == 0
+    runs = _fewc_runs(ch // 2 if pair else ch)
+    rf = 16 if pair else 32
+    frames = 3 * runs * rf + 41                    # several tiles, ragged tail (flat length not a multiple of 64)
     x = oracle_mod.fill_i16(frames * ch, 26000 + k + ch)
     with mavg.Plan(frames, k, channels=ch, dtype="i16") as plan:
         y = plan.run_host(x)
         i = plan.info
-        if 2 <= k <= 256 and (k + 31) // 32 <= runs:
-            assert i.path == 1 and i.mode == 4 and i.run == 32, "expected the few-channel int16 kernel"
+        if 2 <= k <= 256 and (k + rf - 1) // rf <= runs:
+            assert i.path == 1 and i.mode == 4 and i.run == rf, "expected the few-channel int16 kernel"
     assert np.array_equal(y, oracle_mod.mavg_i16(x, k, ch))
 
 
 def test_few_channel_i16_extremes_and_negative_truncation(mavg, oracle_mod):
     """Saturated inputs (window sums up to 256 * 32768 in magnitude) and sign-alternating ramps whose sums straddle
     zero: the multiply-high division has to truncate toward zero exactly as C's `/` does."""
-    ch = 6
-    frames = 4 * 80 * 32 + 5
-    for val in (-32768, 32767, -1, 1):
-        x = np.full(frames * ch, val, dtype=np.int16)
-        for k in (2, 3, 7, 100, 255, 256):
-            with mavg.Plan(frames, k, channels=ch, dtype="i16") as plan:
-                assert plan.info.mode == 4
-                assert np.array_equal(plan.run_host(x), oracle_mod.mavg_i16(x, k, ch)), (val, k)
-    x = ((np.arange(frames * ch) % 11 - 5) * 997).astype(np.int16)
-    for k in (2, 3, 5, 6, 7, 9, 10, 11, 12, 13, 100):
-        assert np.array_equal(mavg.moving_average(x, k, channels=ch), oracle_mod.mavg_i16(x, k, ch)), k
+    for ch in (6, 5):                              # pair kernel, scalar kernel
+        frames = 4 * 80 * 32 + 5
+        for val in (-32768, 32767, -1, 1):
+            x = np.full(frames * ch, val, dtype=np.int16)
+            for k in (2, 3, 7, 100, 255, 256):
+                with mavg.Plan(frames, k, channels=ch, dtype="i16") as plan:
+                    assert plan.info.mode == 4
+                    assert np.array_equal(plan.run_host(x), oracle_mod.mavg_i16(x, k, ch)), (ch, val, k)
+        x = ((np.arange(frames * ch) % 11 - 5) * 997).astype(np.int16)
+        for k in (2, 3, 5, 6, 7, 9, 10, 11, 12, 13, 100):
+            assert np.array_equal(mavg.moving_average(x, k, channels=ch), oracle_mod.mavg_i16(x, k, ch)), (ch, k)
 
 
-@pytest.mark.parametrize("case", [(6, 64), (3, 5), (7, 200)])
+@pytest.mark.parametrize("case", [(6, 64), (3, 5), (7, 200), (8, 256), (4, 2)])
 def test_few_channel_i16_shard_with_halo_bit_exact(mavg, oracle_mod, torch_cuda, case):
     torch = torch_cuda
     ch, k = case
@@ -588,3 +591,76 @@ def test_few_channel_i16_shard_with_halo_bit_exact(mavg, oracle_mod, torch_cuda,
         plan.run_device_halo(dx.data_ptr() + 2 * cut * ch, dz.data_ptr(), dx.data_ptr() + 2 * (cut - halo) * ch)
         plan.synchronize()
     assert np.array_equal(dz.cpu().numpy(), oracle_mod.mavg_i16(x, k, ch)[cut * ch:])
+
+
+# ------------------------------------------------------------------ few-channel kernels, long windows (prefix mode)
+@pytest.mark.parametrize("ch", [3, 4, 5, 6, 8, 12, 24, 30])
+@pytest.mark.parametrize("k", [257, 272, 273, 512, 545, 1000, 1024, 2048, 4096])
+@pytest.mark.parametrize("dtype", ["f32", "i16"])
+def test_few_channel_long_windows(mavg, oracle_mod, ch, k, dtype):
+    """Windows longer than 16 runs: run totals become per-tile prefixes, the window start is a prefix difference
+    reaching up to H tiles back.  Whatever does not fit shared memory falls back to the generic kernel; either
+    way the result has to match the oracle (bit-exact for int16)."""
+    frames = 26000 + 41
+    if dtype == "f32":
+        x = oracle_mod.fill_f32(frames * ch, 28000 + k + ch)
+    else:
+        x = oracle_mod.fill_i16(frames * ch, 28000 + k + ch)
+    with mavg.Plan(frames, k, channels=ch, dtype=dtype) as plan:
+        y = plan.run_host(x)
+        i = plan.info
+        if ch <= 8 and k <= 1024:
+            assert i.path == 1 and i.mode == 4, "expected a few-channel streaming kernel"
+    if dtype == "f32":
+        assert _rel(y, oracle_mod.mavg_f64(x, k, ch)) < TOL
+    else:
+        assert np.array_equal(y, oracle_mod.mavg_i16(x, k, ch))
+
+
+@pytest.mark.parametrize("dist", ["USYM", "DC1E4"])
+def test_few_channel_long_window_conditioning(mavg, oracle_mod, dist):
+    """Zero-mean and large-offset inputs through the prefix mode: forward error against sum |x| / k stays tiny
+    (prefix differences never leave one tile)."""
+    ch, k, frames = 6, 1000, 60000
+    x = oracle_mod.fill_f32(frames * ch, 29000, dist=getattr(oracle_mod, "DIST_" + dist))
+    with mavg.Plan(frames, k, channels=ch) as plan:
+        assert plan.info.mode == 4
+        y = plan.run_host(x)
+    e = oracle_mod.mavg_f64(x, k, ch)
+    scale = oracle_mod.mavg_f64(np.abs(x), k, ch)
+    assert np.max(np.abs(y - e) / np.maximum(scale, 1e-30)) < TOL
+
+
+@pytest.mark.parametrize("case", [("f32", 6, 1000), ("f32", 3, 4096), ("i16", 6, 1000), ("i16", 5, 2048)])
+def test_few_channel_long_window_shard_with_halo(mavg, oracle_mod, torch_cuda, case):
+    torch = torch_cuda
+    dtype, ch, k = case
+    es = 4 if dtype == "f32" else 2
+    tdt = torch.float32 if dtype == "f32" else torch.int16
+    with mavg.Plan(1_000_000, k, channels=ch, dtype=dtype) as probe:
+        halo = int(probe.info.halo_frames)
+        tiles_back = int(probe.info.history_tiles)
+        assert probe.info.mode == 4 and halo >= k and tiles_back >= 1
+    tf = halo // tiles_back
+    frames, cut = 23 * tf + 123, 7 * tf
+    x = (oracle_mod.fill_f32 if dtype == "f32" else oracle_mod.fill_i16)(frames * ch, 30000 + k)
+    dx = torch.from_numpy(x).cuda()
+    dy = torch.zeros(frames * ch, dtype=tdt, device="cuda")
+    dz = torch.zeros((frames - cut) * ch, dtype=tdt, device="cuda")
+    torch.cuda.synchronize()
+    with mavg.Plan(frames, k, channels=ch, dtype=dtype) as plan:
+        plan.run_device([dx.data_ptr()], [dy.data_ptr()])
+        plan.synchronize()
+    with mavg.Plan(frames - cut, k, channels=ch, dtype=dtype, first_frame=cut) as plan:
+        assert int(plan.info.halo_frames) == halo
+        plan.run_device_halo(dx.data_ptr() + es * cut * ch, dz.data_ptr(), dx.data_ptr() + es * (cut - halo) * ch)
+        plan.synchronize()
+    whole, part = dy.cpu().numpy(), dz.cpu().numpy()
+    if dtype == "f32":
+        stream_frames = ((frames - cut) * ch // 32) * 32 // ch     # the rest is the generic tail
+        assert np.array_equal(part[:stream_frames * ch], whole[cut * ch:(cut + stream_frames) * ch])
+        assert _rel(whole, oracle_mod.mavg_f64(x, k, ch)) < TOL
+        assert _rel(part, oracle_mod.mavg_f64(x, k, ch)[cut * ch:]) < TOL
+    else:
+        e = oracle_mod.mavg_i16(x, k, ch)
+        assert np.array_equal(whole, e) and np.array_equal(part, e[cut * ch:])
