@@ -131,7 +131,7 @@ void i16_mulhi_consts(uint32_t k, uint32_t* mul, uint32_t* shift, uint32_t* wsca
 StreamGeom plan_stream_i16(uint32_t k, uint32_t C, const mavg_tuning& tu)
 {
     StreamGeom g;
-    g.NT = 512;  // 256 threads x 2 CTAs per SM measured no faster: the kernel is bound by instruction issue
+    g.NT = tu.threads == 256 ? 256 : 512;
     g.R = 32;    // 16-sample runs with two CTAs per SM were measured 10-20 % slower (per-run overheads dominate)
     g.elem = 2;
     g.C = C;
@@ -770,7 +770,8 @@ int launch_shard(mavg_plan* p, DevCtx& d, const void* in, void* out, const void*
     sp.has_halo = halo ? 1 : 0;
 
     StreamKernel kern = g.elem == 4 ? pick_kernel(g, p->desc.window)
-                                    : (g.C == 1 ? pick_i16<512, 32, 1>(g.MIS, g.mode) : pick_i16<512, 32, 2>(g.MIS, g.mode));
+                        : g.NT == 256 ? (g.C == 1 ? pick_i16<256, 32, 1>(g.MIS, g.mode) : pick_i16<256, 32, 2>(g.MIS, g.mode))
+                                      : (g.C == 1 ? pick_i16<512, 32, 1>(g.MIS, g.mode) : pick_i16<512, 32, 2>(g.MIS, g.mode));
     if (!kern) return fail(MAVG_ERR_UNSUPPORTED, "no stream kernel variant for this window");
     MAVG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
     const unsigned grid = (unsigned)std::min<uint64_t>(ctas, (uint64_t)sp.total_chunks);

@@ -24,6 +24,9 @@ METRICS = [
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
     "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
     "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
     "smsp__average_warp_latency_issue_stalled_long_scoreboard.pct",
     "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
