@@ -251,12 +251,14 @@ def test_generic_path_with_halo(mavg, oracle_mod, torch_cuda):
         plan.run_device_halo(dx.data_ptr() + 2 * cut * ch, dz.data_ptr(), dx.data_ptr() + 2 * (cut - halo) * ch)
         plan.synchronize()
     assert np.array_equal(dz.cpu().numpy(), oracle_mod.mavg_i16(x, k, ch)[cut * ch:])
-    # three-channel float32 takes the generic kernel by itself
+    # 40-channel int16 takes the generic kernel by itself (no streaming kernel for that shape); float32 forced
+    with mavg.Plan(frames, k, channels=40, dtype="i16") as plan:
+        assert plan.info.path == 2
     xf = oracle_mod.fill_f32(frames * 3, 18)
     dxf = torch.from_numpy(xf).cuda()
     dzf = torch.zeros((frames - cut) * 3, dtype=torch.float32, device="cuda")
     torch.cuda.synchronize()
-    with mavg.Plan(frames - cut, k, channels=3, first_frame=cut) as plan:
+    with mavg.Plan(frames - cut, k, channels=3, first_frame=cut, path="generic") as plan:
         halo = int(plan.info.halo_frames)
         assert halo == k and plan.info.path == 2
         plan.run_device_halo(dxf.data_ptr() + 4 * cut * 3, dzf.data_ptr(), dxf.data_ptr() + 4 * (cut - halo) * 3)
@@ -273,7 +275,10 @@ def test_timing_and_info(mavg, oracle_mod):
         assert t.compute_ms > 0 and t.h2d_ms > 0 and t.d2h_ms > 0
         assert abs(t.total_ms - (t.h2d_ms + t.compute_ms + t.d2h_ms)) < 1e-3
         i = plan.info
-        assert i.path == 1 and i.launches_per_run == 1 and i.grid > 0
+        assert i.path == 1 and i.launches_per_run == 4 and i.grid > 0     # 16 MiB of samples = four 4 MiB slices
+    with mavg.Plan(n, 64, slice_bytes=64 << 20) as plan:
+        assert np.array_equal(plan.run_host(x), mavg.moving_average(x, 64))   # slicing never changes a bit
+        assert plan.info.launches_per_run == 1
 
 
 def test_owned_buffers_synthetic_run(mavg, oracle_mod, torch_cuda):
