@@ -100,6 +100,8 @@ SYMBOLS = [
     ("mavg_device_free", _i, [_vp]),
     ("mavg_host_alloc", _i, [_u64, ctypes.POINTER(_vp)]),
     ("mavg_host_free", _i, [_vp]),
+    ("mavg_host_register", _i, [_vp, _u64]),
+    ("mavg_host_unregister", _i, [_vp]),
 ]
 
 

@@ -1415,4 +1415,33 @@ int mavg_host_free(void* h_ptr)
     return MAVG_OK;
 }
 
+int mavg_host_register(void* h_ptr, uint64_t bytes)
+{
+    if (!h_ptr) return fail(MAVG_ERR_INVALID_ARG, "null argument");
+    if (bytes == 0) return MAVG_OK;
+    const cudaError_t e = cudaHostRegister(h_ptr, bytes, cudaHostRegisterPortable);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) {
+        cudaGetLastError();
+        return MAVG_OK;
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? MAVG_ERR_NO_DEVICE : MAVG_ERR_ALLOC,
+                    "cudaHostRegister(%llu bytes) failed: %s", (unsigned long long)bytes, cudaGetErrorString(e));
+    }
+    return MAVG_OK;
+}
+
+int mavg_host_unregister(void* h_ptr)
+{
+    if (!h_ptr) return MAVG_OK;
+    const cudaError_t e = cudaHostUnregister(h_ptr);
+    if (e == cudaErrorHostMemoryNotRegistered) {
+        cudaGetLastError();
+        return MAVG_OK;
+    }
+    MAVG_CUDA(e);
+    return MAVG_OK;
+}
+
 }  // extern "C"

@@ -174,6 +174,40 @@ class PinnedArray:
             pass
 
 
+class pinned:
+    """Context manager that page-locks NumPy arrays the caller already owns (mavg_host_register) for the duration
+    of the block, so that `Plan.run_host` on them runs at pinned-copy speed:
+
+        with mavg.pinned(x, y):
+            for k in windows:
+                plans[k].run_host(x, out=y)
+    """
+
+    def __init__(self, *arrays: np.ndarray):
+        self._lib = _lib.load()
+        self._arrays = arrays
+        self._done = []
+
+    def __enter__(self):
+        for a in self._arrays:
+            if not a.flags["C_CONTIGUOUS"]:
+                raise ValueError("only contiguous arrays can be page-locked")
+            if a.nbytes == 0:
+                continue
+            ptr = ctypes.c_void_p(a.ctypes.data)
+            try:
+                check(self._lib.mavg_host_register(ptr, a.nbytes))
+            except Exception:
+                self.__exit__()
+                raise
+            self._done.append(ptr)
+        return self
+
+    def __exit__(self, *exc):
+        while self._done:
+            self._lib.mavg_host_unregister(self._done.pop())
+
+
 def prefix_sum_device(in_ptr: int, out_ptr: int, dtype: str, frames: int, channels: int = 1, stream: int = 0) -> None:
     """Per-channel inclusive prefix sum on device buffers (int16 -> int64, float32 -> float64), one pass."""
     check(_lib.load().mavg_prefix_sum(_DTYPES[dtype], ctypes.c_void_p(in_ptr), ctypes.c_void_p(out_ptr), frames,

@@ -494,6 +494,26 @@ def test_pinned_host_buffers(mavg, oracle_mod):
         assert _rel(hout.array, oracle_mod.mavg_f64(hin.array, k)) < TOL
 
 
+def test_caller_owned_buffers_page_locked_in_place(mavg, oracle_mod):
+    """mavg_host_register on NumPy-owned memory (what a std::vector is to the reference's GpuLoad functions): same
+    result, and the arrays stay ordinary arrays afterwards."""
+    n, k = (1 << 22) + 5, 77
+    x = oracle_mod.fill_f32(n, 23100)
+    y = np.empty_like(x)
+    e = oracle_mod.mavg_f64(x, k)
+    with mavg.Plan(n, k) as plan:
+        with mavg.pinned(x, y):
+            with mavg.pinned(x):                   # registering twice is harmless
+                assert plan.run_host(x, out=y) is y
+            assert _rel(y, e) < TOL
+        y[:] = 0
+        plan.run_host(x, out=y)                    # pageable again
+        assert _rel(y, e) < TOL
+    with pytest.raises(ValueError):
+        with mavg.pinned(x[::2]):
+            pass
+
+
 # ------------------------------------------------------------------ 3..31 interleaved float32 channels (few-channel kernel)
 @pytest.mark.parametrize("ch", [3, 5, 6, 7, 8, 12, 24, 31])
 @pytest.mark.parametrize("k", [1, 2, 3, 8, 9, 16, 17, 64, 100, 255, 256, 300])
