@@ -156,6 +156,19 @@ def test_single_process_multi_device_plan(mavg, oracle_mod):
         y6 = plan.run_host(x6)
     e6 = oracle_mod.mavg_f64(x6, 100, 6)
     assert np.max(np.abs(y6 - e6) / np.abs(e6)) < 1e-5
+    # few-channel kernels with windows that reach several tiles back (prefix mode), float32 and int16 pairs
+    with mavg.Plan(50 * 1280 + 17, 2000, channels=6, devices=devs) as plan:
+        assert plan.info.mode == 4 and plan.info.history_tiles >= 2
+        y6l = plan.run_host(x6)
+    with mavg.Plan(50 * 1280 + 17, 2000, channels=6) as plan:
+        assert np.array_equal(plan.run_host(x6), y6l)
+    e6 = oracle_mod.mavg_f64(x6, 2000, 6)
+    assert np.max(np.abs(y6l - e6) / np.abs(e6)) < 1e-5
+    xi6 = oracle_mod.fill_i16(6 * (50 * 1280 + 17), 13)
+    for k in (100, 1500):
+        with mavg.Plan(50 * 1280 + 17, k, channels=6, dtype="i16", devices=devs) as plan:
+            assert plan.info.mode == 4
+            assert np.array_equal(plan.run_host(xi6), oracle_mod.mavg_i16(xi6, k, 6)), k
     xp = oracle_mod.fill_f32(6 * 8192 * 3, 6)
     with mavg.Plan(8192 * 3, 64, channels=6, layout="planar", devices=devs) as plan:
         yp = plan.run_host(xp)
