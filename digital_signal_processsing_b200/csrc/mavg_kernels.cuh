@@ -290,6 +290,20 @@ __device__ __forceinline__ uint32_t swz(uint32_t addr) { return addr ^ ((addr >>
 
 constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;  // L2 cache hint: streaming input
 
+// Pre-swizzled tile offsets (few-channel kernels' scalar accesses, int16 kernel's 16-byte chunks).  Tile, staging and ring
+// bases are multiples of 1024 bytes, so the SWIZZLE_128B XOR (bits 4-6 with bits 7-9) of base + x only depends
+// on x: swz(base + x) = base + (x ^ ((x >> 3) & 0x70)), also for negative x in two's complement (offsets into
+// history tiles).  Computing these once per thread removes ~18 of 33 instructions per sample (ncu source view of
+// the first version: LOP3 + SHF + IMAD + VIADD + ISETP address arithmetic).
+__device__ __forceinline__ int pre_swz(int x) { return x ^ ((x >> 3) & 0x70); }
+// address of pre-swizzled offset xs (relative to the current tile, negative = history) in the stage ring:
+// b0 = ring + st * tile_bytes, b1 = b0 + ring_bytes (wrapped), neg_st = -(st * tile_bytes)
+__device__ __forceinline__ uint32_t ring_addr(int xs, uint32_t b0, uint32_t b1, int neg_st)
+{
+    return (uint32_t)xs + (xs < neg_st ? b1 : b0);
+}
+
+
 // ----------------------------------------------------------------------------------
 // Streaming kernel
 // ----------------------------------------------------------------------------------
@@ -857,6 +871,11 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : 1))
     // dp2a byte weights (+w / -w on the low or the high half; w = 2 when k == 2, see plan_stream_i16)
     const uint32_t w_lo = p.wscale, w_hi = p.wscale << 8;
     const uint32_t n_lo = (0u - p.wscale) & 0xffu, n_hi = n_lo << 8;
+    int xo[CH_OWN], xg[CH_LAG];                          // pre-swizzled chunk offsets: own run, lag run
+#pragma unroll
+    for (int c = 0; c < CH_OWN; ++c) xo[c] = pre_swz(tid * (R * 2) + 16 * c);
+#pragma unroll
+    for (int c = 0; c < CH_LAG; ++c) xg[c] = pre_swz((tid * CH_OWN - (int)p.lag_chunks + c) * 16);
 
     for (int chunk = blockIdx.x; chunk < p.total_chunks; chunk += gridDim.x) {
         int sig, t0, t1;
@@ -875,7 +894,7 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : 1))
             uint32_t xw[R / 2];                              // own run, packed
 #pragma unroll
             for (int c = 0; c < CH_OWN; ++c) {
-                const uint4 v = lds128u(swz(cur + (uint32_t)tid * (R * 2) + 16u * c));
+                const uint4 v = lds128u(cur + (uint32_t)xo[c]);
                 xw[4 * c] = v.x, xw[4 * c + 1] = v.y, xw[4 * c + 2] = v.z, xw[4 * c + 3] = v.w;
             }
             uint32_t gtot[C], incl[C];
@@ -949,10 +968,11 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : 1))
                 {
                     // lag run as aligned 16-byte chunks; the head of the run (first m_part elements) is summed
                     // straight from the packed words with the plan's byte-weight table
-                    const int lin = (tid * CH_OWN - (int)p.lag_chunks) * 16;
+                    const uint32_t b0 = cur, b1 = cur + tr.ring_bytes;
+                    const int neg_st = (int)tr.ring - (int)cur;
 #pragma unroll
                     for (int c = 0; c < CH_LAG; ++c) {
-                        const uint4 v = lds128u(swz(tr.rel(lin + 16 * c)));
+                        const uint4 v = lds128u(ring_addr(xg[c], b0, b1, neg_st));
                         xlw[4 * c] = v.x, xlw[4 * c + 1] = v.y, xlw[4 * c + 2] = v.z, xlw[4 * c + 3] = v.w;
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
@@ -1006,7 +1026,7 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : 1))
                         }
                     }
                 }
-                const uint32_t ob = tr.out_tile() + (uint32_t)tid * (R * 2);
+                const uint32_t ob = tr.out_tile();
                 const int mul = (int)p.div_mul;
                 const uint32_t sh = p.div_shift;
 #pragma unroll
@@ -1026,7 +1046,7 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : 1))
                         }
                         wds[q] = __byte_perm(y[0], y[1], 0x5410);
                     }
-                    sts128u(swz(ob + 16u * c), wds[0], wds[1], wds[2], wds[3]);
+                    sts128u(ob + (uint32_t)xo[c], wds[0], wds[1], wds[2], wds[3]);
                 }
                 tr.staged(tile, sig);
             }
@@ -1326,19 +1346,6 @@ __host__ __device__ inline uint32_t fewc_smem_bytes(uint32_t tile_bytes, int S, 
 {
     return 1024u + (uint32_t)S * tile_bytes + 2u * tile_bytes + (uint32_t)(H + 2) * active_threads * total_bytes +
            (uint32_t)S * 8 + 64;
-}
-
-// Pre-swizzled tile offsets for the few-channel kernels' scalar shared-memory accesses.  Tile, staging and ring
-// bases are multiples of 1024 bytes, so the SWIZZLE_128B XOR (bits 4-6 with bits 7-9) of base + x only depends
-// on x: swz(base + x) = base + (x ^ ((x >> 3) & 0x70)), also for negative x in two's complement (offsets into
-// history tiles).  Computing these once per thread removes ~18 of 33 instructions per sample (ncu source view of
-// the first version: LOP3 + SHF + IMAD + VIADD + ISETP address arithmetic).
-__device__ __forceinline__ int pre_swz(int x) { return x ^ ((x >> 3) & 0x70); }
-// address of pre-swizzled offset xs (relative to the current tile, negative = history) in the stage ring:
-// b0 = ring + st * tile_bytes, b1 = b0 + ring_bytes (wrapped), neg_st = -(st * tile_bytes)
-__device__ __forceinline__ uint32_t ring_addr(int xs, uint32_t b0, uint32_t b1, int neg_st)
-{
-    return (uint32_t)xs + (xs < neg_st ? b1 : b0);
 }
 
 // ---- long windows in the few-channel kernels (more than 16 whole runs between the lag run and the own run) ----
