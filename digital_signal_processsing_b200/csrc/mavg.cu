@@ -276,7 +276,7 @@ StreamGeom plan_fewc(uint32_t k, uint32_t C, const mavg_tuning& tu, uint32_t ele
     // whole runs of the window: summed one by one up to direct_max_k frames (at most 16 runs, this tile and the
     // previous one), through per-tile prefixes beyond
     g.long_mode = k > (tu.direct_max_k ? tu.direct_max_k : 256u) || g.n_full > 16 || g.H > 1;
-    if (g.long_mode && k <= 8) g.long_mode = false;
+    if (g.long_mode && (k <= 8 || g.n_full == 0)) g.long_mode = false;   // nothing to sum through prefixes
     if (!g.long_mode && g.H > 1) return g;
     g.ctas_per_sm = 1;
     g.P = tu.prefetch ? (int)tu.prefetch : 2;

@@ -1,0 +1,149 @@
+"""CPU restatement of the index algebra of the few-channel kernels (stream_fewc_* in csrc/mavg_kernels.cuh) and of
+the packed-word dp2a arithmetic of the int16 kernels.  TEST INFRASTRUCTURE: integer NumPy models checked against the
+oracle, so that the run/tile/prefix bookkeeping and the byte-weight constants are verified without a GPU; the GPU
+tests check the CUDA code itself."""
+import numpy as np
+import pytest
+
+
+def fewc_geometry(k, C, R, threads=512):
+    """plan_fewc (csrc/mavg.cu): run length R frames, NR runs per tile, n_full whole runs + m_part head frames."""
+    s = (R - k % R) % R
+    m_part = R - s
+    n_full = (k + s) // R - 1
+    NR = threads // C
+    while NR > 0 and (NR * C) % 16:
+        NR -= 1
+    H = (n_full + 1 + NR - 1) // NR
+    return dict(m_part=m_part, n_full=n_full, NR=NR, H=H)
+
+
+def fewc_model(x, k, R, NR, long_mode):
+    """x: [F, C] integers.  Mirrors the kernel: per tile (NR runs of R frames) run totals, optional in-place prefix,
+    window start = whole runs (one by one, or prefix differences reaching back over tiles) + head of the lag run,
+    then the slide.  Returns exact window sums [F, C] (division is tested separately)."""
+    F, C = x.shape
+    g = fewc_geometry(k, C, R)
+    n_full, m_part = g["n_full"], g["m_part"]
+    T = NR * R
+    tiles = (F + T - 1) // T
+    xp = np.zeros((tiles * T, C), dtype=np.int64)
+    xp[:F] = x
+    get = lambda i: xp[i] if i >= 0 else np.zeros(C, dtype=np.int64)      # TMA zero fill = left padding
+    tot = xp.reshape(tiles, NR, R, C).sum(axis=2)                         # [tile][run][c]
+    pre = np.cumsum(tot, axis=1)                                          # fewc_scan_slot, per tile
+    out = np.zeros_like(xp)
+    zero = np.zeros(C, dtype=np.int64)
+    P = lambda t, r: pre[t, r] if t >= 0 else zero                        # history before the signal is all zero
+    for t in range(tiles):
+        for run in range(NR):
+            own = t * T + run * R
+            if long_mode:                                                  # fewc_window_long
+                q0 = run - n_full
+                if q0 >= 0:
+                    acc = P(t, run - 1) - (P(t, q0 - 1) if q0 > 0 else 0)
+                else:
+                    acc = (P(t, run - 1) if run > 0 else zero).copy()
+                    m, tt = -q0, t
+                    while m > NR:
+                        tt -= 1
+                        acc = acc + P(tt, NR - 1)
+                        m -= NR
+                    tt -= 1
+                    acc = acc + P(tt, NR - 1) - (P(tt, NR - 1 - m) if m < NR else 0)
+            else:                                                          # one by one: this tile, then the previous one
+                acc = zero.copy()
+                for w in range(1, n_full + 1):
+                    r2, t2 = run - w, t
+                    if r2 < 0:
+                        r2, t2 = r2 + NR, t - 1
+                    assert r2 >= 0, "direct mode looks at most one tile back"
+                    if t2 >= 0:
+                        acc = acc + tot[t2, r2]
+            for r in range(R):
+                if r < m_part:
+                    acc = acc + get(own - k + r)
+            for r in range(R):
+                acc = acc + xp[own + r] - get(own - k + r)
+                out[own + r] = acc
+    return out[:F]
+
+
+def exact_sums(x, k):
+    c = np.cumsum(np.vstack([np.zeros((1, x.shape[1]), dtype=np.int64), x.astype(np.int64)]), axis=0)
+    hi = np.arange(1, x.shape[0] + 1)
+    lo = np.maximum(hi - k, 0)
+    return c[hi] - c[lo]
+
+
+@pytest.mark.parametrize("C,R,NR", [(3, 4, 5), (6, 4, 3), (5, 8, 4)])
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 7, 8, 9, 16, 17, 31, 40, 64, 100, 161])
+def test_window_bookkeeping_matches_exact_sums(C, R, NR, k):
+    """Small run / tile sizes so that windows span many runs and several tiles."""
+    rng = np.random.default_rng(k * 31 + C)
+    F = 7 * NR * R + 5
+    x = rng.integers(-32768, 32768, size=(F, C))
+    g = fewc_geometry(k, C, R)
+    want = exact_sums(x, k)
+    if g["n_full"] >= 1:                                                  # plan_fewc never picks the prefix mode otherwise
+        assert np.array_equal(fewc_model(x, k, R, NR, long_mode=True), want)
+    if g["n_full"] <= NR:                                                 # direct mode: H == 1 in the plan
+        assert np.array_equal(fewc_model(x, k, R, NR, long_mode=False), want)
+
+
+def test_plan_geometry_identities():
+    for C in range(3, 32):
+        for R in (16, 32):
+            for k in (2, 9, 16, 17, 255, 256, 257, 1000, 4096):
+                g = fewc_geometry(k, C, R)
+                if g["NR"] == 0:
+                    continue
+                assert g["n_full"] * R + g["m_part"] == k and 1 <= g["m_part"] <= R
+                assert (g["NR"] * C) % 16 == 0 and g["NR"] * C <= 512
+                assert g["H"] * g["NR"] >= g["n_full"] + 1                # the lag run is inside the history tiles
+
+
+# ---------------------------------------------------------------- packed-word arithmetic of the int16 kernels
+def dp2a_lo_s32(a, b, c):
+    """PTX dp2a.lo.s32.s32: c + a.lo16 * b.byte0 + a.hi16 * b.byte1, halves and bytes signed."""
+    a = np.asarray(a, dtype=np.uint32)
+    lo = (a & 0xFFFF).astype(np.int64)
+    hi = (a >> 16).astype(np.int64)
+    lo = np.where(lo >= 32768, lo - 65536, lo)
+    hi = np.where(hi >= 32768, hi - 65536, hi)
+    sb = lambda v: v - 256 if v >= 128 else v
+    return c + lo * sb(b & 0xFF) + hi * sb((b >> 8) & 0xFF)
+
+
+@pytest.mark.parametrize("wscale", [1, 2])
+def test_dp2a_weights_select_add_and_subtract_halves(wscale):
+    rng = np.random.default_rng(3)
+    s = rng.integers(-32768, 32768, size=(1000, 2))
+    words = ((s[:, 1].astype(np.int64) & 0xFFFF) << 16 | (s[:, 0].astype(np.int64) & 0xFFFF)).astype(np.uint32)
+    w_lo, w_hi = wscale, wscale << 8
+    n_lo = (-wscale) & 0xFF
+    n_hi = n_lo << 8
+    assert np.array_equal(dp2a_lo_s32(words, w_lo, 0), wscale * s[:, 0])
+    assert np.array_equal(dp2a_lo_s32(words, w_hi, 0), wscale * s[:, 1])
+    assert np.array_equal(dp2a_lo_s32(words, n_lo, 7), 7 - wscale * s[:, 0])
+    assert np.array_equal(dp2a_lo_s32(words, n_hi, 7), 7 - wscale * s[:, 1])
+    assert np.array_equal(dp2a_lo_s32(words, w_lo | w_hi, 0), wscale * (s[:, 0] + s[:, 1]))     # mono run totals
+
+
+def test_pre_swizzled_offsets_equal_swizzled_addresses():
+    """swz(base + x) == base + pre_swz(x) for 1024-byte aligned bases and offsets of either sign (two's complement),
+    and the ring wrap decision is the same for x and pre_swz(x)."""
+    swz = lambda a: a ^ ((a >> 3) & 0x70)
+    rng = np.random.default_rng(4)
+    ring, tb, S = 3 * 1024, 30 * 1024, 5
+    for _ in range(20000):
+        st = int(rng.integers(0, S))
+        x = int(rng.integers(-3 * tb, tb))
+        if st * tb + x < -(S - 1) * tb:
+            continue
+        o = st * tb + x
+        want = swz(ring + (o + S * tb if o < 0 else o))
+        xs = x ^ ((x >> 3) & 0x70)                                         # Python ints: arithmetic shift, like the kernel
+        b0 = ring + st * tb
+        got = xs + (b0 + S * tb if xs < -(st * tb) else b0)
+        assert got == want

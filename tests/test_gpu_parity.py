@@ -689,3 +689,22 @@ def test_few_channel_long_window_shard_with_halo(mavg, oracle_mod, torch_cuda, c
     else:
         e = oracle_mod.mavg_i16(x, k, ch)
         assert np.array_equal(whole, e) and np.array_equal(part, e[cut * ch:])
+
+
+@pytest.mark.parametrize("case", [("f32", 3, 1 << 24, 1000), ("f32", 6, 1 << 23, 64), ("i16", 6, 1 << 23, 700),
+                                  ("i16", 5, 1 << 23, 48)])
+def test_few_channel_many_tiles_per_cta(mavg, oracle_mod, case):
+    """Tens of tiles per persistent CTA (ring wrap-around, staging double buffer, chunk boundaries with history
+    replay) on 50 M samples; every output checked."""
+    dtype, ch, frames, k = case
+    if dtype == "f32":
+        x = oracle_mod.fill_f32(frames * ch, 31000 + k)
+    else:
+        x = oracle_mod.fill_i16(frames * ch, 31000 + k)
+    with mavg.Plan(frames, k, channels=ch, dtype=dtype) as plan:
+        assert plan.info.mode == 4
+        y = plan.run_host(x)
+    if dtype == "f32":
+        assert _rel(y, oracle_mod.mavg_f64(x, k, ch)) < TOL
+    else:
+        assert np.array_equal(y, oracle_mod.mavg_i16_mt(x, k, ch, 8))
