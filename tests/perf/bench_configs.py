@@ -63,7 +63,7 @@ def timed(fn, stream, iters, warmup, world):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--config", required=True, choices=["4", "5p", "5i", "i16", "g3", "g6i", "s2", "scan"])
+    ap.add_argument("--config", required=True, choices=["4", "5p", "5i", "i16", "g3", "g6i", "gen", "s2", "scan"])
     ap.add_argument("--log2", type=int, default=32, help="total samples (log2) for configs 4/5")
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
@@ -208,6 +208,28 @@ def main():
             lib.mavg_device_free(d_in)
             lib.mavg_device_free(d_out)
         out.update(workload="mavg_prefix_sum on 2^28 samples (bytes = input + 8-byte output per sample)", per_k=res)
+
+    elif args.config == "gen":  # shapes that still take the generic kernel
+        res = {}
+        for name, dtype, C, frames, k in (("i16_c64_k64", "i16", 64, 1 << 21, 64), ("i16_c256_k64", "i16", 256, 1 << 19, 64),
+                                          ("f32_c34_k64", "f32", 34, 1 << 22, 64), ("f32_c64_k2048", "f32", 64, 1 << 21, 2048),
+                                          ("f32_c1_k60000", "f32", 1, 1 << 27, 60000), ("i16_c2_k40000", "i16", 2, 1 << 26, 40000)):
+            es = 4 if dtype == "f32" else 2
+            n = frames * C
+            d_in, d_out = alloc(es * n), alloc(es * n)
+            mavg.fill_synthetic_device(d_in.value, dtype, n, 0, SEED, 0, stream.cuda_stream)
+            stream.synchronize()
+            plan = mavg.Plan(frames, k, channels=C, dtype=dtype, **tune)
+            plan.set_stream(stream.cuda_stream)
+            plan.enable_timing(False)
+            ms = timed(lambda: plan.run_device([d_in.value], [d_out.value]), stream, 3, 1, world)
+            res[name] = {"ms": round(ms, 4), "gsamples_s": round(n / ms / 1e6, 1), "hbm_gbs": round(2 * es * n / ms / 1e6, 1),
+                         "path": "stream" if plan.info.path == 1 else "generic", "mode": int(plan.info.mode),
+                         "launches": int(plan.info.launches_per_run)}
+            plan.close()
+            lib.mavg_device_free(d_in)
+            lib.mavg_device_free(d_out)
+        out.update(workload="shapes served by the generic kernel (2^27 samples each)", per_k=res)
 
     elif args.config == "g3":  # shapes only the generic kernel takes: 3-channel interleaved float32
         n_frames, C = 1 << 25, 3
