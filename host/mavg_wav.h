@@ -7,6 +7,8 @@
 //   * float32 files (audioFormat 3, 32 bit) are accepted next to int16 -- the north-star extension;
 //   * RIFF/WAVE magic is validated, non-canonical layouts (fact/LIST chunks, 18/40-byte fmt, extensible format)
 //     are walked chunk by chunk, and the sample count is clamped to the bytes present;
+//   * payloads of 4 GiB and more use RF64 (EBU Tech 3306: "RF64" magic, 32-bit sizes set to 0xFFFFFFFF, the real
+//     64-bit sizes in a `ds64` chunk) on input and on output -- the reference's uint32 counts stop at 2^32 bytes;
 //   * failures are reported through the return value, nothing is printed from library code.
 #pragma once
 
@@ -47,6 +49,8 @@ inline SampleKind kind_of(const WAVHeader& h)
     return SampleKind::Unsupported;
 }
 
+inline uint32_t clamp32(uint64_t v) { return v > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)v; }
+
 inline bool magic_ok(const WAVHeader& h)
 {
     return !memcmp(h.riff, "RIFF", 4) && !memcmp(h.wave, "WAVE", 4) && !memcmp(h.data, "data", 4);
@@ -64,9 +68,10 @@ inline bool read_file(const std::string& path, WAVHeader& h, std::vector<unsigne
     if (!f) { if (why) *why = "could not open file"; return false; }
     auto fail = [&](const char* msg) { if (why) *why = msg; fclose(f); return false; };
     if (fread(&h, sizeof h, 1, f) != 1) return fail("file shorter than a WAV header");
-    if (memcmp(h.riff, "RIFF", 4) || memcmp(h.wave, "WAVE", 4)) return fail("not a RIFF/WAVE file");
-    uint64_t data_bytes = 0;
-    if (magic_ok(h) && h.fmtSize == 16) {
+    const bool rf64 = !memcmp(h.riff, "RF64", 4);
+    if ((memcmp(h.riff, "RIFF", 4) && !rf64) || memcmp(h.wave, "WAVE", 4)) return fail("not a RIFF/WAVE file");
+    uint64_t data_bytes = 0, ds64_data = 0;
+    if (!rf64 && magic_ok(h) && h.fmtSize == 16) {
         data_bytes = h.dataBytes;                              // canonical: payload follows directly
     } else {
         // general RIFF walk from the first chunk (offset 12)
@@ -87,8 +92,13 @@ inline bool read_file(const std::string& path, WAVHeader& h, std::vector<unsigne
                 if (tag == 0xFFFE && take >= 26) memcpy(&tag, buf + 24, 2);   // extensible: sub-format GUID starts with the tag
                 have_fmt = true;
                 if (fseek(f, (long)(size - take) + (size & 1), SEEK_CUR) != 0) break;
+            } else if (rf64 && !memcmp(id, "ds64", 4)) {
+                unsigned char buf[28];
+                if (size < 28 || fread(buf, 1, 28, f) != 28) return fail("truncated ds64 chunk");
+                memcpy(&ds64_data, buf + 8, 8);                  // riffSize, dataSize, sampleCount, tableLength
+                if (fseek(f, (long)(size - 28) + (size & 1), SEEK_CUR) != 0) break;
             } else if (!memcmp(id, "data", 4)) {
-                data_bytes = size;
+                data_bytes = (rf64 && size == 0xFFFFFFFFu) ? ds64_data : size;
                 have_data = true;
                 break;                                           // payload starts here
             } else if (fseek(f, (long)size + (size & 1), SEEK_CUR) != 0) {
@@ -96,11 +106,11 @@ inline bool read_file(const std::string& path, WAVHeader& h, std::vector<unsigne
             }
         }
         if (!have_fmt || !have_data) return fail("no fmt/data chunk found");
-        memcpy(h.fmt, "fmt ", 4); memcpy(h.data, "data", 4);
+        memcpy(h.riff, "RIFF", 4); memcpy(h.fmt, "fmt ", 4); memcpy(h.data, "data", 4);
         h.fmtSize = 16; h.audioFormat = tag; h.numChannels = channels; h.sampleRate = rate; h.byteRate = brate;
         h.blockAlign = align; h.bitsPerSample = bits;
-        h.dataBytes = (uint32_t)data_bytes;
-        h.sizeOfFile = 36 + h.dataBytes;
+        h.dataBytes = clamp32(data_bytes);                       // callers take the true count from bytes.size()
+        h.sizeOfFile = clamp32(36 + data_bytes);
     }
     if (kind_of(h) == SampleKind::Unsupported) {
         if (why) *why = "unsupported bits per sample: " + std::to_string(h.bitsPerSample);
@@ -111,17 +121,34 @@ inline bool read_file(const std::string& path, WAVHeader& h, std::vector<unsigne
     const size_t got = data_bytes ? fread(bytes.data(), 1, data_bytes, f) : 0;
     const size_t step = h.bitsPerSample / 8;
     bytes.resize(got / step * step);  // clamp to whole samples actually present
-    if (bytes.size() != data_bytes) { h.dataBytes = (uint32_t)bytes.size(); h.sizeOfFile = 36 + h.dataBytes; }
+    if (bytes.size() != data_bytes) { h.dataBytes = clamp32(bytes.size()); h.sizeOfFile = clamp32(36 + (uint64_t)bytes.size()); }
     fclose(f);
     return true;
 }
 
+// Header verbatim + samples (wav_header.h:50-59) while the payload fits the 32-bit size fields; RF64 beyond
+// (or when forced, for tests): "RF64" 0xFFFFFFFF "WAVE", ds64 {riff size, data size, sample count, 0}, the header's
+// fmt fields, "data" 0xFFFFFFFF, samples.
 template <typename T>
-inline bool write_file(const std::string& path, const WAVHeader& h, const T* samples, size_t count)
+inline bool write_file(const std::string& path, const WAVHeader& h, const T* samples, size_t count, bool force_rf64 = false)
 {
     FILE* f = fopen(path.c_str(), "wb");
     if (!f) return false;
-    bool ok = fwrite(&h, sizeof h, 1, f) == 1 && (count == 0 || fwrite(samples, sizeof(T), count, f) == count);
+    const uint64_t payload = (uint64_t)count * sizeof(T);
+    bool ok;
+    if (!force_rf64 && payload <= 0xFFFFFFFFull - 36) {
+        ok = fwrite(&h, sizeof h, 1, f) == 1;
+    } else {
+        const uint32_t ff = 0xFFFFFFFFu, ds_size = 28, fmt_size = 16, table = 0;
+        const uint64_t riff_size = 4 + (8 + 28) + (8 + 16) + 8 + payload + (payload & 1);
+        const uint64_t frames = h.blockAlign ? payload / h.blockAlign : 0;
+        ok = fwrite("RF64", 4, 1, f) == 1 && fwrite(&ff, 4, 1, f) == 1 && fwrite("WAVE", 4, 1, f) == 1 &&
+             fwrite("ds64", 4, 1, f) == 1 && fwrite(&ds_size, 4, 1, f) == 1 && fwrite(&riff_size, 8, 1, f) == 1 &&
+             fwrite(&payload, 8, 1, f) == 1 && fwrite(&frames, 8, 1, f) == 1 && fwrite(&table, 4, 1, f) == 1 &&
+             fwrite("fmt ", 4, 1, f) == 1 && fwrite(&fmt_size, 4, 1, f) == 1 && fwrite(&h.audioFormat, 16, 1, f) == 1 &&
+             fwrite("data", 4, 1, f) == 1 && fwrite(&ff, 4, 1, f) == 1;
+    }
+    ok = ok && (count == 0 || fwrite(samples, sizeof(T), count, f) == count);
     return fclose(f) == 0 && ok;
 }
 
@@ -137,8 +164,8 @@ inline WAVHeader make_header(size_t samples, uint16_t channels, uint32_t rate = 
     h.bitsPerSample = (uint16_t)(8 * sizeof(T));
     h.blockAlign = (uint16_t)(channels * sizeof(T));
     h.byteRate = rate * h.blockAlign;
-    h.dataBytes = (uint32_t)(samples * sizeof(T));
-    h.sizeOfFile = 36 + h.dataBytes;
+    h.dataBytes = clamp32((uint64_t)samples * sizeof(T));     // 0xFFFFFFFF = "see ds64" (write_file switches to RF64)
+    h.sizeOfFile = clamp32(36 + (uint64_t)samples * sizeof(T));
     return h;
 }
 
