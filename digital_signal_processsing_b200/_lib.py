@@ -83,6 +83,7 @@ SYMBOLS = [
     ("mavg_plan_info", _i, [_vp, ctypes.POINTER(Info)]),
     ("mavg_run_host", _i, [_vp, _vp, _vp]),
     ("mavg_run_device", _i, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_vp)]),
+    ("mavg_run_cascade", _i, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.c_uint32]),
     ("mavg_run_device_halo", _i, [_vp, _vp, _vp, _vp]),
     ("mavg_synchronize", _i, [_vp]),
     ("mavg_get_timing", _i, [_vp, ctypes.POINTER(Timing)]),

@@ -389,6 +389,8 @@ struct DevCtx {
     void* d_out = nullptr;
     void* d_halo = nullptr;     // halo_frames * channels elements of left context (frame sharding)
     void* d_bsum = nullptr;     // generic path, long windows: 64-frame block sums
+    void* d_scratch = nullptr;  // mavg_run_cascade intermediates
+    cudaEvent_t ev_pass = nullptr;  // mavg_run_cascade: end of this device's latest pass
     size_t bsum_bytes = 0;
     int sm_count = 0;
     bool timed = false;
@@ -1050,6 +1052,8 @@ int mavg_plan_destroy(mavg_plan* p)
         if (d.d_out) cudaFree(d.d_out);
         if (d.d_halo) cudaFree(d.d_halo);
         if (d.d_bsum) cudaFree(d.d_bsum);
+        if (d.d_scratch) cudaFree(d.d_scratch);
+        if (d.ev_pass) cudaEventDestroy(d.ev_pass);
         if (d.s_h2d) { cudaStreamSynchronize(d.s_h2d); cudaStreamDestroy(d.s_h2d); }
         if (d.s_d2h) { cudaStreamSynchronize(d.s_d2h); cudaStreamDestroy(d.s_d2h); }
         for (cudaEvent_t e : d.pool) cudaEventDestroy(e);
@@ -1170,6 +1174,90 @@ int mavg_run_device(mavg_plan* p, const void* const* d_in, void* const* d_out)
         record(p, d, 3);
         d.timed = p->timing_on;
     }
+    p->launches_last_run = launches;
+    return MAVG_OK;
+}
+
+int mavg_run_cascade(mavg_plan* p, const void* const* d_in, void* const* d_out, void* const* d_scratch, uint32_t passes)
+{
+    if (!p || !d_in || !d_out) return fail(MAVG_ERR_INVALID_ARG, "null argument");
+    if (passes == 0) return fail(MAVG_ERR_INVALID_ARG, "passes must be >= 1");
+    if (passes == 1) return mavg_run_device(p, d_in, d_out);
+    if (p->desc.first_frame != 0) return fail(MAVG_ERR_UNSUPPORTED, "cascades need whole-signal plans (first_frame == 0)");
+    DeviceGuard guard;
+    const size_t nd = p->dev.size();
+    const size_t es = elem_size(p->desc.dtype);
+    void* scratch[MAVG_MAX_DEVICES];
+    for (size_t r = 0; r < nd; ++r) {
+        DevCtx& d = p->dev[r];
+        if (!d_in[r] || !d_out[r]) return fail(MAVG_ERR_INVALID_ARG, "null shard pointer for device index %zu", r);
+        if (d_in[r] == d_out[r]) return fail(MAVG_ERR_INVALID_ARG, "output must not alias input");
+        scratch[r] = d_scratch ? d_scratch[r] : nullptr;
+        if (!scratch[r]) {
+            if (!d.d_scratch) {
+                const size_t bytes = std::max<size_t>(shard_elems(p, d) * es, 256);
+                MAVG_CUDA(cudaSetDevice(d.device));
+                if (cudaMalloc(&d.d_scratch, bytes) != cudaSuccess) {
+                    cudaGetLastError();
+                    return fail(MAVG_ERR_ALLOC, "cudaMalloc of %zu scratch bytes failed on device %d", bytes, d.device);
+                }
+            }
+            scratch[r] = d.d_scratch;
+        }
+        if (scratch[r] == d_in[r] || scratch[r] == d_out[r]) return fail(MAVG_ERR_INVALID_ARG, "scratch must not alias input or output");
+        if (!d.ev_pass) {
+            MAVG_CUDA(cudaSetDevice(d.device));
+            MAVG_CUDA(cudaEventCreateWithFlags(&d.ev_pass, cudaEventDisableTiming));
+        }
+    }
+    // one timed region around all passes: start events here, per-pass recording off, end events after the last pass
+    const bool was_timed = p->timing_on;
+    if (was_timed)
+        for (size_t r = 0; r < nd; ++r) {
+            MAVG_CUDA(cudaSetDevice(p->dev[r].device));
+            record(p, p->dev[r], 0);
+            record(p, p->dev[r], 1);
+        }
+    uint32_t launches = 0;
+    const void* src[MAVG_MAX_DEVICES];
+    void* dst[MAVG_MAX_DEVICES];
+    int rc = MAVG_OK;
+    p->timing_on = false;
+    for (uint32_t i = 0; i < passes && rc == MAVG_OK; ++i) {
+        // ping-pong so that the last pass writes d_out: pass i writes d_out when (passes - 1 - i) is even
+        for (size_t r = 0; r < nd; ++r) {
+            src[r] = (i == 0) ? d_in[r] : dst[r];
+            dst[r] = ((passes - 1 - i) % 2 == 0) ? d_out[r] : scratch[r];
+        }
+        // a pass reads its left neighbour's previous output (halo) and overwrites the buffer its right neighbour
+        // read one pass earlier: every device waits for every device's previous pass
+        if (i > 0 && nd > 1) {
+            for (size_t r = 0; r < nd && rc == MAVG_OK; ++r) {
+                if (cudaSetDevice(p->dev[r].device) != cudaSuccess) rc = fail(MAVG_ERR_CUDA, "cudaSetDevice failed");
+                for (size_t q = 0; q < nd && rc == MAVG_OK; ++q)
+                    if (q != r && cudaStreamWaitEvent(p->dev[r].stream, p->dev[q].ev_pass, 0) != cudaSuccess)
+                        rc = fail(MAVG_ERR_CUDA, "cudaStreamWaitEvent failed");
+            }
+            if (rc != MAVG_OK) break;
+        }
+        rc = mavg_run_device(p, src, dst);
+        launches += p->launches_last_run;
+        if (rc == MAVG_OK && nd > 1)
+            for (size_t r = 0; r < nd; ++r) {
+                cudaSetDevice(p->dev[r].device);
+                if (cudaEventRecord(p->dev[r].ev_pass, p->dev[r].stream) != cudaSuccess)
+                    rc = fail(MAVG_ERR_CUDA, "cudaEventRecord failed");
+            }
+    }
+    p->timing_on = was_timed;
+    if (rc != MAVG_OK) return rc;
+    if (was_timed)
+        for (size_t r = 0; r < nd; ++r) {
+            MAVG_CUDA(cudaSetDevice(p->dev[r].device));
+            record(p, p->dev[r], 2);
+            record(p, p->dev[r], 3);
+            p->dev[r].timed = true;
+        }
     p->launches_last_run = launches;
     return MAVG_OK;
 }

@@ -111,6 +111,15 @@ class Plan:
         outs = (ctypes.c_void_p * n)(*out_ptrs)
         check(self._lib.mavg_run_device(self._h, ins, outs))
 
+    def run_cascade(self, in_ptrs: Sequence[int], out_ptrs: Sequence[int], passes: int,
+                    scratch_ptrs: Optional[Sequence[int]] = None) -> None:
+        """The moving average applied `passes` times in a row (box-filter cascade); the last pass lands in out."""
+        n = len(in_ptrs)
+        ins = (ctypes.c_void_p * n)(*in_ptrs)
+        outs = (ctypes.c_void_p * n)(*out_ptrs)
+        scr = (ctypes.c_void_p * n)(*scratch_ptrs) if scratch_ptrs is not None else None
+        check(self._lib.mavg_run_cascade(self._h, ins, outs, scr, passes))
+
     def run_device_halo(self, in_ptr: int, out_ptr: int, halo_ptr: Optional[int]) -> None:
         check(self._lib.mavg_run_device_halo(self._h, ctypes.c_void_p(in_ptr), ctypes.c_void_p(out_ptr),
                                              ctypes.c_void_p(halo_ptr or 0)))

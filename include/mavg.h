@@ -242,6 +242,16 @@ int mavg_ipc_close(void *d_ptr);
 int mavg_device_alloc(uint64_t bytes, void **d_ptr);
 int mavg_device_free(void *d_ptr);
 
+/* Box-filter cascade: the plan's moving average applied `passes` times in a row on device-resident shards
+ * (three passes approximate a Gaussian; what running a reference binary on its own output does, without the
+ * round trips).  Pass i reads what pass i-1 wrote, including the left neighbour's tail on sharded plans, so the
+ * library orders the passes across devices; the last pass lands in d_out.  d_scratch[r] (same size as the
+ * shard) holds intermediates; pass NULL to let the plan allocate them.  int16 truncates after every pass, like
+ * the reference would.  Whole-signal plans only (desc.first_frame == 0).  Builds on the kernel launches of
+ * basics/profilable_sm_vload4.cu:135 (box-filter cascades). */
+int mavg_run_cascade(mavg_plan *plan, const void *const *d_in, void *const *d_out, void *const *d_scratch,
+                     uint32_t passes);
+
 /* Page-locked host memory for mavg_run_host buffers (cudaHostAlloc / cudaFreeHost): copies from
  * pinned memory run at full PCIe speed and overlap with the kernels.  Replaces the host half
  * of MemoryTraits (gpu_utils.h:33-65). */

@@ -199,3 +199,49 @@ def test_run_host_pipeline_slices_bit_identical(mavg, oracle_mod):
         assert np.array_equal(y, dy.cpu().numpy())
     xi = oracle_mod.fill_i16(2 * (1 << 24) + 2, 9)
     assert np.array_equal(mavg.moving_average(xi, 77, channels=2), oracle_mod.mavg_i16(xi, 77, 2))
+
+
+@pytest.mark.gpu
+def test_box_filter_cascade(mavg, oracle_mod):
+    """mavg_run_cascade: the filter applied p times on the device == the oracle applied p times (int16 truncates
+    after every pass, exactly like running the reference on its own output); sharded plans order the passes across
+    devices and stay bit-identical to the single-device run."""
+    import torch
+    ndev = mavg.device_count()
+    devs = [0, 1] if ndev >= 2 else [0, 0]
+    frames = 24 * 8192 + 100
+    for dtype, ch, k in (("f32", 1, 33), ("f32", 2, 300), ("i16", 2, 7), ("i16", 1, 1000), ("f32", 6, 50)):
+        n = frames * ch
+        tdt = torch.float32 if dtype == "f32" else torch.int16
+        x = oracle_mod.fill_f32(n, 41 + k) if dtype == "f32" else oracle_mod.fill_i16(n, 41 + k)
+        dx = torch.from_numpy(x).cuda()
+        for passes in (1, 2, 3, 4):
+            e = x
+            for _ in range(passes):
+                e = oracle_mod.mavg_f64(e, k, ch).astype(np.float32) if dtype == "f32" else oracle_mod.mavg_i16(e, k, ch)
+            dy = torch.zeros(n, dtype=tdt, device="cuda")
+            with mavg.Plan(frames, k, channels=ch, dtype=dtype) as plan:
+                plan.run_cascade([dx.data_ptr()], [dy.data_ptr()], passes)
+                plan.synchronize()
+                assert plan.timing().compute_ms > 0
+            y1 = dy.cpu().numpy()
+            if dtype == "f32":
+                assert np.max(np.abs(y1 - e) / np.abs(e)) < 1e-5, (dtype, ch, k, passes)
+            else:
+                assert np.array_equal(y1, e), (dtype, ch, k, passes)
+            # two shards (two devices, or the same device twice): passes are ordered across devices
+            with mavg.Plan(frames, k, channels=ch, dtype=dtype, devices=devs) as plan:
+                f0 = int(plan.info.shard_frames[0])
+                bufs = []
+                for r, dev in enumerate(devs):
+                    lo, hi = (0, f0 * ch) if r == 0 else (f0 * ch, n)
+                    with torch.cuda.device(dev):
+                        bufs.append((torch.from_numpy(x[lo:hi]).cuda(dev), torch.zeros(hi - lo, dtype=tdt, device=f"cuda:{dev}")))
+                torch.cuda.synchronize()
+                plan.run_cascade([b[0].data_ptr() for b in bufs], [b[1].data_ptr() for b in bufs], passes)
+                plan.synchronize()
+                y2 = np.concatenate([b[1].cpu().numpy() for b in bufs])
+            assert np.array_equal(y1, y2), (dtype, ch, k, passes)
+    with mavg.Plan(1000, 5) as plan:
+        with pytest.raises(Exception):
+            plan.run_cascade([dx.data_ptr()], [dx.data_ptr() + 4096], 0)
