@@ -102,6 +102,19 @@ class Plan:
         check(self._lib.mavg_run_host(self._h, ctypes.c_void_p(x.ctypes.data), ctypes.c_void_p(out.ctypes.data)))
         return out
 
+    def run_host_with_context(self, buf: np.ndarray, context_frames: int, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """Shard plans (first_frame > 0): `buf` holds `context_frames` (= info.halo_frames) frames of left context
+        followed by the shard; mavg_run_host reads the context in front of the pointer it is given."""
+        buf = np.ascontiguousarray(buf, dtype=self.np_dtype).reshape(-1)
+        ctx = context_frames * int(self.desc.channels)
+        if buf.size != ctx + self.samples:
+            raise ValueError(f"expected {ctx} + {self.samples} samples, got {buf.size}")
+        if out is None:
+            out = np.empty(self.samples, dtype=self.np_dtype)
+        check(self._lib.mavg_run_host(self._h, ctypes.c_void_p(buf.ctypes.data + ctx * buf.itemsize),
+                                      ctypes.c_void_p(out.ctypes.data)))
+        return out
+
     def run_host_ptr(self, in_ptr: int, out_ptr: int) -> None:
         check(self._lib.mavg_run_host(self._h, ctypes.c_void_p(in_ptr), ctypes.c_void_p(out_ptr)))
 
