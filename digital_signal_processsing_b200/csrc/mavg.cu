@@ -984,8 +984,9 @@ int mavg_plan_create(const mavg_desc* desc, mavg_plan** out)
     int cur = 0;
     cudaGetDevice(&cur);
     p->dev.resize(nd);
-    // frame shards start on tile boundaries (stream) so every device runs the same tile grid
-    const uint64_t align = (p->path == MAVG_PATH_STREAM && frame_sharded(p)) ? tile_frames(p) : 1;
+    // frame shards start on tile boundaries (stream) so every device runs the same tile grid; the generic kernel's
+    // 64-frame runs are anchored at the shard start, so its shards start on multiples of 64 frames
+    const uint64_t align = !frame_sharded(p) ? 1 : (p->path == MAVG_PATH_STREAM ? tile_frames(p) : 64);
     for (uint32_t r = 0; r < nd; ++r) {
         DevCtx& d = p->dev[r];
         d.device = desc->num_devices >= 1 ? desc->devices[r] : cur;
