@@ -137,3 +137,53 @@ def test_random_shapes_on_two_shards_bit_identical(mavg, oracle_mod, seed):
         if not ok:
             bad.append((seed, case, dtype, ch, layout, k, frames, stream, int(np.count_nonzero(y1 != y2))))
     assert not bad, bad
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_random_tiny_and_degenerate_shapes(mavg, oracle_mod, torch_cuda_mod, seed):
+    """Signals shorter than a tile, a row or the window itself; windows longer than the signal; device pointers
+    that are not 16-byte aligned (the streaming kernels hand those to the generic kernel)."""
+    torch = torch_cuda_mod
+    rng = np.random.default_rng(4000 + seed)
+    for case in range(40):
+        dtype = "f32" if rng.random() < 0.5 else "i16"
+        ch = int(rng.integers(1, 41))
+        frames = int(rng.integers(1, 300))
+        k = int(rng.integers(1, 600))
+        layout = "planar" if (ch > 1 and rng.random() < 0.2) else "interleaved"
+        n = frames * ch
+        x = oracle_mod.fill_f32(n, 80_000 + 100 * seed + case) if dtype == "f32" else \
+            oracle_mod.fill_i16(n, 80_000 + 100 * seed + case)
+        tag = (seed, case, dtype, ch, layout, k, frames)
+
+        def expect(seg, c):
+            return oracle_mod.mavg_f64(seg, k, c) if dtype == "f32" else oracle_mod.mavg_i16(seg, k, c)
+
+        def check(y):
+            parts = [(slice(c * frames, (c + 1) * frames), 1) for c in range(ch)] if layout == "planar" else [(slice(0, n), ch)]
+            for seg, c in parts:
+                e = expect(x[seg], c)
+                if dtype == "f32":
+                    assert np.max(np.abs(y[seg] - e) / np.abs(e)) < TOL, tag
+                else:
+                    assert np.array_equal(y[seg], e), tag
+
+        with mavg.Plan(frames, k, channels=ch, dtype=dtype, layout=layout) as plan:
+            check(plan.run_host(x))
+            # the same plan on device buffers shifted off 16-byte alignment by one element
+            tdt = torch.float32 if dtype == "f32" else torch.int16
+            dx = torch.zeros(n + 8, dtype=tdt, device="cuda")
+            dy = torch.zeros(n + 8, dtype=tdt, device="cuda")
+            dx[1:n + 1] = torch.from_numpy(x).cuda()
+            es = 4 if dtype == "f32" else 2
+            plan.run_device([dx.data_ptr() + es], [dy.data_ptr() + es])
+            plan.synchronize()
+            check(dy[1:n + 1].cpu().numpy())
+            assert float(dy[0]) == 0 and float(dy[n + 1]) == 0, tag      # nothing written outside the signal
+
+
+@pytest.fixture(scope="module")
+def torch_cuda_mod():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch
