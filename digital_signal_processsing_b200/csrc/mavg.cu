@@ -56,17 +56,22 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+EncodeTiledFn lookup_encoder()
+{
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    const cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return reinterpret_cast<EncodeTiledFn>(fn);
+}
+
 int get_encoder(EncodeTiledFn* out)
 {
-    static EncodeTiledFn cached = nullptr;
-    if (!cached) {
-        void* fn = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
-        if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn)
-            return fail(MAVG_ERR_DRIVER, "cuTensorMapEncodeTiled unavailable: %s", cudaGetErrorString(e));
-        cached = reinterpret_cast<EncodeTiledFn>(fn);
-    }
+    static const EncodeTiledFn cached = lookup_encoder();   // initialised once, thread-safe (plans may live on different threads)
+    if (!cached) return fail(MAVG_ERR_DRIVER, "cuTensorMapEncodeTiled unavailable in this driver");
     *out = cached;
     return MAVG_OK;
 }
@@ -76,7 +81,7 @@ int get_encoder(EncodeTiledFn* out)
 int make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t signals, uint64_t signal_stride_bytes,
              uint32_t tile_rows, uint32_t elem_bytes, bool swizzle = true)
 {
-    EncodeTiledFn enc;
+    EncodeTiledFn enc = nullptr;
     MAVG_TRY(get_encoder(&enc));
     const uint32_t row_elems = 128 / elem_bytes;
     cuuint64_t dims[3] = {row_elems, rows, signals};
@@ -580,7 +585,7 @@ bool stream_eligible(const mavg_plan* p, const DevCtx& d, const void* in, const 
 int make_map_2d(CUtensorMap* map, const void* base, uint64_t channels, uint64_t frames, uint32_t tile_frames_,
                 uint32_t tile_channels)
 {
-    EncodeTiledFn enc;
+    EncodeTiledFn enc = nullptr;
     MAVG_TRY(get_encoder(&enc));
     cuuint64_t dims[2] = {channels, frames};
     cuuint64_t strides[1] = {channels * 4};

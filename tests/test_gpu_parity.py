@@ -708,3 +708,35 @@ def test_few_channel_many_tiles_per_cta(mavg, oracle_mod, case):
         assert _rel(y, oracle_mod.mavg_f64(x, k, ch)) < TOL
     else:
         assert np.array_equal(y, oracle_mod.mavg_i16_mt(x, k, ch, 8))
+
+
+def test_distinct_plans_on_concurrent_threads(mavg, oracle_mod):
+    """a plan is not thread-safe, distinct plans are.  Four host threads, each with its own plan
+    (different dtype / channels / window, i.e. different kernels), run concurrently on one GPU."""
+    import threading
+    cases = [("f32", 1, 64, 1 << 21), ("i16", 2, 300, 1 << 20), ("f32", 6, 100, 1 << 18), ("i16", 5, 1000, 1 << 18)]
+    inputs = [oracle_mod.fill_f32(f * c, 90 + i) if d == "f32" else oracle_mod.fill_i16(f * c, 90 + i)
+              for i, (d, c, k, f) in enumerate(cases)]
+    want = [oracle_mod.mavg_f64(x, k, c) if d == "f32" else oracle_mod.mavg_i16(x, k, c)
+            for x, (d, c, k, f) in zip(inputs, cases)]
+    errors = []
+
+    def work(i):
+        try:
+            d, c, k, f = cases[i]
+            with mavg.Plan(f, k, channels=c, dtype=d) as plan:
+                for _ in range(6):
+                    y = plan.run_host(inputs[i])
+                    if d == "f32":
+                        assert _rel(y, want[i]) < TOL
+                    else:
+                        assert np.array_equal(y, want[i])
+        except Exception as exc:                     # surfaced in the main thread
+            errors.append((i, repr(exc)))
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(len(cases))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
