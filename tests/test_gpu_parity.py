@@ -740,3 +740,20 @@ def test_distinct_plans_on_concurrent_threads(mavg, oracle_mod):
     for t in threads:
         t.join()
     assert not errors, errors
+
+
+def test_errors_are_returned_not_fatal(mavg, oracle_mod):
+    """Every entry point returns a status: an impossible device allocation, a null shard pointer
+    and aliased buffers are reported through MavgError, and the library keeps working afterwards."""
+    from digital_signal_processsing_b200 import _lib
+    with mavg.Plan(1 << 38, 64) as plan:                       # 1 TiB of float32 per buffer: cudaMalloc must refuse
+        with pytest.raises(_lib.MavgError) as ei:
+            plan.run_owned()
+        assert ei.value.status == _lib.ERR_ALLOC and "cudaMalloc" in str(ei.value)
+    with mavg.Plan(1000, 5) as plan:
+        with pytest.raises(_lib.MavgError):
+            plan.run_device([0], [0])
+        x = oracle_mod.fill_f32(1000, 3)
+        with pytest.raises(_lib.MavgError):
+            plan.run_host(x, out=x)                              # output must not alias input
+        assert _rel(plan.run_host(x), oracle_mod.mavg_f64(x, 5)) < TOL     # still usable
