@@ -215,13 +215,23 @@ StreamGeom plan_stream(uint32_t k, const mavg_tuning& tu, uint32_t C = 1)
 
 // many-channel interleaved float32: 16 warps x 16 frames per tile of [256 frames][32 channels]
 constexpr int kColsNW = 16, kColsRF = 16;
-StreamGeom plan_cols(uint32_t k, uint32_t C, const mavg_tuning& tu)
+// float32: C >= 32, C % 4 == 0.  int16 (i16 = true): the kernel sees C/2 word columns (channel pairs), so
+// C >= 64, C % 8 == 0, 2 <= k <= 32768 (exact int32 sums and division).
+StreamGeom plan_cols(uint32_t k, uint32_t C, const mavg_tuning& tu, bool i16 = false)
 {
     StreamGeom g;
     g.NT = kColsNW * 32;
     g.R = kColsRF;
     g.C = C;
     g.mode = 3;
+    if (i16) {
+        if (C % 8 != 0 || k < 2 || k > 32768u) return g;
+        C /= 2;
+        g.C = C;
+        g.pair = true;
+        g.elem = 4;
+        i16_mulhi_consts(k, &g.div_mul, &g.div_shift, &g.wscale);
+    }
     if (C < 32 || C % 4 != 0) return g;
     const uint32_t R = kColsRF;
     const uint32_t s = (R - k % R) % R;
@@ -238,7 +248,7 @@ StreamGeom plan_cols(uint32_t k, uint32_t C, const mavg_tuning& tu)
         bool fits = false;
         for (;;) {
             g.S = g.H + 1 + g.P;
-            g.smem = mavg::cols_smem_bytes(kColsNW, kColsRF, g.S, g.H);
+            g.smem = mavg::cols_smem_bytes(kColsNW, kColsRF, g.S, g.H, i16 ? 8u : 4u);
             if (g.smem <= kMaxSmem) { fits = true; break; }
             if (cww == 1 && g.P > 1) { --g.P; continue; }   // only the narrowest shape trades prefetch for history
             break;
@@ -605,7 +615,7 @@ int launch_cols(mavg_plan* p, DevCtx& d, const void* in, void* out, const void* 
                 uint32_t* launches)
 {
     const StreamGeom& g = p->geom;
-    const uint32_t C = p->desc.channels;
+    const uint32_t C = g.pair ? g.C : p->desc.channels;  // columns as the kernel sees them (int16: channel-pair words)
     const uint32_t FT = (kColsNW / g.cww) * kColsRF;
     const uint32_t CW = 32u * g.cww;
     CUtensorMap in_map, halo_map;
@@ -636,13 +646,26 @@ int launch_cols(mavg_plan* p, DevCtx& d, const void* in, void* out, const void* 
     cp.stages = g.S;
     cp.prefetch = g.P;
     cp.has_halo = halo ? 1 : 0;
+    const unsigned grid = (unsigned)std::min<uint64_t>(ctas, (uint64_t)cp.total_chunks);
+    if (g.pair) {
+        void (*kern16)(const CUtensorMap, const CUtensorMap, uint32_t*, const mavg::ColsParams, const uint32_t, const uint32_t,
+                       const uint32_t) =
+            g.cww == 8   ? mavg::stream_cols_i16x2_kernel<kColsNW, kColsRF, 8>
+            : g.cww == 4 ? mavg::stream_cols_i16x2_kernel<kColsNW, kColsRF, 4>
+            : g.cww == 2 ? mavg::stream_cols_i16x2_kernel<kColsNW, kColsRF, 2>
+                         : mavg::stream_cols_i16x2_kernel<kColsNW, kColsRF, 1>;
+        MAVG_CUDA(cudaFuncSetAttribute(kern16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+        kern16<<<grid, kColsNW * 32, g.smem, d.stream>>>(in_map, halo_map, (uint32_t*)out, cp, g.div_mul, g.div_shift, g.wscale);
+        MAVG_CUDA(cudaGetLastError());
+        ++*launches;
+        return MAVG_OK;
+    }
     void (*kern)(const CUtensorMap, const CUtensorMap, float*, const mavg::ColsParams) =
         g.cww == 8   ? mavg::stream_cols_f32_kernel<kColsNW, kColsRF, 8>
         : g.cww == 4 ? mavg::stream_cols_f32_kernel<kColsNW, kColsRF, 4>
         : g.cww == 2 ? mavg::stream_cols_f32_kernel<kColsNW, kColsRF, 2>
                      : mavg::stream_cols_f32_kernel<kColsNW, kColsRF, 1>;
     MAVG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
-    const unsigned grid = (unsigned)std::min<uint64_t>(ctas, (uint64_t)cp.total_chunks);
     kern<<<grid, kColsNW * 32, g.smem, d.stream>>>(in_map, halo_map, (float*)out, cp);
     MAVG_CUDA(cudaGetLastError());
     ++*launches;
@@ -965,7 +988,10 @@ int mavg_plan_create(const mavg_desc* desc, mavg_plan** out)
     } else {
         stream_shape = desc->channels <= 2 || planar;
         p->geom = plan_stream_i16(desc->window, planar ? 1u : desc->channels, desc->tuning);
-        if (!planar && desc->channels >= 3) {
+        if (!planar && desc->channels >= 32) {
+            p->geom = plan_cols(desc->window, desc->channels, desc->tuning, true);
+            stream_shape = p->geom.ok;
+        } else if (!planar && desc->channels >= 3) {
             p->geom = plan_fewc(desc->window, desc->channels, desc->tuning, 2);
             stream_shape = p->geom.ok;
         }

@@ -1087,10 +1087,10 @@ struct ColsParams {
 };
 
 // NWT warps in total; tile bytes and summary sizes do not depend on how they are split into columns
-__host__ __device__ inline uint32_t cols_smem_bytes(int NWT, int RF, int S, int H)
+__host__ __device__ inline uint32_t cols_smem_bytes(int NWT, int RF, int S, int H, uint32_t total_bytes = 4)
 {
-    return 1024u + (uint32_t)S * NWT * RF * 128u + (uint32_t)(H + 2) * NWT * 32 * 4 + (uint32_t)(H + 2) * 256 * 4 +
-           (uint32_t)S * 8;
+    return 1024u + (uint32_t)S * NWT * RF * 128u + (uint32_t)(H + 2) * NWT * 32 * total_bytes +
+           (uint32_t)(H + 2) * 256 * total_bytes + (uint32_t)S * 8;
 }
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
@@ -1312,6 +1312,201 @@ __global__ void __launch_bounds__(NWT * 32)
                         acc += x[r] - xl[r];
                         if (r < nvalid) dst[(uint32_t)r * cstride] = acc * inv;
                     }
+                }
+            }
+
+            ++it;
+            st = (st + 1 == S) ? 0 : st + 1;
+            slot = (slot + 1 == GS) ? 0 : slot + 1;
+        }
+        __syncthreads();   // ring stages may be refilled by the next chunk's prologue
+    }
+}
+
+// ----------------------------------------------------------------------------------
+// Column kernel for interleaved int16 with many channels (C >= 64, C % 8 == 0; sensor arrays, multichannel PCM):
+// stream_cols_f32_kernel's layout over 32-bit WORDS -- a frame is C/2 words, each a pair of neighbouring channels,
+// lane = word column, warp = RF-frame run -- with stream_i16_kernel's exact arithmetic: dp2a on the packed words
+// for run totals, head and slide, signed multiply-high division, one byte permute per output word.
+// p.channels = C/2 (words per frame).  Bit-identical to profilable_cpu_computations.  4 B/sample.
+// ----------------------------------------------------------------------------------
+template <int NWT, int RF, int CWW>
+__global__ void __launch_bounds__(NWT * 32)
+    stream_cols_i16x2_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap halo_map,
+                             uint32_t* __restrict__ out, const ColsParams p, const uint32_t div_mul,
+                             const uint32_t div_shift, const uint32_t wscale)
+{
+    constexpr int NW = NWT / CWW;            // frame-warps
+    constexpr int CW = 32 * CWW;             // words per tile row
+    constexpr uint32_t ROWB = CW * 4u;       // bytes per tile row (one frame)
+    constexpr uint32_t GROW = CW * 8u;       // bytes per row of the [..][CW] int2 summary arrays
+    constexpr int FT = NW * RF;              // frames per tile
+    constexpr uint32_t TB = FT * ROWB;       // bytes per tile
+    static_assert(NWT % CWW == 0 && FT <= 256 && CW <= 256, "a TMA box holds at most 256 x 256 elements");
+
+    extern __shared__ uint8_t smem_raw[];
+    const int tid = threadIdx.x;
+    const int lane = (tid & 31) + 32 * ((tid >> 5) % CWW);   // word column inside the tile
+    const int warp = (tid >> 5) / CWW;                       // frame-warp
+    const int S = p.stages;
+    const int H = p.hist_tiles;
+    const int P = p.prefetch;
+    const int GS = H + 2;
+
+    const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t ring_bytes = (uint32_t)S * TB;
+    const uint32_t gsum = ring + ring_bytes;                    // int2 [GS][NW][CW]  (low / high channel of the pair)
+    const uint32_t ttot = gsum + (uint32_t)GS * NW * GROW;      // int2 [GS][CW]
+    const uint32_t bars = ttot + (uint32_t)GS * GROW;
+    const uint32_t w_lo = wscale, w_hi = wscale << 8;
+    const uint32_t n_lo = (0u - wscale) & 0xffu, n_hi = n_lo << 8;
+
+    if (tid == 0) {
+        prefetch_tmap(&in_map);
+        if (p.has_halo) prefetch_tmap(&halo_map);
+        for (int s = 0; s < S; ++s) mbar_init(bars + 8u * s, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    auto issue_load = [&](int tile, int cb, int st) {
+        const uint32_t bar = bars + 8u * st;
+        mbar_arrive_expect_tx(bar, TB);
+        if (tile < 0 && p.has_halo)
+            tma_load_2d(ring + (uint32_t)st * TB, &halo_map, bar, cb * CW, (tile + H) * FT, kEvictFirst);
+        else
+            tma_load_2d(ring + (uint32_t)st * TB, &in_map, bar, cb * CW, tile * FT, kEvictFirst);
+    };
+
+    uint32_t it = 0;
+    int st = 0, slot = 0;
+
+    for (int chunk = blockIdx.x; chunk < p.total_chunks; chunk += gridDim.x) {
+        const int rng = chunk / p.col_blocks;
+        const int cb = chunk - rng * p.col_blocks;
+        const int t0 = rng * p.chunk_tiles;
+        int t1 = t0 + p.chunk_tiles;
+        if (t1 > p.tiles_per_col) t1 = p.tiles_per_col;
+        if (t0 >= t1) continue;
+        const int first = t0 - H;
+        const int ntl = t1 - first;
+        const uint32_t ch = (uint32_t)cb * CW + lane;
+        const bool ch_ok = ch < p.channels;
+
+        if (tid == 0) {
+            int s2 = st;
+            for (int j = 0; j < P && j < ntl; ++j) {
+                issue_load(first + j, cb, s2);
+                s2 = (s2 + 1 == S) ? 0 : s2 + 1;
+            }
+        }
+
+        for (int j = 0; j < ntl; ++j) {
+            const int tile = first + j;
+            const bool is_out = (j >= H);
+            const uint32_t cur = ring + (uint32_t)st * TB;
+
+            mbar_wait(bars + 8u * st, (it / (uint32_t)S) & 1u);
+
+            uint32_t x[RF];
+            int g0 = 0, g1 = 0;
+#pragma unroll
+            for (int r = 0; r < RF; ++r) {
+                x[r] = lds32u(cur + ((uint32_t)(warp * RF + r) * CW + lane) * 4u);
+                g0 = dp2a_s(x[r], w_lo, g0);
+                g1 = dp2a_s(x[r], w_hi, g1);
+            }
+            sts64i(gsum + (((uint32_t)slot * NW + warp) * CW + lane) * 8u, g0, g1);
+
+            __syncthreads();
+
+            if (tid == 0 && j + P < ntl) {
+                int s2 = st + P;
+                if (s2 >= S) s2 -= S;
+                issue_load(first + j + P, cb, s2);
+            }
+
+            // where the lag run starts: `lw` = group (warp slot), `h` = tiles back (both warp-uniform)
+            int lw = warp - (int)(p.n_full + 1u);
+            int h = 0;
+            if (lw < 0) {
+                h = (-lw + NW - 1) / NW;
+                lw += h * NW;
+            }
+            int e0 = 0, e1 = 0;      // groups of this tile in front of the own group
+            if (h > 0 || (H > 1 && warp == NW - 1)) {
+                const uint32_t gb = gsum + ((uint32_t)slot * NW * CW + lane) * 8u;
+#pragma unroll 4
+                for (int w2 = 0; w2 < warp; ++w2) {
+                    const int2 t = lds64i(gb + (uint32_t)w2 * GROW);
+                    e0 += t.x, e1 += t.y;
+                }
+            }
+            if (H > 1 && warp == NW - 1) sts64i(ttot + ((uint32_t)slot * CW + lane) * 8u, e0 + g0, e1 + g1);
+
+            if (is_out) {
+                uint32_t xl[RF];
+                {
+                    int row0 = (int)((uint32_t)st * (uint32_t)FT) + warp * RF - (int)p.k;   // ring row of the first lag frame
+                    const int ring_rows = S * FT;
+                    if (row0 + RF <= 0) row0 += ring_rows;
+                    if (row0 >= 0) {
+                        const uint32_t a0 = ring + (uint32_t)row0 * ROWB + (uint32_t)lane * 4u;
+#pragma unroll
+                        for (int r = 0; r < RF; ++r) xl[r] = lds32u(a0 + ROWB * r);
+                    } else {  // rows row0..-1 live at the end of the ring
+                        const uint32_t a0 = ring + (uint32_t)lane * 4u;
+#pragma unroll
+                        for (int r = 0; r < RF; ++r) {
+                            const int rr = row0 + r;
+                            xl[r] = lds32u(a0 + (uint32_t)(rr < 0 ? rr + ring_rows : rr) * ROWB);
+                        }
+                    }
+                }
+                int a0 = 0, a1 = 0;
+                if (h == 0) {
+                    const uint32_t gb = gsum + ((uint32_t)slot * NW * CW + lane) * 8u;
+#pragma unroll 4
+                    for (int w2 = lw + 1; w2 < warp; ++w2) {
+                        const int2 t = lds64i(gb + (uint32_t)w2 * GROW);
+                        a0 += t.x, a1 += t.y;
+                    }
+                } else {
+                    int ls = slot - h;
+                    if (ls < 0) ls += GS;
+                    const uint32_t gb = gsum + ((uint32_t)ls * NW * CW + lane) * 8u;
+#pragma unroll 4
+                    for (int w2 = lw + 1; w2 < NW; ++w2) {
+                        const int2 t = lds64i(gb + (uint32_t)w2 * GROW);
+                        a0 += t.x, a1 += t.y;
+                    }
+                    int ms = ls;
+                    for (int v = 1; v < h; ++v) {
+                        ms = (ms + 1 == GS) ? 0 : ms + 1;
+                        const int2 t = lds64i(ttot + ((uint32_t)ms * CW + lane) * 8u);
+                        a0 += t.x, a1 += t.y;
+                    }
+                    a0 += e0, a1 += e1;
+                }
+#pragma unroll
+                for (int r = 0; r < RF; ++r)
+                    if ((uint32_t)r < p.m_part) {
+                        a0 = dp2a_s(xl[r], w_lo, a0);
+                        a1 = dp2a_s(xl[r], w_hi, a1);
+                    }
+
+                const uint64_t f_base = (uint64_t)tile * FT + (uint64_t)warp * RF;
+                uint32_t* dst = out + f_base * p.channels + ch;
+                int nvalid = 0;
+                if (ch_ok && f_base < p.frames) nvalid = (p.frames - f_base < (uint64_t)RF) ? (int)(p.frames - f_base) : RF;
+                const uint32_t cstride = p.channels;
+                const int mul = (int)div_mul;
+#pragma unroll
+                for (int r = 0; r < RF; ++r) {
+                    a0 = dp2a_s(xl[r], n_lo, dp2a_s(x[r], w_lo, a0));
+                    a1 = dp2a_s(xl[r], n_hi, dp2a_s(x[r], w_hi, a1));
+                    const uint32_t y = __byte_perm(div_trunc_mulhi(a0, mul, div_shift), div_trunc_mulhi(a1, mul, div_shift), 0x5410);
+                    if (r < nvalid) dst[(uint32_t)r * cstride] = y;
                 }
             }
 

@@ -757,3 +757,46 @@ def test_errors_are_returned_not_fatal(mavg, oracle_mod):
         with pytest.raises(_lib.MavgError):
             plan.run_host(x, out=x)                              # output must not alias input
         assert _rel(plan.run_host(x), oracle_mod.mavg_f64(x, 5)) < TOL     # still usable
+
+
+# ------------------------------------------------------------------ many-channel interleaved int16 (column kernel over channel pairs)
+@pytest.mark.parametrize("ch", [64, 72, 96, 128, 256, 520])
+@pytest.mark.parametrize("k", [1, 2, 3, 8, 9, 64, 100, 300, 1000, 1500])
+def test_many_channel_interleaved_i16_bit_exact(mavg, oracle_mod, ch, k):
+    frames = 5 * 256 + 37
+    x = oracle_mod.fill_i16(frames * ch, 32000 + k + ch)
+    with mavg.Plan(frames, k, channels=ch, dtype="i16") as plan:
+        y = plan.run_host(x)
+        if 2 <= k <= 96:
+            assert plan.info.path == 1 and plan.info.mode == 3, "expected the int16 column kernel"
+    assert np.array_equal(y, oracle_mod.mavg_i16(x, k, ch))
+
+
+def test_many_channel_i16_extremes_shards_and_odd_counts(mavg, oracle_mod, torch_cuda):
+    torch = torch_cuda
+    ch, frames = 64, 3000
+    for val in (-32768, 32767):
+        x = np.full(frames * ch, val, dtype=np.int16)
+        for k in (2, 7, 64, 255, 1000):
+            assert np.array_equal(mavg.moving_average(x, k, channels=ch), oracle_mod.mavg_i16(x, k, ch)), (val, k)
+    # channel counts the pair layout cannot take (C % 8 != 0) stay on the generic kernel and stay exact
+    for odd in (66, 100, 33):
+        x = oracle_mod.fill_i16(2000 * odd, 33000 + odd)
+        with mavg.Plan(2000, 50, channels=odd, dtype="i16") as plan:
+            assert plan.info.path == 2
+            assert np.array_equal(plan.run_host(x), oracle_mod.mavg_i16(x, 50, odd))
+    # shard with halo == whole run
+    k = 100
+    with mavg.Plan(100_000, k, channels=ch, dtype="i16") as probe:
+        assert probe.info.mode == 3
+        halo, tiles_back = int(probe.info.halo_frames), int(probe.info.history_tiles)
+    tf = halo // tiles_back
+    frames, cut = 40 * tf + 77, 11 * tf
+    x = oracle_mod.fill_i16(frames * ch, 34000)
+    dx = torch.from_numpy(x).cuda()
+    dz = torch.zeros((frames - cut) * ch, dtype=torch.int16, device="cuda")
+    torch.cuda.synchronize()
+    with mavg.Plan(frames - cut, k, channels=ch, dtype="i16", first_frame=cut) as plan:
+        plan.run_device_halo(dx.data_ptr() + 2 * cut * ch, dz.data_ptr(), dx.data_ptr() + 2 * (cut - halo) * ch)
+        plan.synchronize()
+    assert np.array_equal(dz.cpu().numpy(), oracle_mod.mavg_i16(x, k, ch)[cut * ch:])
