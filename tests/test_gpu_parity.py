@@ -800,3 +800,25 @@ def test_many_channel_i16_extremes_shards_and_odd_counts(mavg, oracle_mod, torch
         plan.run_device_halo(dx.data_ptr() + 2 * cut * ch, dz.data_ptr(), dx.data_ptr() + 2 * (cut - halo) * ch)
         plan.synchronize()
     assert np.array_equal(dz.cpu().numpy(), oracle_mod.mavg_i16(x, k, ch)[cut * ch:])
+
+
+@pytest.mark.parametrize("case", [("f32", 1, 600_000, 60_000, "interleaved"), ("i16", 2, 300_000, 40_000, "interleaved"),
+                                  ("f32", 3, 200_000, 9_000, "interleaved"), ("f32", 3, 150_000, 70_000, "planar"),
+                                  ("i16", 1, 400_000, 150_000, "interleaved"), ("f32", 40, 30_000, 5_000, "interleaved"),
+                                  ("f32", 1, 100_000, 4096 * 20 + 1, "interleaved")])
+def test_very_long_windows_on_the_generic_kernel(mavg, oracle_mod, case):
+    """Windows whose history exceeds shared memory run on the generic kernel (run starts from 64-frame block sums)."""
+    dtype, ch, frames, k, layout = case
+    n = frames * ch
+    x = oracle_mod.fill_f32(n, 35000 + k) if dtype == "f32" else oracle_mod.fill_i16(n, 35000 + k)
+    with mavg.Plan(frames, k, channels=ch, dtype=dtype, layout=layout) as plan:
+        assert plan.info.path == 2
+        y = plan.run_host(x)
+    if layout == "planar":
+        for c in range(ch):
+            seg = slice(c * frames, (c + 1) * frames)
+            assert _rel(y[seg], oracle_mod.mavg_f64(x[seg], k)) < TOL
+    elif dtype == "f32":
+        assert _rel(y, oracle_mod.mavg_f64(x, k, ch)) < TOL
+    else:
+        assert np.array_equal(y, oracle_mod.mavg_i16(x, k, ch))
