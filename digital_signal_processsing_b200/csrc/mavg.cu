@@ -315,6 +315,27 @@ StreamGeom plan_fewc(uint32_t k, uint32_t C, const mavg_tuning& tu, uint32_t ele
     return g;
 }
 
+// float32 mono / planar with a window too long for the ring of plan_stream: the lag samples come back through a
+// second TMA stream (stream_far_f32_kernel).  H = warm-up tiles = left context in whole tiles.
+StreamGeom plan_far(uint32_t k)
+{
+    StreamGeom g;
+    g.NT = 512;
+    g.R = 16;
+    g.C = 1;
+    g.mode = 5;
+    const uint32_t T = 8192;
+    if (k < T || k > 0x40000000u) return g;
+    g.H = (int)((k + T - 1) / T);
+    g.P = 1;
+    g.S = 2;
+    g.MIS = (int)((4 - k % 4) % 4);
+    g.ctas_per_sm = 1;
+    g.smem = mavg::far_smem_bytes(g.NT, g.R, g.S);
+    g.ok = g.smem <= kMaxSmem;
+    return g;
+}
+
 typedef void (*StreamKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const mavg::StreamParams);
 
 template <int NT, int R, int C = 1>
@@ -568,6 +589,47 @@ int launch_generic_t(const mavg_plan* p, DevCtx& d, const T* in, T* out, const T
     return MAVG_OK;
 }
 
+// The frames a streaming kernel leaves behind (a fraction of a 128-byte row): tail_kernel, one CTA per signal.
+template <typename T>
+int launch_tail_t(const mavg_plan* p, DevCtx& d, const T* in, T* out, const T* halo, uint64_t frames, uint64_t out_begin,
+                  uint64_t out_end, uint32_t* launches)
+{
+    mavg::GenericParams gp;
+    memset(&gp, 0, sizeof gp);
+    uint32_t signals = 1;
+    if (planar_batch(p)) {
+        gp.frames = p->desc.frames;
+        gp.channels = 1;
+        gp.sig_stride = p->desc.frames;
+        signals = d.channels;
+    } else {
+        gp.frames = frames;
+        gp.channels = p->desc.channels;
+    }
+    gp.out_begin = out_begin;
+    gp.out_end = out_end;
+    gp.halo_frames = halo ? p->halo_frames : 0;
+    gp.k = p->desc.window;
+    mavg::tail_kernel<T><<<signals, 256, 0, d.stream>>>(in, out, halo, gp);
+    MAVG_CUDA(cudaGetLastError());
+    ++*launches;
+    return MAVG_OK;
+}
+
+int launch_generic(const mavg_plan* p, DevCtx& d, const void* in, void* out, const void* halo, uint64_t frames,
+                   uint64_t out_begin, uint64_t out_end, uint32_t* launches);
+
+int launch_tail(const mavg_plan* p, DevCtx& d, const void* in, void* out, const void* halo, uint64_t frames,
+                uint64_t out_begin, uint64_t out_end, uint32_t* launches)
+{
+    if (out_begin >= out_end) return MAVG_OK;
+    if (out_end - out_begin > 128) return launch_generic(p, d, in, out, halo, frames, out_begin, out_end, launches);
+    if (p->desc.dtype == MAVG_F32)
+        return launch_tail_t<float>(p, d, (const float*)in, (float*)out, (const float*)halo, frames, out_begin, out_end, launches);
+    return launch_tail_t<int16_t>(p, d, (const int16_t*)in, (int16_t*)out, (const int16_t*)halo, frames, out_begin, out_end,
+                                  launches);
+}
+
 int launch_generic(const mavg_plan* p, DevCtx& d, const void* in, void* out, const void* halo, uint64_t frames,
                    uint64_t out_begin, uint64_t out_end, uint32_t* launches)
 {
@@ -723,7 +785,62 @@ int launch_fewc(mavg_plan* p, DevCtx& d, const void* in, void* out, const void* 
     MAVG_CUDA(cudaGetLastError());
     ++*launches;
     // flat samples past the last whole 128-byte row: the frames that touch them go to the generic kernel
-    if (rows * row < n) MAVG_TRY(launch_generic(p, d, in, out, halo, frames, rows * row / C, frames, launches));
+    if (rows * row < n) MAVG_TRY(launch_tail(p, d, in, out, halo, frames, rows * row / C, frames, launches));
+    return MAVG_OK;
+}
+
+// float32 mono / planar, window longer than the ring: far-lag kernel.  `halo`, when given, lies directly in front of `in`.
+int launch_far(mavg_plan* p, DevCtx& d, const void* in, void* out, const void* halo, uint64_t frames, uint32_t* launches)
+{
+    const StreamGeom& g = p->geom;
+    uint64_t n, signals, stride;
+    shard_signals(p, d, frames, &n, &signals, &stride);
+    const uint64_t rows = n / 32;
+    const uint32_t tile_rows = 256;
+    const uint64_t T = 8192;
+    const uint64_t row_base = halo ? (uint64_t)g.H * tile_rows : 0;
+    const void* base = halo ? halo : in;
+    CUtensorMap in_map, out_map, lag_map;
+    MAVG_TRY(make_map(&in_map, base, rows + row_base, signals, stride * 4, tile_rows, 4));
+    MAVG_TRY(make_map(&lag_map, base, rows + row_base, signals, stride * 4, 129, 4));
+    MAVG_TRY(make_map(&out_map, out, rows, signals, stride * 4, tile_rows, 4));
+    mavg::FarParams fp;
+    memset(&fp, 0, sizeof fp);
+    mavg::StreamParams& sp = fp.sp;
+    const uint32_t k = p->desc.window;
+    sp.inv_k = 1.0f / (float)k;
+    sp.k = k;
+    const uint64_t tiles = (rows * 32 + T - 1) / T;
+    sp.tiles_per_signal = (int32_t)tiles;
+    const uint64_t ctas = (uint64_t)d.sm_count;
+    uint64_t cps = std::max<uint64_t>(1, ctas * std::max<uint32_t>(1u, p->desc.tuning.chunks_per_cta) / signals);
+    cps = std::min<uint64_t>(cps, tiles);
+    uint64_t chunk_tiles = (tiles + cps - 1) / cps;
+    cps = (tiles + chunk_tiles - 1) / chunk_tiles;
+    if (cps * signals > 0x7fffffffull) return fail(MAVG_ERR_UNSUPPORTED, "too many tile ranges");
+    sp.chunk_tiles = (int32_t)chunk_tiles;
+    sp.chunks_per_signal = (int32_t)cps;
+    sp.total_chunks = (int32_t)(cps * signals);
+    sp.hist_tiles = 0;
+    sp.stages = g.S;
+    sp.prefetch = g.P;
+    sp.has_halo = 0;
+    fp.warm_tiles = g.H;
+    fp.row_base = (int32_t)row_base;
+    fp.koff = (32 - k % 32) % 32;
+    fp.lag_rows = (int32_t)((k + fp.koff) / 32);
+    fp.lag_prefetch = 2;
+    void (*kern)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const mavg::FarParams) =
+        g.MIS == 0   ? mavg::stream_far_f32_kernel<512, 16, 0>
+        : g.MIS == 1 ? mavg::stream_far_f32_kernel<512, 16, 1>
+        : g.MIS == 2 ? mavg::stream_far_f32_kernel<512, 16, 2>
+                     : mavg::stream_far_f32_kernel<512, 16, 3>;
+    MAVG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+    const unsigned grid = (unsigned)std::min<uint64_t>(ctas, (uint64_t)sp.total_chunks);
+    kern<<<grid, g.NT, g.smem, d.stream>>>(in_map, out_map, lag_map, fp);
+    MAVG_CUDA(cudaGetLastError());
+    ++*launches;
+    if (rows * 32 < n) MAVG_TRY(launch_tail(p, d, in, out, halo, frames, rows * 32, frames, launches));
     return MAVG_OK;
 }
 
@@ -739,6 +856,16 @@ int launch_shard(mavg_plan* p, DevCtx& d, const void* in, void* out, const void*
         const uint64_t nflat = frames * p->desc.channels;
         if ((((uintptr_t)in | (uintptr_t)out | (uintptr_t)halo) & 15u) == 0 && nflat >= 64 && nflat / 32 < (1ull << 31) - 65536)
             return launch_fewc(p, d, in, out, halo, frames, launches);
+        return launch_generic(p, d, in, out, halo, frames, 0, frames, launches);
+    }
+    if (p->path == MAVG_PATH_STREAM && p->geom.ok && p->geom.mode == 5) {
+        // the left context has to sit directly in front of the shard (run_host slices, contiguous callers);
+        // a context somewhere else (a peer's tail) is served by the generic kernel
+        const size_t hb = (size_t)p->halo_frames * sizeof(float);
+        const bool contiguous = halo == nullptr || (const char*)halo + hb == (const char*)in;
+        const uint64_t rows_all = (planar_batch(p) ? p->desc.frames : frames) / 32 + (halo ? p->halo_frames / 32 : 0);
+        if (contiguous && stream_eligible(p, d, in, out, halo, frames) && rows_all < 0x7fffffffull - 65536)
+            return launch_far(p, d, in, out, halo, frames, launches);
         return launch_generic(p, d, in, out, halo, frames, 0, frames, launches);
     }
     if (p->path == MAVG_PATH_STREAM && p->geom.ok && p->geom.mode == 3) {
@@ -811,7 +938,7 @@ int launch_shard(mavg_plan* p, DevCtx& d, const void* in, void* out, const void*
 
     // samples past the last whole 128-byte row (per signal): generic kernel
     if (rows * row < n) {
-        MAVG_TRY(launch_generic(p, d, in, out, halo, frames, rows * row / g.C, frames, launches));
+        MAVG_TRY(launch_tail(p, d, in, out, halo, frames, rows * row / g.C, frames, launches));
     }
     return MAVG_OK;
 }
@@ -978,6 +1105,7 @@ int mavg_plan_create(const mavg_desc* desc, mavg_plan** out)
     if (desc->dtype == MAVG_F32) {
         stream_shape = desc->channels <= 2 || planar;
         p->geom = plan_stream(desc->window, desc->tuning, planar ? 1u : desc->channels);
+        if (!p->geom.ok && (planar || desc->channels == 1)) p->geom = plan_far(desc->window);
         if (!planar && desc->channels >= 32) {
             p->geom = plan_cols(desc->window, desc->channels, desc->tuning);
             stream_shape = p->geom.ok;

@@ -206,6 +206,48 @@ __global__ void __launch_bounds__(256) generic_kernel(const T* __restrict__ x, T
     }
 }
 
+// The few trailing frames a streaming kernel leaves (samples past the last whole 128-byte row): one CTA per signal
+// sums the k frames in front of them IN PARALLEL (256 threads, fp64 / int64, fixed partition and order, so the
+// result does not depend on how the signal was sliced), then one thread slides over the handful of outputs.
+// (generic_kernel would give the whole k-term start sum to a single thread: 0.14 ms at k = 4096, milliseconds for
+// the far-lag kernel's windows.)
+template <typename T>
+__global__ void __launch_bounds__(256) tail_kernel(const T* __restrict__ x, T* __restrict__ y, const T* __restrict__ halo,
+                                                   const GenericParams p)
+{
+    typedef typename GenericAcc<T>::type Acc;
+    __shared__ Acc red[8];
+    const uint32_t C = p.channels;
+    x += (uint64_t)blockIdx.x * p.sig_stride;
+    y += (uint64_t)blockIdx.x * p.sig_stride;
+    const long long k = (long long)p.k;
+    const long long hf = (long long)p.halo_frames;
+    const double inv = 1.0 / (double)p.k;
+    for (uint32_t c = 0; c < C; ++c) {
+        Acc a = 0;
+        for (long long f = (long long)p.out_begin - k + threadIdx.x; f < (long long)p.out_begin; f += 256) {
+            if (f >= 0) a += (Acc)x[(uint64_t)f * C + c];
+            else if (halo != nullptr && f >= -hf) a += (Acc)halo[(uint64_t)(f + hf) * C + c];
+        }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) a += __shfl_down_sync(0xffffffffu, a, d);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            Acc w = ((red[0] + red[1]) + (red[2] + red[3])) + ((red[4] + red[5]) + (red[6] + red[7]));
+            for (uint64_t f = p.out_begin; f < p.out_end; ++f) {
+                Acc old = 0;
+                const long long fo = (long long)f - k;
+                if (fo >= 0) old = (Acc)x[(uint64_t)fo * C + c];
+                else if (halo != nullptr && fo >= -hf) old = (Acc)halo[(uint64_t)(fo + hf) * C + c];
+                w += (Acc)x[f * C + c] - old;
+                y[f * C + c] = GenericAcc<T>::finish(w, p.k, inv);
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // ----------------------------------------------------------------------------------
 // PTX helpers (mbarrier, TMA tensor load/store, proxy fence)
 // ----------------------------------------------------------------------------------
@@ -289,6 +331,7 @@ __device__ __forceinline__ void sts32(uint32_t addr, float v)
 __device__ __forceinline__ uint32_t swz(uint32_t addr) { return addr ^ ((addr >> 3) & 0x70u); }
 
 constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;  // L2 cache hint: streaming input
+constexpr uint64_t kEvictNormal = 0x1000000000000000ull; // L2 cache hint: data that is read again (far-lag kernel)
 
 // Pre-swizzled tile offsets (few-channel kernels' scalar accesses, int16 kernel's 16-byte chunks).  Tile, staging and ring
 // bases are multiples of 1024 bytes, so the SWIZZLE_128B XOR (bits 4-6 with bits 7-9) of base + x only depends
@@ -371,6 +414,8 @@ struct TileRing {
     uint32_t st_buf;
     const CUtensorMap *in_map, *out_map, *halo_map;
     bool has_halo;
+    int row_base;        // rows in front of row 0 of in_map (far-lag kernel: left context contiguous with the input)
+    uint64_t load_hint;  // L2 policy of the tile loads
 
     // returns the first shared address after the staging tiles (where the kernel puts its summaries)
     __device__ __forceinline__ uint32_t setup(uint32_t smem_base, const StreamParams& p, const CUtensorMap* in,
@@ -386,6 +431,7 @@ struct TileRing {
         it = 0; st = 0; slot = 0; otiles = 0;
         st_pending = st_inflight = false; st_tile = st_sig = 0; st_buf = 0;
         in_map = in; out_map = out; halo_map = halo; has_halo = p.has_halo != 0;
+        row_base = 0; load_hint = kEvictFirst;
         return outb + 2u * tbv();
     }
     __device__ __forceinline__ void init_barriers(uint32_t bars_addr)
@@ -407,9 +453,9 @@ struct TileRing {
         const uint32_t bar = bars + 8u * stage;
         mbar_arrive_expect_tx(bar, tbv());
         if (tile < 0 && has_halo)
-            tma_load_3d(ring + (uint32_t)stage * tbv(), halo_map, bar, 0, (tile + H) * rowsv(), 0, kEvictFirst);
+            tma_load_3d(ring + (uint32_t)stage * tbv(), halo_map, bar, 0, (tile + H) * rowsv(), 0, load_hint);
         else
-            tma_load_3d(ring + (uint32_t)stage * tbv(), in_map, bar, 0, tile * rowsv(), sig, kEvictFirst);
+            tma_load_3d(ring + (uint32_t)stage * tbv(), in_map, bar, 0, tile * rowsv() + row_base, sig, load_hint);
     }
     __device__ __forceinline__ void prologue(int first, int ntl, int sig) const
     {
@@ -1053,6 +1099,200 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : 1))
             tr.advance();
         }
 
+        tr.epilogue();
+    }
+    tr.finish();
+}
+
+// ----------------------------------------------------------------------------------
+// Far-lag kernel -- float32 mono / planar, windows longer than the shared-memory history (k >~ 49 000 samples).
+// The lag samples x[i-k] can no longer wait in the CTA's ring, so they come back through a SECOND TMA stream: for
+// output tile j the 257 rows that hold samples [jT-k, jT-k+T) are loaded as two 129-row boxes (a TMA box holds at
+// most 256 rows) into a 2-stage lag ring.  The same CTA read those bytes as its own tile k samples earlier
+// (148 CTAs x k x 4 B = 35 MB at k = 60 000), so with a normal L2 policy they are still in the 126 MB L2 and DRAM
+// traffic stays near 8 B/sample.
+// Window sums: W = sum of the k samples in front of the tile is carried per CTA in fp64,
+//     W(j+1) = W(j) + sum_t d[t],   d[t] = (total of thread t's own run) - (total of its lag run),
+// and a thread's run starts from W + (exclusive scan of d over the tile's 512 threads), then slides in fp32.
+// A chunk builds its first W by streaming the ceil(k/T) tiles in front of it through the same loop (own totals only,
+// the first of them masked to the window).  Rounding: every fp32 quantity is a difference of 16-sample sums, the
+// carried W is fp64, so the relative error of y stays ~1e-7 for any k and any signal length.
+// Shards: the left context must be contiguous with the input (row_base rows in front of it), which is how
+// mavg_run_host slices and shard plans fed through mavg_run_host present it.
+// ----------------------------------------------------------------------------------
+struct FarParams {
+    StreamParams sp;        // k, inv_k, chunking; ring: stages = 1 + prefetch, hist_tiles = 0
+    int32_t warm_tiles;     // HT = ceil(k / T)
+    int32_t row_base;       // rows of left context in front of row 0
+    int32_t lag_rows;       // (k + koff) / 32: rows from the lag box's first row to the tile's first row
+    uint32_t koff;          // (32 - k % 32) % 32: first lag sample inside its 128-byte row
+    int32_t lag_prefetch;   // lag boxes in flight: 1 or 2
+};
+constexpr uint32_t kFarLagHalf = 17408;   // one 129-row box, padded to whole 1024-byte swizzle atoms
+constexpr int kFarLagStages = 2;
+
+__host__ __device__ inline uint32_t far_smem_bytes(int NT, int R, int S)
+{
+    const uint32_t TB = (uint32_t)NT * R * 4;
+    return 1024u + (uint32_t)S * TB + 2u * TB + (uint32_t)kFarLagStages * 2u * kFarLagHalf + 2u * 32 * 4 +
+           (uint32_t)kFarLagStages * 8 + (uint32_t)S * 8 + 64;
+}
+
+template <int NT, int R, int MIS>
+__global__ void __launch_bounds__(NT)
+    stream_far_f32_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map,
+                          const __grid_constant__ CUtensorMap lag_map, const FarParams fp)
+{
+    const StreamParams& p = fp.sp;
+    constexpr int T = NT * R;
+    constexpr uint32_t TB = T * 4;
+    constexpr int ROWS = T / 32;
+    constexpr int NW = NT / 32;
+    constexpr int CH_OWN = R / 4;
+    constexpr int CH_LAG = CH_OWN + (MIS ? 1 : 0);
+    constexpr int SL = kFarLagStages;
+    static_assert(NT == 512 && R == 16 && MIS >= 0 && MIS < 4, "two 129-row lag boxes cover exactly one 256-row tile");
+
+    extern __shared__ uint8_t smem_raw[];
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    TileRing<TB, ROWS> tr;
+    const uint32_t lagbuf = tr.setup(smem_u32(smem_raw), p, &in_map, &out_map, &in_map);   // 1024-aligned: ring + whole tiles
+    tr.row_base = fp.row_base;
+    tr.load_hint = kEvictNormal;
+    const uint32_t wraw = lagbuf + (uint32_t)SL * 2u * kFarLagHalf;   // float [2][32]
+    const uint32_t lbars = wraw + 2u * 32 * 4;                        // u64 [SL]
+    if (tid == 0) {
+        prefetch_tmap(&lag_map);
+        for (int s2 = 0; s2 < SL; ++s2) mbar_init(lbars + 8u * s2, 1);
+    }
+    tr.init_barriers(lbars + (uint32_t)SL * 8);                       // fences the inits above as well, then syncs
+
+    int xo[CH_OWN], xg[CH_LAG];   // pre-swizzled chunk offsets: own run (tile / staging), lag run (lag stage)
+#pragma unroll
+    for (int c = 0; c < CH_OWN; ++c) xo[c] = pre_swz(tid * (R * 4) + 16 * c);
+    {
+        const int half = tid >> 8;
+        const int c0 = (int)(fp.koff >> 2) + CH_OWN * (tid & 255);
+#pragma unroll
+        for (int c = 0; c < CH_LAG; ++c) xg[c] = pre_swz((c0 + c) * 16) + half * (int)kFarLagHalf;
+    }
+    const int PL = fp.lag_prefetch;
+    auto issue_lag = [&](int tile, int sig, int stage) {              // thread 0
+        const uint32_t bar = lbars + 8u * (uint32_t)stage;
+        mbar_arrive_expect_tx(bar, 2u * 129u * 128u);
+        const int r0 = tile * ROWS - fp.lag_rows + fp.row_base;
+        const uint32_t dst = lagbuf + (uint32_t)stage * 2u * kFarLagHalf;
+        tma_load_3d(dst, &lag_map, bar, 0, r0, sig, kEvictNormal);
+        tma_load_3d(dst + kFarLagHalf, &lag_map, bar, 0, r0 + 128, sig, kEvictNormal);
+    };
+    uint32_t lagit = 0;   // lag boxes consumed so far by this CTA, never reset
+    int lst = 0;          // lagit % SL
+
+    for (int chunk = blockIdx.x; chunk < p.total_chunks; chunk += gridDim.x) {
+        int sig, t0, t1;
+        if (!chunk_range(p, chunk, sig, t0, t1)) continue;
+        const int HT = fp.warm_tiles;
+        const int first = t0 - HT;
+        const int ntl = t1 - first;
+        tr.prologue(first, ntl, sig);
+        if (tid == 0) {
+            int s2 = lst;
+            for (int i = 0; i < PL && t0 + i < t1; ++i) {
+                issue_lag(t0 + i, sig, s2);
+                s2 = (s2 + 1 == SL) ? 0 : s2 + 1;
+            }
+        }
+        double W = 0.0;   // sum of the k samples in front of the current tile (complete once the warm-up tiles are through)
+
+        for (int j = 0; j < ntl; ++j) {
+            const int tile = first + j;
+            const bool is_out = (j >= HT);
+            const uint32_t cur = tr.wait_tile();
+            const uint32_t it = tr.it;
+
+            float x[R];
+#pragma unroll
+            for (int c = 0; c < CH_OWN; ++c) {
+                const float4 v = lds128(cur + (uint32_t)xo[c]);
+                x[4 * c + 0] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
+            }
+            float xl[CH_LAG * 4];
+            float d;
+            if (is_out) {
+                mbar_wait(lbars + 8u * (uint32_t)lst, (lagit / (uint32_t)SL) & 1u);
+                const uint32_t lb = lagbuf + (uint32_t)lst * 2u * kFarLagHalf;
+#pragma unroll
+                for (int c = 0; c < CH_LAG; ++c) {
+                    const float4 v = lds128(lb + (uint32_t)xg[c]);
+                    xl[4 * c + 0] = v.x; xl[4 * c + 1] = v.y; xl[4 * c + 2] = v.z; xl[4 * c + 3] = v.w;
+                }
+                float q4[CH_OWN], l4[CH_OWN];
+#pragma unroll
+                for (int c = 0; c < CH_OWN; ++c) {
+                    q4[c] = (x[4 * c] + x[4 * c + 1]) + (x[4 * c + 2] + x[4 * c + 3]);
+                    l4[c] = (xl[MIS + 4 * c] + xl[MIS + 4 * c + 1]) + (xl[MIS + 4 * c + 2] + xl[MIS + 4 * c + 3]);
+                }
+                d = ((q4[0] + q4[1]) + (q4[2] + q4[3])) - ((l4[0] + l4[1]) + (l4[2] + l4[3]));
+            } else {
+#pragma unroll
+                for (int i = 0; i < CH_LAG * 4; ++i) xl[i] = 0.f;
+                // warm-up: the tile lies in front of the chunk; only its samples inside the first window count
+                const int m0 = (j == 0) ? HT * T - (int)p.k : 0;      // local index of the first sample that counts
+                float a = 0.f;
+#pragma unroll
+                for (int r = 0; r < R; ++r) a += (tid * R + r >= m0) ? x[r] : 0.f;
+                d = a;
+            }
+            float incl = d;
+#pragma unroll
+            for (int s2 = 1; s2 < 32; s2 <<= 1) {
+                const float up = __shfl_up_sync(0xffffffffu, incl, s2);
+                if (lane >= s2) incl += up;
+            }
+            if (lane == 31) sts32(wraw + ((it & 1u) * 32u + (uint32_t)warp) * 4u, incl);
+
+            tr.before_sync();
+            __syncthreads();
+            tr.after_sync(j, ntl, first, sig);
+            if (tid == 0 && is_out && tile + PL < t1) {
+                int s2 = lst + PL;
+                if (s2 >= SL) s2 -= SL;
+                issue_lag(tile + PL, sig, s2);       // that stage was read into registers before the barrier
+            }
+
+            const float v = (lane < NW) ? lds32(wraw + ((it & 1u) * 32u + (uint32_t)lane) * 4u) : 0.f;
+            float wi = v;
+#pragma unroll
+            for (int s2 = 1; s2 < NW; s2 <<= 1) {
+                const float up = __shfl_up_sync(0xffffffffu, wi, s2);
+                if (lane >= s2) wi += up;
+            }
+            const float dtot = __shfl_sync(0xffffffffu, wi, NW - 1);
+            const float own_off = __shfl_sync(0xffffffffu, wi - v, warp);
+
+            if (is_out) {
+                float acc = (float)(W + (double)(own_off + (incl - d)));
+                const float inv = p.inv_k;
+                const uint32_t ob = tr.out_tile();
+#pragma unroll
+                for (int c = 0; c < CH_OWN; ++c) {
+                    float y[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        acc += x[4 * c + q] - xl[MIS + 4 * c + q];
+                        y[q] = acc * inv;
+                    }
+                    sts128(ob + (uint32_t)xo[c], y[0], y[1], y[2], y[3]);
+                }
+                tr.staged(tile, sig);
+                ++lagit;
+                lst = (lst + 1 == SL) ? 0 : lst + 1;
+            }
+            W += (double)dtot;
+            tr.advance();
+        }
         tr.epilogue();
     }
     tr.finish();

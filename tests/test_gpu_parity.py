@@ -812,7 +812,8 @@ def test_very_long_windows_on_the_generic_kernel(mavg, oracle_mod, case):
     n = frames * ch
     x = oracle_mod.fill_f32(n, 35000 + k) if dtype == "f32" else oracle_mod.fill_i16(n, 35000 + k)
     with mavg.Plan(frames, k, channels=ch, dtype=dtype, layout=layout) as plan:
-        assert plan.info.path == 2
+        far = dtype == "f32" and (ch == 1 or layout == "planar")      # mono / planar float32: far-lag streaming kernel
+        assert (plan.info.path, plan.info.mode) == ((1, 5) if far else (2, plan.info.mode))
         y = plan.run_host(x)
     if layout == "planar":
         for c in range(ch):
@@ -822,3 +823,68 @@ def test_very_long_windows_on_the_generic_kernel(mavg, oracle_mod, case):
         assert _rel(y, oracle_mod.mavg_f64(x, k, ch)) < TOL
     else:
         assert np.array_equal(y, oracle_mod.mavg_i16(x, k, ch))
+
+
+# ------------------------------------------------------------------ far-lag kernel (mono / planar float32, k beyond the ring)
+@pytest.mark.parametrize("k", [49_153, 50_000, 60_001, 65_536, 65_538, 99_999, 131_075, 300_000, 1_000_000])
+def test_far_lag_kernel_windows(mavg, oracle_mod, k):
+    """Every lag misalignment (k mod 4, k mod 32), windows from just past the ring up to a million samples, a signal
+    that is not a whole number of tiles or rows, several tiles per CTA."""
+    n = 148 * 8192 * 3 + 8192 * 5 + 77
+    x = oracle_mod.fill_f32(n, 36000 + k % 1000)
+    with mavg.Plan(n, k) as plan:
+        assert plan.info.path == 1 and plan.info.mode == 5
+        y = plan.run_host(x)
+    assert _rel(y, oracle_mod.mavg_f64(x, k)) < TOL
+
+
+@pytest.mark.parametrize("dist", ["USYM", "DC1E4"])
+def test_far_lag_kernel_conditioning(mavg, oracle_mod, dist):
+    n, k = 6_000_000, 77_777
+    x = oracle_mod.fill_f32(n, 37000, dist=getattr(oracle_mod, "DIST_" + dist))
+    with mavg.Plan(n, k) as plan:
+        assert plan.info.mode == 5
+        y = plan.run_host(x)
+    e = oracle_mod.mavg_f64(x, k)
+    scale = oracle_mod.mavg_f64(np.abs(x), k)
+    assert np.max(np.abs(y - e) / np.maximum(scale, 1e-30)) < TOL
+
+
+def test_far_lag_kernel_slices_shards_and_short_signals(mavg, oracle_mod, torch_cuda):
+    torch = torch_cuda
+    k = 100_003
+    # 2^24 samples through mavg_run_host: 8 MiB slices, each reading its left context in place in front of it
+    n = 1 << 24
+    x = oracle_mod.fill_f32(n, 38000)
+    e = oracle_mod.mavg_f64(x, k)
+    with mavg.Plan(n, k) as plan:
+        y = plan.run_host(x)
+        assert plan.info.launches_per_run >= 4
+        halo = int(plan.info.halo_frames)
+    assert _rel(y, e) < TOL
+    # device run in one piece against the sliced host run: the window sum carried from tile to tile (fp64) starts
+    # from a different warm-up in every slice, so the two agree to rounding (~1e-7), not bit for bit
+    dx = torch.from_numpy(x).cuda()
+    dy = torch.zeros(n, dtype=torch.float32, device="cuda")
+    with mavg.Plan(n, k) as plan:
+        plan.run_device([dx.data_ptr()], [dy.data_ptr()])
+        plan.synchronize()
+    whole = dy.cpu().numpy()
+    assert _rel(whole, e) < TOL and float(np.max(np.abs(whole - y) / np.abs(e))) < 1e-6
+    # shard plan whose context sits right in front of it in device memory
+    cut = halo + 5 * 8192
+    dz = torch.zeros(n - cut, dtype=torch.float32, device="cuda")
+    with mavg.Plan(n - cut, k, first_frame=cut) as plan:
+        plan.run_device_halo(dx.data_ptr() + 4 * cut, dz.data_ptr(), dx.data_ptr() + 4 * (cut - halo))
+        plan.synchronize()
+    assert _rel(dz.cpu().numpy(), e[cut:]) < TOL
+    # window longer than the signal (pure warm-up), and a planar batch of three signals
+    xs = oracle_mod.fill_f32(70_000, 38001)
+    assert _rel(mavg.moving_average(xs, 90_000), oracle_mod.mavg_f64(xs, 90_000)) < TOL
+    xp = oracle_mod.fill_f32(3 * 200_000, 38002)
+    with mavg.Plan(200_000, 60_000, channels=3, layout="planar") as plan:
+        assert plan.info.mode == 5
+        yp = plan.run_host(xp)
+    for c in range(3):
+        seg = slice(c * 200_000, (c + 1) * 200_000)
+        assert _rel(yp[seg], oracle_mod.mavg_f64(xp[seg], 60_000)) < TOL
