@@ -317,19 +317,20 @@ StreamGeom plan_fewc(uint32_t k, uint32_t C, const mavg_tuning& tu, uint32_t ele
 
 // float32 mono / planar with a window too long for the ring of plan_stream: the lag samples come back through a
 // second TMA stream (stream_far_f32_kernel).  H = warm-up tiles = left context in whole tiles.
-StreamGeom plan_far(uint32_t k)
+StreamGeom plan_far(uint32_t k, uint32_t C = 1)
 {
     StreamGeom g;
     g.NT = 512;
     g.R = 16;
-    g.C = 1;
+    g.C = C;
     g.mode = 5;
-    const uint32_t T = 8192;
-    if (k < T || k > 0x40000000u) return g;
-    g.H = (int)((k + T - 1) / T);
+    const uint64_t T = 8192;
+    const uint64_t L = (uint64_t)k * C;               // lag distance in flat samples
+    if (L < T || L > 0x40000000u || C > 2) return g;
+    g.H = (int)((L + T - 1) / T);
     g.P = 1;
     g.S = 2;
-    g.MIS = (int)((4 - k % 4) % 4);
+    g.MIS = (int)((4 - L % 4) % 4);
     g.ctas_per_sm = 1;
     g.smem = mavg::far_smem_bytes(g.NT, g.R, g.S);
     g.ok = g.smem <= kMaxSmem;
@@ -807,8 +808,8 @@ int launch_far(mavg_plan* p, DevCtx& d, const void* in, void* out, const void* h
     mavg::FarParams fp;
     memset(&fp, 0, sizeof fp);
     mavg::StreamParams& sp = fp.sp;
-    const uint32_t k = p->desc.window;
-    sp.inv_k = 1.0f / (float)k;
+    const uint32_t k = (uint32_t)((uint64_t)p->desc.window * g.C);   // lag distance in flat samples
+    sp.inv_k = 1.0f / (float)p->desc.window;
     sp.k = k;
     const uint64_t tiles = (rows * 32 + T - 1) / T;
     sp.tiles_per_signal = (int32_t)tiles;
@@ -831,7 +832,8 @@ int launch_far(mavg_plan* p, DevCtx& d, const void* in, void* out, const void* h
     fp.lag_rows = (int32_t)((k + fp.koff) / 32);
     fp.lag_prefetch = 2;
     void (*kern)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const mavg::FarParams) =
-        g.MIS == 0   ? mavg::stream_far_f32_kernel<512, 16, 0>
+        g.C == 2 ? (g.MIS == 0 ? mavg::stream_far_f32_kernel<512, 16, 0, 2> : mavg::stream_far_f32_kernel<512, 16, 2, 2>)
+        : g.MIS == 0 ? mavg::stream_far_f32_kernel<512, 16, 0>
         : g.MIS == 1 ? mavg::stream_far_f32_kernel<512, 16, 1>
         : g.MIS == 2 ? mavg::stream_far_f32_kernel<512, 16, 2>
                      : mavg::stream_far_f32_kernel<512, 16, 3>;
@@ -840,7 +842,7 @@ int launch_far(mavg_plan* p, DevCtx& d, const void* in, void* out, const void* h
     kern<<<grid, g.NT, g.smem, d.stream>>>(in_map, out_map, lag_map, fp);
     MAVG_CUDA(cudaGetLastError());
     ++*launches;
-    if (rows * 32 < n) MAVG_TRY(launch_tail(p, d, in, out, halo, frames, rows * 32, frames, launches));
+    if (rows * 32 < n) MAVG_TRY(launch_tail(p, d, in, out, halo, frames, rows * 32 / g.C, frames, launches));
     return MAVG_OK;
 }
 
@@ -861,9 +863,9 @@ int launch_shard(mavg_plan* p, DevCtx& d, const void* in, void* out, const void*
     if (p->path == MAVG_PATH_STREAM && p->geom.ok && p->geom.mode == 5) {
         // the left context has to sit directly in front of the shard (run_host slices, contiguous callers);
         // a context somewhere else (a peer's tail) is served by the generic kernel
-        const size_t hb = (size_t)p->halo_frames * sizeof(float);
+        const size_t hb = (size_t)p->halo_frames * (planar_batch(p) ? 1 : p->desc.channels) * sizeof(float);
         const bool contiguous = halo == nullptr || (const char*)halo + hb == (const char*)in;
-        const uint64_t rows_all = (planar_batch(p) ? p->desc.frames : frames) / 32 + (halo ? p->halo_frames / 32 : 0);
+        const uint64_t rows_all = (planar_batch(p) ? p->desc.frames : frames * p->desc.channels) / 32 + (uint64_t)p->geom.H * 256;
         if (contiguous && stream_eligible(p, d, in, out, halo, frames) && rows_all < 0x7fffffffull - 65536)
             return launch_far(p, d, in, out, halo, frames, launches);
         return launch_generic(p, d, in, out, halo, frames, 0, frames, launches);
@@ -1105,7 +1107,7 @@ int mavg_plan_create(const mavg_desc* desc, mavg_plan** out)
     if (desc->dtype == MAVG_F32) {
         stream_shape = desc->channels <= 2 || planar;
         p->geom = plan_stream(desc->window, desc->tuning, planar ? 1u : desc->channels);
-        if (!p->geom.ok && (planar || desc->channels == 1)) p->geom = plan_far(desc->window);
+        if (!p->geom.ok && (planar || desc->channels <= 2)) p->geom = plan_far(desc->window, planar ? 1u : desc->channels);
         if (!planar && desc->channels >= 32) {
             p->geom = plan_cols(desc->window, desc->channels, desc->tuning);
             stream_shape = p->geom.ok;

@@ -1105,7 +1105,8 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : 1))
 }
 
 // ----------------------------------------------------------------------------------
-// Far-lag kernel -- float32 mono / planar, windows longer than the shared-memory history (k >~ 49 000 samples).
+// Far-lag kernel -- float32 mono / planar / interleaved stereo, windows longer than the shared-memory history
+// (k >~ 49 000 frames mono, 24 000 stereo).
 // The lag samples x[i-k] can no longer wait in the CTA's ring, so they come back through a SECOND TMA stream: for
 // output tile j the 257 rows that hold samples [jT-k, jT-k+T) are loaded as two 129-row boxes (a TMA box holds at
 // most 256 rows) into a 2-stage lag ring.  The same CTA read those bytes as its own tile k samples earlier
@@ -1134,15 +1135,17 @@ constexpr int kFarLagStages = 2;
 __host__ __device__ inline uint32_t far_smem_bytes(int NT, int R, int S)
 {
     const uint32_t TB = (uint32_t)NT * R * 4;
-    return 1024u + (uint32_t)S * TB + 2u * TB + (uint32_t)kFarLagStages * 2u * kFarLagHalf + 2u * 32 * 4 +
+    return 1024u + (uint32_t)S * TB + 2u * TB + (uint32_t)kFarLagStages * 2u * kFarLagHalf + 2u * 32 * 2 * 4 +
            (uint32_t)kFarLagStages * 8 + (uint32_t)S * 8 + 64;
 }
 
-template <int NT, int R, int MIS>
+template <int NT, int R, int MIS, int C = 1>
 __global__ void __launch_bounds__(NT)
     stream_far_f32_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map,
                           const __grid_constant__ CUtensorMap lag_map, const FarParams fp)
 {
+    // C = 2: interleaved stereo; the flat stream is filtered with lag distance L = k * C (sp.k holds L), one
+    // carried sum / scan / running sum per channel, channel of run element r = r % C (R % C == 0, MIS % C == 0)
     const StreamParams& p = fp.sp;
     constexpr int T = NT * R;
     constexpr uint32_t TB = T * 4;
@@ -1152,6 +1155,7 @@ __global__ void __launch_bounds__(NT)
     constexpr int CH_LAG = CH_OWN + (MIS ? 1 : 0);
     constexpr int SL = kFarLagStages;
     static_assert(NT == 512 && R == 16 && MIS >= 0 && MIS < 4, "two 129-row lag boxes cover exactly one 256-row tile");
+    static_assert((C == 1 || C == 2) && MIS % C == 0, "mono or interleaved stereo");
 
     extern __shared__ uint8_t smem_raw[];
     const int tid = threadIdx.x;
@@ -1161,8 +1165,8 @@ __global__ void __launch_bounds__(NT)
     const uint32_t lagbuf = tr.setup(smem_u32(smem_raw), p, &in_map, &out_map, &in_map);   // 1024-aligned: ring + whole tiles
     tr.row_base = fp.row_base;
     tr.load_hint = kEvictNormal;
-    const uint32_t wraw = lagbuf + (uint32_t)SL * 2u * kFarLagHalf;   // float [2][32]
-    const uint32_t lbars = wraw + 2u * 32 * 4;                        // u64 [SL]
+    const uint32_t wraw = lagbuf + (uint32_t)SL * 2u * kFarLagHalf;   // float [2][32][2]
+    const uint32_t lbars = wraw + 2u * 32 * 2 * 4;                    // u64 [SL]
     if (tid == 0) {
         prefetch_tmap(&lag_map);
         for (int s2 = 0; s2 < SL; ++s2) mbar_init(lbars + 8u * s2, 1);
@@ -1204,7 +1208,9 @@ __global__ void __launch_bounds__(NT)
                 s2 = (s2 + 1 == SL) ? 0 : s2 + 1;
             }
         }
-        double W = 0.0;   // sum of the k samples in front of the current tile (complete once the warm-up tiles are through)
+        double W[C];      // per channel: sum of the k frames in front of the current tile (complete after the warm-up)
+#pragma unroll
+        for (int c = 0; c < C; ++c) W[c] = 0.0;
 
         for (int j = 0; j < ntl; ++j) {
             const int tile = first + j;
@@ -1219,7 +1225,7 @@ __global__ void __launch_bounds__(NT)
                 x[4 * c + 0] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
             }
             float xl[CH_LAG * 4];
-            float d;
+            float d[C];
             if (is_out) {
                 mbar_wait(lbars + 8u * (uint32_t)lst, (lagit / (uint32_t)SL) & 1u);
                 const uint32_t lb = lagbuf + (uint32_t)lst * 2u * kFarLagHalf;
@@ -1228,30 +1234,51 @@ __global__ void __launch_bounds__(NT)
                     const float4 v = lds128(lb + (uint32_t)xg[c]);
                     xl[4 * c + 0] = v.x; xl[4 * c + 1] = v.y; xl[4 * c + 2] = v.z; xl[4 * c + 3] = v.w;
                 }
-                float q4[CH_OWN], l4[CH_OWN];
+                if constexpr (C == 1) {
+                    float q4[CH_OWN], l4[CH_OWN];
 #pragma unroll
-                for (int c = 0; c < CH_OWN; ++c) {
-                    q4[c] = (x[4 * c] + x[4 * c + 1]) + (x[4 * c + 2] + x[4 * c + 3]);
-                    l4[c] = (xl[MIS + 4 * c] + xl[MIS + 4 * c + 1]) + (xl[MIS + 4 * c + 2] + xl[MIS + 4 * c + 3]);
+                    for (int c = 0; c < CH_OWN; ++c) {
+                        q4[c] = (x[4 * c] + x[4 * c + 1]) + (x[4 * c + 2] + x[4 * c + 3]);
+                        l4[c] = (xl[MIS + 4 * c] + xl[MIS + 4 * c + 1]) + (xl[MIS + 4 * c + 2] + xl[MIS + 4 * c + 3]);
+                    }
+                    d[0] = ((q4[0] + q4[1]) + (q4[2] + q4[3])) - ((l4[0] + l4[1]) + (l4[2] + l4[3]));
+                } else {
+                    float go[C], gl[C];
+#pragma unroll
+                    for (int c = 0; c < C; ++c) go[c] = gl[c] = 0.f;
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        go[r % C] += x[r];
+                        gl[r % C] += xl[MIS + r];
+                    }
+#pragma unroll
+                    for (int c = 0; c < C; ++c) d[c] = go[c] - gl[c];
                 }
-                d = ((q4[0] + q4[1]) + (q4[2] + q4[3])) - ((l4[0] + l4[1]) + (l4[2] + l4[3]));
             } else {
 #pragma unroll
                 for (int i = 0; i < CH_LAG * 4; ++i) xl[i] = 0.f;
                 // warm-up: the tile lies in front of the chunk; only its samples inside the first window count
                 const int m0 = (j == 0) ? HT * T - (int)p.k : 0;      // local index of the first sample that counts
-                float a = 0.f;
 #pragma unroll
-                for (int r = 0; r < R; ++r) a += (tid * R + r >= m0) ? x[r] : 0.f;
-                d = a;
+                for (int c = 0; c < C; ++c) d[c] = 0.f;
+#pragma unroll
+                for (int r = 0; r < R; ++r) d[r % C] += (tid * R + r >= m0) ? x[r] : 0.f;
             }
-            float incl = d;
+            float incl[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) incl[c] = d[c];
 #pragma unroll
             for (int s2 = 1; s2 < 32; s2 <<= 1) {
-                const float up = __shfl_up_sync(0xffffffffu, incl, s2);
-                if (lane >= s2) incl += up;
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const float up = __shfl_up_sync(0xffffffffu, incl[c], s2);
+                    if (lane >= s2) incl[c] += up;
+                }
             }
-            if (lane == 31) sts32(wraw + ((it & 1u) * 32u + (uint32_t)warp) * 4u, incl);
+            if (lane == 31) {
+#pragma unroll
+                for (int c = 0; c < C; ++c) sts32(wraw + (((it & 1u) * 32u + (uint32_t)warp) * 2u + c) * 4u, incl[c]);
+            }
 
             tr.before_sync();
             __syncthreads();
@@ -1262,18 +1289,23 @@ __global__ void __launch_bounds__(NT)
                 issue_lag(tile + PL, sig, s2);       // that stage was read into registers before the barrier
             }
 
-            const float v = (lane < NW) ? lds32(wraw + ((it & 1u) * 32u + (uint32_t)lane) * 4u) : 0.f;
-            float wi = v;
+            float acc[C];
 #pragma unroll
-            for (int s2 = 1; s2 < NW; s2 <<= 1) {
-                const float up = __shfl_up_sync(0xffffffffu, wi, s2);
-                if (lane >= s2) wi += up;
+            for (int c = 0; c < C; ++c) {
+                const float v = (lane < NW) ? lds32(wraw + (((it & 1u) * 32u + (uint32_t)lane) * 2u + c) * 4u) : 0.f;
+                float wi = v;
+#pragma unroll
+                for (int s2 = 1; s2 < NW; s2 <<= 1) {
+                    const float up = __shfl_up_sync(0xffffffffu, wi, s2);
+                    if (lane >= s2) wi += up;
+                }
+                const float dtot = __shfl_sync(0xffffffffu, wi, NW - 1);
+                const float own_off = __shfl_sync(0xffffffffu, wi - v, warp);
+                acc[c] = (float)(W[c] + (double)(own_off + (incl[c] - d[c])));
+                W[c] += (double)dtot;
             }
-            const float dtot = __shfl_sync(0xffffffffu, wi, NW - 1);
-            const float own_off = __shfl_sync(0xffffffffu, wi - v, warp);
 
             if (is_out) {
-                float acc = (float)(W + (double)(own_off + (incl - d)));
                 const float inv = p.inv_k;
                 const uint32_t ob = tr.out_tile();
 #pragma unroll
@@ -1281,8 +1313,9 @@ __global__ void __launch_bounds__(NT)
                     float y[4];
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        acc += x[4 * c + q] - xl[MIS + 4 * c + q];
-                        y[q] = acc * inv;
+                        const int r = 4 * c + q;
+                        acc[r % C] += x[r] - xl[MIS + r];
+                        y[q] = acc[r % C] * inv;
                     }
                     sts128(ob + (uint32_t)xo[c], y[0], y[1], y[2], y[3]);
                 }
@@ -1290,7 +1323,6 @@ __global__ void __launch_bounds__(NT)
                 ++lagit;
                 lst = (lst + 1 == SL) ? 0 : lst + 1;
             }
-            W += (double)dtot;
             tr.advance();
         }
         tr.epilogue();

@@ -888,3 +888,14 @@ def test_far_lag_kernel_slices_shards_and_short_signals(mavg, oracle_mod, torch_
     for c in range(3):
         seg = slice(c * 200_000, (c + 1) * 200_000)
         assert _rel(yp[seg], oracle_mod.mavg_f64(xp[seg], 60_000)) < TOL
+
+
+@pytest.mark.parametrize("k", [24_577, 30_000, 50_001, 65_536, 200_000])
+def test_far_lag_kernel_stereo(mavg, oracle_mod, k):
+    """Interleaved stereo float32 beyond the ring: lag distance 2k flat samples, one carried sum per channel."""
+    frames = 148 * 4096 * 2 + 4096 * 3 + 19
+    x = oracle_mod.fill_f32(2 * frames, 39000 + k % 1000)
+    with mavg.Plan(frames, k, channels=2) as plan:
+        assert plan.info.path == 1 and plan.info.mode == 5
+        y = plan.run_host(x)
+    assert _rel(y, oracle_mod.mavg_f64(x, k, 2)) < TOL
