@@ -40,7 +40,7 @@ extern "C" {
 #endif
 
 #define MAVG_VERSION_MAJOR 0
-#define MAVG_VERSION_MINOR 1
+#define MAVG_VERSION_MINOR 2
 #define MAVG_VERSION_PATCH 0
 
 typedef enum mavg_status {
@@ -67,10 +67,12 @@ typedef enum mavg_layout {
 /* Kernel family.  AUTO picks STREAM whenever its preconditions hold. */
 typedef enum mavg_path {
     MAVG_PATH_AUTO = 0,
-    MAVG_PATH_STREAM = 1,  /* TMA-staged shared-memory streaming kernels: float32 mono /
-                              stereo / planar, int16 mono / stereo / planar, float32 with
-                              >= 32 interleaved channels (direct window sums for small k,
-                              tile-rebased prefix scan above)                              */
+    MAVG_PATH_STREAM = 1,  /* TMA-staged shared-memory streaming kernels, float32 and int16:
+                              mono / stereo / planar, 3..31 interleaved channels, many
+                              interleaved channels (float32: multiples of 4 from 32 on,
+                              int16: multiples of 8 from 64 on); direct window sums for
+                              short windows, per-tile prefix scans above, a second TMA
+                              stream for float32 windows beyond the shared-memory history */
     MAVG_PATH_GENERIC = 2  /* register sliding-window kernel on global memory; any shape  */
 } mavg_path;
 

@@ -57,7 +57,7 @@ def test_struct_layout_matches_header(mavg, tmp_path):
 def test_version_and_strerror(mavg):
     from digital_signal_processsing_b200 import _lib
     lib = _lib.load()
-    assert lib.mavg_version() == 100
+    assert lib.mavg_version() == 200
     assert lib.mavg_strerror(0) == b"ok"
     assert b"block size" in lib.mavg_strerror(_lib.ERR_BLOCK_SIZE)
     assert lib.mavg_strerror(-99) == b"unknown status"
