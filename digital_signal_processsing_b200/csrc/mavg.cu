@@ -114,6 +114,7 @@ struct StreamGeom {
     uint32_t C = 1;           // channels interleaved inside one kernel signal (int16 stereo: 2)
     uint32_t div_mul = 0, div_shift = 0, wscale = 1;
     bool long_mode = false;     // few-channel kernels: prefix mode
+    int lag_stages = 2;         // far-lag kernel: stages of the lag ring
     bool pair = false;          // few-channel int16 with an even channel count: the kernel works on channel-pair words
     int cww = 1;              // column kernel: 32-channel column-warps side by side in one tile
     int runs = 0;             // few-channel kernel: 16-frame runs per tile
@@ -317,7 +318,7 @@ StreamGeom plan_fewc(uint32_t k, uint32_t C, const mavg_tuning& tu, uint32_t ele
 
 // float32 mono / planar with a window too long for the ring of plan_stream: the lag samples come back through a
 // second TMA stream (stream_far_f32_kernel).  H = warm-up tiles = left context in whole tiles.
-StreamGeom plan_far(uint32_t k, uint32_t C = 1)
+StreamGeom plan_far(uint32_t k, uint32_t C, const mavg_tuning& tu)
 {
     StreamGeom g;
     g.NT = 512;
@@ -328,11 +329,14 @@ StreamGeom plan_far(uint32_t k, uint32_t C = 1)
     const uint64_t L = (uint64_t)k * C;               // lag distance in flat samples
     if (L < T || L > 0x40000000u || C > 2) return g;
     g.H = (int)((L + T - 1) / T);
-    g.P = 1;
-    g.S = 2;
+    // 227 KB hold either one own tile in flight and a two-stage lag ring (default: 0.249 ms on 2^27 samples at
+    // k = 60 000) or two and one (tuning.prefetch = 2: 0.289 ms -- the lag box is the exposed latency)
+    g.P = tu.prefetch == 2 ? 2 : 1;
+    g.S = 1 + g.P;
+    g.lag_stages = g.P == 2 ? 1 : 2;
     g.MIS = (int)((4 - L % 4) % 4);
     g.ctas_per_sm = 1;
-    g.smem = mavg::far_smem_bytes(g.NT, g.R, g.S);
+    g.smem = mavg::far_smem_bytes(g.NT, g.R, g.S, g.lag_stages);
     g.ok = g.smem <= kMaxSmem;
     return g;
 }
@@ -830,7 +834,8 @@ int launch_far(mavg_plan* p, DevCtx& d, const void* in, void* out, const void* h
     fp.row_base = (int32_t)row_base;
     fp.koff = (32 - k % 32) % 32;
     fp.lag_rows = (int32_t)((k + fp.koff) / 32);
-    fp.lag_prefetch = 2;
+    fp.lag_stages = g.lag_stages;
+    fp.lag_prefetch = g.lag_stages;
     void (*kern)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const mavg::FarParams) =
         g.C == 2 ? (g.MIS == 0 ? mavg::stream_far_f32_kernel<512, 16, 0, 2> : mavg::stream_far_f32_kernel<512, 16, 2, 2>)
         : g.MIS == 0 ? mavg::stream_far_f32_kernel<512, 16, 0>
@@ -1107,7 +1112,7 @@ int mavg_plan_create(const mavg_desc* desc, mavg_plan** out)
     if (desc->dtype == MAVG_F32) {
         stream_shape = desc->channels <= 2 || planar;
         p->geom = plan_stream(desc->window, desc->tuning, planar ? 1u : desc->channels);
-        if (!p->geom.ok && (planar || desc->channels <= 2)) p->geom = plan_far(desc->window, planar ? 1u : desc->channels);
+        if (!p->geom.ok && (planar || desc->channels <= 2)) p->geom = plan_far(desc->window, planar ? 1u : desc->channels, desc->tuning);
         if (!planar && desc->channels >= 32) {
             p->geom = plan_cols(desc->window, desc->channels, desc->tuning);
             stream_shape = p->geom.ok;

@@ -1128,15 +1128,15 @@ struct FarParams {
     int32_t lag_rows;       // (k + koff) / 32: rows from the lag box's first row to the tile's first row
     uint32_t koff;          // (32 - k % 32) % 32: first lag sample inside its 128-byte row
     int32_t lag_prefetch;   // lag boxes in flight: 1 or 2
+    int32_t lag_stages;     // stages of the lag ring: 1 or 2 (>= lag_prefetch)
 };
 constexpr uint32_t kFarLagHalf = 17408;   // one 129-row box, padded to whole 1024-byte swizzle atoms
-constexpr int kFarLagStages = 2;
 
-__host__ __device__ inline uint32_t far_smem_bytes(int NT, int R, int S)
+__host__ __device__ inline uint32_t far_smem_bytes(int NT, int R, int S, int SL)
 {
     const uint32_t TB = (uint32_t)NT * R * 4;
-    return 1024u + (uint32_t)S * TB + 2u * TB + (uint32_t)kFarLagStages * 2u * kFarLagHalf + 2u * 32 * 2 * 4 +
-           (uint32_t)kFarLagStages * 8 + (uint32_t)S * 8 + 64;
+    return 1024u + (uint32_t)S * TB + 2u * TB + (uint32_t)SL * 2u * kFarLagHalf + 2u * 32 * 2 * 4 + (uint32_t)SL * 8 +
+           (uint32_t)S * 8 + 64;
 }
 
 template <int NT, int R, int MIS, int C = 1>
@@ -1153,7 +1153,7 @@ __global__ void __launch_bounds__(NT)
     constexpr int NW = NT / 32;
     constexpr int CH_OWN = R / 4;
     constexpr int CH_LAG = CH_OWN + (MIS ? 1 : 0);
-    constexpr int SL = kFarLagStages;
+    const int SL = fp.lag_stages;
     static_assert(NT == 512 && R == 16 && MIS >= 0 && MIS < 4, "two 129-row lag boxes cover exactly one 256-row tile");
     static_assert((C == 1 || C == 2) && MIS % C == 0, "mono or interleaved stereo");
 
