@@ -1,4 +1,4 @@
-"""CPU restatement of the index algebra of the few-channel kernels (stream_fewc_* in csrc/mavg_kernels.cuh) and of
+"""CPU restatement of the index algebra of the few-channel and far-lag kernels (csrc/mavg_kernels.cuh) and of
 the packed-word dp2a arithmetic of the int16 kernels.  TEST INFRASTRUCTURE: integer NumPy models checked against the
 oracle, so that the run/tile/prefix bookkeeping and the byte-weight constants are verified without a GPU; the GPU
 tests check the CUDA code itself."""
@@ -147,3 +147,52 @@ def test_pre_swizzled_offsets_equal_swizzled_addresses():
         b0 = ring + st * tb
         got = xs + (b0 + S * tb if xs < -(st * tb) else b0)
         assert got == want
+
+
+# ---------------------------------------------------------------- far-lag kernel (stream_far_f32_kernel) geometry
+def test_far_lag_boxes_and_warm_up_cover_exactly_the_window():
+    """Index algebra of the far-lag kernel with its real constants (tiles of 8192 samples = 256 rows of 32, two
+    129-row lag boxes per tile, koff / lag_rows / MIS from launch_far): every thread's lag run is x[i - L .. i - L + 16)
+    for its own run start i, and the masked warm-up tiles in front of a chunk sum exactly the L samples in front of
+    it.  Integer data, so equality is exact."""
+    T, ROW, NT, R = 8192, 32, 512, 16
+    rng = np.random.default_rng(9)
+    for L in (8192, 8193, 9001, 12_346, 16_384, 20_007, 40_000):       # lag distance in flat samples (k, or 2k stereo)
+        n = 7 * T
+        x = rng.integers(-1000, 1000, size=n).astype(np.int64)
+        koff = (ROW - L % ROW) % ROW
+        lag_rows = (L + koff) // ROW
+        mis = (4 - L % 4) % 4
+        assert koff % 4 == mis and (L + koff) % ROW == 0
+        HT = (L + T - 1) // T
+        rows = n // ROW
+        xr = x.reshape(rows, ROW)
+
+        def box(r0, nrows):                                             # TMA box with zero fill outside the tensor
+            out = np.zeros((nrows, ROW), dtype=np.int64)
+            lo, hi = max(r0, 0), min(r0 + nrows, rows)
+            if lo < hi:
+                out[lo - r0:hi - r0] = xr[lo:hi]
+            return out.reshape(-1)
+
+        for j in (0, 1, 3, 6):
+            r0 = j * (T // ROW) - lag_rows
+            halves = [box(r0, 129), box(r0 + 128, 129)]
+            for t in (0, 1, 255, 256, 300, 511):
+                c0 = koff // 4 + 4 * (t & 255)                          # first 16-byte chunk the thread loads
+                chunks = halves[t >> 8][4 * c0: 4 * (c0 + 5)]
+                lag_run = chunks[mis: mis + R]
+                i = j * T + R * t
+                want = np.array([x[i - L + r] if i - L + r >= 0 else 0 for r in range(R)])
+                assert np.array_equal(lag_run, want), (L, j, t)
+                assert 4 * (c0 + 4 + (1 if mis else 0)) <= 129 * ROW    # the chunks stay inside the 129-row box
+        # warm-up in front of a chunk that starts at tile t0: HT tiles, the first one masked from m0 on
+        for t0 in (0, 2, 5):
+            W = 0
+            for jj in range(HT):
+                u = t0 - HT + jj
+                tile = box(u * (T // ROW), T // ROW)
+                m0 = HT * T - L if jj == 0 else 0
+                W += int(tile[m0:].sum())
+            lo = t0 * T - L
+            assert W == int(x[max(lo, 0): t0 * T].sum()), (L, t0)
