@@ -84,6 +84,13 @@ def test_argument_validation_without_gpu(mavg):
     assert b"multiple of 32" in lib.mavg_last_error()
     assert lib.mavg_plan_destroy(None) == 0
     assert lib.mavg_run_host(None, None, None) == _lib.ERR_INVALID_ARG
+    assert lib.mavg_run_device(None, None, None) == _lib.ERR_INVALID_ARG
+    assert lib.mavg_run_cascade(None, None, None, None, 3) == _lib.ERR_INVALID_ARG
+    assert lib.mavg_host_register(None, 64) == _lib.ERR_INVALID_ARG
+    assert lib.mavg_host_unregister(None) == 0
+    assert lib.mavg_plan_info(None, None) == _lib.ERR_INVALID_ARG
+    assert lib.mavg_get_timing(None, None) == _lib.ERR_INVALID_ARG
+    assert lib.mavg_prefix_sum(0, None, None, 10, 1, None) == _lib.ERR_INVALID_ARG
 
 
 def test_fails_loudly_without_gpu(mavg):
