@@ -112,7 +112,8 @@ def test_random_shapes_on_two_shards_bit_identical(mavg, oracle_mod, seed):
     """One process driving two shards (two GPUs when present, else the same GPU twice): the result is the
     single-shard result bit for bit on every streaming path (tile grid anchored at frame 0) and for int16 everywhere
     (exact arithmetic).  The generic float32 kernel builds its run-start sums in fp64 from differently partitioned
-    partial sums on a shard, so it is only held to 1e-6 of the single-shard result."""
+    partial sums on a shard (and so does the far-lag kernel with its carried window sum), so those are held to 1e-6
+    of the single-shard result."""
     rng = np.random.default_rng(3000 + seed)
     devs = [0, 1] if mavg.device_count() >= 2 else [0, 0]
     bad = []
@@ -123,7 +124,7 @@ def test_random_shapes_on_two_shards_bit_identical(mavg, oracle_mod, seed):
             oracle_mod.fill_i16(n, 70_000 + 100 * seed + case)
         with mavg.Plan(frames, k, channels=ch, dtype=dtype, layout=layout) as plan:
             y1 = plan.run_host(x)
-            stream = int(plan.info.path) == 1
+            stream = int(plan.info.path) == 1 and int(plan.info.mode) != 5   # the far-lag kernel carries fp64 sums per chunk
         try:
             with mavg.Plan(frames, k, channels=ch, dtype=dtype, layout=layout, devices=devs) as plan:
                 y2 = plan.run_host(x)
