@@ -49,7 +49,7 @@ def lib_sources() -> list[str]:
 def build_lib(force: bool = False, verbose: bool = False) -> str:
     srcs = lib_sources()
     if force or _stale(LIB, srcs):
-        cmd = [_nvcc()] + NVCC_FLAGS + ["-shared", "-o", LIB, srcs[0]]
+        cmd = [_nvcc()] + NVCC_FLAGS + ["-shared", "-o", LIB, srcs[0], "-lpthread"]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), file=sys.stderr)

@@ -9,7 +9,11 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <condition_variable>
 #include <cstdarg>
+#include <deque>
+#include <mutex>
+#include <thread>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -1463,6 +1467,89 @@ int mavg_get_timing(mavg_plan* p, mavg_timing* t)
     return MAVG_OK;
 }
 
+namespace {
+
+// cudaMemcpyAsync into PAGEABLE host memory blocks the calling thread for the whole copy, so one thread issuing the
+// H2D and the D2H copies of mavg_run_host runs the two directions one after the other (measured: 1.75 Gsamples/s
+// on 2^28 float32 samples).  With a pageable destination a helper thread issues the D2H copies, so that they overlap
+// the caller thread's H2D copies and kernel launches.  Page-locked buffers never come here.
+class D2HWorker {
+public:
+    struct Job {
+        int device;
+        cudaStream_t stream;
+        cudaEvent_t after;   // the slice's kernels
+        void* dst;
+        const void* src;
+        size_t bytes;
+    };
+    ~D2HWorker() { finish(); }
+    bool active() const { return started_; }
+    void start()
+    {
+        started_ = true;
+        th_ = std::thread([this] { loop(); });
+    }
+    void push(const Job& j)
+    {
+        {
+            std::lock_guard<std::mutex> g(m_);
+            q_.push_back(j);
+        }
+        cv_.notify_one();
+    }
+    // no more jobs: wait for the queued copies to be issued (and therefore finished: pageable copies are synchronous)
+    cudaError_t finish()
+    {
+        if (started_ && th_.joinable()) {
+            {
+                std::lock_guard<std::mutex> g(m_);
+                done_ = true;
+            }
+            cv_.notify_one();
+            th_.join();
+        }
+        return err_;
+    }
+
+private:
+    void loop()
+    {
+        for (;;) {
+            Job j;
+            {
+                std::unique_lock<std::mutex> g(m_);
+                cv_.wait(g, [this] { return done_ || !q_.empty(); });
+                if (q_.empty()) return;
+                j = q_.front();
+                q_.pop_front();
+            }
+            cudaError_t e = cudaSetDevice(j.device);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(j.stream, j.after, 0);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(j.dst, j.src, j.bytes, cudaMemcpyDeviceToHost, j.stream);
+            if (e != cudaSuccess && err_ == cudaSuccess) err_ = e;
+        }
+    }
+    std::thread th_;
+    std::mutex m_;
+    std::condition_variable cv_;
+    std::deque<Job> q_;
+    bool done_ = false, started_ = false;
+    cudaError_t err_ = cudaSuccess;
+};
+
+bool is_pageable(const void* ptr)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+}  // namespace
+
 int mavg_run_host(mavg_plan* p, const void* h_in, void* h_out)
 {
     if (!p || !h_in || !h_out) return fail(MAVG_ERR_INVALID_ARG, "null argument");
@@ -1471,6 +1558,8 @@ int mavg_run_host(mavg_plan* p, const void* h_in, void* h_out)
     const size_t es = elem_size(p->desc.dtype);
     const uint64_t C = p->desc.channels;
     uint32_t launches = 0;
+    D2HWorker worker;   // joins in its destructor on every return path
+    if ((uint64_t)p->desc.frames * C * es >= (8ull << 20) && is_pageable(h_out)) worker.start();
     for (DevCtx& d : p->dev) {
         MAVG_TRY(alloc_owned(p, d));
         MAVG_CUDA(cudaSetDevice(d.device));
@@ -1549,15 +1638,25 @@ int mavg_run_host(mavg_plan* p, const void* h_in, void* h_out)
                                   &launches));
             MAVG_CUDA(cudaEventRecord(e_k, d.stream));
             if (i + 1 == nslices && p->timing_on) cudaEventRecord(d.ev[2], d.stream);
-            MAVG_CUDA(cudaStreamWaitEvent(d.s_d2h, e_k, 0));
-            MAVG_CUDA(cudaMemcpyAsync(dst + off_e * es, (char*)d.d_out + off_e * es, cnt_e * es, cudaMemcpyDeviceToHost,
-                                      d.s_d2h));
+            if (worker.active()) {
+                worker.push({d.device, d.s_d2h, e_k, dst + off_e * es, (char*)d.d_out + off_e * es, (size_t)(cnt_e * es)});
+            } else {
+                MAVG_CUDA(cudaStreamWaitEvent(d.s_d2h, e_k, 0));
+                MAVG_CUDA(cudaMemcpyAsync(dst + off_e * es, (char*)d.d_out + off_e * es, cnt_e * es, cudaMemcpyDeviceToHost,
+                                          d.s_d2h));
+            }
         }
         if (elems == 0 && p->timing_on) {
             cudaEventRecord(d.ev[1], d.s_h2d);
             cudaEventRecord(d.ev[2], d.stream);
         }
-        if (p->timing_on) cudaEventRecord(d.ev[3], d.s_d2h);
+    }
+    MAVG_CUDA(worker.finish());
+    for (DevCtx& d : p->dev) {
+        if (p->timing_on) {
+            MAVG_CUDA(cudaSetDevice(d.device));
+            cudaEventRecord(d.ev[3], d.s_d2h);
+        }
         d.timed = p->timing_on;
     }
     p->launches_last_run = launches;

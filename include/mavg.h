@@ -264,7 +264,8 @@ int mavg_host_free(void *h_ptr);
 /* Page-lock memory the caller already owns (cudaHostRegister / cudaHostUnregister), e.g. the std::vector
  * buffers the reference hands to its XxxGpuLoad functions (basics/profilable_sm_vload4.cu:90-91), whose
  * pageable cudaMemcpy (gpu_utils.h:43,47) runs 7x slower than pinned copies on this hardware (measured:
- * 1.75 Gsamples/s pageable, 10.3 registered, 11.8 with mavg_host_alloc buffers through mavg_run_host, 2^28
+ * 1.75 Gsamples/s pageable (2.45 since mavg_run_host issues pageable D2H copies from a helper thread), 10.3
+ * registered, 11.8 with mavg_host_alloc buffers through mavg_run_host, 2^28
  * float32 samples).  Registering costs about 0.35 s per GiB, i.e. it pays off from the fifth call on the same
  * buffers: do it once per buffer, not per call.  The caller unregisters BEFORE freeing the memory.
  * MAVG_ERR_ALLOC when the range cannot be locked (the buffer then still works, at pageable speed). */
