@@ -11,6 +11,9 @@ digital_signal_processsing_b200/csrc/mavg_kernels.cuh forms each output:
     (warp-level Hillis-Steele, exclusive warp offsets, tile totals);
   * then w += x[i] - x[i-k], y = w * (1/k).
 
+`far_lag_model` restates stream_far_f32_kernel the same way (fp64 carried window sum, fp32
+differences of 16-sample run totals, per-tile scan, fp32 slide).
+
 It lets the CPU-only test-suite check the index algebra (n_full, m_part, lag
 misalignment, history tiles) and the 1e-5 error budget for every k without a GPU; the
 GPU tests check the CUDA implementation itself.
@@ -152,4 +155,60 @@ def stream_model(x: np.ndarray, k: int, NT: int = 256, R: int = 16, direct_max: 
         for r in range(R):
             w = (w + (X[:, r] - buf[lag0 + r]).astype(f32)).astype(f32)
             y[t * T + tid * R + r] = w * inv
+    return y[:n]
+
+
+def far_lag_model(x: np.ndarray, L: int, chunk_tiles: int = 4) -> np.ndarray:
+    """stream_far_f32_kernel (mono), operation for operation in fp32 / fp64: per chunk of `chunk_tiles` tiles the
+    window sum W in front of the tile is built by ceil(L / T) masked warm-up tiles and carried in fp64; inside a
+    tile every thread forms d = (own run total) - (lag run total) pairwise in fp32, the tile scans d (warp-level
+    Hillis-Steele, then the 16 warp totals), a run starts from float(W + exclusive prefix) and slides in fp32."""
+    NT, R, NW = 512, 16, 16
+    T = NT * R
+    x = np.asarray(x, dtype=f32)
+    n = x.size
+    ntiles = (n + T - 1) // T
+    HT = (L + T - 1) // T
+    pad = (HT + 1) * T + L
+    buf = np.zeros(pad + ntiles * T, dtype=f32)
+    buf[pad:pad + n] = x
+    y = np.zeros(ntiles * T, dtype=f32)
+    inv = f32(1.0) / f32(L)
+    tid = np.arange(NT)
+
+    def scan_tile(d):
+        incl = _warp_inclusive(d)
+        raw = incl.reshape(NW, 32)[:, 31].copy()
+        lanes = np.zeros(32, dtype=f32)
+        lanes[:NW] = raw
+        winc = _warp_inclusive(lanes, width=NW)[:NW]
+        own_off = (winc - raw).astype(f32)[tid >> 5]
+        return incl, own_off, winc[NW - 1]
+
+    for t0 in range(0, ntiles, chunk_tiles):
+        W = np.float64(0.0)
+        for j in range(HT):                                   # warm-up tiles in front of the chunk
+            u = t0 - HT + j
+            X = buf[pad + u * T: pad + (u + 1) * T].reshape(NT, R).copy()
+            if j == 0:
+                m0 = HT * T - L
+                idx = (tid[:, None] * R + np.arange(R)[None, :])
+                X[idx < m0] = 0
+            d = np.zeros(NT, dtype=f32)
+            for r in range(R):
+                d = (d + X[:, r]).astype(f32)
+            _, _, dtot = scan_tile(d)
+            W = W + np.float64(dtot)
+        for t in range(t0, min(t0 + chunk_tiles, ntiles)):
+            base = pad + t * T
+            X = buf[base: base + T].reshape(NT, R)
+            XL = buf[base - L: base - L + T].reshape(NT, R)
+            d = (_pairwise_group_total(X) - _pairwise_group_total(XL)).astype(f32)
+            incl, own_off, dtot = scan_tile(d)
+            e_run = (own_off + (incl - d).astype(f32)).astype(f32)
+            acc = (W + e_run.astype(np.float64)).astype(f32)
+            for r in range(R):
+                acc = (acc + (X[:, r] - XL[:, r]).astype(f32)).astype(f32)
+                y[t * T + tid * R + r] = acc * inv
+            W = W + np.float64(dtot)
     return y[:n]

@@ -98,3 +98,18 @@ def test_int16_head_weights_cover_exactly_the_head():
                             if tab[c][wi] >> (8 * hh) & 1)
             assert picked == [(r, r % C) for r in range(m_part)]
             assert mis % C == 0 and 0 <= mis < 8
+
+
+@pytest.mark.parametrize("dist", ["U01", "USYM", "DC1E4"])
+def test_far_lag_model_error_budget(oracle_mod, dist):
+    """The far-lag kernel's arithmetic (fp64 carried window sum, fp32 differences of 16-sample sums) in NumPy:
+    forward error relative to the mean absolute window content stays orders of magnitude inside 1e-5, also for
+    zero-mean and large-offset inputs and across chunk boundaries."""
+    from algo_model import far_lag_model
+    n, L = 11 * 8192 + 123, 20_011
+    x = oracle_mod.fill_f32(n, 777, dist=getattr(oracle_mod, "DIST_" + dist))
+    y = far_lag_model(x, L, chunk_tiles=3)
+    e = oracle_mod.mavg_f64(x, L)
+    scale = oracle_mod.mavg_f64(np.abs(x), L)
+    err = float(np.max(np.abs(y - e) / np.maximum(scale, 1e-30)))
+    assert err < 2e-6, err
