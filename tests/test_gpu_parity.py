@@ -899,3 +899,20 @@ def test_far_lag_kernel_stereo(mavg, oracle_mod, k):
         assert plan.info.path == 1 and plan.info.mode == 5
         y = plan.run_host(x)
     assert _rel(y, oracle_mod.mavg_f64(x, k, 2)) < TOL
+
+
+@pytest.mark.parametrize("L", [20_011, 9_000])
+def test_far_lag_kernel_matches_numpy_model_bitwise(mavg, oracle_mod, L):
+    """The far-lag kernel performs exactly the operations of tests/algo_model.far_lag_model (one tile per chunk here:
+    fewer tiles than SMs), so the two agree bit for bit on every sample the streaming kernel produces."""
+    from algo_model import far_lag_model
+    n = 11 * 8192 + 123
+    x = oracle_mod.fill_f32(n, 777)
+    with mavg.Plan(n, L, path="stream") as plan:
+        assert plan.info.mode in (1, 5)
+        if plan.info.mode != 5:
+            pytest.skip("this window still fits the ring of the ordinary kernel")
+        y = plan.run_host(x)
+    m = far_lag_model(x, L, chunk_tiles=1)
+    whole_rows = n // 32 * 32                  # the last partial row belongs to tail_kernel
+    assert np.array_equal(y[:whole_rows], m[:whole_rows])
