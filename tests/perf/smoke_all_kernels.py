@@ -29,6 +29,17 @@ for k in (4, 700):
 xp = oracle.fill_f32(4 * 8192 * 2, 6)
 yp = mavg.moving_average(xp, 64, channels=4, layout="planar")
 assert rel(yp[:16384], oracle.mavg_f64(xp[:16384], 64)) < 1e-5
+x6 = oracle.fill_i16(6 * 9001, 8)                                 # few-channel int16: channel pairs (6), scalar (5)
+for k in (3, 100, 1000):
+    assert np.array_equal(mavg.moving_average(x6, k, channels=6), oracle.mavg_i16(x6, k, 6)), k
+x5 = oracle.fill_i16(5 * 9001, 9)
+assert np.array_equal(mavg.moving_average(x5, 48, channels=5), oracle.mavg_i16(x5, 48, 5))
+x64 = oracle.fill_i16(64 * 3001, 10)                              # int16 column kernel
+assert np.array_equal(mavg.moving_average(x64, 64, channels=64), oracle.mavg_i16(x64, 64, 64))
+xf = oracle.fill_f32(12 * 8192 + 45, 11)                          # far-lag kernel (mono, stereo) + tail kernel
+assert rel(mavg.moving_average(xf, 60001), oracle.mavg_f64(xf, 60001)) < 1e-5
+xf2 = oracle.fill_f32(2 * (12 * 4096 + 21), 12)
+assert rel(mavg.moving_average(xf2, 30001, channels=2), oracle.mavg_f64(xf2, 30001, 2)) < 1e-5
 d = torch.from_numpy(oracle.fill_i16(2 * 50001, 7)).cuda()
 o = torch.zeros(2 * 50001, dtype=torch.int64, device="cuda")
 torch.cuda.synchronize()
