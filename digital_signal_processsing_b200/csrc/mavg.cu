@@ -263,7 +263,8 @@ StreamGeom plan_cols(uint32_t k, uint32_t C, const mavg_tuning& tu, bool i16 = f
     return g;
 }
 
-// 3..31 interleaved channels, k <= 256: thread = (run of R frames, channel), flat TMA tiles.
+// 3..31 interleaved channels: thread = (run of R frames, channel), flat TMA tiles; windows up to 256 frames sum
+// the whole runs one by one, longer ones through per-tile prefixes (as many history tiles as fit shared memory).
 // float32: 16-frame runs.  int16, odd channel counts: 32-frame runs of 2-byte samples.  int16, even channel
 // counts: the kernel sees C/2 "channels" of 32-bit words (channel pairs), 16-frame runs (g.pair, g.C = C/2,
 // g.elem = 4).  int16 needs k >= 2 (k == 1, the identity, stays on the generic kernel).

@@ -1791,7 +1791,7 @@ __global__ void __launch_bounds__(NWT * 32)
 }
 
 // ----------------------------------------------------------------------------------
-// Few-channel kernel -- interleaved float32 with 3..32 channels (5.1 / 7.1 audio, ...), windows up to 256 frames.
+// Few-channel kernel -- interleaved float32 with 3..31 channels (5.1 / 7.1 audio, ...).
 // Flat TMA tiles of the interleaved stream exactly like the mono kernel (TileRing, TMA store), but the work is
 // split the way the column kernel does it: thread = (run of RF frames, channel), neighbouring threads take
 // neighbouring channels of the same run.  NR = floor(512 / C) runs per tile, rounded down so that NR * C is a
@@ -2029,7 +2029,7 @@ __global__ void __launch_bounds__(512)
 }
 
 // ----------------------------------------------------------------------------------
-// Few-channel int16 twin: 3..31 interleaved int16 channels (multichannel PCM WAV), 2 <= k <= 256.  Same layout
+// Few-channel int16 twin: 3..31 interleaved int16 channels (multichannel PCM WAV), k >= 2.  Same layout
 // and work split as stream_fewc_f32_kernel with 32-frame runs; int32-exact window sums and the multiply-high
 // truncating division, so results stay bit-identical to profilable_cpu_computations.  4 B/sample.
 // ----------------------------------------------------------------------------------
