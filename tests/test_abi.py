@@ -113,3 +113,27 @@ def test_product_does_not_import_the_oracle():
                     text = open(os.path.join(dirpath, f), errors="ignore").read()
                     assert not re.search(r"^\s*(import|from)\s+oracle\b", text, flags=re.M), f
                     assert "mavg_oracle.h" not in text and "libmavg_oracle" not in text, f
+
+
+def test_links_and_runs_from_plain_c(mavg, tmp_path):
+    """A C99 program (no C++, no Python) includes include/mavg.h, links against libmavg.so and gets status codes
+    back -- the shape of a cgo / JNI / Rust FFI binding."""
+    from digital_signal_processsing_b200 import _lib
+    src = tmp_path / "client.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <string.h>\n#include "mavg.h"\n'
+        'int main(void) {\n'
+        '    mavg_desc d; mavg_plan *p = NULL; int rc;\n'
+        '    memset(&d, 0, sizeof d);\n'
+        '    d.struct_size = sizeof d; d.dtype = MAVG_I16; d.channels = 2; d.frames = 1000; d.window = 0;\n'
+        '    rc = mavg_plan_create(&d, &p);\n'
+        '    printf("%d %d %s|%s\\n", mavg_version(), rc, mavg_strerror(rc), mavg_last_error());\n'
+        '    return (rc == MAVG_ERR_INVALID_ARG && p == NULL) ? 0 : 1;\n'
+        '}\n')
+    exe = tmp_path / "client"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src),
+                    "-o", str(exe), "-L", libdir, "-lmavg", f"-Wl,-rpath,{libdir}"], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.split()[0] == "200" and "window" in out.stdout
