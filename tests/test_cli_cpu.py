@@ -50,3 +50,40 @@ def test_fails_loudly_without_a_gpu(bin_dir, mavg, tmp_path):
     r = _run(bin_dir, "bin_vec4", "ok.wav", 5, 256, cwd=tmp_path)
     assert r.returncode != 0 and "libmavg" in (r.stderr + r.stdout)
     assert not (tmp_path / "benchmark_data.csv").exists()
+
+
+def test_csv_logger_keeps_the_reference_schema(mavg, tmp_path):
+    """CsvLogger (host/mavg_workspace.h, reached through the compat name gpu_utils.h): the first 14 columns are the
+    reference's (gpu_utils.h:196-199), in order, with the same formulas (:202-227); the new columns follow."""
+    from digital_signal_processsing_b200 import _lib
+    root = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+    src = tmp_path / "csv.cpp"
+    src.write_text('''
+#include "gpu_utils.h"
+#include "benchmark.h"
+int main() {
+    ProfileResult r{};
+    r.transfer_h2d_ms = 1.0f; r.compute_ms = 0.5f; r.transfer_d2h_ms = 1.5f; r.total_ms = 3.0f; r.initialization_ms = 7.0f;
+    CsvLogger("out.csv").log("Vectorized_int4", "Standard", 1000000, 64, 256, r, 2, 2, 1, "int16", "interleaved");
+    CsvLogger("out.csv").log("Vectorized_int4", "Standard", 1000000, 64, 256, r, 2, 2, 1, "int16", "interleaved");
+    return 0;
+}''')
+    exe = tmp_path / "csv"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.run(["g++", "-O1", "-std=c++17", "-I", os.path.join(root, "include"), "-I", os.path.join(root, "host"), str(src),
+                    "-o", str(exe), "-L", libdir, "-lmavg", f"-Wl,-rpath,{libdir}", "-lpthread"], check=True)
+    subprocess.run([str(exe)], cwd=tmp_path, check=True, capture_output=True)
+    lines = (tmp_path / "out.csv").read_text().strip().split("\n")
+    assert len(lines) == 3                                             # one header, two rows (appended)
+    cols = lines[0].split(",")
+    assert cols[:14] == ["Algorithm", "MemoryMode", "N_Samples", "Grade", "BlockSize", "H2D_ms", "Compute_ms", "D2H_ms",
+                         "Total_ms", "Init_ms", "ColdStart_Total_ms", "Bandwidth_GBs", "Throughput_MSs", "ColdStart_MSs"]
+    assert cols[14:] == ["GPUs", "Dtype", "Layout", "Gsamples_s", "HBM_GBs", "Pct_HBM_nominal", "Pct_HBM_measured"]
+    row = dict(zip(cols, lines[1].split(",")))
+    assert row["Algorithm"] == "Vectorized_int4" and row["N_Samples"] == "1000000" and row["Grade"] == "64"
+    assert float(row["ColdStart_Total_ms"]) == 10.0
+    # six significant digits, like the reference's default ostream precision
+    assert abs(float(row["Bandwidth_GBs"]) - 1e6 * 4 / 1e9 / 3e-3) < 1e-4          # N * (in + out bytes) / total time
+    assert abs(float(row["Throughput_MSs"]) - 1.0 / 3e-3) < 1e-3                   # Msamples per second, steady state
+    assert abs(float(row["ColdStart_MSs"]) - 1.0 / 10e-3) < 1e-3
+    assert abs(float(row["Gsamples_s"]) - 1e6 / 1e9 / 0.5e-3) < 1e-4               # kernel-only
