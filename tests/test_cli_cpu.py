@@ -87,3 +87,27 @@ int main() {
     assert abs(float(row["Throughput_MSs"]) - 1.0 / 3e-3) < 1e-3                   # Msamples per second, steady state
     assert abs(float(row["ColdStart_MSs"]) - 1.0 / 10e-3) < 1e-3
     assert abs(float(row["Gsamples_s"]) - 1e6 / 1e9 / 0.5e-3) < 1e-4               # kernel-only
+
+
+def test_sweep_driver_counts_runs_and_failures(bin_dir, mavg, monkeypatch, tmp_path, capsys):
+    """The run_benchmarks.py successor on a box without a GPU: inputs are seeded (two generations are identical),
+    grades >= frames are skipped like the reference does (run_benchmarks.py:78), every GPU child fails loudly and
+    is counted as a failure, the exit status says so.  With the reference's own CPU binary beside it (when
+    oracle/_ref was built here) those runs succeed and write the reference's CSV."""
+    if mavg.device_count() > 0:
+        pytest.skip("a GPU is present: the GPU children would succeed (covered by tests/test_gpu_dropin.py)")
+    from digital_signal_processsing_b200 import run_benchmarks as rb
+    monkeypatch.chdir(tmp_path)
+    rb.generate_wav("a.wav", 4000, 2, "int16")
+    rb.generate_wav("b.wav", 4000, 2, "int16")
+    assert (tmp_path / "a.wav").read_bytes() == (tmp_path / "b.wav").read_bytes()
+    ref_cpu = os.path.join(os.path.dirname(__file__), "..", "oracle", "_ref", "bin_cpu")
+    cpu_bin = os.path.abspath(ref_cpu) if os.path.exists(ref_cpu) else ""
+    exes = [e for e in rb.EXECUTABLES if e["path"] in ("bin_vec4", "bin_hillis")]
+    counter, failures, rows = rb.run_suite([4000], [3, 64, 5000], [128, 256], [1], exes, "int16", 2, cpu_bin, verbose=False)
+    gpu_runs = 2 * 2 * 2                                   # binaries x grades below 2000 frames x block sizes
+    assert len(rows) == gpu_runs and all(r[-1] != 0 for r in rows)
+    assert counter == gpu_runs + (2 if cpu_bin else 0) and failures == gpu_runs
+    assert not os.path.exists(rb.TEMP_WAV)
+    assert "Total Failures/Crashes: %d" % gpu_runs in capsys.readouterr().out
+    assert rb.main(["--sizes", "4000", "--grades", "3", "--bins", "bin_vec4"]) == 1
