@@ -81,6 +81,17 @@ def ncu_traffic_bytes():
 
 
 # ---------------------------------------------------------------------------- reference arm
+def metric_name(samples_log2, ks):
+    """BASELINE.json's metric on its named configuration; both arms print the same string."""
+    return "Gsamples/s, 2^%d-sample mono float32 moving average per GPU, k sweep %s" % (samples_log2, ks)
+
+
+def workload_name(samples_log2, world, ks):
+    n = 1 << samples_log2
+    return ("mono float32 synthetic U[0,1) signal, 2^%d samples per GPU (contiguous shards of one %d-sample signal), "
+            "window sweep k=%s, device resident" % (samples_log2, world * n, ks))
+
+
 def cpu_reference_line(args, ks, world):
     """The reference's own CPU implementation (oracle/_ref, built from /root/reference) timed on the
     host cores.  It is single threaded by construction (basics/profilable_moving_averager.cpp:14-37),
@@ -110,12 +121,14 @@ def cpu_reference_line(args, ks, world):
     sample = f"mono int16, 2^24 samples x k in {ks} per step, single thread"
     line = {
         "impl": "reference",
-        "metric": "moving-average throughput, mono signal, k sweep %s" % ks,
+        "metric": metric_name(args.samples_log2, ks),
         "value": value, "unit": "Gsamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "i16", "data": "synthetic",
-        "config": {"workload": "reference CPU path profilable_cpu_computations on a bounded sample of the "
-                               "2^28-sample k sweep", "sample": sample},
+        "config": {"workload": workload_name(args.samples_log2, world, ks),
+                   "reference_arm": "the reference's CPU path profilable_cpu_computations (int16, its only sample type) on "
+                                    "a bounded sample of that workload, rank 0 only",
+                   "sample": sample},
         "cpu_baseline": {"value": value, "unit": "Gsamples/s", "cores": 1, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "Gsamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -409,12 +422,11 @@ def main():
 
     info = plans[ks[-1]].info
     line = {
-        "metric": "Gsamples/s, 2^%d-sample mono float32 moving average per GPU, k sweep %s" % (args.samples_log2, ks),
+        "metric": metric_name(args.samples_log2, ks),
         "value": value, "unit": "Gsamples/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "mono float32 synthetic U[0,1) signal, 2^%d samples per GPU (contiguous shards of one "
-                               "%d-sample signal), window sweep k=%s, device resident" % (args.samples_log2, world * n, ks),
+        "config": {"workload": workload_name(args.samples_log2, world, ks),
                    "samples_per_gpu": n, "ks": ks, "halo": halo_mode,
                    "launch_mode": ("CUDA graph replay, one graph = one step of %d kernel nodes" % len(ks)) if graph is not None
                    else "stream launches",
