@@ -32,7 +32,7 @@ class Tuning(ctypes.Structure):
         ("chunks_per_cta", ctypes.c_uint32),
         ("direct_max_k", ctypes.c_uint32),
         ("slice_bytes", ctypes.c_uint32),
-        ("reserved", ctypes.c_uint32 * 1),
+        ("overlap", ctypes.c_uint32),
     ]
 
 

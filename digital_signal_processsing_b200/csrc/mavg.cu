@@ -15,6 +15,7 @@
 #include <mutex>
 #include <thread>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -347,6 +348,43 @@ StreamGeom plan_far(uint32_t k, uint32_t C, const mavg_tuning& tu)
 }
 
 typedef void (*StreamKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const mavg::StreamParams);
+
+// mavg_tuning.overlap -> StreamParams.pdl (0 off, 1 wait before the first load, 2 before the first store).
+// MAVG_OVERLAP in the environment overrides the library default (for A/B measurements without a rebuild).
+int pdl_mode(const mavg_tuning& tu)
+{
+    uint32_t o = tu.overlap;
+    if (o == 0) {
+        static const int env_default = [] {
+            const char* e = getenv("MAVG_OVERLAP");
+            const int v = e ? atoi(e) : 1;
+            return (v >= 1 && v <= 3) ? v : 1;
+        }();
+        o = (uint32_t)env_default;
+    }
+    return o == 1 ? 1 : o == 2 ? 2 : 0;
+}
+
+// Launch of a TileRing kernel, with the programmatic-stream-serialization attribute when the plan overlaps launches:
+// the kernel then starts while the previous kernel of the stream drains and orders itself with griddepcontrol.wait.
+template <typename P>
+cudaError_t launch_ring(void (*kern)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const P), unsigned grid,
+                        unsigned threads, uint32_t smem, cudaStream_t st, int pdl, const CUtensorMap& a,
+                        const CUtensorMap& b, const CUtensorMap& c, const P& prm)
+{
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(grid, 1, 1);
+    cfg.blockDim = dim3(threads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, a, b, c, prm);
+}
 
 template <int NT, int R, int C = 1>
 StreamKernel pick_variant(int mis, int mode, uint32_t k)
@@ -783,6 +821,7 @@ int launch_fewc(mavg_plan* p, DevCtx& d, const void* in, void* out, const void* 
     sp.stages = g.S;
     sp.prefetch = g.P;
     sp.has_halo = halo ? 1 : 0;
+    sp.pdl = pdl_mode(p->desc.tuning);
     fp.channels = C;
     fp.runs = (uint32_t)g.runs;
     fp.long_mode = g.long_mode ? 1u : 0u;
@@ -791,8 +830,7 @@ int launch_fewc(mavg_plan* p, DevCtx& d, const void* in, void* out, const void* 
                : g.elem == 4 ? mavg::stream_fewc_f32_kernel<16> : mavg::stream_fewc_i16_kernel<32>;
     MAVG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
     const unsigned grid = (unsigned)std::min<uint64_t>(ctas, cps);
-    kern<<<grid, 512, g.smem, d.stream>>>(in_map, out_map, halo_map, fp);
-    MAVG_CUDA(cudaGetLastError());
+    MAVG_CUDA(launch_ring(kern, grid, 512, g.smem, d.stream, sp.pdl, in_map, out_map, halo_map, fp));
     ++*launches;
     // flat samples past the last whole 128-byte row: the frames that touch them go to the generic kernel
     if (rows * row < n) MAVG_TRY(launch_tail(p, d, in, out, halo, frames, rows * row / C, frames, launches));
@@ -937,6 +975,7 @@ int launch_shard(mavg_plan* p, DevCtx& d, const void* in, void* out, const void*
     sp.stages = g.S;
     sp.prefetch = g.P;
     sp.has_halo = halo ? 1 : 0;
+    sp.pdl = pdl_mode(p->desc.tuning);
 
     StreamKernel kern = g.elem == 4 ? pick_kernel(g, p->desc.window)
                         : g.NT == 256 ? (g.C == 1 ? pick_i16<256, 32, 1>(g.MIS, g.mode) : pick_i16<256, 32, 2>(g.MIS, g.mode))
@@ -944,8 +983,7 @@ int launch_shard(mavg_plan* p, DevCtx& d, const void* in, void* out, const void*
     if (!kern) return fail(MAVG_ERR_UNSUPPORTED, "no stream kernel variant for this window");
     MAVG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
     const unsigned grid = (unsigned)std::min<uint64_t>(ctas, (uint64_t)sp.total_chunks);
-    kern<<<grid, g.NT, g.smem, d.stream>>>(in_map, out_map, halo_map, sp);
-    MAVG_CUDA(cudaGetLastError());
+    MAVG_CUDA(launch_ring(kern, grid, (unsigned)g.NT, g.smem, d.stream, sp.pdl, in_map, out_map, halo_map, sp));
     ++*launches;
 
     // samples past the last whole 128-byte row (per signal): generic kernel
@@ -1384,6 +1422,9 @@ int mavg_run_cascade(mavg_plan* p, const void* const* d_in, void* const* d_out, 
     }
     // one timed region around all passes: start events here, per-pass recording off, end events after the last pass
     const bool was_timed = p->timing_on;
+    // pass i + 1 reads what pass i wrote: tile loads must not start before the previous kernel has completed
+    const uint32_t overlap_saved = p->desc.tuning.overlap;
+    if (pdl_mode(p->desc.tuning) == 2) p->desc.tuning.overlap = 1;
     if (was_timed)
         for (size_t r = 0; r < nd; ++r) {
             MAVG_CUDA(cudaSetDevice(p->dev[r].device));
@@ -1422,6 +1463,7 @@ int mavg_run_cascade(mavg_plan* p, const void* const* d_in, void* const* d_out, 
             }
     }
     p->timing_on = was_timed;
+    p->desc.tuning.overlap = overlap_saved;
     if (rc != MAVG_OK) return rc;
     if (was_timed)
         for (size_t r = 0; r < nd; ++r) {

@@ -305,6 +305,11 @@ __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map)
 {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
+// Programmatic dependent launch: `launch_dependents` lets the next kernel in the stream become resident as soon as
+// every CTA of this grid has issued it (or exited); `wait` blocks the calling thread until the PREVIOUS grid has
+// completed and its memory operations are visible.  Both are no-ops in a launch without the attribute.
+__device__ __forceinline__ void gdc_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void gdc_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __device__ __forceinline__ float4 lds128(uint32_t addr)
 {
@@ -364,6 +369,8 @@ struct StreamParams {
     int32_t stages;             // S = H + 1 + prefetch
     int32_t prefetch;           // P
     int32_t has_halo;           // tiles before tile 0 come from halo_map instead of zero fill
+    int32_t pdl;                // programmatic dependent launch: 0 off, 1 wait for the previous grid before the first
+                                // load, 2 before the first store only (caller: inputs not written by earlier work)
     // int16 paths: multiply-high constants of the exact truncating division (plan_stream_i16 / plan_fewc)
     uint32_t div_mul;
     uint32_t div_shift;
@@ -414,6 +421,8 @@ struct TileRing {
     uint32_t st_buf;
     const CUtensorMap *in_map, *out_map, *halo_map;
     bool has_halo;
+    bool pdl_wait_loads; // thread 0: griddepcontrol.wait before the first tile load (pdl == 1)
+    bool gdc_pending;    // thread 0: griddepcontrol.wait still owed before the first global store (pdl == 2)
     int row_base;        // rows in front of row 0 of in_map (far-lag kernel: left context contiguous with the input)
     uint64_t load_hint;  // L2 policy of the tile loads
 
@@ -431,6 +440,13 @@ struct TileRing {
         it = 0; st = 0; slot = 0; otiles = 0;
         st_pending = st_inflight = false; st_tile = st_sig = 0; st_buf = 0;
         in_map = in; out_map = out; halo_map = halo; has_halo = p.has_halo != 0;
+        gdc_pending = p.pdl == 2;
+        if (p.pdl != 0 && threadIdx.x == 0) {
+            // the next launch may take this SM as soon as every CTA of this grid got here or exited; its own
+            // griddepcontrol.wait keeps it from storing (pdl 2) or loading (pdl 1) before this grid has completed
+            gdc_launch_dependents();
+        }
+        pdl_wait_loads = p.pdl == 1;
         row_base = 0; load_hint = kEvictFirst;
         return outb + 2u * tbv();
     }
@@ -443,6 +459,7 @@ struct TileRing {
             if (has_halo) prefetch_tmap(halo_map);
             for (int s = 0; s < S; ++s) mbar_init(bars + 8u * s, 1);
             fence_mbar_init();
+            if (pdl_wait_loads) gdc_wait();   // only thread 0 touches global memory (TMA loads and stores)
         }
         __syncthreads();
     }
@@ -496,6 +513,10 @@ struct TileRing {
     __device__ __forceinline__ void flush_store()
     {
         if (st_pending) {
+            if (gdc_pending) {   // first store of this CTA: the previous grid may still be writing the same buffer
+                gdc_wait();
+                gdc_pending = false;
+            }
             tma_store_3d(out_map, st_buf, 0, st_tile * rowsv(), st_sig);
             tma_commit();
             st_pending = false;

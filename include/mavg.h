@@ -96,7 +96,12 @@ typedef struct mavg_tuning {
     uint32_t chunks_per_cta; /* contiguous tile ranges each CTA walks (>=1)                */
     uint32_t direct_max_k;   /* largest k*channels served by direct group sums (default 256) */
     uint32_t slice_bytes;    /* mavg_run_host: bytes per pipelined H2D/kernel/D2H slice (default 16 MiB) */
-    uint32_t reserved[1];
+    uint32_t overlap;        /* programmatic dependent launch of the streaming kernels (the next launch's prologue
+                                runs under the previous kernel's tail; nothing is written before the previous
+                                kernel has completed).  0 = library default (1); 1 = wait for the previous kernel
+                                before the first load -- always safe; 2 = wait only before the first store: the
+                                caller asserts that this plan's INPUT (and halo) buffers are not written by work
+                                queued earlier on the same stream, so tile loads may start early; 3 = off    */
 } mavg_tuning;
 
 /* Plan description.  Replaces the DspWorkspace constructor arguments

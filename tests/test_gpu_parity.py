@@ -294,8 +294,10 @@ def test_owned_buffers_synthetic_run(mavg, oracle_mod, torch_cuda):
 
 
 # ------------------------------------------------------------------ BASELINE.json full size
-@pytest.mark.parametrize("k", [3, 256, 4096])
+@pytest.mark.parametrize("k", [3, 9, 16, 64, 256, 257, 1024, 4095, 4096])
 def test_full_size_2p28_vs_oracle(mavg, oracle_mod, k):
+    """Every window of the headline sweep (BASELINE.json configs[1], [2]) at the full 2^28 samples, plus the first
+    window of each arithmetic mode past a seam (9, 257) and an odd window with a misaligned lag run (4095)."""
     n = 1 << 28
     x = oracle_mod.fill_f32(n, 0x5EED0000 + k)
     with mavg.Plan(n, k) as plan:
