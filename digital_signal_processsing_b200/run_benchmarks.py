@@ -65,6 +65,19 @@ def generate_wav(path: str, num_samples: int, channels: int = 2, dtype: str = "i
     wav.write_samples(path, wav.make_header(data.size, channels, data.dtype), data)
 
 
+def hbm_peak_args():
+    """--hbm-peak for the binaries' Pct_HBM_measured column: MAVG_HBM_PEAK_GBS, else the driver-written
+    MEASURED_PEAKS.json at the repository root, else nothing (the binaries then quote the B200_PROFILING.md figure)."""
+    if os.environ.get("MAVG_HBM_PEAK_GBS"):
+        return []          # the binaries read the variable themselves
+    p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
+    try:
+        import json
+        return ["--hbm-peak", str(float(json.load(open(p))["hbm_gbs"]))]
+    except Exception:
+        return []
+
+
 def run_suite(sizes, grades, blocks, gpus_list, executables, dtype, channels, cpu_bin, csv_name=CSV_NAME,
               bin_dir=BIN_DIR, verbose=True):
     start, counter, failures = time.time(), 0, 0
@@ -89,7 +102,7 @@ def run_suite(sizes, grades, blocks, gpus_list, executables, dtype, channels, cp
                         continue
                     for b in (blocks if exe["needs_block"] else [256]):
                         counter += 1
-                        cmd = [path, TEMP_WAV, str(grade), str(b), "--gpus", str(gpus), "--csv", csv_name]
+                        cmd = [path, TEMP_WAV, str(grade), str(b), "--gpus", str(gpus), "--csv", csv_name] + hbm_peak_args()
                         r = subprocess.run(cmd, capture_output=True, text=True)
                         rows.append((exe["name"], n_samples, grade, b, gpus, r.returncode))
                         if r.returncode != 0:

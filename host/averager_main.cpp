@@ -6,7 +6,7 @@
 // invoked under (argv[0]) selects the "Algorithm" label written to the CSV.
 //
 // Same command line as the reference mains (e.g. basics/profilable_sm_vload4.cu:221-239):
-//     <bin> <wav_path> <grade> <block_size> [--gpus N] [--out out.wav] [--csv file] [--rounds M]
+//     <bin> <wav_path> <grade> <block_size> [--gpus N] [--out out.wav] [--csv file] [--rounds M] [--hbm-peak GB/s]
 //   * fewer than 3 positional arguments  -> usage on stderr, exit 1
 //   * block_size outside 32..1024 or not a multiple of 32 -> same message, exit 1 (it is only a hint now)
 //   * input: canonical 44-byte-header WAV, int16 as in the reference, or float32 (extension)
@@ -117,6 +117,7 @@ int main(int argc, char* argv[])
         else if (a == "--csv") o.csv = need("--csv");
         else if (a == "--rounds") o.rounds = atoi(need("--rounds"));
         else if (a == "--warmup") o.warmup = atoi(need("--warmup"));
+        else if (a == "--hbm-peak") hbm_measured_override() = atof(need("--hbm-peak"));
         else pos.push_back(argv[i]);
     }
     if (pos.size() < 3) {

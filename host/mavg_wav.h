@@ -15,6 +15,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <exception>
 #include <string>
 #include <utility>
 #include <vector>
@@ -117,7 +118,23 @@ inline bool read_file(const std::string& path, WAVHeader& h, std::vector<unsigne
         fclose(f);
         return false;
     }
-    bytes.resize(data_bytes);
+    // the header's payload size is a claim (0xFFFFFFFF in streamed WAVs, anything in a damaged ds64 chunk): never
+    // allocate more than the file holds behind the payload offset
+    {
+        const long here = ftell(f);
+        if (here >= 0 && fseek(f, 0, SEEK_END) == 0) {
+            const long end = ftell(f);
+            if (end >= here && (uint64_t)(end - here) < data_bytes) data_bytes = (uint64_t)(end - here);
+            fseek(f, here, SEEK_SET);
+        }
+    }
+    try {
+        bytes.resize(data_bytes);
+    } catch (const std::exception&) {
+        if (why) *why = "cannot allocate " + std::to_string(data_bytes) + " bytes for the samples";
+        fclose(f);
+        return false;
+    }
     const size_t got = data_bytes ? fread(bytes.data(), 1, data_bytes, f) : 0;
     const size_t step = h.bitsPerSample / 8;
     bytes.resize(got / step * step);  // clamp to whole samples actually present

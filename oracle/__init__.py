@@ -23,7 +23,7 @@ DIST_U01, DIST_USYM, DIST_I16, DIST_DC1E4 = 0, 1, 2, 3
 
 def build(ref: bool = True) -> None:
     """Compile the C restatement and, when /root/reference exists, oracle/_ref."""
-    targets = ["all"] + (["ref"] if ref else [])
+    targets = ["all"] + (["ref", "dropin"] if ref else [])
     subprocess.run(["make", "-s", "-C", _HERE] + targets, check=True)
 
 
