@@ -425,7 +425,8 @@ def block_dense_k(cx, d_in, d_out, n, first, left_full, peak, reps=10):
         p = cx.plan(n, k, first_frame=first, overlap=cx.args.overlap)
         h = int(p.info.halo_frames)
         hp = left_full.ptr(h)
-        ms = cx.time_launches(lambda: p.run_device_halo(d_in.value, d_out.value, hp), reps)
+        run = lambda: p.run_device_halo(d_in.value, d_out.value, hp)
+        ms = min(cx.time_launches(run, reps), cx.time_launches(run, reps, warm=0))   # best of two passes of `reps` launches
         cx.stream.synchronize()
         err, _ = spot_check_f32(cx, d_out.value, n, first, k, rng, npoints=64)
         err = cx.allmax([err])[0]
@@ -440,7 +441,7 @@ def block_dense_k(cx, d_in, d_out, n, first, left_full, peak, reps=10):
             "all_stream_path": all(v[3] == 1 for v in res.values()),
             "per_k_ms": {str(k): round(v[0], 4) for k, v in res.items()},
             "per_k_frac": {str(k): round(v[1], 4) for k, v in res.items()},
-            "note": "%d back-to-back launches per k on the bench stream (launch gaps included), max over ranks; "
+            "note": "best of two passes of %d back-to-back launches per k on the bench stream (launch gaps included), max over ranks; "
                     "frac = 8 B x samples / ms / measured peak; error spot-checked at the shard head + 64 random positions" % reps}
 
 

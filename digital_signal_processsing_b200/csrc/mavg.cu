@@ -161,7 +161,7 @@ StreamGeom plan_stream_i16(uint32_t k, uint32_t C, const mavg_tuning& tu)
     g.n_full = (uint32_t)((L + s) / R - 1);
     g.lag_chunks = (uint32_t)((L + 7) / 8);
     g.MIS = (int)(8ull * g.lag_chunks - L);
-    g.mode = g.n_full <= 16 ? 0 : 1;
+    g.mode = 6;                                        // one arithmetic for every window: exclusive scan of run deltas
     const uint64_t T = (uint64_t)g.NT * R;
     g.H = (int)(((uint64_t)(g.n_full + 1) * R + T - 1) / T);
     g.ctas_per_sm = tu.ctas_per_sm ? (int)tu.ctas_per_sm : (g.NT == 256 ? 2 : 1);
@@ -429,12 +429,11 @@ StreamKernel pick_kernel(const StreamGeom& g, uint32_t k)
 }
 
 template <int NT, int R, int C>
-StreamKernel pick_i16(int mis, int mode)
+StreamKernel pick_i16(int mis)
 {
     using namespace mavg;
-#define MAVG_I16_CASE(M)                                                          \
-    case M: return mode == 0 ? (StreamKernel)stream_i16_kernel<NT, R, C, M, 0>    \
-                             : (StreamKernel)stream_i16_kernel<NT, R, C, M, 1>;
+#define MAVG_I16_CASE(M) \
+    case M: return (StreamKernel)stream_i16_kernel<NT, R, C, M>;
     switch (mis) {
         MAVG_I16_CASE(0)
         MAVG_I16_CASE(2)
@@ -950,15 +949,6 @@ int launch_shard(mavg_plan* p, DevCtx& d, const void* in, void* out, const void*
     sp.div_shift = g.div_shift;
     sp.wscale = g.wscale;
     memset(sp.wtab, 0, sizeof sp.wtab);
-    if (g.elem == 2) {
-        // dp2a byte weights: element e of the aligned lag words is run element r = e - MIS; it belongs to the
-        // head of the lag run when r < m_part, and to channel r % C
-        for (uint32_t wi = 0; wi < 20; ++wi)
-            for (uint32_t hh = 0; hh < 2; ++hh) {
-                const int r = (int)(2 * wi + hh) - g.MIS;
-                if (r >= 0 && (uint32_t)r < g.m_part) sp.wtab[(uint32_t)r % g.C][wi] |= g.wscale << (8 * hh);
-            }
-    }
     const uint64_t tiles = (rows * row + T - 1) / T;
     sp.tiles_per_signal = (int32_t)tiles;
     const uint64_t ctas = (uint64_t)d.sm_count * g.ctas_per_sm;
@@ -978,8 +968,8 @@ int launch_shard(mavg_plan* p, DevCtx& d, const void* in, void* out, const void*
     sp.pdl = pdl_mode(p->desc.tuning);
 
     StreamKernel kern = g.elem == 4 ? pick_kernel(g, p->desc.window)
-                        : g.NT == 256 ? (g.C == 1 ? pick_i16<256, 32, 1>(g.MIS, g.mode) : pick_i16<256, 32, 2>(g.MIS, g.mode))
-                                      : (g.C == 1 ? pick_i16<512, 32, 1>(g.MIS, g.mode) : pick_i16<512, 32, 2>(g.MIS, g.mode));
+                        : g.NT == 256 ? (g.C == 1 ? pick_i16<256, 32, 1>(g.MIS) : pick_i16<256, 32, 2>(g.MIS))
+                                      : (g.C == 1 ? pick_i16<512, 32, 1>(g.MIS) : pick_i16<512, 32, 2>(g.MIS));
     if (!kern) return fail(MAVG_ERR_UNSUPPORTED, "no stream kernel variant for this window");
     MAVG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
     const unsigned grid = (unsigned)std::min<uint64_t>(ctas, (uint64_t)sp.total_chunks);

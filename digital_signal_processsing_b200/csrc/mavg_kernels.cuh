@@ -834,17 +834,31 @@ __global__ void __launch_bounds__(NT)
 // int16 streaming kernel -- the reference's own sample format (wav_header.h:26-48), mono or
 // interleaved stereo.  Same skeleton as stream_f32_kernel (persistent CTAs, TMA ring, one
 // __syncthreads per tile, TMA store); arithmetic is exact: int32 window sums (|w| <= k * 32768,
-// k < 65536) and C truncating division by multiply-high, so results are bit-identical to
-// profilable_cpu_computations (basics/profilable_moving_averager.cpp:14-37), unlike the reference
-// GPU kernels that multiply by a float reciprocal.  Interleaved channels are handled on the flat
-// sample stream: window stride C, lag distance k*C, one running sum per channel per thread.
-// HBM traffic: 2 B read + 2 B written per sample.
+// k <= 32768, everything modulo 2^32) and C truncating division by multiply-high, so results are
+// bit-identical to profilable_cpu_computations (basics/profilable_moving_averager.cpp:14-37),
+// unlike the reference GPU kernels that multiply by a float reciprocal.  Interleaved channels are
+// handled on the flat sample stream: window stride C, lag distance L = k*C, one running sum per
+// channel per thread.  HBM traffic: 2 B read + 2 B written per sample.
+//
+// One arithmetic for every window (round 2; rounds 0-1 had a direct-sum mode for short windows and a prefix-scan
+// mode with a lag look-up for long ones, 13.3 / 16.0 executed instructions per sample).  A thread owns a run of R
+// consecutive flat samples and keeps, per channel, the window sum at the run start:
+//     start(t) = W + sum_{u < t} d(u),      d(u) = (total of u's run) - (total of u's lag run, the R samples L earlier)
+// where W = window sum at the first sample of the tile, carried in registers from tile to tile (W += sum_t d(t)).
+// The slide itself yields everything: s[r] = sum_{i <= r} (x[i] - x[i - L]) is computed BEFORE the tile's barrier with
+// two dp2a per sample on the packed words and kept in registers, d = s[R-1]; one exclusive scan of d over the CTA
+// (warp shuffles + 16 warp totals through shared memory) gives start(t); the outputs are
+//     y[r] = trunc((start + s[r]) / k) = (t >> sh) + (t >>> 31),  t = mulhi(start + s[r], M)
+// (a 64-bit multiply-add hi32(s[r] * M + start * M) would fold the addition away, but ptxas splits mad.wide into
+// IMAD.WIDE + IADD3 + IMAD.X -- three instructions instead of two).  No run totals, no head-of-lag sums, no summary
+// ring, no lag look-up: the same instruction count for any k.  A chunk obtains its first W from the H = ceil(L / tile) tiles in front of it:
+// their samples at or behind (chunk start - L) are summed with the same scan (the first of them masked).
 // ----------------------------------------------------------------------------------
 __host__ __device__ inline uint32_t stream_i16_smem_bytes(int NT, int R, int S, int H, int C)
 {
+    (void)H;
     const uint32_t TB = (uint32_t)NT * R * 2;
-    return 1024u + (uint32_t)S * TB + 2u * TB + (uint32_t)(H + 2) * NT * C * 4 + (uint32_t)(H + 2) * 32 * C * 4 +
-           2u * 32 * C * 4 + (uint32_t)S * 8;
+    return 1024u + (uint32_t)S * TB + 2u * TB + 2u * 32 * C * 4 + (uint32_t)S * 8;
 }
 
 __device__ __forceinline__ uint4 lds128u(uint32_t addr)
@@ -887,62 +901,55 @@ __device__ __forceinline__ void sts64i(uint32_t addr, int a, int b)
 {
     asm volatile("st.shared.v2.s32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
 }
-// Instruction budget (ncu: the first version was issue-bound at 62-75 % of the HBM roofline, ALU pipe 77 %; a
-// biased-unsigned rework reached 67-80 % at 17 instructions per sample).  This version never unpacks a sample:
-// every sum is a dp2a on the PACKED words -- d = c + a.lo16 * b.byte0 + a.hi16 * b.byte1, signed -- with byte
-// weights that pick a half (+w), drop it (0) or subtract it (-w):
-//   run totals    gtot[ch] = dp2a(x_word, own weights of ch)          1 (mono) or 2 (stereo) per word
-//   head of lag   acc[ch]  = dp2a(lag_word, plan's table)             1 or 2 per lag word
-//   slide         acc     += x[r] - x[r-k]  = two dp2a with +w / -w   2 per sample
-// and C's truncating division is the signed multiply-high form  t = mulhi(acc, M); y = (t >> s) + (t >>> 31)
-// (exactness: plan_stream_i16).  Two results are merged with one byte permute.  About 8 instructions per
-// sample, most of them on the FMA pipe (dp2a, mulhi), the shifts and the permute on the ALU pipe.
-// TMA zero fill is the signal's zero padding as it is.
+// dp2a on the PACKED sample words -- d = c + a.lo16 * b.byte0 + a.hi16 * b.byte1, signed -- with byte weights that
+// pick a half (+w), drop it (0) or subtract it (-w): the int16 kernels never unpack a sample.
 __device__ __forceinline__ int dp2a_s(uint32_t a, uint32_t b, int c)
 {
     int d;
     asm("dp2a.lo.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
     return d;
 }
-// trunc(w / k) for |w| <= 32768 k (times the weight scale), k <= 32768
+// trunc(w / k) for |w| <= 32768 k (times the weight scale), k <= 32768: t = mulhi(w, M); (t >> s) + (t >>> 31)
+// (exactness: plan_stream_i16 in mavg.cu)
 __device__ __forceinline__ uint32_t div_trunc_mulhi(int w, int mul, uint32_t sh)
 {
     const int t = __mulhi(w, mul);
     return (uint32_t)((t >> sh) + (int)((uint32_t)t >> 31));
 }
 
-template <int NT, int R, int C, int MIS, int MODE>
+template <int NT, int R, int C, int MIS>
 __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : 1))
     stream_i16_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map,
                       const __grid_constant__ CUtensorMap halo_map, const StreamParams p)
 {
-    // R int16 samples per thread run (32 = 64 bytes, 16 = 32 bytes)
+    // R int16 samples per thread run (32 = 64 bytes)
     constexpr int T = NT * R;
     constexpr uint32_t TB = T * 2;
     constexpr int ROWS = T / 64;     // 128-byte rows per tile
     constexpr int NW = NT / 32;
     constexpr int CH_OWN = R / 8;
     constexpr int CH_LAG = CH_OWN + (MIS ? 1 : 0);
-    static_assert(R % C == 0 && NW <= 16 && MIS >= 0 && MIS < 8 && MIS % C == 0, "shape");
+    static_assert(R % C == 0 && R % 8 == 0 && NW <= 16 && MIS >= 0 && MIS < 8 && MIS % C == 0, "shape");
 
     extern __shared__ uint8_t smem_raw[];
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
     TileRing<TB, ROWS> tr;
-    const uint32_t gsum = tr.setup(smem_u32(smem_raw), p, &in_map, &out_map, &halo_map);   // int [GS][NT][C]
-    const int H = tr.H, GS = tr.GS;
-    const uint32_t wexc = gsum + (uint32_t)GS * NT * C * 4;   // int [GS][32][C]  ([31] = tile total)
-    const uint32_t wraw = wexc + (uint32_t)GS * 32 * C * 4;   // int [2][32][C]
+    const uint32_t wraw = tr.setup(smem_u32(smem_raw), p, &in_map, &out_map, &halo_map);   // int [2][32][C] warp totals
+    const int H = tr.H;
     tr.init_barriers(wraw + 2u * 32 * C * 4);
     // dp2a byte weights (+w / -w on the low or the high half; w = 2 when k == 2, see plan_stream_i16)
     const uint32_t w_lo = p.wscale, w_hi = p.wscale << 8;
     const uint32_t n_lo = (0u - p.wscale) & 0xffu, n_hi = n_lo << 8;
+    const int L = (int)(p.k * (uint32_t)C);              // lag distance in flat samples
     int xo[CH_OWN], xg[CH_LAG];                          // pre-swizzled chunk offsets: own run, lag run
 #pragma unroll
     for (int c = 0; c < CH_OWN; ++c) xo[c] = pre_swz(tid * (R * 2) + 16 * c);
 #pragma unroll
     for (int c = 0; c < CH_LAG; ++c) xg[c] = pre_swz((tid * CH_OWN - (int)p.lag_chunks + c) * 16);
+    const int mul = (int)p.div_mul;
+    const uint32_t sh = p.div_shift;
 
     for (int chunk = blockIdx.x; chunk < p.total_chunks; chunk += gridDim.x) {
         int sig, t0, t1;
@@ -950,152 +957,107 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : 1))
         const int first = t0 - H;
         const int ntl = t1 - first;
         tr.prologue(first, ntl, sig);
+        uint32_t W[C];                                   // window sum (per channel) at the first sample of the tile
+#pragma unroll
+        for (int c = 0; c < C; ++c) W[c] = 0u;
 
         for (int j = 0; j < ntl; ++j) {
             const int tile = first + j;
-            const bool is_out = (j >= H);
+            const bool is_out = (j >= H);                // CTA-uniform
             const uint32_t cur = tr.wait_tile();
-            const int slot = tr.slot;
             const uint32_t it = tr.it;
 
-            uint32_t xw[R / 2];                              // own run, packed
+            uint32_t xw[R / 2];                          // own run, packed
 #pragma unroll
             for (int c = 0; c < CH_OWN; ++c) {
                 const uint4 v = lds128u(cur + (uint32_t)xo[c]);
                 xw[4 * c] = v.x, xw[4 * c + 1] = v.y, xw[4 * c + 2] = v.z, xw[4 * c + 3] = v.w;
             }
-            uint32_t gtot[C], incl[C];
-            {
-                int gt[C];
+            uint32_t s[R];                               // s[r] = sum_{i <= r, same channel} (x[i] - x[i - L])
+            uint32_t d[C];                               // this run's contribution to the carried window sums
+            if (is_out) {
+                uint32_t xlw[CH_LAG * 4];                // lag run, packed, as aligned 16-byte chunks
+                const uint32_t b0 = cur, b1 = cur + tr.ring_bytes;
+                const int neg_st = (int)tr.ring - (int)cur;
 #pragma unroll
-                for (int c = 0; c < C; ++c) gt[c] = 0;
+                for (int c = 0; c < CH_LAG; ++c) {
+                    const uint4 v = lds128u(ring_addr(xg[c], b0, b1, neg_st));
+                    xlw[4 * c] = v.x, xlw[4 * c + 1] = v.y, xlw[4 * c + 2] = v.z, xlw[4 * c + 3] = v.w;
+                }
+                int a[C];
+#pragma unroll
+                for (int c = 0; c < C; ++c) a[c] = 0;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int e = MIS + r;               // the lag partner of run element r in the aligned lag words
+                    int a2 = dp2a_s(xw[r >> 1], (r & 1) ? w_hi : w_lo, a[r % C]);
+                    a2 = dp2a_s(xlw[e >> 1], (e & 1) ? n_hi : n_lo, a2);
+                    a[r % C] = a2;
+                    s[r] = (uint32_t)a2;
+                }
+#pragma unroll
+                for (int c = 0; c < C; ++c) d[c] = (uint32_t)a[c];
+            } else {
+                // warm-up tile in front of the chunk: samples at or behind (chunk start - L) belong to the first
+                // output's window; `rel` leading elements of this run lie in front of it (only in the first warm-up tile)
+                const int rel = (t0 - tile) * T - L - tid * R;
+                int a[C];
+#pragma unroll
+                for (int c = 0; c < C; ++c) a[c] = 0;
 #pragma unroll
                 for (int q = 0; q < R / 2; ++q) {
+                    const uint32_t m0 = (2 * q >= rel) ? w_lo : 0u, m1 = (2 * q + 1 >= rel) ? w_hi : 0u;
                     if constexpr (C == 1) {
-                        gt[0] = dp2a_s(xw[q], w_lo | w_hi, gt[0]);
+                        a[0] = dp2a_s(xw[q], m0 | m1, a[0]);
                     } else {
-                        gt[0] = dp2a_s(xw[q], w_lo, gt[0]);
-                        gt[1] = dp2a_s(xw[q], w_hi, gt[1]);
+                        a[0] = dp2a_s(xw[q], m0, a[0]);
+                        a[1] = dp2a_s(xw[q], m1, a[1]);
                     }
                 }
 #pragma unroll
-                for (int c = 0; c < C; ++c) incl[c] = gtot[c] = (uint32_t)gt[c];
+                for (int c = 0; c < C; ++c) d[c] = (uint32_t)a[c];
+#pragma unroll
+                for (int r = 0; r < R; ++r) s[r] = 0u;
             }
 
-            if constexpr (MODE == 0) {
+            // ---- exclusive scan of d over the CTA: inside the warp by shuffles, across warps through shared memory
+            uint32_t incl[C];
 #pragma unroll
-                for (int c = 0; c < C; ++c) sts32i(gsum + (((uint32_t)slot * NT + tid) * C + c) * 4u, (int)gtot[c]);
-            } else {
+            for (int c = 0; c < C; ++c) incl[c] = d[c];
 #pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-#pragma unroll
-                    for (int c = 0; c < C; ++c) {
-                        const uint32_t up = __shfl_up_sync(0xffffffffu, incl[c], d);
-                        if (lane >= d) incl[c] += up;
-                    }
-                }
+            for (int dd = 1; dd < 32; dd <<= 1) {
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
-                    sts32i(gsum + (((uint32_t)slot * NT + tid) * C + c) * 4u, (int)incl[c]);
-                    if (lane == 31) sts32i(wraw + (((it & 1u) * 32u + warp) * C + c) * 4u, (int)incl[c]);
+                    const uint32_t up = __shfl_up_sync(0xffffffffu, incl[c], dd);
+                    if (lane >= dd) incl[c] += up;
                 }
+            }
+            if (lane == 31) {
+#pragma unroll
+                for (int c = 0; c < C; ++c) sts32u(wraw + (((it & 1u) * 32u + warp) * C + c) * 4u, incl[c]);
             }
 
             tr.before_sync();
             __syncthreads();
             tr.after_sync(j, ntl, first, sig);
 
-            uint32_t own_off[C], wex[C];
+            uint32_t start[C], total[C];
 #pragma unroll
-            for (int c = 0; c < C; ++c) own_off[c] = wex[c] = 0u;
-            if constexpr (MODE == 1) {
+            for (int c = 0; c < C; ++c) {
+                const uint32_t v = (lane < NW) ? lds32u(wraw + (((it & 1u) * 32u + lane) * C + c) * 4u) : 0u;
+                uint32_t wi = v;
 #pragma unroll
-                for (int c = 0; c < C; ++c) {
-                    const uint32_t v = (lane < NW) ? (uint32_t)lds32i(wraw + (((it & 1u) * 32u + lane) * C + c) * 4u) : 0u;
-                    uint32_t wi = v;
-#pragma unroll
-                    for (int d = 1; d < NW; d <<= 1) {
-                        const uint32_t up = __shfl_up_sync(0xffffffffu, wi, d);
-                        if (lane >= d) wi += up;
-                    }
-                    wex[c] = wi - v;
-                    if (warp == 0) {
-                        if (lane < NW) sts32i(wexc + (((uint32_t)slot * 32u + lane) * C + c) * 4u, (int)wex[c]);
-                        if (lane == NW - 1) sts32i(wexc + (((uint32_t)slot * 32u + 31u) * C + c) * 4u, (int)wi);
-                    }
-                    own_off[c] = __shfl_sync(0xffffffffu, wex[c], warp);
+                for (int dd = 1; dd < NW; dd <<= 1) {
+                    const uint32_t up = __shfl_up_sync(0xffffffffu, wi, dd);
+                    if (lane >= dd) wi += up;
                 }
+                const uint32_t own_off = __shfl_sync(0xffffffffu, wi - v, warp);   // totals of the warps in front
+                total[c] = __shfl_sync(0xffffffffu, wi, NW - 1);
+                start[c] = W[c] + own_off + (incl[c] - d[c]);
             }
 
             if (is_out) {
-                uint32_t xlw[CH_LAG * 4];                    // lag run, packed
-                uint32_t acc[C];
-#pragma unroll
-                for (int c = 0; c < C; ++c) acc[c] = 0u;
-                {
-                    // lag run as aligned 16-byte chunks; the head of the run (first m_part elements) is summed
-                    // straight from the packed words with the plan's byte-weight table
-                    const uint32_t b0 = cur, b1 = cur + tr.ring_bytes;
-                    const int neg_st = (int)tr.ring - (int)cur;
-#pragma unroll
-                    for (int c = 0; c < CH_LAG; ++c) {
-                        const uint4 v = lds128u(ring_addr(xg[c], b0, b1, neg_st));
-                        xlw[4 * c] = v.x, xlw[4 * c + 1] = v.y, xlw[4 * c + 2] = v.z, xlw[4 * c + 3] = v.w;
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-#pragma unroll
-                            for (int ch = 0; ch < C; ++ch)
-                                acc[ch] = (uint32_t)dp2a_s(xlw[4 * c + q], p.wtab[ch][4 * c + q], (int)acc[ch]);
-                        }
-                    }
-                }
-                if constexpr (MODE == 0) {
-                    const int gi = slot * NT + tid;
-                    const int n1 = ((int)p.n_full < gi) ? (int)p.n_full : gi;
-                    uint32_t ga = gsum + (uint32_t)gi * (C * 4u);
-                    for (int n = 0; n < n1; ++n) {
-                        ga -= C * 4u;
-#pragma unroll
-                        for (int c = 0; c < C; ++c) acc[c] += (uint32_t)lds32i(ga + 4u * c);
-                    }
-                    ga = gsum + (uint32_t)(GS * NT) * (C * 4u);
-                    for (int n = n1; n < (int)p.n_full; ++n) {
-                        ga -= C * 4u;
-#pragma unroll
-                        for (int c = 0; c < C; ++c) acc[c] += (uint32_t)lds32i(ga + 4u * c);
-                    }
-                } else {
-                    int lt = tid - (int)(p.n_full + 1u);
-                    int h = 0;
-                    if (lt < 0) {
-                        h = (-lt + NT - 1) / NT;
-                        lt += h * NT;
-                    }
-                    int ls = slot - h;
-                    if (ls < 0) ls += GS;
-#pragma unroll
-                    for (int c = 0; c < C; ++c) {
-                        const uint32_t wsame = __shfl_sync(0xffffffffu, wex[c], lt >> 5);
-                        const uint32_t wold = (uint32_t)lds32i(wexc + (((uint32_t)ls * 32u + (uint32_t)(lt >> 5)) * C + c) * 4u);
-                        const uint32_t cp_lag =
-                            (uint32_t)lds32i(gsum + (((uint32_t)ls * NT + lt) * C + c) * 4u) + (h == 0 ? wsame : wold);
-                        const uint32_t e_own = own_off[c] + (incl[c] - gtot[c]);
-                        if (h == 0) {
-                            acc[c] += e_own - cp_lag;
-                        } else {
-                            uint32_t rest = (uint32_t)lds32i(wexc + (((uint32_t)ls * 32u + 31u) * C + c) * 4u) - cp_lag;
-                            int ms = ls;
-                            for (int v2 = 1; v2 < h; ++v2) {
-                                ms = (ms + 1 == GS) ? 0 : ms + 1;
-                                rest += (uint32_t)lds32i(wexc + (((uint32_t)ms * 32u + 31u) * C + c) * 4u);
-                            }
-                            acc[c] += e_own + rest;
-                        }
-                    }
-                }
                 const uint32_t ob = tr.out_tile();
-                const int mul = (int)p.div_mul;
-                const uint32_t sh = p.div_shift;
 #pragma unroll
                 for (int c = 0; c < CH_OWN; ++c) {
                     uint32_t wds[4];
@@ -1104,12 +1066,8 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : 1))
                         uint32_t y[2];
 #pragma unroll
                         for (int hh = 0; hh < 2; ++hh) {
-                            const int r = 8 * c + 2 * q + hh;       // run element; its lag partner is element MIS + r
-                            const int e = MIS + r;                  // of the aligned lag words
-                            int a2 = dp2a_s(xw[r >> 1], hh ? w_hi : w_lo, (int)acc[r % C]);
-                            a2 = dp2a_s(xlw[e >> 1], (e & 1) ? n_hi : n_lo, a2);
-                            acc[r % C] = (uint32_t)a2;
-                            y[hh] = div_trunc_mulhi(a2, mul, sh);
+                            const int r = 8 * c + 2 * q + hh;
+                            y[hh] = div_trunc_mulhi((int)(start[r % C] + s[r]), mul, sh);
                         }
                         wds[q] = __byte_perm(y[0], y[1], 0x5410);
                     }
@@ -1117,6 +1075,8 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : 1))
                 }
                 tr.staged(tile, sig);
             }
+#pragma unroll
+            for (int c = 0; c < C; ++c) W[c] += total[c];
             tr.advance();
         }
 

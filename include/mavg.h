@@ -141,7 +141,8 @@ typedef struct mavg_info {
     uint32_t mode;             /* stream kernel arithmetic: 0 direct group sums, 1 tile-rebased
                                   prefix scan, 2 additions-only (k <= 8), 3 column kernel,
                                   4 few-channel kernel (3..31 interleaved channels), 5 far-lag
-                                  kernel (mono / planar float32, windows beyond the ring)    */
+                                  kernel (mono / planar float32, windows beyond the ring), 6 int16
+                                  mono / stereo / planar: exclusive scan of run deltas (any k)   */
     uint32_t threads, run;     /* stream kernel shape                                     */
     uint32_t tile_samples;     /* samples per shared-memory tile                          */
     uint32_t history_tiles;    /* tiles of left context each tile range replays           */
