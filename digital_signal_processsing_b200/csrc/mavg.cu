@@ -1029,65 +1029,76 @@ int gather_timing(mavg_plan* p)
 }  // namespace
 
 namespace {
-template <typename TIn, typename TLoc, typename TAcc, int C>
-int launch_scan_c(const TIn* in, TAcc* out, uint64_t n, cudaStream_t st, uint32_t* ticket, uint32_t* status, TAcc* aggr,
-                  TAcc* pref, unsigned grid)
+// Scratch of mavg_prefix_sum comes from a library-owned memory pool (one per device, created on first use) whose
+// release threshold keeps freed blocks cached: the device's DEFAULT pool is left alone -- changing its threshold
+// would change the behaviour of every other cudaMallocAsync user in the host process.
+std::mutex g_pool_mutex;
+cudaMemPool_t g_scan_pool[64] = {nullptr};
+
+int scan_pool(int dev, cudaMemPool_t* out)
 {
+    if (dev < 0 || dev >= 64) return fail(MAVG_ERR_INVALID_ARG, "device index %d out of range", dev);
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    if (!g_scan_pool[dev]) {
+        cudaMemPoolProps props;
+        memset(&props, 0, sizeof props);
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        cudaMemPool_t pool = nullptr;
+        MAVG_CUDA(cudaMemPoolCreate(&pool, &props));
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        cudaGetLastError();
+        g_scan_pool[dev] = pool;
+    }
+    *out = g_scan_pool[dev];
+    return MAVG_OK;
+}
+
+template <typename TIn, typename TLoc, typename TAcc, int C>
+int launch_scan_c(const void* d_in, void* d_out, uint64_t n, cudaStream_t st)
+{
+    const uint64_t chunk = (uint64_t)mavg::scan_chunk_elems<TLoc, C>();
+    const uint64_t tiles = (n + chunk - 1) / chunk;
+    if (tiles > 0x7fffffffull) return fail(MAVG_ERR_UNSUPPORTED, "signal too long for mavg_prefix_sum");
     auto kern = mavg::scan_lookback_kernel<TIn, TLoc, TAcc, C>;
     const uint32_t smem = mavg::scan_smem_bytes<TLoc, C>();
     MAVG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, 256, smem, st>>>(in, out, n, ticket, status, aggr, pref);
+    // scratch: ticket (padded to 256 bytes), 16-byte descriptors [chunks][C]; all zero = "not published"
+    const size_t total = 256 + (size_t)tiles * C * sizeof(ulonglong2);
+    int dev = 0;
+    MAVG_CUDA(cudaGetDevice(&dev));
+    cudaMemPool_t pool = nullptr;
+    MAVG_TRY(scan_pool(dev, &pool));
+    char* scratch = nullptr;
+    MAVG_CUDA(cudaMallocFromPoolAsync((void**)&scratch, total, pool, st));
+    cudaError_t e = cudaMemsetAsync(scratch, 0, total, st);
+    if (e == cudaSuccess) {
+        kern<<<(unsigned)tiles, mavg::kScanThreads, smem, st>>>((const TIn*)d_in, (TAcc*)d_out, n, (uint32_t*)scratch,
+                                                               (ulonglong2*)(scratch + 256));
+        e = cudaGetLastError();
+    }
+    cudaFreeAsync(scratch, st);     // on every path: stream-ordered, after the kernel
+    if (e != cudaSuccess) return fail(MAVG_ERR_CUDA, "prefix-sum launch failed: %s", cudaGetErrorString(e));
     return MAVG_OK;
 }
 
 template <typename TIn, typename TLoc, typename TAcc>
 int launch_scan(const void* d_in, void* d_out, uint64_t n, uint32_t C, cudaStream_t st)
 {
-    const uint64_t chunk = mavg::kScanChunkBytes / sizeof(TLoc);
-    const uint64_t tiles = (n + chunk - 1) / chunk;
-    if (tiles > 0x7fffffffull) return fail(MAVG_ERR_UNSUPPORTED, "signal too long for mavg_prefix_sum");
-    // scratch: ticket (padded), status[chunks], aggregates[chunks][C], prefixes[chunks][C]
-    const size_t status_off = 256, aggr_off = status_off + ((tiles * 4 + 255) / 256) * 256;
-    const size_t pref_off = aggr_off + tiles * C * sizeof(TAcc);
-    const size_t total = pref_off + tiles * C * sizeof(TAcc);
-    // keep freed scratch cached in the device's default pool: with the default release threshold (0) every
-    // synchronisation hands the memory back to the OS and the next call pays a millisecond-scale allocation
-    {
-        int dev = 0;
-        MAVG_CUDA(cudaGetDevice(&dev));
-        static bool pool_tuned[64] = {false};
-        if (dev >= 0 && dev < 64 && !pool_tuned[dev]) {
-            cudaMemPool_t pool;
-            if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-                unsigned long long keep = ~0ull;
-                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-            }
-            cudaGetLastError();
-            pool_tuned[dev] = true;
-        }
-    }
-    char* scratch = nullptr;
-    MAVG_CUDA(cudaMallocAsync((void**)&scratch, total, st));
-    MAVG_CUDA(cudaMemsetAsync(scratch, 0, aggr_off, st));
-    uint32_t* ticket = (uint32_t*)scratch;
-    uint32_t* status = (uint32_t*)(scratch + status_off);
-    TAcc* aggr = (TAcc*)(scratch + aggr_off);
-    TAcc* pref = (TAcc*)(scratch + pref_off);
-    const TIn* in = (const TIn*)d_in;
-    TAcc* out = (TAcc*)d_out;
-    const unsigned grid = (unsigned)tiles;
-    int rc;
     switch (C) {
-    case 1: rc = launch_scan_c<TIn, TLoc, TAcc, 1>(in, out, n, st, ticket, status, aggr, pref, grid); break;
-    case 2: rc = launch_scan_c<TIn, TLoc, TAcc, 2>(in, out, n, st, ticket, status, aggr, pref, grid); break;
-    case 4: rc = launch_scan_c<TIn, TLoc, TAcc, 4>(in, out, n, st, ticket, status, aggr, pref, grid); break;
-    default: rc = launch_scan_c<TIn, TLoc, TAcc, 8>(in, out, n, st, ticket, status, aggr, pref, grid); break;
+    case 1: return launch_scan_c<TIn, TLoc, TAcc, 1>(d_in, d_out, n, st);
+    case 2: return launch_scan_c<TIn, TLoc, TAcc, 2>(d_in, d_out, n, st);
+    case 3: return launch_scan_c<TIn, TLoc, TAcc, 3>(d_in, d_out, n, st);
+    case 4: return launch_scan_c<TIn, TLoc, TAcc, 4>(d_in, d_out, n, st);
+    case 5: return launch_scan_c<TIn, TLoc, TAcc, 5>(d_in, d_out, n, st);
+    case 6: return launch_scan_c<TIn, TLoc, TAcc, 6>(d_in, d_out, n, st);
+    case 7: return launch_scan_c<TIn, TLoc, TAcc, 7>(d_in, d_out, n, st);
+    case 8: return launch_scan_c<TIn, TLoc, TAcc, 8>(d_in, d_out, n, st);
+    default: return fail(MAVG_ERR_UNSUPPORTED, "mavg_prefix_sum takes 1 to 8 interleaved channels (got %u)", C);
     }
-    cudaError_t e = cudaGetLastError();
-    cudaFreeAsync(scratch, st);
-    if (rc != MAVG_OK) return rc;
-    if (e != cudaSuccess) return fail(MAVG_ERR_CUDA, "scan launch failed: %s", cudaGetErrorString(e));
-    return MAVG_OK;
 }
 }  // namespace
 
@@ -1774,8 +1785,8 @@ int mavg_device_free(void* d_ptr)
 int mavg_prefix_sum(int dtype, const void* d_in, void* d_out, uint64_t frames, uint32_t channels, void* cuda_stream)
 {
     if (dtype != MAVG_F32 && dtype != MAVG_I16) return fail(MAVG_ERR_INVALID_ARG, "unknown dtype %d", dtype);
-    if (!(channels == 1 || channels == 2 || channels == 4 || channels == 8))
-        return fail(MAVG_ERR_UNSUPPORTED, "mavg_prefix_sum takes 1, 2, 4 or 8 interleaved channels (got %u)", channels);
+    if (channels < 1 || channels > 8)
+        return fail(MAVG_ERR_UNSUPPORTED, "mavg_prefix_sum takes 1 to 8 interleaved channels (got %u)", channels);
     if (frames == 0) return MAVG_OK;
     if (!d_in || !d_out) return fail(MAVG_ERR_INVALID_ARG, "null argument");
     if (mavg_device_count() <= 0) return fail(MAVG_ERR_NO_DEVICE, "no CUDA device available: libmavg has no CPU fallback");

@@ -11,8 +11,9 @@
 // The moving-average kernels do NOT use it: a window needs only the previous ceil(k/T) tiles, which they
 // keep in shared memory, so no global prefix (and no fp32 cancellation across the signal) is needed.
 //
-// int16 -> int64 (exact), float32 -> float64.  Interleaved channels: element r of a thread's 16-element run
-// belongs to channel r % C (C divides 16), so every thread carries C running sums.
+// int16 -> int64 (exact), float32 -> float64.  Interleaved channels, any count from 1 to 8: a thread's run is a whole
+// number of frames (its length is a multiple of lcm(C, 2)), so element r of the run belongs to channel r % C at
+// compile time and every thread carries C running sums.
 // Traffic: sizeof(in) + 8 bytes per sample.
 #pragma once
 
@@ -47,59 +48,99 @@ __device__ __forceinline__ TAcc shfl_up_acc(TAcc v, int d)
     return acc_from_bits<TAcc>(((long long)hi << 32) | (unsigned int)lo);
 }
 template <typename TAcc>
-__device__ __forceinline__ TAcc shfl_idx_acc(TAcc v, int src)
+__device__ __forceinline__ TAcc shfl_xor_acc(TAcc v, int d)
 {
     const long long b = acc_bits<TAcc>(v);
-    const int lo = __shfl_sync(0xffffffffu, (int)(b & 0xffffffffll), src);
-    const int hi = __shfl_sync(0xffffffffu, (int)(b >> 32), src);
+    const int lo = __shfl_xor_sync(0xffffffffu, (int)(b & 0xffffffffll), d);
+    const int hi = __shfl_xor_sync(0xffffffffu, (int)(b >> 32), d);
     return acc_from_bits<TAcc>(((long long)hi << 32) | (unsigned int)lo);
 }
-
-__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p)
-{
-    uint32_t v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v)
-{
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
 template <typename T>
 __device__ __forceinline__ T shfl_up_t(T v, int d)
 {
     if constexpr (sizeof(T) == 4) return __shfl_up_sync(0xffffffffu, v, d);
     else return shfl_up_acc<T>(v, d);
 }
+template <typename T>
+__device__ __forceinline__ T shfl_xor_t(T v, int d)
+{
+    if constexpr (sizeof(T) == 4) return __shfl_xor_sync(0xffffffffu, v, d);
+    else return shfl_xor_acc<T>(v, d);
+}
 
-constexpr int kScanChunkBytes = 65536;   // shared-memory bytes of chunk-local prefixes per CTA
+// Chunk descriptor {status, value bits}: ONE 16-byte word, written and read with single 128-bit accesses (the scheme of
+// CUB's ScanTileState for 8-byte values), so the value travels with its flag -- no fence between a value store and a
+// flag store, no second dependent load on the reading side.  That halves the latency of one hop of the look-back
+// chain (round 1 used separate status / aggregate / prefix arrays: flag acquire -> value load -> fence -> flag release,
+// ~1.7 us per hop, which capped the primitive at 32 chunks per hop = 3.1 TB/s).
+__device__ __forceinline__ ulonglong2 ld_desc(const ulonglong2* p)
+{
+    ulonglong2 v;
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_desc(ulonglong2* p, unsigned long long status, unsigned long long bits)
+{
+    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(status), "l"(bits) : "memory");
+}
 
-// One CTA = one chunk of E = kScanChunkBytes / sizeof(TLoc) elements (8192 for int16 input, 4096 for float32).
+constexpr int kScanChunkBytes = 65536;   // shared-memory bytes of chunk-local prefixes per CTA (before padding)
+constexpr int kScanThreads = 256;
+
+// Run length per thread: the largest multiple of lcm(C, 2) not above kScanChunkBytes / sizeof(TLoc) / 256, so that a
+// run holds whole frames (the channel of run element i is i % C at compile time) and an even number of elements
+// (two results per 16-byte store).  C = 1, 2, 4, 8: 64 (int16) / 32 (float32); C = 3, 5, 6: 60 / 30; C = 7: 56 / 28.
+template <typename TLoc, int C>
+__host__ __device__ constexpr int scan_run_len()
+{
+    constexpr int rmax = kScanChunkBytes / (int)sizeof(TLoc) / kScanThreads;
+    constexpr int m = (C % 2 == 0) ? C : 2 * C;
+    return rmax / m * m;
+}
+template <typename TLoc, int C>
+__host__ __device__ constexpr int scan_chunk_elems() { return kScanThreads * scan_run_len<TLoc, C>(); }
+// register block of the in-place run scan: the largest divisor of the run that is a multiple of C and at most 16
+template <int R, int C>
+__host__ __device__ constexpr int scan_block_len()
+{
+    int best = C;
+    for (int b = C; b <= 16; b += C)
+        if (R % b == 0) best = b;
+    return best;
+}
+
+// One CTA = one chunk of E = 256 * R elements (16384 for int16 input, 8192 for float32, a little less for odd C).
 //   1. coalesced 16-byte loads, converted to the chunk-local type TLoc (int32 is enough for an int16 chunk:
-//      8192 * 32768 < 2^31; double for float32) into a padded shared-memory array;
-//   2. every thread scans its run of R = E / 256 elements in place (per channel), then warp-shuffle + block
-//      scan of the run totals gives per-thread offsets and the chunk aggregate;
-//   3. the aggregate is published at once (long before any output is written), warp 0 resolves the chunk's
-//      exclusive prefix by decoupled look-back over chunk descriptors while other CTAs of the SM keep working;
+//      16384 * 32768 < 2^31; double for float32) into a padded shared-memory array.  Where the channel of a loaded
+//      element is known at compile time (C divides the vector width) the chunk AGGREGATE is reduced on the way and
+//      published right behind the load barrier -- a whole run scan earlier than the look-back needs its
+//      predecessors' aggregates, so the look-back no longer spins on unpublished descriptors;
+//   2. every thread scans its run in place (per channel), then warp-shuffle + block scan of the run totals gives
+//      per-thread offsets (and, for the other channel counts, the aggregate);
+//   3. warp 0 resolves the chunk's exclusive prefix by decoupled look-back over the 16-byte chunk descriptors, 32
+//      predecessors per round, the next round's descriptors already in flight; publishes the inclusive prefix;
 //   4. striped output pass: out[e] = prefix + thread offset + local prefix, 16-byte stores, fully coalesced.
 // Each element is read from HBM once and written once; chunk ids come from an atomic ticket so a chunk only
-// ever waits on chunks that are already running.  Scratch: ticket, status[chunks], aggr/pref[chunks][C].
+// ever waits on chunks that are already running.  Scratch: ticket, desc[chunks][C].
 template <typename TIn, typename TLoc, typename TAcc, int C>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kScanThreads)
     scan_lookback_kernel(const TIn* __restrict__ in, TAcc* __restrict__ out, uint64_t n, uint32_t* __restrict__ ticket,
-                         uint32_t* __restrict__ status, TAcc* __restrict__ aggr, TAcc* __restrict__ pref)
+                         ulonglong2* __restrict__ desc)
 {
-    constexpr int NT = 256, NW = NT / 32;
-    constexpr int E = kScanChunkBytes / (int)sizeof(TLoc);      // elements per chunk
-    constexpr int R = E / NT;                         // run per thread (32 or 16)
+    constexpr int NT = kScanThreads, NW = NT / 32;
+    constexpr int R = scan_run_len<TLoc, C>();        // run per thread
+    constexpr int E = NT * R;                         // elements per chunk
+    constexpr int BL = scan_block_len<R, C>();
     constexpr int VE = 16 / (int)sizeof(TIn);         // input elements per 16-byte load
-    static_assert(R % C == 0 && R % 16 == 0, "a run holds whole frames");
+    constexpr bool EARLY = (VE % C == 0);             // channel of a loaded element known at compile time
+    static_assert(R % C == 0 && R % 2 == 0 && R % BL == 0 && BL % C == 0 && E % VE == 0, "a run holds whole frames");
     extern __shared__ __align__(16) uint8_t scan_smem[];
     TLoc* loc = reinterpret_cast<TLoc*>(scan_smem);                    // [E + E/32], index e + (e >> 5)
     TLoc* toff = loc + (E + E / 32);                                   // [NT][C] exclusive offset of each run
-    TLoc* s_warp = toff + NT * C;                                      // [NW][C]
+    TLoc* s_warp = toff + NT * C;                                      // [NW][C] scan: warp totals
+    TLoc* s_part = s_warp + NW * C;                                    // [NW][C] early aggregate: warp partial sums
     __shared__ TAcc s_excl[C];           // exclusive prefix of the chunk, broadcast from warp 0
+    __shared__ TAcc s_tot[C];            // chunk aggregate as published
     __shared__ uint32_t s_tile;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -108,50 +149,81 @@ __global__ void __launch_bounds__(256)
     const uint32_t tile = s_tile;
     const uint64_t cbase = (uint64_t)tile * E;
     auto pidx = [](int e) { return e + (e >> 5); };
+    ulonglong2* my_desc = desc + (uint64_t)tile * C;
 
-    // ---- 1. load + convert (zero past the end)
+    // ---- 1. load + convert (zero past the end); early per-channel partial sums
+    TLoc csum[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) csum[c] = 0;
     const bool vec_ok = (reinterpret_cast<uintptr_t>(in) & 15u) == 0;
 #pragma unroll 2
     for (int q = tid; q < E / VE; q += NT) {
         const uint64_t e0 = cbase + (uint64_t)q * VE;
         const int l0 = q * VE;
+        TLoc v[VE];
         if (vec_ok && e0 + VE <= n) {
             const uint4 raw = __ldg(reinterpret_cast<const uint4*>(in + e0));
             if constexpr (sizeof(TIn) == 2) {
                 const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    loc[pidx(l0 + 2 * i)] = (TLoc)((int)(w[i] << 16) >> 16);
-                    loc[pidx(l0 + 2 * i + 1)] = (TLoc)((int)w[i] >> 16);
+                    v[2 * i] = (TLoc)((int)(w[i] << 16) >> 16);
+                    v[2 * i + 1] = (TLoc)((int)w[i] >> 16);
                 }
             } else {
-                loc[pidx(l0 + 0)] = (TLoc)__uint_as_float(raw.x);
-                loc[pidx(l0 + 1)] = (TLoc)__uint_as_float(raw.y);
-                loc[pidx(l0 + 2)] = (TLoc)__uint_as_float(raw.z);
-                loc[pidx(l0 + 3)] = (TLoc)__uint_as_float(raw.w);
+                v[0] = (TLoc)__uint_as_float(raw.x);
+                v[1] = (TLoc)__uint_as_float(raw.y);
+                v[2] = (TLoc)__uint_as_float(raw.z);
+                v[3] = (TLoc)__uint_as_float(raw.w);
             }
         } else {
 #pragma unroll
-            for (int i = 0; i < VE; ++i) loc[pidx(l0 + i)] = (e0 + i < n) ? (TLoc)in[e0 + i] : (TLoc)0;
+            for (int i = 0; i < VE; ++i) v[i] = (e0 + i < n) ? (TLoc)in[e0 + i] : (TLoc)0;
+        }
+#pragma unroll
+        for (int i = 0; i < VE; ++i) {
+            loc[pidx(l0 + i)] = v[i];
+            if constexpr (EARLY) csum[i % C] += v[i];
+        }
+    }
+    if constexpr (EARLY) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) csum[c] += shfl_xor_t<TLoc>(csum[c], d);
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) s_part[warp * C + c] = csum[c];
         }
     }
     __syncthreads();
+    if constexpr (EARLY) {
+        if (tid < C) {   // fixed order over the warps: the aggregate does not depend on scheduling
+            TLoc t = 0;
+#pragma unroll
+            for (int w2 = 0; w2 < NW; ++w2) t += s_part[w2 * C + tid];
+            const TAcc tot = (TAcc)t;
+            s_tot[tid] = tot;
+            st_desc(my_desc + tid, tile == 0 ? kScanPrefix : kScanAggregate, (unsigned long long)acc_bits<TAcc>(tot));
+        }
+    }
 
-    // ---- 2. in-place scan of the own run, 16 elements at a time, one carry per channel
+    // ---- 2. in-place scan of the own run, BL elements at a time, one carry per channel
     TLoc carry[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) carry[c] = 0;
-    for (int b = 0; b < R; b += 16) {
-        TLoc v[16];
+    for (int b = 0; b < R; b += BL) {
+        TLoc v[BL];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = loc[pidx(tid * R + b + i)];
+        for (int i = 0; i < BL; ++i) v[i] = loc[pidx(tid * R + b + i)];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
+        for (int i = 0; i < BL; ++i) {
             carry[i % C] += v[i];
             v[i] = carry[i % C];
         }
 #pragma unroll
-        for (int i = 0; i < 16; ++i) loc[pidx(tid * R + b + i)] = v[i];
+        for (int i = 0; i < BL; ++i) loc[pidx(tid * R + b + i)] = v[i];
     }
     TLoc inc[C];
 #pragma unroll
@@ -169,72 +241,57 @@ __global__ void __launch_bounds__(256)
         for (int c = 0; c < C; ++c) s_warp[warp * C + c] = inc[c];
     }
     __syncthreads();
-    TAcc chunk_tot[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) {
         TLoc a = 0;
         for (int w2 = 0; w2 < warp; ++w2) a += s_warp[w2 * C + c];
         toff[tid * C + c] = a + (inc[c] - carry[c]);         // exclusive offset of this run inside the chunk
-        TLoc t = a;
-        for (int w2 = warp; w2 < NW; ++w2) t += s_warp[w2 * C + c];
-        chunk_tot[c] = (TAcc)t;
+    }
+    if constexpr (!EARLY) {
+        if (tid < C) {
+            TLoc t = 0;
+#pragma unroll
+            for (int w2 = 0; w2 < NW; ++w2) t += s_warp[w2 * C + tid];
+            const TAcc tot = (TAcc)t;
+            s_tot[tid] = tot;
+            st_desc(my_desc + tid, tile == 0 ? kScanPrefix : kScanAggregate, (unsigned long long)acc_bits<TAcc>(tot));
+        }
+        __syncwarp();
     }
 
-    // ---- 3. publish the aggregate, look back for the exclusive prefix (warp 0), publish the inclusive prefix.
-    // (A CTA-wide look-back, 256 predecessors per round, was tried: it was slower -- 1.0 vs 0.87 ms on 2^28
-    // int16 samples -- because the wait is for predecessors to publish at all, not for the number of rounds.)
+    // ---- 3. look back for the exclusive prefix (warp 0), publish the inclusive prefix
     if (warp == 0) {
-        if (lane == 0) {
-#pragma unroll
-            for (int c = 0; c < C; ++c) aggr[(uint64_t)tile * C + c] = chunk_tot[c];
-            if (tile == 0) {
-#pragma unroll
-                for (int c = 0; c < C; ++c) pref[c] = chunk_tot[c];
-            }
-            __threadfence();
-            st_release_u32(status + tile, tile == 0 ? kScanPrefix : kScanAggregate);
-        }
-        TAcc excl[C];
-#pragma unroll
-        for (int c = 0; c < C; ++c) excl[c] = 0;
-        if (tile > 0) {
-            // each lane inspects one predecessor; windows of 32 chunks move backwards until a prefix is found
-            long long look = (long long)tile - 1 - lane;
-            for (;;) {
-                uint32_t st = kScanPrefix;   // lanes before chunk 0 behave like a terminating zero prefix
-                if (look >= 0) {
-                    do { st = ld_acquire_u32(status + look); } while (st == kScanInvalid);
-                }
-                const unsigned has_prefix = __ballot_sync(0xffffffffu, st == kScanPrefix);
-                const int first = has_prefix ? __ffs(has_prefix) - 1 : 32;   // nearest predecessor with a full prefix
-#pragma unroll
-                for (int c = 0; c < C; ++c) {
-                    TAcc val = 0;
-                    if (look >= 0 && lane <= first)
-                        val = (st == kScanPrefix) ? __ldcg(pref + (uint64_t)look * C + c) : __ldcg(aggr + (uint64_t)look * C + c);
+        if (tile == 0) {
+            if (lane < C) s_excl[lane] = 0;
+        } else {
+#pragma unroll 1
+            for (int c = 0; c < C; ++c) {
+                // each lane inspects one predecessor per round; rounds of 32 chunks move backwards until a prefix is
+                // found.  The descriptors of the following round are requested before this round's are examined.
+                long long look = (long long)tile - 1 - lane;
+                ulonglong2 cur = make_ulonglong2(kScanPrefix, 0ull);   // lanes before chunk 0: a terminating zero prefix
+                if (look >= 0) cur = ld_desc(desc + (uint64_t)look * C + c);
+                TAcc acc = 0;
+                for (;;) {
+                    ulonglong2 nxt = make_ulonglong2(kScanPrefix, 0ull);
+                    if (look - 32 >= 0) nxt = ld_desc(desc + (uint64_t)(look - 32) * C + c);
+                    while (cur.x == kScanInvalid) cur = ld_desc(desc + (uint64_t)look * C + c);
+                    const unsigned has_prefix = __ballot_sync(0xffffffffu, cur.x == kScanPrefix);
+                    const int first = has_prefix ? __ffs(has_prefix) - 1 : 32;   // nearest predecessor with a full prefix
+                    TAcc val = (lane <= first) ? acc_from_bits<TAcc>((long long)cur.y) : (TAcc)0;
                     // fixed-shape butterfly: the same association for a given `first`
 #pragma unroll
-                    for (int d = 16; d >= 1; d >>= 1) {
-                        const long long ob = acc_bits<TAcc>(val);
-                        const int lo = __shfl_xor_sync(0xffffffffu, (int)(ob & 0xffffffffll), d);
-                        const int hi = __shfl_xor_sync(0xffffffffu, (int)(ob >> 32), d);
-                        val += acc_from_bits<TAcc>(((long long)hi << 32) | (unsigned int)lo);
-                    }
-                    excl[c] += val;
+                    for (int d = 16; d >= 1; d >>= 1) val += shfl_xor_acc<TAcc>(val, d);
+                    acc += val;
+                    if (has_prefix) break;
+                    look -= 32;
+                    cur = nxt;
                 }
-                if (has_prefix) break;
-                look -= 32;
+                if (lane == 0) {
+                    s_excl[c] = acc;
+                    st_desc(my_desc + c, kScanPrefix, (unsigned long long)acc_bits<TAcc>(acc + s_tot[c]));
+                }
             }
-            if (lane == 0) {
-#pragma unroll
-                for (int c = 0; c < C; ++c) pref[(uint64_t)tile * C + c] = excl[c] + chunk_tot[c];
-                __threadfence();
-                st_release_u32(status + tile, kScanPrefix);
-            }
-        }
-        if (lane == 0) {
-#pragma unroll
-            for (int c = 0; c < C; ++c) s_excl[c] = excl[c];
         }
     }
     __syncthreads();
@@ -251,8 +308,14 @@ __global__ void __launch_bounds__(256)
         if (g >= n) break;
         const int run = e / R;                       // e and e + 1 lie in the same run (R is even)
         const int c0 = e % C, c1 = (e + 1) % C;
-        const TAcc a = base[c0] + (TAcc)(toff[run * C + c0] + loc[pidx(e)]);
-        const TAcc b = base[c1] + (TAcc)(toff[run * C + c1] + loc[pidx(e + 1)]);
+        TAcc b0 = 0, b1 = 0;                         // base[] with a run-time channel: selects, no local memory
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            if (c == c0) b0 = base[c];
+            if (c == c1) b1 = base[c];
+        }
+        const TAcc a = b0 + (TAcc)(toff[run * C + c0] + loc[pidx(e)]);
+        const TAcc b = b1 + (TAcc)(toff[run * C + c1] + loc[pidx(e + 1)]);
         if (out_vec && g + 1 < n) {
             *reinterpret_cast<double2*>(out + g) = make_double2(*reinterpret_cast<const double*>(&a),
                                                                 *reinterpret_cast<const double*>(&b));
@@ -267,8 +330,8 @@ __global__ void __launch_bounds__(256)
 template <typename TLoc, int C>
 constexpr uint32_t scan_smem_bytes()
 {
-    constexpr uint32_t E = kScanChunkBytes / sizeof(TLoc);
-    return (E + E / 32) * sizeof(TLoc) + 256 * C * sizeof(TLoc) + (8 * C + 1) * sizeof(TLoc) + C * 8 + 16;
+    constexpr uint32_t E = (uint32_t)scan_chunk_elems<TLoc, C>();
+    return (E + E / 32) * sizeof(TLoc) + kScanThreads * C * sizeof(TLoc) + 2 * (kScanThreads / 32) * C * sizeof(TLoc) + 64;
 }
 
 }  // namespace mavg

@@ -234,8 +234,8 @@ int mavg_run_owned(mavg_plan *plan);
  * (decoupled look-back), what recursive_hillis_steele / recursive_blelloch compute with multi-level
  * recursion (basics/hillis_steele_averager.cu:69-84, basics/blelloch_scan_averager.cu:134-167):
  *   out[f*C + c] = sum_{j <= f} in[j*C + c]
- * dtype MAVG_I16 -> int64 output (exact), MAVG_F32 -> float64 output.  channels must be 1, 2, 4 or 8.
- * Asynchronous on `cuda_stream`; scratch is taken from and returned to the stream-ordered allocator.
+ * dtype MAVG_I16 -> int64 output (exact), MAVG_F32 -> float64 output.  1 <= channels <= 8.
+ * Asynchronous on `cuda_stream`; scratch is taken from and returned to a library-owned stream-ordered memory pool.
  * The moving-average kernels do not call it (they never need a prefix over the whole signal). */
 int mavg_prefix_sum(int dtype, const void *d_in, void *d_out, uint64_t frames, uint32_t channels,
                     void *cuda_stream);
