@@ -18,6 +18,7 @@ F32, I16 = 0, 1
 INTERLEAVED, PLANAR = 0, 1
 PATH_AUTO, PATH_STREAM, PATH_GENERIC = 0, 1, 2
 DIST_U01, DIST_USYM, DIST_I16, DIST_DC1E4 = 0, 1, 2, 3
+OP_MEAN, OP_RMS = 0, 1
 
 OK = 0
 ERR_INVALID_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_NO_DEVICE, ERR_ALLOC, ERR_BLOCK_SIZE, ERR_DRIVER = -1, -2, -3, -4, -5, -6, -7
@@ -50,6 +51,8 @@ class Desc(ctypes.Structure):
         ("devices", ctypes.c_int32 * MAVG_MAX_DEVICES),
         ("first_frame", ctypes.c_uint64),
         ("tuning", Tuning),
+        ("op", ctypes.c_uint32),
+        ("reserved", ctypes.c_uint32),
     ]
 
 

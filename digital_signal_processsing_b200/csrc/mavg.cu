@@ -386,42 +386,45 @@ cudaError_t launch_ring(void (*kern)(const CUtensorMap, const CUtensorMap, const
     return cudaLaunchKernelEx(&cfg, kern, a, b, c, prm);
 }
 
-template <int NT, int R, int C = 1>
+template <int NT, int R, int C = 1, bool RMS = false>
 StreamKernel pick_variant(int mis, int mode, uint32_t k)
 {
     using namespace mavg;
     if (mode == 2) {
         switch (k) {
-        case 1: return stream_f32_kernel<NT, R, 0, 2, 1, C>;
-        case 2: return stream_f32_kernel<NT, R, 0, 2, 2, C>;
-        case 3: return stream_f32_kernel<NT, R, 0, 2, 3, C>;
-        case 4: return stream_f32_kernel<NT, R, 0, 2, 4, C>;
-        case 5: return stream_f32_kernel<NT, R, 0, 2, 5, C>;
-        case 6: return stream_f32_kernel<NT, R, 0, 2, 6, C>;
-        case 7: return stream_f32_kernel<NT, R, 0, 2, 7, C>;
-        default: return stream_f32_kernel<NT, R, 0, 2, 8, C>;
+        case 1: return stream_f32_kernel<NT, R, 0, 2, 1, C, RMS>;
+        case 2: return stream_f32_kernel<NT, R, 0, 2, 2, C, RMS>;
+        case 3: return stream_f32_kernel<NT, R, 0, 2, 3, C, RMS>;
+        case 4: return stream_f32_kernel<NT, R, 0, 2, 4, C, RMS>;
+        case 5: return stream_f32_kernel<NT, R, 0, 2, 5, C, RMS>;
+        case 6: return stream_f32_kernel<NT, R, 0, 2, 6, C, RMS>;
+        case 7: return stream_f32_kernel<NT, R, 0, 2, 7, C, RMS>;
+        default: return stream_f32_kernel<NT, R, 0, 2, 8, C, RMS>;
         }
     }
     if (mode == 0) {
-        if (mis == 0) return stream_f32_kernel<NT, R, 0, 0, 0, C>;
-        if (mis == 2) return stream_f32_kernel<NT, R, 2, 0, 0, C>;
+        if (mis == 0) return stream_f32_kernel<NT, R, 0, 0, 0, C, RMS>;
+        if (mis == 2) return stream_f32_kernel<NT, R, 2, 0, 0, C, RMS>;
         if constexpr (C == 1) {
-            if (mis == 1) return stream_f32_kernel<NT, R, 1, 0, 0, C>;
-            if (mis == 3) return stream_f32_kernel<NT, R, 3, 0, 0, C>;
+            if (mis == 1) return stream_f32_kernel<NT, R, 1, 0, 0, C, RMS>;
+            if (mis == 3) return stream_f32_kernel<NT, R, 3, 0, 0, C, RMS>;
         }
         return nullptr;
     }
-    if (mis == 0) return stream_f32_kernel<NT, R, 0, 1, 0, C>;
-    if (mis == 2) return stream_f32_kernel<NT, R, 2, 1, 0, C>;
+    if (mis == 0) return stream_f32_kernel<NT, R, 0, 1, 0, C, RMS>;
+    if (mis == 2) return stream_f32_kernel<NT, R, 2, 1, 0, C, RMS>;
     if constexpr (C == 1) {
-        if (mis == 1) return stream_f32_kernel<NT, R, 1, 1, 0, C>;
-        if (mis == 3) return stream_f32_kernel<NT, R, 3, 1, 0, C>;
+        if (mis == 1) return stream_f32_kernel<NT, R, 1, 1, 0, C, RMS>;
+        if (mis == 3) return stream_f32_kernel<NT, R, 3, 1, 0, C, RMS>;
     }
     return nullptr;
 }
 
-StreamKernel pick_kernel(const StreamGeom& g, uint32_t k)
+// moving RMS is built for the default kernel shape only (512 threads x 16 samples); plan_create rejects the tuning
+// overrides of the shape for RMS plans
+StreamKernel pick_kernel(const StreamGeom& g, uint32_t k, bool rms)
 {
+    if (rms) return g.C == 2 ? pick_variant<512, 16, 2, true>(g.MIS, g.mode, k) : pick_variant<512, 16, 1, true>(g.MIS, g.mode, k);
     if (g.C == 2) return pick_variant<512, 16, 2>(g.MIS, g.mode, k);
     if (g.NT == 256 && g.R == 16) return pick_variant<256, 16>(g.MIS, g.mode, k);
     if (g.NT == 256 && g.R == 32) return pick_variant<256, 32>(g.MIS, g.mode, k);
@@ -589,6 +592,8 @@ int launch_generic_t(const mavg_plan* p, DevCtx& d, const T* in, T* out, const T
     gp.k = p->desc.window;
     gp.bsum = nullptr;
     gp.nblk = 0;
+    gp.rms = p->desc.op == MAVG_OP_RMS ? 1u : 0u;
+    gp.pad_ = 0;
     // long windows: one extra pass builds RG-frame block sums so each run starts from k/RG table entries
     if (gp.k >= 256 && out_begin == 0 && gp.frames >= 4 * (uint64_t)RG) {
         typedef typename mavg::GenericAcc<T>::type Acc;
@@ -609,7 +614,7 @@ int launch_generic_t(const mavg_plan* p, DevCtx& d, const T* in, T* out, const T
         if (bblocks <= 0x7fffffffull && signals <= 65535u) {
             dim3 bgrid((unsigned)bblocks, signals, 1);
             mavg::block_sums_kernel<T, RG><<<bgrid, 256, 0, d.stream>>>(in, (Acc*)d.d_bsum, gp.frames, gp.sig_stride,
-                                                                      gp.channels, nblk);
+                                                                      gp.channels, nblk, gp.rms);
             MAVG_CUDA(cudaGetLastError());
             ++*launches;
             gp.bsum = d.d_bsum;
@@ -626,7 +631,7 @@ int launch_generic_t(const mavg_plan* p, DevCtx& d, const T* in, T* out, const T
         dim3 grid((unsigned)blocks, ns, 1);
         const T* in_s = in + (uint64_t)s0 * gp.sig_stride;
         T* out_s = out + (uint64_t)s0 * gp.sig_stride;
-        if (std::is_same<T, float>::value && gp.k >= 9)
+        if (std::is_same<T, float>::value && gp.k >= 9 && !gp.rms)
             mavg::generic_kernel<T, RG, std::is_same<T, float>::value><<<grid, 256, 0, d.stream>>>(in_s, out_s, halo, gp);
         else
             mavg::generic_kernel<T, RG, false><<<grid, 256, 0, d.stream>>>(in_s, out_s, halo, gp);
@@ -657,6 +662,7 @@ int launch_tail_t(const mavg_plan* p, DevCtx& d, const T* in, T* out, const T* h
     gp.out_end = out_end;
     gp.halo_frames = halo ? p->halo_frames : 0;
     gp.k = p->desc.window;
+    gp.rms = p->desc.op == MAVG_OP_RMS ? 1u : 0u;
     mavg::tail_kernel<T><<<signals, 256, 0, d.stream>>>(in, out, halo, gp);
     MAVG_CUDA(cudaGetLastError());
     ++*launches;
@@ -967,7 +973,7 @@ int launch_shard(mavg_plan* p, DevCtx& d, const void* in, void* out, const void*
     sp.has_halo = halo ? 1 : 0;
     sp.pdl = pdl_mode(p->desc.tuning);
 
-    StreamKernel kern = g.elem == 4 ? pick_kernel(g, p->desc.window)
+    StreamKernel kern = g.elem == 4 ? pick_kernel(g, p->desc.window, p->desc.op == MAVG_OP_RMS)
                         : g.NT == 256 ? (g.C == 1 ? pick_i16<256, 32, 1>(g.MIS) : pick_i16<256, 32, 2>(g.MIS))
                                       : (g.C == 1 ? pick_i16<512, 32, 1>(g.MIS) : pick_i16<512, 32, 2>(g.MIS));
     if (!kern) return fail(MAVG_ERR_UNSUPPORTED, "no stream kernel variant for this window");
@@ -991,6 +997,7 @@ int validate(const mavg_desc* d)
     if (d->dtype > MAVG_I16) return fail(MAVG_ERR_INVALID_ARG, "unknown dtype %u", d->dtype);
     if (d->layout > MAVG_PLANAR) return fail(MAVG_ERR_INVALID_ARG, "unknown layout %u", d->layout);
     if (d->path > MAVG_PATH_GENERIC) return fail(MAVG_ERR_INVALID_ARG, "unknown path %u", d->path);
+    if (d->op > MAVG_OP_RMS) return fail(MAVG_ERR_INVALID_ARG, "unknown op %u", d->op);
     if (d->channels == 0) return fail(MAVG_ERR_INVALID_ARG, "channels must be >= 1");
     if (d->window == 0) return fail(MAVG_ERR_INVALID_ARG, "window must be >= 1");
     if (d->num_devices > MAVG_MAX_DEVICES) return fail(MAVG_ERR_INVALID_ARG, "too many devices");
@@ -1153,7 +1160,17 @@ int mavg_plan_create(const mavg_desc* desc, mavg_plan** out)
     // ---- kernel family
     const bool planar = desc->layout == MAVG_PLANAR && desc->channels > 1;
     bool stream_shape;
-    if (desc->dtype == MAVG_F32) {
+    if (desc->op == MAVG_OP_RMS) {
+        // moving RMS: the float32 TMA streaming kernel (mono / stereo / planar, default shape) squares on load and
+        // takes the root on store; every other shape is served by the generic kernel (fp64 / exact int64 sums of squares)
+        stream_shape = desc->dtype == MAVG_F32 && (desc->channels <= 2 || planar);
+        if (stream_shape) {
+            mavg_tuning tu = desc->tuning;
+            tu.threads = 0;
+            tu.run = 0;
+            p->geom = plan_stream(desc->window, tu, planar ? 1u : desc->channels);
+        }
+    } else if (desc->dtype == MAVG_F32) {
         stream_shape = desc->channels <= 2 || planar;
         p->geom = plan_stream(desc->window, desc->tuning, planar ? 1u : desc->channels);
         if (!p->geom.ok && (planar || desc->channels <= 2)) p->geom = plan_far(desc->window, planar ? 1u : desc->channels, desc->tuning);

@@ -85,12 +85,19 @@ struct GenericParams {
     uint32_t k;
     const void* bsum;      // optional: per-channel sums of 64-frame blocks [signal][block][channel] (Acc type)
     uint64_t nblk;         // blocks per signal in bsum
+    uint32_t rms;          // mavg_op: 0 moving average, 1 moving RMS (samples squared on load, root of the mean on store)
+    uint32_t pad_;
 };
 
 template <typename T> struct GenericAcc;
 template <> struct GenericAcc<float> {
     typedef double type;
     __device__ static __forceinline__ float finish(double w, uint32_t k, double inv) { (void)k; return (float)(w * inv); }
+    __device__ static __forceinline__ float finish_rms(double w, uint32_t k, double inv)
+    {
+        (void)k;
+        return (float)sqrt(fmax(w, 0.0) * inv);
+    }
 };
 template <> struct GenericAcc<int16_t> {
     typedef long long type;
@@ -101,13 +108,28 @@ template <> struct GenericAcc<int16_t> {
         if (k < 65536u) return (int16_t)((int)w / (int)k);
         return (int16_t)(w / (long long)k);
     }
+    // exact int64 sum of squares; IEEE double division and square root, truncated, saturated (oracle_mrms_i16)
+    __device__ static __forceinline__ int16_t finish_rms(long long w, uint32_t k, double inv)
+    {
+        (void)inv;
+        const double r = sqrt((double)w / (double)k);
+        return (int16_t)(r > 32767.0 ? 32767.0 : r);
+    }
 };
+// a sample as it enters a window sum: itself, or its square for the moving RMS
+template <typename Acc, typename T>
+__device__ __forceinline__ Acc gen_term(T v, uint32_t rms)
+{
+    const Acc a = (Acc)v;
+    return rms ? a * a : a;
+}
 
 // Sums of RG-frame blocks per channel, so that long windows start from k/RG block sums instead of k
 // samples.  Same thread mapping as generic_kernel: consecutive threads = consecutive channels.
 template <typename T, int RG>
 __global__ void __launch_bounds__(256) block_sums_kernel(const T* __restrict__ x, typename GenericAcc<T>::type* __restrict__ bs,
-                                                         uint64_t frames, uint64_t sig_stride, uint32_t C, uint64_t nblk)
+                                                         uint64_t frames, uint64_t sig_stride, uint32_t C, uint64_t nblk,
+                                                         uint32_t rms)
 {
     typedef typename GenericAcc<T>::type Acc;
     const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -118,7 +140,7 @@ __global__ void __launch_bounds__(256) block_sums_kernel(const T* __restrict__ x
     const uint64_t f0 = b * RG;
     const uint64_t f1 = (f0 + RG < frames) ? f0 + RG : frames;
     Acc a = 0;
-    for (uint64_t f = f0; f < f1; ++f) a += (Acc)x[f * C + c];
+    for (uint64_t f = f0; f < f1; ++f) a += gen_term<Acc>(x[f * C + c], rms);
     bs[((uint64_t)blockIdx.y * nblk + b) * C + c] = a;
 }
 
@@ -141,6 +163,7 @@ __global__ void __launch_bounds__(256) generic_kernel(const T* __restrict__ x, T
     y += (uint64_t)blockIdx.y * p.sig_stride;
     const uint64_t k = p.k;
     const double inv = 1.0 / (double)p.k;
+    const uint32_t rms = p.rms;
 
     // window sum over frames [f0-k, f0): negative frames come from the halo, else zero
     Acc w = 0;
@@ -149,7 +172,7 @@ __global__ void __launch_bounds__(256) generic_kernel(const T* __restrict__ x, T
         const Acc* bs = (const Acc*)p.bsum + (uint64_t)blockIdx.y * p.nblk * C;
         const uint64_t lo = f0 - k;
         const uint64_t jb = (lo + RG - 1) / RG;
-        for (uint64_t f = lo; f < jb * RG; ++f) w += (Acc)x[f * C + c];
+        for (uint64_t f = lo; f < jb * RG; ++f) w += gen_term<Acc>(x[f * C + c], rms);
         for (uint64_t j = jb; j < f0 / RG; ++j) w += bs[j * C + c];
     } else {
         const long long lo = (long long)f0 - (long long)k;
@@ -159,11 +182,11 @@ __global__ void __launch_bounds__(256) generic_kernel(const T* __restrict__ x, T
                 long long hlo = -(long long)p.halo_frames;
                 if (j < hlo) j = hlo;
                 const long long hend = (long long)f0 < 0 ? (long long)f0 : 0;
-                for (; j < hend; ++j) w += (Acc)halo[(uint64_t)(j + (long long)p.halo_frames) * C + c];
+                for (; j < hend; ++j) w += gen_term<Acc>(halo[(uint64_t)(j + (long long)p.halo_frames) * C + c], rms);
             }
             j = 0;
         }
-        for (; j < (long long)f0; ++j) w += (Acc)x[(uint64_t)j * C + c];
+        for (; j < (long long)f0; ++j) w += gen_term<Acc>(x[(uint64_t)j * C + c], rms);
     }
     if constexpr (F32SLIDE) {
         float wf = (float)w;
@@ -195,13 +218,13 @@ __global__ void __launch_bounds__(256) generic_kernel(const T* __restrict__ x, T
     for (uint64_t f = f0; f < f1; ++f) {
         Acc old = 0;
         if (f >= k) {
-            old = (Acc)x[(f - k) * C + c];
+            old = gen_term<Acc>(x[(f - k) * C + c], rms);
         } else if (halo != nullptr) {
             const uint64_t back = k - f;  // frames before frame 0
-            if (back <= p.halo_frames) old = (Acc)halo[(p.halo_frames - back) * C + c];
+            if (back <= p.halo_frames) old = gen_term<Acc>(halo[(p.halo_frames - back) * C + c], rms);
         }
-        w += (Acc)x[f * C + c] - old;
-        y[f * C + c] = GenericAcc<T>::finish(w, p.k, inv);
+        w += gen_term<Acc>(x[f * C + c], rms) - old;
+        y[f * C + c] = rms ? GenericAcc<T>::finish_rms(w, p.k, inv) : GenericAcc<T>::finish(w, p.k, inv);
     }
     }
 }
@@ -223,11 +246,12 @@ __global__ void __launch_bounds__(256) tail_kernel(const T* __restrict__ x, T* _
     const long long k = (long long)p.k;
     const long long hf = (long long)p.halo_frames;
     const double inv = 1.0 / (double)p.k;
+    const uint32_t rms = p.rms;
     for (uint32_t c = 0; c < C; ++c) {
         Acc a = 0;
         for (long long f = (long long)p.out_begin - k + threadIdx.x; f < (long long)p.out_begin; f += 256) {
-            if (f >= 0) a += (Acc)x[(uint64_t)f * C + c];
-            else if (halo != nullptr && f >= -hf) a += (Acc)halo[(uint64_t)(f + hf) * C + c];
+            if (f >= 0) a += gen_term<Acc>(x[(uint64_t)f * C + c], rms);
+            else if (halo != nullptr && f >= -hf) a += gen_term<Acc>(halo[(uint64_t)(f + hf) * C + c], rms);
         }
 #pragma unroll
         for (int d = 16; d >= 1; d >>= 1) a += __shfl_down_sync(0xffffffffu, a, d);
@@ -238,10 +262,10 @@ __global__ void __launch_bounds__(256) tail_kernel(const T* __restrict__ x, T* _
             for (uint64_t f = p.out_begin; f < p.out_end; ++f) {
                 Acc old = 0;
                 const long long fo = (long long)f - k;
-                if (fo >= 0) old = (Acc)x[(uint64_t)fo * C + c];
-                else if (halo != nullptr && fo >= -hf) old = (Acc)halo[(uint64_t)(fo + hf) * C + c];
-                w += (Acc)x[f * C + c] - old;
-                y[f * C + c] = GenericAcc<T>::finish(w, p.k, inv);
+                if (fo >= 0) old = gen_term<Acc>(x[(uint64_t)fo * C + c], rms);
+                else if (halo != nullptr && fo >= -hf) old = gen_term<Acc>(halo[(uint64_t)(fo + hf) * C + c], rms);
+                w += gen_term<Acc>(x[f * C + c], rms) - old;
+                y[f * C + c] = rms ? GenericAcc<T>::finish_rms(w, p.k, inv) : GenericAcc<T>::finish(w, p.k, inv);
             }
         }
         __syncthreads();
@@ -609,7 +633,10 @@ __device__ __forceinline__ void small_window_sums(const float (&v)[R + 7 * C], f
 // MODE 2: compile-time K <= 8, additions only (MIS unused).
 // C = channels interleaved in the flat sample stream (1 mono/planar, 2 stereo, 4): window stride C,
 // lag distance k*C, one running sum per channel per thread.
-template <int NT, int R, int MIS, int MODE, int K, int C = 1>
+// RMS = moving root-mean-square instead of the moving average (mavg_op): samples are
+// squared as they leave shared memory, the window mean goes through a square root on its way to the staging tile;
+// everything between (window sums, tile-local rebasing, slide) is the same code.
+template <int NT, int R, int MIS, int MODE, int K, int C = 1, bool RMS = false>
 __global__ void __launch_bounds__(NT)
     stream_f32_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map,
                       const __grid_constant__ CUtensorMap halo_map, const StreamParams p)
@@ -657,6 +684,10 @@ __global__ void __launch_bounds__(NT)
             for (int c = 0; c < CH_OWN; ++c) {
                 const float4 v = lds128(swz(cur + (uint32_t)tid * (R * 4) + 16u * c));
                 x[4 * c + 0] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
+            }
+            if constexpr (RMS) {
+#pragma unroll
+                for (int i = 0; i < R; ++i) x[i] *= x[i];
             }
             // per-channel group totals, fixed order
             float gtot[C], incl[C];
@@ -734,6 +765,10 @@ __global__ void __launch_bounds__(NT)
                         const float4 v = lds128(swz(tr.rel(lin + 16 * c)));
                         xl[4 * c + 0] = v.x; xl[4 * c + 1] = v.y; xl[4 * c + 2] = v.z; xl[4 * c + 3] = v.w;
                     }
+                    if constexpr (RMS) {
+#pragma unroll
+                        for (int i = 0; i < CH_LAG * 4; ++i) xl[i] *= xl[i];
+                    }
                 }
 
                 const float inv = p.inv_k;
@@ -749,9 +784,14 @@ __global__ void __launch_bounds__(NT)
                     for (int i = 0; i < R; ++i) v[(K - 1) * C + i] = x[i];
                     small_window_sums<K, R, C>(v, w);
 #pragma unroll
-                    for (int c = 0; c < CH_OWN; ++c)
-                        sts128(swz(ob + 16u * c), w[4 * c] * inv, w[4 * c + 1] * inv, w[4 * c + 2] * inv,
-                               w[4 * c + 3] * inv);
+                    for (int c = 0; c < CH_OWN; ++c) {
+                        if constexpr (RMS)
+                            sts128(swz(ob + 16u * c), sqrtf(w[4 * c] * inv), sqrtf(w[4 * c + 1] * inv),
+                                   sqrtf(w[4 * c + 2] * inv), sqrtf(w[4 * c + 3] * inv));   // sums of squares: never negative
+                        else
+                            sts128(swz(ob + 16u * c), w[4 * c] * inv, w[4 * c + 1] * inv, w[4 * c + 2] * inv,
+                                   w[4 * c + 3] * inv);
+                    }
                 } else {
                     // ---- per-channel window sum over [a-k*C, a): whole groups between, then the tail of the lag group
                     float acc[C];
@@ -816,6 +856,7 @@ __global__ void __launch_bounds__(NT)
                             const int r = 4 * c4 + q;
                             acc[r % C] += x[r] - xl[MIS + r];
                             y[q] = acc[r % C] * inv;
+                            if constexpr (RMS) y[q] = sqrtf(fmaxf(y[q], 0.f));   // a slid sum of squares may round below 0
                         }
                         sts128(swz(ob + 16u * c4), y[0], y[1], y[2], y[3]);
                     }

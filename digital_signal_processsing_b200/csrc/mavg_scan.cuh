@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(kScanThreads)
 #pragma unroll
     for (int c = 0; c < C; ++c) csum[c] = 0;
     const bool vec_ok = (reinterpret_cast<uintptr_t>(in) & 15u) == 0;
-#pragma unroll 2
+#pragma unroll 4
     for (int q = tid; q < E / VE; q += NT) {
         const uint64_t e0 = cbase + (uint64_t)q * VE;
         const int l0 = q * VE;
@@ -267,14 +267,21 @@ __global__ void __launch_bounds__(kScanThreads)
 #pragma unroll 1
             for (int c = 0; c < C; ++c) {
                 // each lane inspects one predecessor per round; rounds of 32 chunks move backwards until a prefix is
-                // found.  The descriptors of the following round are requested before this round's are examined.
+                // found.  The descriptors of the next kAhead rounds are requested before this round's are examined, so
+                // a walk over several rounds costs one memory latency, not one per round (the chain of prefix
+                // publications advances by up to 32 * (kAhead + 1) chunks per hop).
+                constexpr int kAhead = 3;
                 long long look = (long long)tile - 1 - lane;
-                ulonglong2 cur = make_ulonglong2(kScanPrefix, 0ull);   // lanes before chunk 0: a terminating zero prefix
-                if (look >= 0) cur = ld_desc(desc + (uint64_t)look * C + c);
+                const ulonglong2 done = make_ulonglong2(kScanPrefix, 0ull);   // lanes before chunk 0: a terminating zero prefix
+                ulonglong2 cur = look >= 0 ? ld_desc(desc + (uint64_t)look * C + c) : done;
+                ulonglong2 ahead[kAhead];
+#pragma unroll
+                for (int a = 0; a < kAhead; ++a) {
+                    const long long la = look - 32 * (a + 1);
+                    ahead[a] = la >= 0 ? ld_desc(desc + (uint64_t)la * C + c) : done;
+                }
                 TAcc acc = 0;
                 for (;;) {
-                    ulonglong2 nxt = make_ulonglong2(kScanPrefix, 0ull);
-                    if (look - 32 >= 0) nxt = ld_desc(desc + (uint64_t)(look - 32) * C + c);
                     while (cur.x == kScanInvalid) cur = ld_desc(desc + (uint64_t)look * C + c);
                     const unsigned has_prefix = __ballot_sync(0xffffffffu, cur.x == kScanPrefix);
                     const int first = has_prefix ? __ffs(has_prefix) - 1 : 32;   // nearest predecessor with a full prefix
@@ -285,7 +292,11 @@ __global__ void __launch_bounds__(kScanThreads)
                     acc += val;
                     if (has_prefix) break;
                     look -= 32;
-                    cur = nxt;
+                    cur = ahead[0];
+#pragma unroll
+                    for (int a = 0; a + 1 < kAhead; ++a) ahead[a] = ahead[a + 1];
+                    const long long la = look - 32 * kAhead;
+                    ahead[kAhead - 1] = la >= 0 ? ld_desc(desc + (uint64_t)la * C + c) : done;
                 }
                 if (lane == 0) {
                     s_excl[c] = acc;

@@ -20,6 +20,7 @@ _DTYPES = {"f32": _lib.F32, "float32": _lib.F32, "i16": _lib.I16, "int16": _lib.
 _LAYOUTS = {"interleaved": _lib.INTERLEAVED, "planar": _lib.PLANAR}
 _PATHS = {"auto": _lib.PATH_AUTO, "stream": _lib.PATH_STREAM, "generic": _lib.PATH_GENERIC}
 _NP = {_lib.F32: np.float32, _lib.I16: np.int16}
+_OPS = {"mean": _lib.OP_MEAN, "average": _lib.OP_MEAN, "rms": _lib.OP_RMS}
 
 
 def device_count() -> int:
@@ -33,7 +34,7 @@ def version() -> int:
 class Plan:
     def __init__(self, frames: int, window: int, channels: int = 1, dtype: str = "f32",
                  layout: str = "interleaved", block_size: int = 0, path: str = "auto",
-                 devices: Optional[Sequence[int]] = None, first_frame: int = 0, **tuning: int):
+                 devices: Optional[Sequence[int]] = None, first_frame: int = 0, op: str = "mean", **tuning: int):
         self._lib = _lib.load()
         d = Desc()
         d.struct_size = ctypes.sizeof(Desc)
@@ -49,6 +50,7 @@ class Plan:
             for i, dev in enumerate(devices):
                 d.devices[i] = dev
         d.first_frame = first_frame
+        d.op = _OPS[op]
         for key, val in tuning.items():
             if not hasattr(d.tuning, key):
                 raise TypeError(f"unknown tuning field {key!r}")
@@ -236,8 +238,13 @@ def prefix_sum_device(in_ptr: int, out_ptr: int, dtype: str, frames: int, channe
                                       channels, ctypes.c_void_p(stream)))
 
 
+def moving_rms(x: np.ndarray, window: int, channels: int = 1, layout: str = "interleaved") -> np.ndarray:
+    """One-shot convenience: moving RMS (sqrt of the windowed mean of squares) of a host array on the GPU."""
+    return moving_average(x, window, channels, layout, op="rms")
+
+
 def moving_average(x: np.ndarray, window: int, channels: int = 1, layout: str = "interleaved",
-                   block_size: int = 0, path: str = "auto") -> np.ndarray:
+                   block_size: int = 0, path: str = "auto", op: str = "mean") -> np.ndarray:
     """One-shot convenience: moving average of a host array on the GPU (int16 or float32)."""
     x = np.asarray(x)
     if x.dtype == np.int16:
@@ -251,5 +258,5 @@ def moving_average(x: np.ndarray, window: int, channels: int = 1, layout: str = 
         raise ValueError("sample count must be a multiple of channels")
     if flat.size == 0:
         return flat.copy().reshape(x.shape)
-    with Plan(flat.size // channels, window, channels, dtype, layout, block_size, path) as plan:
+    with Plan(flat.size // channels, window, channels, dtype, layout, block_size, path, op=op) as plan:
         return plan.run_host(flat).reshape(x.shape)

@@ -40,7 +40,7 @@ extern "C" {
 #endif
 
 #define MAVG_VERSION_MAJOR 0
-#define MAVG_VERSION_MINOR 2
+#define MAVG_VERSION_MINOR 3
 #define MAVG_VERSION_PATCH 0
 
 typedef enum mavg_status {
@@ -85,6 +85,16 @@ typedef enum mavg_dist {
     MAVG_DIST_DC1E4 = 3  /* 1e4 + U[-1,1)                                                */
 } mavg_dist;
 
+/* Windowed reduction a plan computes ("other windowed reductions").  Window, zero
+ * padding on the left and the division by the full k while the window fills are the same for both. */
+typedef enum mavg_op {
+    MAVG_OP_MEAN = 0, /* the moving average of the reference (basics/profilable_moving_averager.cpp:14-37)    */
+    MAVG_OP_RMS = 1   /* moving RMS: sqrt(mean of squares).  float32: <= 1e-5 relative against fp64; int16: exact
+                         int64 sum of squares, y = min(32767, trunc(sqrt((double) sum / k))).  float32 mono, stereo
+                         and planar signals run on the TMA streaming kernel (squares on load, root on store); every
+                         other shape runs on the generic kernel                                               */
+} mavg_op;
+
 #define MAVG_MAX_DEVICES 16
 
 /* Optional tuning overrides; 0 = library default. */
@@ -125,6 +135,8 @@ typedef struct mavg_desc {
                               (one-process-per-GPU sharding); 0 otherwise.  When > 0 the
                               left context is supplied through mavg_run_device_halo.      */
     mavg_tuning tuning;
+    uint32_t op;           /* mavg_op                                                     */
+    uint32_t reserved;     /* must be 0                                                   */
 } mavg_desc;
 
 /* Phase times of the last run, as GpuTimer::get_result (benchmark.h:88-96) reports

@@ -36,6 +36,10 @@ def _load():
     lib.oracle_mavg_i16.restype = None
     lib.oracle_mavg_f32_to_f64.argtypes = [vp, vp, u64, u32, u32]
     lib.oracle_mavg_f32_to_f64.restype = None
+    lib.oracle_mrms_f32_to_f64.argtypes = [vp, vp, u64, u32, u32]
+    lib.oracle_mrms_f32_to_f64.restype = None
+    lib.oracle_mrms_i16.argtypes = [vp, vp, u64, u32, u32]
+    lib.oracle_mrms_i16.restype = None
     lib.oracle_mavg_f32_running.argtypes = [vp, vp, u64, u32, u32]
     lib.oracle_mavg_f32_running.restype = None
     lib.oracle_mavg_f32_running_mt.argtypes = [vp, vp, u64, u32, u32, i32]
@@ -88,6 +92,22 @@ def mavg_f64(x: np.ndarray, k: int, channels: int = 1) -> np.ndarray:
     x = np.ascontiguousarray(x, dtype=np.float32)
     y = np.empty(x.shape, dtype=np.float64)
     lib().oracle_mavg_f32_to_f64(_ptr(x), _ptr(y), _frames(x, channels), channels, k)
+    return y
+
+
+def mrms_f64(x: np.ndarray, k: int, channels: int = 1) -> np.ndarray:
+    """Moving RMS of fp32 input evaluated in fp64: sqrt(mean of squares over the causal, zero-padded window)."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    y = np.empty(x.shape, dtype=np.float64)
+    lib().oracle_mrms_f32_to_f64(_ptr(x), _ptr(y), _frames(x, channels), channels, k)
+    return y
+
+
+def mrms_i16(x: np.ndarray, k: int, channels: int = 1) -> np.ndarray:
+    """Moving RMS of int16 input: exact int64 sum of squares, (int16) trunc(sqrt((double) sum / k))."""
+    x = np.ascontiguousarray(x, dtype=np.int16)
+    y = np.empty_like(x)
+    lib().oracle_mrms_i16(_ptr(x), _ptr(y), _frames(x, channels), channels, k)
     return y
 
 

@@ -8,6 +8,7 @@
 #define _POSIX_C_SOURCE 200809L
 #include "mavg_oracle.h"
 
+#include <math.h>
 #include <pthread.h>
 #include <stdlib.h>
 #include <string.h>
@@ -83,6 +84,55 @@ void oracle_mavg_f32_to_f64(const float *x, double *y, uint64_t frames,
             y[f * channels + c] = w / (double)k;
         }
     }
+}
+
+/* ------------------------------------------------------------- moving RMS */
+
+void oracle_mrms_f32_to_f64(const float *x, double *y, uint64_t frames,
+                            uint32_t channels, uint32_t k)
+{
+    if (!frames || !channels || !k) return;
+    const uint64_t RESTART = 4096;
+    for (uint32_t c = 0; c < channels; ++c) {
+        double w = 0.0;
+        for (uint64_t f = 0; f < frames; ++f) {
+            if (f % RESTART == 0) {
+                uint64_t lo = (f + 1 > k) ? f + 1 - k : 0;
+                w = 0.0;
+                for (uint64_t j = lo; j <= f; ++j) {
+                    const double v = (double)x[j * channels + c];
+                    w += v * v;
+                }
+            } else {
+                const double v = (double)x[f * channels + c];
+                w += v * v;
+                if (f >= k) {
+                    const double o = (double)x[(f - k) * channels + c];
+                    w -= o * o;
+                }
+            }
+            y[f * channels + c] = sqrt((w > 0.0 ? w : 0.0) / (double)k);
+        }
+    }
+}
+
+void oracle_mrms_i16(const int16_t *x, int16_t *y, uint64_t frames,
+                     uint32_t channels, uint32_t k)
+{
+    if (!frames || !channels || !k) return;
+    int64_t *acc = (int64_t *)calloc(channels, sizeof(int64_t));
+    for (uint64_t f = 0; f < frames; ++f)
+        for (uint32_t c = 0; c < channels; ++c) {
+            const int64_t v = x[f * channels + c];
+            acc[c] += v * v;
+            if (f >= k) {
+                const int64_t o = x[(f - k) * channels + c];
+                acc[c] -= o * o;
+            }
+            const double r = sqrt((double)acc[c] / (double)k);   /* 32768 (all samples at -32768) saturates */
+            y[f * channels + c] = (int16_t)(r > 32767.0 ? 32767.0 : r);
+        }
+    free(acc);
 }
 
 /* --------------------------------------------------------- fp32 CPU port */

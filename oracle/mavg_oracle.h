@@ -51,6 +51,16 @@ void oracle_mavg_i16(const int16_t *x, int16_t *y, uint64_t frames,
 void oracle_mavg_f32_to_f64(const float *x, double *y, uint64_t frames,
                             uint32_t channels, uint32_t k);
 
+/* Moving RMS, the windowed reduction SURVEY.md section 8(f) row 4 asks for beside the average (the reference has no
+ * such binary; the window, padding and divide-by-k-during-warm-up conventions are those of a1):
+ *   y[i,c] = sqrt( (1/k) * sum_{j=max(0,i-k+1)}^{i} x[j,c]^2 )
+ * float32 input evaluated in fp64 (fresh window sums every 4096 frames); int16 input with an exact int64 sum of
+ * squares and  y = (int16) min(32767, trunc( sqrt( (double) sum / k ) ))  (IEEE double division and square root). */
+void oracle_mrms_f32_to_f64(const float *x, double *y, uint64_t frames,
+                            uint32_t channels, uint32_t k);
+void oracle_mrms_i16(const int16_t *x, int16_t *y, uint64_t frames,
+                     uint32_t channels, uint32_t k);
+
 /* Port of the same running-sum loop in fp32 (the apples-to-apples CPU baseline
  * for the fp32 GPU path; NOT an accuracy oracle).  Single thread. */
 void oracle_mavg_f32_running(const float *x, float *y, uint64_t frames,

@@ -57,7 +57,7 @@ def test_struct_layout_matches_header(mavg, tmp_path):
 def test_version_and_strerror(mavg):
     from digital_signal_processsing_b200 import _lib
     lib = _lib.load()
-    assert lib.mavg_version() == 200
+    assert lib.mavg_version() == 300
     assert lib.mavg_strerror(0) == b"ok"
     assert b"block size" in lib.mavg_strerror(_lib.ERR_BLOCK_SIZE)
     assert lib.mavg_strerror(-99) == b"unknown status"
@@ -136,4 +136,4 @@ def test_links_and_runs_from_plain_c(mavg, tmp_path):
                     "-o", str(exe), "-L", libdir, "-lmavg", f"-Wl,-rpath,{libdir}"], check=True)
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
-    assert out.stdout.split()[0] == "200" and "window" in out.stdout
+    assert out.stdout.split()[0] == "300" and "window" in out.stdout

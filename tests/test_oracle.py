@@ -110,3 +110,22 @@ def test_generator_is_counter_based(oracle_mod):
     e = oracle_mod.mavg_f64(x, 100)
     for idx in (0, 50, 99, 100, 2999):
         assert abs(oracle_mod.point_f64(idx, 100, 5) - e[idx]) < 1e-12
+
+
+def test_moving_rms_oracle_against_numpy(oracle_mod):
+    """oracle_mrms_*: sqrt of the windowed mean of squares, same window / padding / divide-by-k conventions as a1."""
+    import math
+    x = oracle_mod.fill_f32(6000, 3, oracle_mod.DIST_USYM)
+    for ch, k in ((1, 1), (1, 7), (2, 64), (3, 5000)):
+        sq = x[: (x.size // ch) * ch].astype(np.float64).reshape(-1, ch) ** 2
+        e = np.array([sq[max(0, i + 1 - k):i + 1].sum(axis=0) / k for i in range(sq.shape[0])])   # fresh window sums
+        y = oracle_mod.mrms_f64(x[: sq.size], k, ch)
+        assert np.max(np.abs(y - np.sqrt(e).reshape(-1))) < 1e-12
+    xi = oracle_mod.fill_i16(9000, 4)
+    for ch, k in ((1, 3), (2, 100), (3, 4000)):
+        sq = xi.astype(np.int64).reshape(-1, ch) ** 2
+        c = np.cumsum(np.vstack([np.zeros((1, ch), dtype=np.int64), sq]), axis=0)
+        e = np.array([[min(32767, math.isqrt(int(v) // k)) for v in (c[i + 1] - c[max(0, i + 1 - k)])]
+                      for i in range(sq.shape[0])]).reshape(-1)      # floor(sqrt(w / k)) == isqrt(w // k)
+        assert np.array_equal(oracle_mod.mrms_i16(xi, k, ch).astype(np.int64), e)
+    assert oracle_mod.mrms_i16(np.full(10, -32768, dtype=np.int16), 1)[0] == 32767
