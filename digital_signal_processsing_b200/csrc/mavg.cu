@@ -254,7 +254,8 @@ StreamGeom plan_cols(uint32_t k, uint32_t C, const mavg_tuning& tu, bool i16 = f
         bool fits = false;
         for (;;) {
             g.S = g.H + 1 + g.P;
-            g.smem = mavg::cols_smem_bytes(kColsNW, kColsRF, g.S, g.H, i16 ? 8u : 4u);
+            g.smem = i16 ? mavg::cols_i16_smem_bytes(kColsNW, kColsRF, g.S)
+                         : mavg::cols_smem_bytes(kColsNW, kColsRF, g.S, g.H, 4u);
             if (g.smem <= kMaxSmem) { fits = true; break; }
             if (cww == 1 && g.P > 1) { --g.P; continue; }   // only the narrowest shape trades prefetch for history
             break;
@@ -476,6 +477,8 @@ struct DevCtx {
     void* d_halo = nullptr;     // halo_frames * channels elements of left context (frame sharding)
     void* d_bsum = nullptr;     // generic path, long windows: 64-frame block sums
     void* d_scratch = nullptr;  // mavg_run_cascade intermediates
+    void* d_far_stage = nullptr;   // far-lag kernel, context not contiguous with the shard: [context | first frames]
+    size_t far_stage_bytes = 0;
     cudaEvent_t ev_pass = nullptr;  // mavg_run_cascade: end of this device's latest pass
     size_t bsum_bytes = 0;
     int sm_count = 0;
@@ -921,6 +924,34 @@ int launch_shard(mavg_plan* p, DevCtx& d, const void* in, void* out, const void*
         const uint64_t rows_all = (planar_batch(p) ? p->desc.frames : frames * p->desc.channels) / 32 + (uint64_t)p->geom.H * 256;
         if (contiguous && stream_eligible(p, d, in, out, halo, frames) && rows_all < 0x7fffffffull - 65536)
             return launch_far(p, d, in, out, halo, frames, launches);
+        if (!contiguous && !planar_batch(p) && stream_eligible(p, d, in, out, halo, frames) &&
+            rows_all < 0x7fffffffull - 65536) {
+            // The left context lives somewhere else (a peer's tail over NVLink, a staged halo).  Only the first
+            // halo_frames frames of the shard can see it: [context | those frames] is copied into a small plan-owned
+            // buffer (two times the window, a few MB) where the context IS contiguous, and filtered from there straight
+            // into the output; the rest of the shard finds its context inside the shard itself.
+            const size_t fb = (size_t)p->desc.channels * sizeof(float);
+            const uint64_t fa = std::min<uint64_t>(frames, p->halo_frames);
+            const size_t need = hb + fa * fb;
+            if (d.far_stage_bytes < need) {
+                if (d.d_far_stage) MAVG_CUDA(cudaFree(d.d_far_stage));
+                d.d_far_stage = nullptr;
+                d.far_stage_bytes = 0;
+                if (cudaMalloc(&d.d_far_stage, need) != cudaSuccess) {
+                    cudaGetLastError();
+                    return fail(MAVG_ERR_ALLOC, "cudaMalloc of %zu far-lag staging bytes failed", need);
+                }
+                d.far_stage_bytes = need;
+            }
+            char* stage = (char*)d.d_far_stage;
+            MAVG_CUDA(cudaMemcpyAsync(stage, halo, hb, cudaMemcpyDefault, d.stream));
+            MAVG_CUDA(cudaMemcpyAsync(stage + hb, in, fa * fb, cudaMemcpyDeviceToDevice, d.stream));
+            MAVG_TRY(launch_far(p, d, stage + hb, out, stage, fa, launches));
+            if (frames > fa)
+                MAVG_TRY(launch_far(p, d, (const char*)in + fa * fb, (char*)out + fa * fb, (const char*)in + fa * fb - hb,
+                                    frames - fa, launches));
+            return MAVG_OK;
+        }
         return launch_generic(p, d, in, out, halo, frames, 0, frames, launches);
     }
     if (p->path == MAVG_PATH_STREAM && p->geom.ok && p->geom.mode == 3) {
@@ -1064,14 +1095,14 @@ int scan_pool(int dev, cudaMemPool_t* out)
     return MAVG_OK;
 }
 
-template <typename TIn, typename TLoc, typename TAcc, int C>
-int launch_scan_c(const void* d_in, void* d_out, uint64_t n, cudaStream_t st)
+template <typename TIn, typename TLoc, typename TAcc, int C, int CB>
+int launch_scan_cb(const void* d_in, void* d_out, uint64_t n, cudaStream_t st)
 {
-    const uint64_t chunk = (uint64_t)mavg::scan_chunk_elems<TLoc, C>();
+    const uint64_t chunk = (uint64_t)mavg::scan_chunk_elems<TLoc, C, CB>();
     const uint64_t tiles = (n + chunk - 1) / chunk;
     if (tiles > 0x7fffffffull) return fail(MAVG_ERR_UNSUPPORTED, "signal too long for mavg_prefix_sum");
-    auto kern = mavg::scan_lookback_kernel<TIn, TLoc, TAcc, C>;
-    const uint32_t smem = mavg::scan_smem_bytes<TLoc, C>();
+    auto kern = mavg::scan_lookback_kernel<TIn, TLoc, TAcc, C, CB>;
+    const uint32_t smem = mavg::scan_smem_bytes<TLoc, C, CB>();
     MAVG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // scratch: ticket (padded to 256 bytes), 16-byte descriptors [chunks][C]; all zero = "not published"
     const size_t total = 256 + (size_t)tiles * C * sizeof(ulonglong2);
@@ -1090,6 +1121,33 @@ int launch_scan_c(const void* d_in, void* d_out, uint64_t n, cudaStream_t st)
     cudaFreeAsync(scratch, st);     // on every path: stream-ordered, after the kernel
     if (e != cudaSuccess) return fail(MAVG_ERR_CUDA, "prefix-sum launch failed: %s", cudaGetErrorString(e));
     return MAVG_OK;
+}
+
+// shared-memory bytes of chunk-local prefixes per CTA: MAVG_SCAN_CHUNK_KB in the environment (16, 32 or 64) overrides
+// the default for measurements
+int scan_chunk_kb()
+{
+    static const int kb = [] {
+        const char* e = getenv("MAVG_SCAN_CHUNK_KB");
+        const int v = e ? atoi(e) : 0;
+        return (v == 16 || v == 32 || v == 64) ? v : 0;
+    }();
+    return kb;
+}
+
+template <typename TIn, typename TLoc, typename TAcc, int C>
+int launch_scan_c(const void* d_in, void* d_out, uint64_t n, cudaStream_t st)
+{
+    // Measured on 2^28 samples (profiles/r02): int16 runs best with 32 KB of chunk-local prefixes per CTA (8192 elements,
+    // six CTAs per SM in different phases), float32 -> float64 with 64 KB (its prefixes are 8 bytes: the same 8192 elements)
+    if constexpr (C == 1 || C == 2) {   // the chunk-size variants exist for the shapes that are measured
+        int kb = scan_chunk_kb();
+        if (kb == 0) kb = sizeof(TLoc) == 4 ? 32 : 64;
+        if (kb == 16) return launch_scan_cb<TIn, TLoc, TAcc, C, 16384>(d_in, d_out, n, st);
+        if (kb == 32) return launch_scan_cb<TIn, TLoc, TAcc, C, 32768>(d_in, d_out, n, st);
+        return launch_scan_cb<TIn, TLoc, TAcc, C, 65536>(d_in, d_out, n, st);
+    }
+    return launch_scan_cb<TIn, TLoc, TAcc, C, (sizeof(TLoc) == 4 ? 32768 : 65536)>(d_in, d_out, n, st);
 }
 
 template <typename TIn, typename TLoc, typename TAcc>
@@ -1281,6 +1339,7 @@ int mavg_plan_destroy(mavg_plan* p)
         if (d.d_halo) cudaFree(d.d_halo);
         if (d.d_bsum) cudaFree(d.d_bsum);
         if (d.d_scratch) cudaFree(d.d_scratch);
+        if (d.d_far_stage) cudaFree(d.d_far_stage);
         if (d.ev_pass) cudaEventDestroy(d.ev_pass);
         if (d.s_h2d) { cudaStreamSynchronize(d.s_h2d); cudaStreamDestroy(d.s_h2d); }
         if (d.s_d2h) { cudaStreamSynchronize(d.s_d2h); cudaStreamDestroy(d.s_d2h); }
@@ -1611,11 +1670,35 @@ bool is_pageable(const void* ptr)
 
 }  // namespace
 
+namespace {
+int run_host_impl(mavg_plan* p, const void* h_in, void* h_out);
+}
+
 int mavg_run_host(mavg_plan* p, const void* h_in, void* h_out)
 {
     if (!p || !h_in || !h_out) return fail(MAVG_ERR_INVALID_ARG, "null argument");
     if (h_in == h_out) return fail(MAVG_ERR_INVALID_ARG, "output must not alias input");
     DeviceGuard guard;
+    const int rc = run_host_impl(p, h_in, h_out);
+    if (rc != MAVG_OK) {
+        // a failure in the middle of the pipeline leaves copies queued on the caller's buffers: drain them before the
+        // caller gets its buffers back (it may free them at once); the first error stays the one reported
+        const std::string first = g_last_error;
+        for (DevCtx& d : p->dev) {
+            if (cudaSetDevice(d.device) != cudaSuccess) continue;
+            if (d.s_h2d) cudaStreamSynchronize(d.s_h2d);
+            if (d.stream) cudaStreamSynchronize(d.stream);
+            if (d.s_d2h) cudaStreamSynchronize(d.s_d2h);
+        }
+        cudaGetLastError();
+        g_last_error = first;
+    }
+    return rc;
+}
+
+namespace {
+int run_host_impl(mavg_plan* p, const void* h_in, void* h_out)
+{
     const size_t es = elem_size(p->desc.dtype);
     const uint64_t C = p->desc.channels;
     uint32_t launches = 0;
@@ -1723,6 +1806,7 @@ int mavg_run_host(mavg_plan* p, const void* h_in, void* h_out)
     p->launches_last_run = launches;
     return mavg_synchronize(p);
 }
+}  // namespace
 
 int mavg_fill_synthetic_device(void* d_dst, int dtype, uint64_t n, uint64_t first_index, uint64_t seed, int dist,
                                void* cuda_stream)

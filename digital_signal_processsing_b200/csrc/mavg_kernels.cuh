@@ -1620,10 +1620,22 @@ __global__ void __launch_bounds__(NWT * 32)
 // ----------------------------------------------------------------------------------
 // Column kernel for interleaved int16 with many channels (C >= 64, C % 8 == 0; sensor arrays, multichannel PCM):
 // stream_cols_f32_kernel's layout over 32-bit WORDS -- a frame is C/2 words, each a pair of neighbouring channels,
-// lane = word column, warp = RF-frame run -- with stream_i16_kernel's exact arithmetic: dp2a on the packed words
-// for run totals, head and slide, signed multiply-high division, one byte permute per output word.
+// lane = word column, warp = RF-frame run -- with stream_i16_kernel's exact delta-scan arithmetic (round 2; the
+// round-1 version summed run totals, group totals and the head of the lag run: 21.9 executed instructions per sample):
+//   * before the tile's barrier a thread slides over its RF frames with two dp2a per sample on the packed words,
+//     s[r] = sum_{i <= r} (x[i] - x[i - k]) per channel of the pair, and publishes d = s[RF - 1];
+//   * after the barrier it adds up the d of the NW frame-warps of its column (all of them: the total advances the
+//     carried window sum W; those in front of its own warp give its start), and
+//     y[r] = trunc((W + start + s[r]) / k) by multiply-high, two results merged by one byte permute, one 32-bit store;
+//   * a chunk builds its first W from the H = ceil(k / tile frames) tiles in front of it (frames at or behind
+//     chunk start - k, the first tile masked).
 // p.channels = C/2 (words per frame).  Bit-identical to profilable_cpu_computations.  4 B/sample.
 // ----------------------------------------------------------------------------------
+__host__ __device__ inline uint32_t cols_i16_smem_bytes(int NWT, int RF, int S)
+{
+    return 1024u + (uint32_t)S * NWT * RF * 128u + 2u * NWT * 32 * 8u + (uint32_t)S * 8;
+}
+
 template <int NWT, int RF, int CWW>
 __global__ void __launch_bounds__(NWT * 32)
     stream_cols_i16x2_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap halo_map,
@@ -1633,7 +1645,7 @@ __global__ void __launch_bounds__(NWT * 32)
     constexpr int NW = NWT / CWW;            // frame-warps
     constexpr int CW = 32 * CWW;             // words per tile row
     constexpr uint32_t ROWB = CW * 4u;       // bytes per tile row (one frame)
-    constexpr uint32_t GROW = CW * 8u;       // bytes per row of the [..][CW] int2 summary arrays
+    constexpr uint32_t GROW = CW * 8u;       // bytes per row of the [NW][CW] int2 delta array
     constexpr int FT = NW * RF;              // frames per tile
     constexpr uint32_t TB = FT * ROWB;       // bytes per tile
     static_assert(NWT % CWW == 0 && FT <= 256 && CW <= 256, "a TMA box holds at most 256 x 256 elements");
@@ -1645,15 +1657,14 @@ __global__ void __launch_bounds__(NWT * 32)
     const int S = p.stages;
     const int H = p.hist_tiles;
     const int P = p.prefetch;
-    const int GS = H + 2;
 
     const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t ring_bytes = (uint32_t)S * TB;
-    const uint32_t gsum = ring + ring_bytes;                    // int2 [GS][NW][CW]  (low / high channel of the pair)
-    const uint32_t ttot = gsum + (uint32_t)GS * NW * GROW;      // int2 [GS][CW]
-    const uint32_t bars = ttot + (uint32_t)GS * GROW;
+    const uint32_t dsum = ring + ring_bytes;                    // int2 [2][NW][CW]: run deltas (low / high channel), by tile parity
+    const uint32_t bars = dsum + 2u * NW * GROW;
     const uint32_t w_lo = wscale, w_hi = wscale << 8;
     const uint32_t n_lo = (0u - wscale) & 0xffu, n_hi = n_lo << 8;
+    const int mul = (int)div_mul;
 
     if (tid == 0) {
         prefetch_tmap(&in_map);
@@ -1673,7 +1684,7 @@ __global__ void __launch_bounds__(NWT * 32)
     };
 
     uint32_t it = 0;
-    int st = 0, slot = 0;
+    int st = 0;
 
     for (int chunk = blockIdx.x; chunk < p.total_chunks; chunk += gridDim.x) {
         const int rng = chunk / p.col_blocks;
@@ -1694,6 +1705,7 @@ __global__ void __launch_bounds__(NWT * 32)
                 s2 = (s2 + 1 == S) ? 0 : s2 + 1;
             }
         }
+        uint32_t W0 = 0u, W1 = 0u;           // window sums of the column's two channels at the first frame of the tile
 
         for (int j = 0; j < ntl; ++j) {
             const int tile = first + j;
@@ -1703,14 +1715,48 @@ __global__ void __launch_bounds__(NWT * 32)
             mbar_wait(bars + 8u * st, (it / (uint32_t)S) & 1u);
 
             uint32_t x[RF];
-            int g0 = 0, g1 = 0;
 #pragma unroll
-            for (int r = 0; r < RF; ++r) {
-                x[r] = lds32u(cur + ((uint32_t)(warp * RF + r) * CW + lane) * 4u);
-                g0 = dp2a_s(x[r], w_lo, g0);
-                g1 = dp2a_s(x[r], w_hi, g1);
+            for (int r = 0; r < RF; ++r) x[r] = lds32u(cur + ((uint32_t)(warp * RF + r) * CW + lane) * 4u);
+            uint32_t s0[RF], s1[RF];
+            int a0 = 0, a1 = 0;
+            if (is_out) {
+                uint32_t xl[RF];
+                int row0 = (int)((uint32_t)st * (uint32_t)FT) + warp * RF - (int)p.k;   // ring row of the first lag frame
+                const int ring_rows = S * FT;
+                if (row0 + RF <= 0) row0 += ring_rows;
+                if (row0 >= 0) {
+                    const uint32_t b0 = ring + (uint32_t)row0 * ROWB + (uint32_t)lane * 4u;
+#pragma unroll
+                    for (int r = 0; r < RF; ++r) xl[r] = lds32u(b0 + ROWB * r);
+                } else {  // rows row0..-1 live at the end of the ring
+                    const uint32_t b0 = ring + (uint32_t)lane * 4u;
+#pragma unroll
+                    for (int r = 0; r < RF; ++r) {
+                        const int rr = row0 + r;
+                        xl[r] = lds32u(b0 + (uint32_t)(rr < 0 ? rr + ring_rows : rr) * ROWB);
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < RF; ++r) {
+                    a0 = dp2a_s(xl[r], n_lo, dp2a_s(x[r], w_lo, a0));
+                    a1 = dp2a_s(xl[r], n_hi, dp2a_s(x[r], w_hi, a1));
+                    s0[r] = (uint32_t)a0;
+                    s1[r] = (uint32_t)a1;
+                }
+            } else {
+                // warm-up tile: frames at or behind (chunk start - k) belong to the first output's window
+                const int rel = (t0 - tile) * FT - (int)p.k - warp * RF;
+#pragma unroll
+                for (int r = 0; r < RF; ++r) {
+                    if (r >= rel) {
+                        a0 = dp2a_s(x[r], w_lo, a0);
+                        a1 = dp2a_s(x[r], w_hi, a1);
+                    }
+                    s0[r] = s1[r] = 0u;
+                }
             }
-            sts64i(gsum + (((uint32_t)slot * NW + warp) * CW + lane) * 8u, g0, g1);
+            const uint32_t dbase = dsum + (it & 1u) * NW * GROW + (uint32_t)lane * 8u;
+            sts64i(dbase + (uint32_t)warp * GROW, a0, a1);
 
             __syncthreads();
 
@@ -1720,93 +1766,32 @@ __global__ void __launch_bounds__(NWT * 32)
                 issue_load(first + j + P, cb, s2);
             }
 
-            // where the lag run starts: `lw` = group (warp slot), `h` = tiles back (both warp-uniform)
-            int lw = warp - (int)(p.n_full + 1u);
-            int h = 0;
-            if (lw < 0) {
-                h = (-lw + NW - 1) / NW;
-                lw += h * NW;
+            uint32_t e0 = 0u, e1 = 0u, tt0 = 0u, tt1 = 0u;   // deltas of the frame-warps in front / of all of them
+#pragma unroll
+            for (int w2 = 0; w2 < NW; ++w2) {
+                const int2 t = lds64i(dbase + (uint32_t)w2 * GROW);
+                tt0 += (uint32_t)t.x, tt1 += (uint32_t)t.y;
+                if (w2 < warp) e0 += (uint32_t)t.x, e1 += (uint32_t)t.y;
             }
-            int e0 = 0, e1 = 0;      // groups of this tile in front of the own group
-            if (h > 0 || (H > 1 && warp == NW - 1)) {
-                const uint32_t gb = gsum + ((uint32_t)slot * NW * CW + lane) * 8u;
-#pragma unroll 4
-                for (int w2 = 0; w2 < warp; ++w2) {
-                    const int2 t = lds64i(gb + (uint32_t)w2 * GROW);
-                    e0 += t.x, e1 += t.y;
-                }
-            }
-            if (H > 1 && warp == NW - 1) sts64i(ttot + ((uint32_t)slot * CW + lane) * 8u, e0 + g0, e1 + g1);
 
             if (is_out) {
-                uint32_t xl[RF];
-                {
-                    int row0 = (int)((uint32_t)st * (uint32_t)FT) + warp * RF - (int)p.k;   // ring row of the first lag frame
-                    const int ring_rows = S * FT;
-                    if (row0 + RF <= 0) row0 += ring_rows;
-                    if (row0 >= 0) {
-                        const uint32_t a0 = ring + (uint32_t)row0 * ROWB + (uint32_t)lane * 4u;
-#pragma unroll
-                        for (int r = 0; r < RF; ++r) xl[r] = lds32u(a0 + ROWB * r);
-                    } else {  // rows row0..-1 live at the end of the ring
-                        const uint32_t a0 = ring + (uint32_t)lane * 4u;
-#pragma unroll
-                        for (int r = 0; r < RF; ++r) {
-                            const int rr = row0 + r;
-                            xl[r] = lds32u(a0 + (uint32_t)(rr < 0 ? rr + ring_rows : rr) * ROWB);
-                        }
-                    }
-                }
-                int a0 = 0, a1 = 0;
-                if (h == 0) {
-                    const uint32_t gb = gsum + ((uint32_t)slot * NW * CW + lane) * 8u;
-#pragma unroll 4
-                    for (int w2 = lw + 1; w2 < warp; ++w2) {
-                        const int2 t = lds64i(gb + (uint32_t)w2 * GROW);
-                        a0 += t.x, a1 += t.y;
-                    }
-                } else {
-                    int ls = slot - h;
-                    if (ls < 0) ls += GS;
-                    const uint32_t gb = gsum + ((uint32_t)ls * NW * CW + lane) * 8u;
-#pragma unroll 4
-                    for (int w2 = lw + 1; w2 < NW; ++w2) {
-                        const int2 t = lds64i(gb + (uint32_t)w2 * GROW);
-                        a0 += t.x, a1 += t.y;
-                    }
-                    int ms = ls;
-                    for (int v = 1; v < h; ++v) {
-                        ms = (ms + 1 == GS) ? 0 : ms + 1;
-                        const int2 t = lds64i(ttot + ((uint32_t)ms * CW + lane) * 8u);
-                        a0 += t.x, a1 += t.y;
-                    }
-                    a0 += e0, a1 += e1;
-                }
-#pragma unroll
-                for (int r = 0; r < RF; ++r)
-                    if ((uint32_t)r < p.m_part) {
-                        a0 = dp2a_s(xl[r], w_lo, a0);
-                        a1 = dp2a_s(xl[r], w_hi, a1);
-                    }
-
+                const uint32_t b0 = W0 + e0, b1 = W1 + e1;
                 const uint64_t f_base = (uint64_t)tile * FT + (uint64_t)warp * RF;
                 uint32_t* dst = out + f_base * p.channels + ch;
                 int nvalid = 0;
                 if (ch_ok && f_base < p.frames) nvalid = (p.frames - f_base < (uint64_t)RF) ? (int)(p.frames - f_base) : RF;
                 const uint32_t cstride = p.channels;
-                const int mul = (int)div_mul;
 #pragma unroll
                 for (int r = 0; r < RF; ++r) {
-                    a0 = dp2a_s(xl[r], n_lo, dp2a_s(x[r], w_lo, a0));
-                    a1 = dp2a_s(xl[r], n_hi, dp2a_s(x[r], w_hi, a1));
-                    const uint32_t y = __byte_perm(div_trunc_mulhi(a0, mul, div_shift), div_trunc_mulhi(a1, mul, div_shift), 0x5410);
+                    const uint32_t y = __byte_perm(div_trunc_mulhi((int)(b0 + s0[r]), mul, div_shift),
+                                                   div_trunc_mulhi((int)(b1 + s1[r]), mul, div_shift), 0x5410);
                     if (r < nvalid) dst[(uint32_t)r * cstride] = y;
                 }
             }
+            W0 += tt0, W1 += tt1;
 
             ++it;
             st = (st + 1 == S) ? 0 : st + 1;
-            slot = (slot + 1 == GS) ? 0 : slot + 1;
         }
         __syncthreads();   // ring stages may be refilled by the next chunk's prologue
     }

@@ -84,21 +84,21 @@ __device__ __forceinline__ void st_desc(ulonglong2* p, unsigned long long status
     asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(status), "l"(bits) : "memory");
 }
 
-constexpr int kScanChunkBytes = 65536;   // shared-memory bytes of chunk-local prefixes per CTA (before padding)
 constexpr int kScanThreads = 256;
 
 // Run length per thread: the largest multiple of lcm(C, 2) not above kScanChunkBytes / sizeof(TLoc) / 256, so that a
 // run holds whole frames (the channel of run element i is i % C at compile time) and an even number of elements
 // (two results per 16-byte store).  C = 1, 2, 4, 8: 64 (int16) / 32 (float32); C = 3, 5, 6: 60 / 30; C = 7: 56 / 28.
-template <typename TLoc, int C>
+// CB = shared-memory bytes of chunk-local prefixes per CTA (before padding)
+template <typename TLoc, int C, int CB>
 __host__ __device__ constexpr int scan_run_len()
 {
-    constexpr int rmax = kScanChunkBytes / (int)sizeof(TLoc) / kScanThreads;
+    constexpr int rmax = CB / (int)sizeof(TLoc) / kScanThreads;
     constexpr int m = (C % 2 == 0) ? C : 2 * C;
     return rmax / m * m;
 }
-template <typename TLoc, int C>
-__host__ __device__ constexpr int scan_chunk_elems() { return kScanThreads * scan_run_len<TLoc, C>(); }
+template <typename TLoc, int C, int CB>
+__host__ __device__ constexpr int scan_chunk_elems() { return kScanThreads * scan_run_len<TLoc, C, CB>(); }
 // register block of the in-place run scan: the largest divisor of the run that is a multiple of C and at most 16
 template <int R, int C>
 __host__ __device__ constexpr int scan_block_len()
@@ -122,13 +122,13 @@ __host__ __device__ constexpr int scan_block_len()
 //   4. striped output pass: out[e] = prefix + thread offset + local prefix, 16-byte stores, fully coalesced.
 // Each element is read from HBM once and written once; chunk ids come from an atomic ticket so a chunk only
 // ever waits on chunks that are already running.  Scratch: ticket, desc[chunks][C].
-template <typename TIn, typename TLoc, typename TAcc, int C>
+template <typename TIn, typename TLoc, typename TAcc, int C, int CB>
 __global__ void __launch_bounds__(kScanThreads)
     scan_lookback_kernel(const TIn* __restrict__ in, TAcc* __restrict__ out, uint64_t n, uint32_t* __restrict__ ticket,
                          ulonglong2* __restrict__ desc)
 {
     constexpr int NT = kScanThreads, NW = NT / 32;
-    constexpr int R = scan_run_len<TLoc, C>();        // run per thread
+    constexpr int R = scan_run_len<TLoc, C, CB>();    // run per thread
     constexpr int E = NT * R;                         // elements per chunk
     constexpr int BL = scan_block_len<R, C>();
     constexpr int VE = 16 / (int)sizeof(TIn);         // input elements per 16-byte load
@@ -141,14 +141,23 @@ __global__ void __launch_bounds__(kScanThreads)
     TLoc* s_part = s_warp + NW * C;                                    // [NW][C] early aggregate: warp partial sums
     __shared__ TAcc s_excl[C];           // exclusive prefix of the chunk, broadcast from warp 0
     __shared__ TAcc s_tot[C];            // chunk aggregate as published
-    __shared__ uint32_t s_tile;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
-    __syncthreads();
-    const uint32_t tile = s_tile;
+    // Chunk id = block index: the hardware hands out the blocks of a 1-D grid in increasing order, so a chunk only ever
+    // waits on chunks that are already resident or done (what CUB's DeviceScan relies on as well).  Round 1 drew the id
+    // from an atomic ticket: one more global round trip and a barrier in front of every chunk's loads.
+    (void)ticket;
+    const uint32_t tile = blockIdx.x;
     const uint64_t cbase = (uint64_t)tile * E;
-    auto pidx = [](int e) { return e + (e >> 5); };
+    // Where element e of the chunk lives in `loc`.  4-byte prefixes: an XOR swizzle of the bank bits with bits 5..10 of e
+    // makes all three access patterns conflict-free -- the striped load phase (lanes 8 elements apart), the run
+    // scan (lanes one run = 64 elements apart) and the striped output phase (lanes 2 apart); the padded layout
+    // e + e/32 of round 1 was 2-way conflicted in the run scan (ncu: 35 % of shared wavefronts were conflicts).
+    // 8-byte prefixes (float32 input) keep the padding.
+    auto pidx = [](int e) {
+        if constexpr (sizeof(TLoc) == 4) return e ^ ((e >> 5) & 31) ^ ((e >> 10) & 1);
+        else return e + (e >> 5);
+    };
     ulonglong2* my_desc = desc + (uint64_t)tile * C;
 
     // ---- 1. load + convert (zero past the end); early per-channel partial sums
@@ -264,43 +273,48 @@ __global__ void __launch_bounds__(kScanThreads)
         if (tile == 0) {
             if (lane < C) s_excl[lane] = 0;
         } else {
-#pragma unroll 1
-            for (int c = 0; c < C; ++c) {
-                // each lane inspects one predecessor per round; rounds of 32 chunks move backwards until a prefix is
-                // found.  The descriptors of the next kAhead rounds are requested before this round's are examined, so
-                // a walk over several rounds costs one memory latency, not one per round (the chain of prefix
-                // publications advances by up to 32 * (kAhead + 1) chunks per hop).
-                constexpr int kAhead = 3;
-                long long look = (long long)tile - 1 - lane;
-                const ulonglong2 done = make_ulonglong2(kScanPrefix, 0ull);   // lanes before chunk 0: a terminating zero prefix
-                ulonglong2 cur = look >= 0 ? ld_desc(desc + (uint64_t)look * C + c) : done;
-                ulonglong2 ahead[kAhead];
+            // Each lane inspects one predecessor per round; rounds of 32 chunks move backwards until every channel has
+            // met a full prefix.  All C descriptors of a predecessor are requested together and the next round's are
+            // requested before this round's are examined, so a round costs one memory latency however many channels.
+            long long look = (long long)tile - 1 - lane;
+            const ulonglong2 stop = make_ulonglong2(kScanPrefix, 0ull);   // lanes before chunk 0: a terminating zero prefix
+            ulonglong2 cur[C], nxt[C];
+            TAcc acc[C];
+            bool open_[C];
 #pragma unroll
-                for (int a = 0; a < kAhead; ++a) {
-                    const long long la = look - 32 * (a + 1);
-                    ahead[a] = la >= 0 ? ld_desc(desc + (uint64_t)la * C + c) : done;
-                }
-                TAcc acc = 0;
-                for (;;) {
-                    while (cur.x == kScanInvalid) cur = ld_desc(desc + (uint64_t)look * C + c);
-                    const unsigned has_prefix = __ballot_sync(0xffffffffu, cur.x == kScanPrefix);
+            for (int c = 0; c < C; ++c) {
+                cur[c] = look >= 0 ? ld_desc(desc + (uint64_t)look * C + c) : stop;
+                acc[c] = 0;
+                open_[c] = true;
+            }
+            for (;;) {
+#pragma unroll
+                for (int c = 0; c < C; ++c) nxt[c] = look - 32 >= 0 ? ld_desc(desc + (uint64_t)(look - 32) * C + c) : stop;
+                bool any_open = false;
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    if (!open_[c]) continue;                                       // warp-uniform
+                    while (cur[c].x == kScanInvalid) cur[c] = ld_desc(desc + (uint64_t)look * C + c);
+                    const unsigned has_prefix = __ballot_sync(0xffffffffu, cur[c].x == kScanPrefix);
                     const int first = has_prefix ? __ffs(has_prefix) - 1 : 32;   // nearest predecessor with a full prefix
-                    TAcc val = (lane <= first) ? acc_from_bits<TAcc>((long long)cur.y) : (TAcc)0;
+                    TAcc val = (lane <= first) ? acc_from_bits<TAcc>((long long)cur[c].y) : (TAcc)0;
                     // fixed-shape butterfly: the same association for a given `first`
 #pragma unroll
                     for (int d = 16; d >= 1; d >>= 1) val += shfl_xor_acc<TAcc>(val, d);
-                    acc += val;
-                    if (has_prefix) break;
-                    look -= 32;
-                    cur = ahead[0];
-#pragma unroll
-                    for (int a = 0; a + 1 < kAhead; ++a) ahead[a] = ahead[a + 1];
-                    const long long la = look - 32 * kAhead;
-                    ahead[kAhead - 1] = la >= 0 ? ld_desc(desc + (uint64_t)la * C + c) : done;
+                    acc[c] += val;
+                    open_[c] = has_prefix == 0;
+                    any_open = any_open || open_[c];
                 }
+                if (!any_open) break;
+                look -= 32;
+#pragma unroll
+                for (int c = 0; c < C; ++c) cur[c] = nxt[c];
+            }
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
                 if (lane == 0) {
-                    s_excl[c] = acc;
-                    st_desc(my_desc + c, kScanPrefix, (unsigned long long)acc_bits<TAcc>(acc + s_tot[c]));
+                    s_excl[c] = acc[c];
+                    st_desc(my_desc + c, kScanPrefix, (unsigned long long)acc_bits<TAcc>(acc[c] + s_tot[c]));
                 }
             }
         }
@@ -338,10 +352,10 @@ __global__ void __launch_bounds__(kScanThreads)
 }
 
 // bytes of dynamic shared memory scan_lookback_kernel needs
-template <typename TLoc, int C>
+template <typename TLoc, int C, int CB>
 constexpr uint32_t scan_smem_bytes()
 {
-    constexpr uint32_t E = (uint32_t)scan_chunk_elems<TLoc, C>();
+    constexpr uint32_t E = (uint32_t)scan_chunk_elems<TLoc, C, CB>();
     return (E + E / 32) * sizeof(TLoc) + kScanThreads * C * sizeof(TLoc) + 2 * (kScanThreads / 32) * C * sizeof(TLoc) + 64;
 }
 

@@ -42,12 +42,23 @@ def exchange_halo(shard: torch.Tensor, halo_elems: int, rank: int, world: int,
     from rank-1 (None on rank 0).  Works on any backend; tensors stay on their device."""
     ops = []
     recv = None
+    if halo_elems <= 0:
+        return None
+    # every left neighbour must own at least the halo (mavg_plan_create: "signal too short to shard"): a shorter
+    # shard would send fewer elements than the right neighbour waits for
+    sizes = [None] * world
+    dist.all_gather_object(sizes, int(shard.numel()), group=group)
+    short = [r for r in range(world - 1) if sizes[r] < halo_elems]
+    if short:
+        raise ValueError(f"shard of rank {short[0]} holds {sizes[short[0]]} elements, fewer than the {halo_elems}-element "
+                         "left context its right neighbour needs: the signal is too short to shard this way")
+    # the bytes travel as uint8: NCCL has no 16-bit integer type (int16 PCM shards)
     if rank + 1 < world:
         tail = shard[-halo_elems:].contiguous()
-        ops.append(dist.P2POp(dist.isend, tail, rank + 1, group))
+        ops.append(dist.P2POp(dist.isend, tail.view(torch.uint8), rank + 1, group))
     if rank > 0:
         recv = torch.empty(halo_elems, dtype=shard.dtype, device=shard.device)
-        ops.append(dist.P2POp(dist.irecv, recv, rank - 1, group))
+        ops.append(dist.P2POp(dist.irecv, recv.view(torch.uint8), rank - 1, group))
     if ops:
         for req in dist.batch_isend_irecv(ops):
             req.wait()
@@ -70,6 +81,10 @@ class PeerHalo:
         dist.all_gather_object(gathered, mine, group=group)
         self._mapped = ctypes.c_void_p()
         self.halo_ptr = 0
+        short = [r for r in range(world - 1) if gathered[r][1] < halo_elems]
+        if short:
+            raise ValueError(f"shard of rank {short[0]} holds {gathered[short[0]][1]} elements, fewer than the "
+                             f"{halo_elems}-element left context its right neighbour needs")
         if rank > 0:
             lh, lelems = gathered[rank - 1]
             buf = (ctypes.c_uint8 * 64).from_buffer_copy(lh)

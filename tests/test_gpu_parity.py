@@ -918,3 +918,36 @@ def test_far_lag_kernel_matches_numpy_model_bitwise(mavg, oracle_mod, L):
     m = far_lag_model(x, L, chunk_tiles=1)
     whole_rows = n // 32 * 32                  # the last partial row belongs to tail_kernel
     assert np.array_equal(y[:whole_rows], m[:whole_rows])
+
+
+@pytest.mark.parametrize("ch,k", [(1, 60_001), (2, 30_000), (1, 300_000)])
+def test_far_lag_kernel_with_context_in_another_allocation(mavg, oracle_mod, torch_cuda, ch, k):
+    """A far-lag shard whose left context is NOT contiguous with it (a peer's tail, a staged halo): the first
+    halo_frames frames go through a small plan-owned [context | frames] buffer, the rest finds its context inside the
+    shard -- two far-lag launches instead of the generic kernel's quadratic run starts."""
+    torch = torch_cuda
+    probe = mavg.Plan(1 << 22, k, channels=ch)
+    assert probe.info.mode == 5
+    halo = int(probe.info.halo_frames)
+    probe.close()
+    frames = 2 * halo + 8192 * 7 + 33                  # shard longer than the context, ragged end
+    cut = halo + 8192 * 3                              # global frame where the shard starts (tile aligned)
+    x = oracle_mod.fill_f32((cut + frames) * ch, 39000 + k % 100)
+    e = oracle_mod.mavg_f64(x, k, ch)[cut * ch:]
+    d_ctx = torch.from_numpy(x[(cut - halo) * ch:cut * ch].copy()).cuda()      # its own allocation
+    d_in = torch.from_numpy(x[cut * ch:].copy()).cuda()
+    d_out = torch.zeros(frames * ch, dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    with mavg.Plan(frames, k, channels=ch, first_frame=cut) as plan:
+        plan.run_device_halo(d_in.data_ptr(), d_out.data_ptr(), d_ctx.data_ptr())
+        plan.synchronize()
+        assert plan.info.path == 1 and plan.info.mode == 5 and plan.info.launches_per_run >= 2
+    assert _rel(d_out.cpu().numpy(), e) < TOL
+    # a shard shorter than the context: everything goes through the staging buffer
+    short = halo // 2 // 32 * 32
+    d_out2 = torch.zeros(short * ch, dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    with mavg.Plan(short, k, channels=ch, first_frame=cut) as plan:
+        plan.run_device_halo(d_in.data_ptr(), d_out2.data_ptr(), d_ctx.data_ptr())
+        plan.synchronize()
+    assert _rel(d_out2.cpu().numpy(), e[:short * ch]) < TOL

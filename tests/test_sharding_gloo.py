@@ -78,3 +78,36 @@ def test_shard_bounds_match_library_rule():
     b = shard_bounds(10 * 4096 + 5, 4, 4096)
     assert [lo for lo, _ in b] == [0, 12288, 24576, 32768] and b[-1][1] == 10 * 4096 + 5
     assert sum(hi - lo for lo, hi in b) == 10 * 4096 + 5
+
+
+def _short_worker(rank, world, port, q):
+    import sys
+    root = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+    sys.path.insert(0, root)
+    from digital_signal_processsing_b200 import sharding
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    shard = torch.zeros(100 if rank == 0 else 5000)          # rank 0 owns fewer elements than the halo
+    try:
+        sharding.exchange_halo(shard, 4096, rank, world)
+        q.put((rank, "no error"))
+    except ValueError as e:
+        q.put((rank, str(e)))
+    dist.destroy_process_group()
+
+
+def test_halo_longer_than_left_shard_is_an_error_on_every_rank():
+    """A left shard shorter than the halo used to yield a short send and a hang; now every rank
+    raises the same ValueError before any send/recv is posted."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_short_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all("too short to shard" in got[r] and "rank 0" in got[r] for r in range(world)), got
