@@ -479,6 +479,8 @@ struct DevCtx {
     void* d_scratch = nullptr;  // mavg_run_cascade intermediates
     void* d_far_stage = nullptr;   // far-lag kernel, context not contiguous with the shard: [context | first frames]
     size_t far_stage_bytes = 0;
+    void* d_prefix = nullptr;      // prefix-difference path: 8-byte prefixes of the shard and of its left context
+    size_t prefix_bytes = 0;
     cudaEvent_t ev_pass = nullptr;  // mavg_run_cascade: end of this device's latest pass
     size_t bsum_bytes = 0;
     int sm_count = 0;
@@ -500,6 +502,7 @@ struct mavg_plan {
     uint32_t launches_last_run = 0;
     bool peer_ok = false;
     bool timing_on = true;
+    bool prefix_diff = false;   // generic-path plans with a far window and <= 8 interleaved channels: single-pass prefix + difference
 };
 
 namespace {
@@ -616,8 +619,12 @@ int launch_generic_t(const mavg_plan* p, DevCtx& d, const T* in, T* out, const T
         const uint64_t bblocks = (bthreads + 255) / 256;
         if (bblocks <= 0x7fffffffull && signals <= 65535u) {
             dim3 bgrid((unsigned)bblocks, signals, 1);
-            mavg::block_sums_kernel<T, RG><<<bgrid, 256, 0, d.stream>>>(in, (Acc*)d.d_bsum, gp.frames, gp.sig_stride,
-                                                                      gp.channels, nblk, gp.rms);
+            if (gp.rms)
+                mavg::block_sums_kernel<T, RG, true><<<bgrid, 256, 0, d.stream>>>(in, (Acc*)d.d_bsum, gp.frames, gp.sig_stride,
+                                                                                gp.channels, nblk);
+            else
+                mavg::block_sums_kernel<T, RG, false><<<bgrid, 256, 0, d.stream>>>(in, (Acc*)d.d_bsum, gp.frames, gp.sig_stride,
+                                                                                 gp.channels, nblk);
             MAVG_CUDA(cudaGetLastError());
             ++*launches;
             gp.bsum = d.d_bsum;
@@ -634,7 +641,9 @@ int launch_generic_t(const mavg_plan* p, DevCtx& d, const T* in, T* out, const T
         dim3 grid((unsigned)blocks, ns, 1);
         const T* in_s = in + (uint64_t)s0 * gp.sig_stride;
         T* out_s = out + (uint64_t)s0 * gp.sig_stride;
-        if (std::is_same<T, float>::value && gp.k >= 9 && !gp.rms)
+        if (gp.rms)
+            mavg::generic_kernel<T, RG, false, true><<<grid, 256, 0, d.stream>>>(in_s, out_s, halo, gp);
+        else if (std::is_same<T, float>::value && gp.k >= 9)
             mavg::generic_kernel<T, RG, std::is_same<T, float>::value><<<grid, 256, 0, d.stream>>>(in_s, out_s, halo, gp);
         else
             mavg::generic_kernel<T, RG, false><<<grid, 256, 0, d.stream>>>(in_s, out_s, halo, gp);
@@ -666,7 +675,8 @@ int launch_tail_t(const mavg_plan* p, DevCtx& d, const T* in, T* out, const T* h
     gp.halo_frames = halo ? p->halo_frames : 0;
     gp.k = p->desc.window;
     gp.rms = p->desc.op == MAVG_OP_RMS ? 1u : 0u;
-    mavg::tail_kernel<T><<<signals, 256, 0, d.stream>>>(in, out, halo, gp);
+    if (gp.rms) mavg::tail_kernel<T, true><<<signals, 256, 0, d.stream>>>(in, out, halo, gp);
+    else mavg::tail_kernel<T, false><<<signals, 256, 0, d.stream>>>(in, out, halo, gp);
     MAVG_CUDA(cudaGetLastError());
     ++*launches;
     return MAVG_OK;
@@ -902,6 +912,46 @@ int launch_far(mavg_plan* p, DevCtx& d, const void* in, void* out, const void* h
     return MAVG_OK;
 }
 
+// Far windows no streaming kernel takes (int16 beyond the ring or beyond 32768 frames, 3..8 channels beyond their
+// history): single-pass prefix sum of the shard (mavg_prefix_sum's kernel) and of its left context, then one
+// difference pass -- the reference's scan binaries, exact, at a cost that does not depend on k (the generic
+// kernel's run starts grow with the window: 55 Gsamples/s for stereo int16 at k = 40 000).
+int launch_prefix_diff(mavg_plan* p, DevCtx& d, const void* in, void* out, const void* halo, uint64_t frames,
+                       uint32_t* launches)
+{
+    const uint32_t C = p->desc.channels;
+    const uint64_t hf = halo ? p->halo_frames : 0;
+    const size_t need = (size_t)(frames + hf) * C * 8;
+    if (d.prefix_bytes < need) {
+        if (d.d_prefix) MAVG_CUDA(cudaFree(d.d_prefix));
+        d.d_prefix = nullptr;
+        d.prefix_bytes = 0;
+        if (cudaMalloc(&d.d_prefix, need) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(MAVG_ERR_ALLOC, "cudaMalloc of %zu prefix bytes failed on device %d", need, d.device);
+        }
+        d.prefix_bytes = need;
+    }
+    char* P = (char*)d.d_prefix;
+    char* HP = P + (size_t)frames * C * 8;
+    MAVG_TRY(mavg_prefix_sum((int)p->desc.dtype, in, P, frames, C, d.stream));
+    ++*launches;
+    if (hf) {
+        MAVG_TRY(mavg_prefix_sum((int)p->desc.dtype, halo, HP, hf, C, d.stream));
+        ++*launches;
+    }
+    const unsigned blocks = (unsigned)std::min<uint64_t>((frames + 255) / 256, (uint64_t)d.sm_count * 16);
+    if (p->desc.dtype == MAVG_F32)
+        mavg::prefix_diff_kernel<float, double><<<blocks, 256, 0, d.stream>>>((const double*)P, hf ? (const double*)HP : nullptr,
+                                                                             (float*)out, frames, C, p->desc.window, hf);
+    else
+        mavg::prefix_diff_kernel<int16_t, long long><<<blocks, 256, 0, d.stream>>>(
+            (const long long*)P, hf ? (const long long*)HP : nullptr, (int16_t*)out, frames, C, p->desc.window, hf);
+    MAVG_CUDA(cudaGetLastError());
+    ++*launches;
+    return MAVG_OK;
+}
+
 // Enqueue the kernels for `frames` frames (a whole shard, or one slice of it whose left context
 // is `halo`) on the device stream.  Planar batches always run whole (frames = desc.frames).
 int launch_shard(mavg_plan* p, DevCtx& d, const void* in, void* out, const void* halo, uint64_t frames,
@@ -959,6 +1009,8 @@ int launch_shard(mavg_plan* p, DevCtx& d, const void* in, void* out, const void*
             return launch_cols(p, d, in, out, halo, frames, launches);
         return launch_generic(p, d, in, out, halo, frames, 0, frames, launches);
     }
+    if (p->path == MAVG_PATH_GENERIC && p->prefix_diff && frames >= 64)
+        return launch_prefix_diff(p, d, in, out, halo, frames, launches);
     if (!stream_eligible(p, d, in, out, halo, frames))
         return launch_generic(p, d, in, out, halo, frames, 0, frames, launches);
     const StreamGeom& g = p->geom;
@@ -1257,6 +1309,8 @@ int mavg_plan_create(const mavg_desc* desc, mavg_plan** out)
     }
     p->path = (desc->path != MAVG_PATH_GENERIC && stream_shape && p->geom.ok) ? MAVG_PATH_STREAM : MAVG_PATH_GENERIC;
 
+    p->prefix_diff = p->path == MAVG_PATH_GENERIC && desc->path != MAVG_PATH_GENERIC && desc->op == MAVG_OP_MEAN &&
+                     !planar && desc->channels <= 8 && (uint64_t)desc->window * desc->channels >= 8192;
     // ---- left context a frame shard needs
     if (p->path == MAVG_PATH_STREAM) {
         p->halo_frames = (uint64_t)p->geom.H * tile_frames(p);  // whole history tiles: sharding keeps bit-identical sums
@@ -1340,6 +1394,7 @@ int mavg_plan_destroy(mavg_plan* p)
         if (d.d_bsum) cudaFree(d.d_bsum);
         if (d.d_scratch) cudaFree(d.d_scratch);
         if (d.d_far_stage) cudaFree(d.d_far_stage);
+        if (d.d_prefix) cudaFree(d.d_prefix);
         if (d.ev_pass) cudaEventDestroy(d.ev_pass);
         if (d.s_h2d) { cudaStreamSynchronize(d.s_h2d); cudaStreamDestroy(d.s_h2d); }
         if (d.s_d2h) { cudaStreamSynchronize(d.s_d2h); cudaStreamDestroy(d.s_d2h); }
@@ -1358,7 +1413,7 @@ int mavg_plan_info(const mavg_plan* p, mavg_info* info)
     if (!p || !info) return fail(MAVG_ERR_INVALID_ARG, "null argument");
     memset(info, 0, sizeof *info);
     info->path = p->path;
-    info->mode = p->geom.mode;
+    info->mode = p->prefix_diff ? 7u : (uint32_t)p->geom.mode;
     info->threads = p->geom.NT;
     info->run = p->geom.R;
     info->tile_samples = p->geom.NT * p->geom.R;

@@ -117,19 +117,19 @@ template <> struct GenericAcc<int16_t> {
     }
 };
 // a sample as it enters a window sum: itself, or its square for the moving RMS
-template <typename Acc, typename T>
-__device__ __forceinline__ Acc gen_term(T v, uint32_t rms)
+template <typename Acc, bool RMS, typename T>
+__device__ __forceinline__ Acc gen_term(T v)
 {
     const Acc a = (Acc)v;
-    return rms ? a * a : a;
+    if constexpr (RMS) return a * a;
+    else return a;
 }
 
 // Sums of RG-frame blocks per channel, so that long windows start from k/RG block sums instead of k
 // samples.  Same thread mapping as generic_kernel: consecutive threads = consecutive channels.
-template <typename T, int RG>
+template <typename T, int RG, bool RMS = false>
 __global__ void __launch_bounds__(256) block_sums_kernel(const T* __restrict__ x, typename GenericAcc<T>::type* __restrict__ bs,
-                                                         uint64_t frames, uint64_t sig_stride, uint32_t C, uint64_t nblk,
-                                                         uint32_t rms)
+                                                         uint64_t frames, uint64_t sig_stride, uint32_t C, uint64_t nblk)
 {
     typedef typename GenericAcc<T>::type Acc;
     const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -140,14 +140,14 @@ __global__ void __launch_bounds__(256) block_sums_kernel(const T* __restrict__ x
     const uint64_t f0 = b * RG;
     const uint64_t f1 = (f0 + RG < frames) ? f0 + RG : frames;
     Acc a = 0;
-    for (uint64_t f = f0; f < f1; ++f) a += gen_term<Acc>(x[f * C + c], rms);
+    for (uint64_t f = f0; f < f1; ++f) a += gen_term<Acc, RMS>(x[f * C + c]);
     bs[((uint64_t)blockIdx.y * nblk + b) * C + c] = a;
 }
 
 // F32SLIDE (float only, k >= 9): the k-term start sum is still formed in fp64, but the RG sliding
 // updates run in fp32 (error <= RG * 2^-24 relative to the window sum), which removes three
 // fp32<->fp64 conversions per sample.  Tiny windows keep the fp64 update: their sums can be ~0.
-template <typename T, int RG, bool F32SLIDE>
+template <typename T, int RG, bool F32SLIDE, bool RMS = false>
 __global__ void __launch_bounds__(256) generic_kernel(const T* __restrict__ x, T* __restrict__ y,
                                                       const T* __restrict__ halo, const GenericParams p)
 {
@@ -163,7 +163,6 @@ __global__ void __launch_bounds__(256) generic_kernel(const T* __restrict__ x, T
     y += (uint64_t)blockIdx.y * p.sig_stride;
     const uint64_t k = p.k;
     const double inv = 1.0 / (double)p.k;
-    const uint32_t rms = p.rms;
 
     // window sum over frames [f0-k, f0): negative frames come from the halo, else zero
     Acc w = 0;
@@ -172,7 +171,7 @@ __global__ void __launch_bounds__(256) generic_kernel(const T* __restrict__ x, T
         const Acc* bs = (const Acc*)p.bsum + (uint64_t)blockIdx.y * p.nblk * C;
         const uint64_t lo = f0 - k;
         const uint64_t jb = (lo + RG - 1) / RG;
-        for (uint64_t f = lo; f < jb * RG; ++f) w += gen_term<Acc>(x[f * C + c], rms);
+        for (uint64_t f = lo; f < jb * RG; ++f) w += gen_term<Acc, RMS>(x[f * C + c]);
         for (uint64_t j = jb; j < f0 / RG; ++j) w += bs[j * C + c];
     } else {
         const long long lo = (long long)f0 - (long long)k;
@@ -182,11 +181,11 @@ __global__ void __launch_bounds__(256) generic_kernel(const T* __restrict__ x, T
                 long long hlo = -(long long)p.halo_frames;
                 if (j < hlo) j = hlo;
                 const long long hend = (long long)f0 < 0 ? (long long)f0 : 0;
-                for (; j < hend; ++j) w += gen_term<Acc>(halo[(uint64_t)(j + (long long)p.halo_frames) * C + c], rms);
+                for (; j < hend; ++j) w += gen_term<Acc, RMS>(halo[(uint64_t)(j + (long long)p.halo_frames) * C + c]);
             }
             j = 0;
         }
-        for (; j < (long long)f0; ++j) w += gen_term<Acc>(x[(uint64_t)j * C + c], rms);
+        for (; j < (long long)f0; ++j) w += gen_term<Acc, RMS>(x[(uint64_t)j * C + c]);
     }
     if constexpr (F32SLIDE) {
         float wf = (float)w;
@@ -218,13 +217,13 @@ __global__ void __launch_bounds__(256) generic_kernel(const T* __restrict__ x, T
     for (uint64_t f = f0; f < f1; ++f) {
         Acc old = 0;
         if (f >= k) {
-            old = gen_term<Acc>(x[(f - k) * C + c], rms);
+            old = gen_term<Acc, RMS>(x[(f - k) * C + c]);
         } else if (halo != nullptr) {
             const uint64_t back = k - f;  // frames before frame 0
-            if (back <= p.halo_frames) old = gen_term<Acc>(halo[(p.halo_frames - back) * C + c], rms);
+            if (back <= p.halo_frames) old = gen_term<Acc, RMS>(halo[(p.halo_frames - back) * C + c]);
         }
-        w += gen_term<Acc>(x[f * C + c], rms) - old;
-        y[f * C + c] = rms ? GenericAcc<T>::finish_rms(w, p.k, inv) : GenericAcc<T>::finish(w, p.k, inv);
+        w += gen_term<Acc, RMS>(x[f * C + c]) - old;
+        y[f * C + c] = RMS ? GenericAcc<T>::finish_rms(w, p.k, inv) : GenericAcc<T>::finish(w, p.k, inv);
     }
     }
 }
@@ -234,7 +233,7 @@ __global__ void __launch_bounds__(256) generic_kernel(const T* __restrict__ x, T
 // result does not depend on how the signal was sliced), then one thread slides over the handful of outputs.
 // (generic_kernel would give the whole k-term start sum to a single thread: 0.14 ms at k = 4096, milliseconds for
 // the far-lag kernel's windows.)
-template <typename T>
+template <typename T, bool RMS = false>
 __global__ void __launch_bounds__(256) tail_kernel(const T* __restrict__ x, T* __restrict__ y, const T* __restrict__ halo,
                                                    const GenericParams p)
 {
@@ -246,12 +245,11 @@ __global__ void __launch_bounds__(256) tail_kernel(const T* __restrict__ x, T* _
     const long long k = (long long)p.k;
     const long long hf = (long long)p.halo_frames;
     const double inv = 1.0 / (double)p.k;
-    const uint32_t rms = p.rms;
     for (uint32_t c = 0; c < C; ++c) {
         Acc a = 0;
         for (long long f = (long long)p.out_begin - k + threadIdx.x; f < (long long)p.out_begin; f += 256) {
-            if (f >= 0) a += gen_term<Acc>(x[(uint64_t)f * C + c], rms);
-            else if (halo != nullptr && f >= -hf) a += gen_term<Acc>(halo[(uint64_t)(f + hf) * C + c], rms);
+            if (f >= 0) a += gen_term<Acc, RMS>(x[(uint64_t)f * C + c]);
+            else if (halo != nullptr && f >= -hf) a += gen_term<Acc, RMS>(halo[(uint64_t)(f + hf) * C + c]);
         }
 #pragma unroll
         for (int d = 16; d >= 1; d >>= 1) a += __shfl_down_sync(0xffffffffu, a, d);
@@ -262,10 +260,10 @@ __global__ void __launch_bounds__(256) tail_kernel(const T* __restrict__ x, T* _
             for (uint64_t f = p.out_begin; f < p.out_end; ++f) {
                 Acc old = 0;
                 const long long fo = (long long)f - k;
-                if (fo >= 0) old = gen_term<Acc>(x[(uint64_t)fo * C + c], rms);
-                else if (halo != nullptr && fo >= -hf) old = gen_term<Acc>(halo[(uint64_t)(fo + hf) * C + c], rms);
-                w += gen_term<Acc>(x[f * C + c], rms) - old;
-                y[f * C + c] = rms ? GenericAcc<T>::finish_rms(w, p.k, inv) : GenericAcc<T>::finish(w, p.k, inv);
+                if (fo >= 0) old = gen_term<Acc, RMS>(x[(uint64_t)fo * C + c]);
+                else if (halo != nullptr && fo >= -hf) old = gen_term<Acc, RMS>(halo[(uint64_t)(fo + hf) * C + c]);
+                w += gen_term<Acc, RMS>(x[f * C + c]) - old;
+                y[f * C + c] = RMS ? GenericAcc<T>::finish_rms(w, p.k, inv) : GenericAcc<T>::finish(w, p.k, inv);
             }
         }
         __syncthreads();

@@ -359,4 +359,36 @@ constexpr uint32_t scan_smem_bytes()
     return (E + E / 32) * sizeof(TLoc) + kScanThreads * C * sizeof(TLoc) + 2 * (kScanThreads / 32) * C * sizeof(TLoc) + 64;
 }
 
+// ----------------------------------------------------------------------------------
+// Windows beyond every shared-memory ring, up to 8 interleaved channels: what the reference's scan binaries do
+// (averager_kernel over the prefix, basics/hillis_steele_averager.cu:87-100) on top of the single-pass prefix above,
+//     y[f, c] = (P[f, c] - P[f - k, c]) / k,
+// in exact int64 (int16 input, C truncating division) or fp64 (float32 input; a prefix over 2^28 samples keeps 25
+// bits of headroom over the window sum).  The cost no longer depends on k.  Frames in front of the shard come from
+// the prefix HP of its left context (hf frames), or are zeros.  One thread per frame, C <= 8 values each.
+// ----------------------------------------------------------------------------------
+template <typename T, typename TAcc>
+__global__ void __launch_bounds__(256)
+    prefix_diff_kernel(const TAcc* __restrict__ P, const TAcc* __restrict__ HP, T* __restrict__ y, uint64_t frames,
+                       uint32_t C, uint64_t k, uint64_t hf)
+{
+    const double inv = 1.0 / (double)k;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t f = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; f < frames; f += stride) {
+        for (uint32_t c = 0; c < C; ++c) {
+            const uint64_t i = f * C + c;
+            TAcc w = P[i];
+            if (f >= k) {
+                w -= P[i - k * C];
+            } else if (HP != nullptr && hf > 0) {
+                const uint64_t want = k - 1 - f;                 // frames of the window that lie in front of the shard
+                TAcc h = HP[(hf - 1) * C + c];                   // the whole context ...
+                if (want < hf) h -= HP[(hf - want - 1) * C + c]; // ... or its last `want` frames
+                if (want > 0) w += h;
+            }
+            y[i] = GenericAcc<T>::finish(w, (uint32_t)k, inv);
+        }
+    }
+}
+
 }  // namespace mavg

@@ -154,7 +154,9 @@ typedef struct mavg_info {
                                   prefix scan, 2 additions-only (k <= 8), 3 column kernel,
                                   4 few-channel kernel (3..31 interleaved channels), 5 far-lag
                                   kernel (mono / planar float32, windows beyond the ring), 6 int16
-                                  mono / stereo / planar: exclusive scan of run deltas (any k)   */
+                                  mono / stereo / planar: exclusive scan of run deltas (any k),
+                                  7 (generic path) single-pass prefix sum + difference: far windows,
+                                  up to 8 interleaved channels                                  */
     uint32_t threads, run;     /* stream kernel shape                                     */
     uint32_t tile_samples;     /* samples per shared-memory tile                          */
     uint32_t history_tiles;    /* tiles of left context each tile range replays           */

@@ -903,17 +903,15 @@ def test_far_lag_kernel_stereo(mavg, oracle_mod, k):
     assert _rel(y, oracle_mod.mavg_f64(x, k, 2)) < TOL
 
 
-@pytest.mark.parametrize("L", [20_011, 9_000])
+@pytest.mark.parametrize("L", [60_013, 100_003])
 def test_far_lag_kernel_matches_numpy_model_bitwise(mavg, oracle_mod, L):
     """The far-lag kernel performs exactly the operations of tests/algo_model.far_lag_model (one tile per chunk here:
     fewer tiles than SMs), so the two agree bit for bit on every sample the streaming kernel produces."""
     from algo_model import far_lag_model
-    n = 11 * 8192 + 123
+    n = 23 * 8192 + 123
     x = oracle_mod.fill_f32(n, 777)
     with mavg.Plan(n, L, path="stream") as plan:
-        assert plan.info.mode in (1, 5)
-        if plan.info.mode != 5:
-            pytest.skip("this window still fits the ring of the ordinary kernel")
+        assert plan.info.mode == 5, "windows of 60 000 samples and more are beyond the ring of the ordinary kernel"
         y = plan.run_host(x)
     m = far_lag_model(x, L, chunk_tiles=1)
     whole_rows = n // 32 * 32                  # the last partial row belongs to tail_kernel
@@ -951,3 +949,44 @@ def test_far_lag_kernel_with_context_in_another_allocation(mavg, oracle_mod, tor
         plan.run_device_halo(d_in.data_ptr(), d_out2.data_ptr(), d_ctx.data_ptr())
         plan.synchronize()
     assert _rel(d_out2.cpu().numpy(), e[:short * ch]) < TOL
+
+
+@pytest.mark.parametrize("dtype,ch,k", [("i16", 2, 40_000), ("i16", 1, 70_000), ("i16", 6, 9_000), ("f32", 3, 20_000),
+                                        ("i16", 2, 3_000_000)])
+def test_prefix_difference_path_far_windows(mavg, oracle_mod, torch_cuda, dtype, ch, k):
+    """Far windows that no streaming kernel takes run as single-pass prefix sum + difference (info.mode 7): whole
+    signal, sliced host run, and a shard whose left context lives in another allocation -- int16 bit-exact."""
+    torch = torch_cuda
+    frames = 1_200_000 // ch + 13
+    n = frames * ch
+    x = oracle_mod.fill_i16(n, 41000 + k % 97) if dtype == "i16" else oracle_mod.fill_f32(n, 41000 + k % 97, oracle_mod.DIST_USYM)
+    e = oracle_mod.mavg_i16(x, k, ch) if dtype == "i16" else oracle_mod.mavg_f64(x, k, ch)
+
+    def check(y, exp):
+        if dtype == "i16":
+            assert np.array_equal(y, exp)
+        else:
+            scale = oracle_mod.mavg_f64(np.abs(x), k, ch)[-exp.size:]
+            assert np.max(np.abs(y - exp) / np.maximum(scale, 1e-30)) < TOL
+
+    with mavg.Plan(frames, k, channels=ch, dtype=dtype) as plan:
+        assert plan.info.path == 2 and plan.info.mode == 7
+        check(plan.run_host(x), e)
+    with mavg.Plan(frames, k, channels=ch, dtype=dtype, slice_bytes=1 << 20) as plan:      # several slices, each with a context
+        check(plan.run_host(x), e)
+    # shard with a separate context buffer
+    with mavg.Plan(frames, k, channels=ch, dtype=dtype) as probe:
+        halo = int(probe.info.halo_frames)
+    cut = min(frames // 2, max(halo, 1000) + 7) if halo < frames // 2 else frames // 3
+    tdt = torch.int16 if dtype == "i16" else torch.float32
+    lo = max(0, cut - halo)
+    ctx = np.zeros(halo * ch, dtype=x.dtype)                      # context shorter than the halo: zeros in front (signal start)
+    ctx[(halo - (cut - lo)) * ch:] = x[lo * ch:cut * ch]
+    d_ctx = torch.from_numpy(ctx).cuda()
+    d_in = torch.from_numpy(x[cut * ch:].copy()).cuda()
+    d_out = torch.zeros((frames - cut) * ch, dtype=tdt, device="cuda")
+    torch.cuda.synchronize()
+    with mavg.Plan(frames - cut, k, channels=ch, dtype=dtype, first_frame=cut) as plan:
+        plan.run_device_halo(d_in.data_ptr(), d_out.data_ptr(), d_ctx.data_ptr())
+        plan.synchronize()
+    check(d_out.cpu().numpy(), e[cut * ch:])
