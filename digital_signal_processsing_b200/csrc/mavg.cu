@@ -1166,9 +1166,30 @@ int launch_scan_cb(const void* d_in, void* d_out, uint64_t n, cudaStream_t st)
     MAVG_CUDA(cudaMallocFromPoolAsync((void**)&scratch, total, pool, st));
     cudaError_t e = cudaMemsetAsync(scratch, 0, total, st);
     if (e == cudaSuccess) {
-        kern<<<(unsigned)tiles, mavg::kScanThreads, smem, st>>>((const TIn*)d_in, (TAcc*)d_out, n, (uint32_t*)scratch,
-                                                               (ulonglong2*)(scratch + 256));
-        e = cudaGetLastError();
+        uint32_t first_tile = 0;
+        // int16 with 1, 2, 4 or 8 channels: the whole chunks go to the vectorised kernel, the ragged last chunk of the
+        // same chain to the general one (stream-ordered behind it)
+        if constexpr (std::is_same<TIn, int16_t>::value && (CB == 32768 || CB == 16384) && (C == 1 || C == 2 || C == 4 || C == 8)) {
+            constexpr int RL = CB / 4 / mavg::kScanThreads;   // run length: 32 or 16
+            const uint64_t whole = n / chunk;
+            const bool aligned = (((uintptr_t)d_in | (uintptr_t)d_out) & 15u) == 0;
+            if (whole > 0 && aligned && !getenv("MAVG_SCAN_GENERAL")) {
+                auto fast = mavg::scan_lookback_i16_kernel<C, RL>;
+                const uint32_t fsmem = mavg::scan_i16_smem_bytes<C, RL>();
+                e = cudaFuncSetAttribute(fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
+                if (e == cudaSuccess) {
+                    fast<<<(unsigned)whole, mavg::kScanThreads, fsmem, st>>>((const int16_t*)d_in, (long long*)d_out,
+                                                                            (ulonglong2*)(scratch + 256));
+                    e = cudaGetLastError();
+                    first_tile = (uint32_t)whole;
+                }
+            }
+        }
+        if (e == cudaSuccess && first_tile < tiles) {
+            kern<<<(unsigned)(tiles - first_tile), mavg::kScanThreads, smem, st>>>((const TIn*)d_in, (TAcc*)d_out, n, first_tile,
+                                                                                  (ulonglong2*)(scratch + 256));
+            e = cudaGetLastError();
+        }
     }
     cudaFreeAsync(scratch, st);     // on every path: stream-ordered, after the kernel
     if (e != cudaSuccess) return fail(MAVG_ERR_CUDA, "prefix-sum launch failed: %s", cudaGetErrorString(e));

@@ -109,6 +109,63 @@ __host__ __device__ constexpr int scan_block_len()
     return best;
 }
 
+// Decoupled look-back of chunk `tile`, executed by ONE warp: each lane inspects one predecessor per round; rounds of
+// 32 chunks move backwards until every channel has met a full prefix.  All C descriptors of a predecessor are
+// requested together and the next round's are requested before this round's are examined, so a round costs one
+// memory latency however many channels.  Writes the chunk's exclusive prefix to s_excl[C] (shared) and publishes
+// {PREFIX, exclusive + s_tot[c]}.
+template <typename TAcc, int C>
+__device__ __forceinline__ void scan_look_back(ulonglong2* __restrict__ desc, uint32_t tile, int lane, TAcc* s_excl,
+                                               const TAcc* s_tot)
+{
+    ulonglong2* my_desc = desc + (uint64_t)tile * C;
+    if (tile == 0) {
+        if (lane < C) s_excl[lane] = 0;
+        return;
+    }
+    long long look = (long long)tile - 1 - lane;
+    const ulonglong2 stop = make_ulonglong2(kScanPrefix, 0ull);   // lanes before chunk 0: a terminating zero prefix
+    ulonglong2 cur[C], nxt[C];
+    TAcc acc[C];
+    bool open_[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        cur[c] = look >= 0 ? ld_desc(desc + (uint64_t)look * C + c) : stop;
+        acc[c] = 0;
+        open_[c] = true;
+    }
+    for (;;) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) nxt[c] = look - 32 >= 0 ? ld_desc(desc + (uint64_t)(look - 32) * C + c) : stop;
+        bool any_open = false;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            if (!open_[c]) continue;                                       // warp-uniform
+            while (cur[c].x == kScanInvalid) cur[c] = ld_desc(desc + (uint64_t)look * C + c);
+            const unsigned has_prefix = __ballot_sync(0xffffffffu, cur[c].x == kScanPrefix);
+            const int first = has_prefix ? __ffs(has_prefix) - 1 : 32;   // nearest predecessor with a full prefix
+            TAcc val = (lane <= first) ? acc_from_bits<TAcc>((long long)cur[c].y) : (TAcc)0;
+            // fixed-shape butterfly: the same association for a given `first`
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) val += shfl_xor_acc<TAcc>(val, d);
+            acc[c] += val;
+            open_[c] = has_prefix == 0;
+            any_open = any_open || open_[c];
+        }
+        if (!any_open) break;
+        look -= 32;
+#pragma unroll
+        for (int c = 0; c < C; ++c) cur[c] = nxt[c];
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        if (lane == 0) {
+            s_excl[c] = acc[c];
+            st_desc(my_desc + c, kScanPrefix, (unsigned long long)acc_bits<TAcc>(acc[c] + s_tot[c]));
+        }
+    }
+}
+
 // One CTA = one chunk of E = 256 * R elements (16384 for int16 input, 8192 for float32, a little less for odd C).
 //   1. coalesced 16-byte loads, converted to the chunk-local type TLoc (int32 is enough for an int16 chunk:
 //      16384 * 32768 < 2^31; double for float32) into a padded shared-memory array.  Where the channel of a loaded
@@ -124,7 +181,7 @@ __host__ __device__ constexpr int scan_block_len()
 // ever waits on chunks that are already running.  Scratch: ticket, desc[chunks][C].
 template <typename TIn, typename TLoc, typename TAcc, int C, int CB>
 __global__ void __launch_bounds__(kScanThreads)
-    scan_lookback_kernel(const TIn* __restrict__ in, TAcc* __restrict__ out, uint64_t n, uint32_t* __restrict__ ticket,
+    scan_lookback_kernel(const TIn* __restrict__ in, TAcc* __restrict__ out, uint64_t n, uint32_t tile_base,
                          ulonglong2* __restrict__ desc)
 {
     constexpr int NT = kScanThreads, NW = NT / 32;
@@ -146,8 +203,8 @@ __global__ void __launch_bounds__(kScanThreads)
     // Chunk id = block index: the hardware hands out the blocks of a 1-D grid in increasing order, so a chunk only ever
     // waits on chunks that are already resident or done (what CUB's DeviceScan relies on as well).  Round 1 drew the id
     // from an atomic ticket: one more global round trip and a barrier in front of every chunk's loads.
-    (void)ticket;
-    const uint32_t tile = blockIdx.x;
+    // tile_base: the int16 fast kernel below takes the whole chunks, this one the ragged last chunk of the same chain.
+    const uint32_t tile = blockIdx.x + tile_base;
     const uint64_t cbase = (uint64_t)tile * E;
     // Where element e of the chunk lives in `loc`.  4-byte prefixes: an XOR swizzle of the bank bits with bits 5..10 of e
     // makes all three access patterns conflict-free -- the striped load phase (lanes 8 elements apart), the run
@@ -269,56 +326,7 @@ __global__ void __launch_bounds__(kScanThreads)
     }
 
     // ---- 3. look back for the exclusive prefix (warp 0), publish the inclusive prefix
-    if (warp == 0) {
-        if (tile == 0) {
-            if (lane < C) s_excl[lane] = 0;
-        } else {
-            // Each lane inspects one predecessor per round; rounds of 32 chunks move backwards until every channel has
-            // met a full prefix.  All C descriptors of a predecessor are requested together and the next round's are
-            // requested before this round's are examined, so a round costs one memory latency however many channels.
-            long long look = (long long)tile - 1 - lane;
-            const ulonglong2 stop = make_ulonglong2(kScanPrefix, 0ull);   // lanes before chunk 0: a terminating zero prefix
-            ulonglong2 cur[C], nxt[C];
-            TAcc acc[C];
-            bool open_[C];
-#pragma unroll
-            for (int c = 0; c < C; ++c) {
-                cur[c] = look >= 0 ? ld_desc(desc + (uint64_t)look * C + c) : stop;
-                acc[c] = 0;
-                open_[c] = true;
-            }
-            for (;;) {
-#pragma unroll
-                for (int c = 0; c < C; ++c) nxt[c] = look - 32 >= 0 ? ld_desc(desc + (uint64_t)(look - 32) * C + c) : stop;
-                bool any_open = false;
-#pragma unroll
-                for (int c = 0; c < C; ++c) {
-                    if (!open_[c]) continue;                                       // warp-uniform
-                    while (cur[c].x == kScanInvalid) cur[c] = ld_desc(desc + (uint64_t)look * C + c);
-                    const unsigned has_prefix = __ballot_sync(0xffffffffu, cur[c].x == kScanPrefix);
-                    const int first = has_prefix ? __ffs(has_prefix) - 1 : 32;   // nearest predecessor with a full prefix
-                    TAcc val = (lane <= first) ? acc_from_bits<TAcc>((long long)cur[c].y) : (TAcc)0;
-                    // fixed-shape butterfly: the same association for a given `first`
-#pragma unroll
-                    for (int d = 16; d >= 1; d >>= 1) val += shfl_xor_acc<TAcc>(val, d);
-                    acc[c] += val;
-                    open_[c] = has_prefix == 0;
-                    any_open = any_open || open_[c];
-                }
-                if (!any_open) break;
-                look -= 32;
-#pragma unroll
-                for (int c = 0; c < C; ++c) cur[c] = nxt[c];
-            }
-#pragma unroll
-            for (int c = 0; c < C; ++c) {
-                if (lane == 0) {
-                    s_excl[c] = acc[c];
-                    st_desc(my_desc + c, kScanPrefix, (unsigned long long)acc_bits<TAcc>(acc[c] + s_tot[c]));
-                }
-            }
-        }
-    }
+    if (warp == 0) scan_look_back<TAcc, C>(desc, tile, lane, s_excl, s_tot);
     __syncthreads();
 
     // ---- 4. striped, coalesced output: two results per 16-byte store
@@ -349,6 +357,182 @@ __global__ void __launch_bounds__(kScanThreads)
             if (g + 1 < n) out[g + 1] = b;
         }
     }
+}
+
+// ----------------------------------------------------------------------------------
+// int16 -> int64 fast kernel (C = 1, 2, 4, 8; whole chunks only).  Same chain, same descriptors, same chunk size as
+// scan_lookback_kernel<short, int, long long, C, 32768> (8192 elements, runs of 32), so the ragged last chunk of a
+// signal is handled by that kernel with tile_base = number of whole chunks.  The ncu source view of the general kernel
+// showed 45 executed instructions per element, most of them address arithmetic around 4-byte shared-memory accesses
+// (11 in the load phase, 10.5 in the run scan, 20 in the output phase).  Here every shared access is a vector:
+//   * chunk-local prefixes live at  pad(e) = e + 4 * (e / 32)  ints -- 16 bytes of padding per 128, which keeps every
+//     8-element load vector, every 32-element run and every output pair contiguous and 16-byte aligned, and makes the
+//     three patterns conflict-free per quarter warp (load phase: lanes 32 B apart, run scan: lanes 144 B apart);
+//   * load phase: one 16-byte global load -> two STS.128; the aggregate is a dp2a on the packed words;
+//   * run scan: 8 LDS.128 + 32 adds + 8 STS.128 per thread;
+//   * output: one LDS.64 (two prefixes), one LDS (run offset), one 16-byte global store per pair.
+// All loops are fully unrolled with compile-time strides, so addresses are one register plus an immediate.
+// ----------------------------------------------------------------------------------
+__device__ __forceinline__ int scan_dp2a(uint32_t a, uint32_t b, int c)
+{
+    int d;
+    asm("dp2a.lo.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+template <int C, int R>
+__global__ void __launch_bounds__(kScanThreads)
+    scan_lookback_i16_kernel(const int16_t* __restrict__ in, long long* __restrict__ out, ulonglong2* __restrict__ desc)
+{
+    constexpr int NT = kScanThreads, NW = NT / 32, E = NT * R;   // 8192 (R = 32) or 4096 (R = 16) elements per chunk
+    constexpr int LV = R / 8;                          // load vectors per thread
+    static_assert(R == 32 || R == 16, "run length");
+    static_assert(C == 1 || C == 2 || C == 4 || C == 8, "channel of a word half known at compile time");
+    constexpr int LOC = E + E / 8;                     // padded ints
+    extern __shared__ __align__(16) uint8_t scan_smem[];
+    int* loc = reinterpret_cast<int*>(scan_smem);      // [LOC]
+    int* toff = loc + LOC;                             // [NT][C] exclusive offset of each run inside the chunk
+    int* s_warp = toff + NT * C;                       // [NW][C]
+    int* s_part = s_warp + NW * C;                     // [NW][C]
+    __shared__ __align__(16) long long s_excl[C < 2 ? 2 : C];
+    __shared__ long long s_tot[C];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t tile = blockIdx.x;
+    const int16_t* cin = in + (uint64_t)tile * E;
+    long long* cout = out + (uint64_t)tile * E;
+
+    // ---- 1. load: thread handles vectors q = tid + 256 * it (8 elements each), it < 4
+    int csum[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) csum[c] = 0;
+    {
+        uint4 raw[LV];
+#pragma unroll
+        for (int it = 0; it < LV; ++it) raw[it] = __ldg(reinterpret_cast<const uint4*>(cin) + tid + NT * it);
+        int* dst = loc + 8 * tid + 4 * (tid >> 2);     // pad(8 q), q = tid; + it * (2048 + 256)
+#pragma unroll
+        for (int it = 0; it < LV; ++it) {
+            const uint32_t w[4] = {raw[it].x, raw[it].y, raw[it].z, raw[it].w};
+            int v[8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                v[2 * j] = (int)(short)(w[j] & 0xffffu);
+                v[2 * j + 1] = (int)w[j] >> 16;
+                if constexpr (C == 1) {
+                    csum[0] = scan_dp2a(w[j], 0x0101u, csum[0]);
+                } else {
+                    csum[(2 * j) % C] = scan_dp2a(w[j], 0x0001u, csum[(2 * j) % C]);
+                    csum[(2 * j + 1) % C] = scan_dp2a(w[j], 0x0100u, csum[(2 * j + 1) % C]);
+                }
+            }
+            int4* d4 = reinterpret_cast<int4*>(dst + it * (8 * NT + NT));
+            d4[0] = make_int4(v[0], v[1], v[2], v[3]);
+            d4[1] = make_int4(v[4], v[5], v[6], v[7]);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) csum[c] += __shfl_xor_sync(0xffffffffu, csum[c], d);
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) s_part[warp * C + c] = csum[c];
+    }
+    __syncthreads();
+    ulonglong2* my_desc = desc + (uint64_t)tile * C;
+    if (tid < C) {   // fixed order over the warps
+        int t = 0;
+#pragma unroll
+        for (int w2 = 0; w2 < NW; ++w2) t += s_part[w2 * C + tid];
+        s_tot[tid] = (long long)t;
+        st_desc(my_desc + tid, tile == 0 ? kScanPrefix : kScanAggregate, (unsigned long long)(long long)t);
+    }
+
+    // ---- 2. in-place scan of the own run: R contiguous ints at pad(R tid)
+    int carry[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) carry[c] = 0;
+    {
+        int4* run = reinterpret_cast<int4*>(loc + R * tid + 4 * ((R * tid) >> 5));
+#pragma unroll
+        for (int b = 0; b < R / 4; ++b) {
+            int4 t = run[b];
+            int v[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                carry[(4 * b + i) % C] += v[i];
+                v[i] = carry[(4 * b + i) % C];
+            }
+            run[b] = make_int4(v[0], v[1], v[2], v[3]);
+        }
+    }
+    int inc[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) inc[c] = carry[c];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const int up = __shfl_up_sync(0xffffffffu, inc[c], d);
+            if (lane >= d) inc[c] += up;
+        }
+    }
+    if (lane == 31) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) s_warp[warp * C + c] = inc[c];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        int a = 0;
+#pragma unroll
+        for (int w2 = 0; w2 < NW; ++w2)
+            if (w2 < warp) a += s_warp[w2 * C + c];
+        toff[tid * C + c] = a + (inc[c] - carry[c]);
+    }
+
+    // ---- 3. look-back (warp 0)
+    if (warp == 0) scan_look_back<long long, C>(desc, tile, lane, s_excl, s_tot);
+    __syncthreads();
+
+    // ---- 4. output: pair q = tid + 256 * it, it < R / 2: elements e = 2 q, e + 1 of run e / R
+    {
+        const int2* lp = reinterpret_cast<const int2*>(loc + 2 * tid + 4 * (tid >> 4));    // pad(2 q); + it * (512 + 64) ints
+        longlong2* op = reinterpret_cast<longlong2*>(cout) + tid;                          // + it * 256
+        constexpr int CP = C < 2 ? 1 : 2;                                                  // channels of a pair
+        const int c0 = (2 * tid) % C;                                                      // 2 q mod C does not depend on it (512 % C == 0)
+        const int* tp = toff + ((2 * tid) / R) * C + c0;                                   // + it * (512 / R) * C
+        long long b0, b1;
+        if constexpr (C == 1) {
+            b0 = b1 = s_excl[0];
+        } else {
+            const longlong2 bb = *reinterpret_cast<const longlong2*>(s_excl + c0);
+            b0 = bb.x, b1 = bb.y;
+        }
+#pragma unroll
+        for (int it = 0; it < R / 2; ++it) {
+            const int2 l = lp[it * 288];
+            int t0, t1;
+            if constexpr (CP == 1) {
+                t0 = t1 = tp[it * (512 / R) * C];
+            } else {
+                const int2 tt = *reinterpret_cast<const int2*>(tp + it * (512 / R) * C);
+                t0 = tt.x, t1 = tt.y;
+            }
+            longlong2 r;
+            r.x = b0 + (long long)(t0 + l.x);
+            r.y = b1 + (long long)(t1 + l.y);
+            op[it * NT] = r;
+        }
+    }
+}
+
+template <int C, int R>
+constexpr uint32_t scan_i16_smem_bytes()
+{
+    return (uint32_t)((kScanThreads * R + kScanThreads * R / 8) * 4 + kScanThreads * C * 4 + 2 * (kScanThreads / 32) * C * 4 + 64);
 }
 
 // bytes of dynamic shared memory scan_lookback_kernel needs
