@@ -320,6 +320,13 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t sr
                  "r"(src), "r"(c0), "r"(c1), "r"(c2)
                  : "memory");
 }
+__device__ __forceinline__ void tma_store_3d_hint(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, uint64_t hint)
+{
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3, %4}], [%1], %5;" ::"l"(
+                     reinterpret_cast<uint64_t>(map)),
+                 "r"(src), "r"(c0), "r"(c1), "r"(c2), "l"(hint)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -359,6 +366,7 @@ __device__ __forceinline__ uint32_t swz(uint32_t addr) { return addr ^ ((addr >>
 
 constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;  // L2 cache hint: streaming input
 constexpr uint64_t kEvictNormal = 0x1000000000000000ull; // L2 cache hint: data that is read again (far-lag kernel)
+constexpr uint64_t kEvictLast = 0x14F0000000000000ull;   // L2 cache hint: keep (far-lag kernel: own tiles come back as lag boxes)
 
 // Pre-swizzled tile offsets (few-channel kernels' scalar accesses, int16 kernel's 16-byte chunks).  Tile, staging and ring
 // bases are multiples of 1024 bytes, so the SWIZZLE_128B XOR (bits 4-6 with bits 7-9) of base + x only depends
@@ -447,6 +455,7 @@ struct TileRing {
     bool gdc_pending;    // thread 0: griddepcontrol.wait still owed before the first global store (pdl == 2)
     int row_base;        // rows in front of row 0 of in_map (far-lag kernel: left context contiguous with the input)
     uint64_t load_hint;  // L2 policy of the tile loads
+    uint64_t store_hint; // L2 policy of the tile stores (0 = none)
 
     // returns the first shared address after the staging tiles (where the kernel puts its summaries)
     __device__ __forceinline__ uint32_t setup(uint32_t smem_base, const StreamParams& p, const CUtensorMap* in,
@@ -469,7 +478,7 @@ struct TileRing {
             gdc_launch_dependents();
         }
         pdl_wait_loads = p.pdl == 1;
-        row_base = 0; load_hint = kEvictFirst;
+        row_base = 0; load_hint = kEvictFirst; store_hint = 0;
         return outb + 2u * tbv();
     }
     __device__ __forceinline__ void init_barriers(uint32_t bars_addr)
@@ -539,7 +548,8 @@ struct TileRing {
                 gdc_wait();
                 gdc_pending = false;
             }
-            tma_store_3d(out_map, st_buf, 0, st_tile * rowsv(), st_sig);
+            if (store_hint) tma_store_3d_hint(out_map, st_buf, 0, st_tile * rowsv(), st_sig, store_hint);
+            else tma_store_3d(out_map, st_buf, 0, st_tile * rowsv(), st_sig);
             tma_commit();
             st_pending = false;
             st_inflight = true;
@@ -1149,6 +1159,9 @@ struct FarParams {
     uint32_t koff;          // (32 - k % 32) % 32: first lag sample inside its 128-byte row
     int32_t lag_prefetch;   // lag boxes in flight: 1 or 2
     int32_t lag_stages;     // stages of the lag ring: 1 or 2 (>= lag_prefetch)
+    int32_t hints;          // L2 policies: 0 everything evict-normal (round 1); 1 lag boxes and output evict-first (a lag box
+                            // is dead once read, the output is never read back: neither should push the own tiles that
+                            // come back as lag boxes out of L2); 2 = 1 + own tiles evict-last
 };
 constexpr uint32_t kFarLagHalf = 17408;   // one 129-row box, padded to whole 1024-byte swizzle atoms
 
@@ -1184,7 +1197,9 @@ __global__ void __launch_bounds__(NT)
     TileRing<TB, ROWS> tr;
     const uint32_t lagbuf = tr.setup(smem_u32(smem_raw), p, &in_map, &out_map, &in_map);   // 1024-aligned: ring + whole tiles
     tr.row_base = fp.row_base;
-    tr.load_hint = kEvictNormal;
+    tr.load_hint = fp.hints == 2 ? kEvictLast : kEvictNormal;
+    tr.store_hint = fp.hints ? kEvictFirst : 0;
+    const uint64_t lag_hint = fp.hints ? kEvictFirst : kEvictNormal;
     const uint32_t wraw = lagbuf + (uint32_t)SL * 2u * kFarLagHalf;   // float [2][32][2]
     const uint32_t lbars = wraw + 2u * 32 * 2 * 4;                    // u64 [SL]
     if (tid == 0) {
@@ -1208,8 +1223,8 @@ __global__ void __launch_bounds__(NT)
         mbar_arrive_expect_tx(bar, 2u * 129u * 128u);
         const int r0 = tile * ROWS - fp.lag_rows + fp.row_base;
         const uint32_t dst = lagbuf + (uint32_t)stage * 2u * kFarLagHalf;
-        tma_load_3d(dst, &lag_map, bar, 0, r0, sig, kEvictNormal);
-        tma_load_3d(dst + kFarLagHalf, &lag_map, bar, 0, r0 + 128, sig, kEvictNormal);
+        tma_load_3d(dst, &lag_map, bar, 0, r0, sig, lag_hint);
+        tma_load_3d(dst + kFarLagHalf, &lag_map, bar, 0, r0 + 128, sig, lag_hint);
     };
     uint32_t lagit = 0;   // lag boxes consumed so far by this CTA, never reset
     int lst = 0;          // lagit % SL
