@@ -1175,18 +1175,21 @@ int launch_scan_cb(const void* d_in, void* d_out, uint64_t n, cudaStream_t st)
     cudaError_t e = cudaMemsetAsync(scratch, 0, total, st);
     if (e == cudaSuccess) {
         uint32_t first_tile = 0;
-        // int16 with 1, 2, 4 or 8 channels: the whole chunks go to the vectorised kernel, the ragged last chunk of the
-        // same chain to the general one (stream-ordered behind it)
-        if constexpr (std::is_same<TIn, int16_t>::value && (CB == 32768 || CB == 16384) && (C == 1 || C == 2 || C == 4 || C == 8)) {
-            constexpr int RL = CB / 4 / mavg::kScanThreads;   // run length: 32 or 16
+        // int16 with 1, 2, 4 or 8 channels, float32 with 1, 2 or 4: the whole chunks go to the vectorised kernel, the
+        // ragged last chunk of the same chain to the general one (stream-ordered behind it)
+        constexpr int RL = CB / (int)sizeof(TLoc) / mavg::kScanThreads;   // run length
+        constexpr bool kFast = (RL == 32 || RL == 16) &&
+                               ((std::is_same<TIn, int16_t>::value && (C == 1 || C == 2 || C == 4 || C == 8)) ||
+                                (std::is_same<TIn, float>::value && (C == 1 || C == 2 || C == 4)));
+        if constexpr (kFast) {
             const uint64_t whole = n / chunk;
             const bool aligned = (((uintptr_t)d_in | (uintptr_t)d_out) & 15u) == 0;
             if (whole > 0 && aligned && !getenv("MAVG_SCAN_GENERAL")) {
-                auto fast = mavg::scan_lookback_i16_kernel<C, RL>;
-                const uint32_t fsmem = mavg::scan_i16_smem_bytes<C, RL>();
+                auto fast = mavg::scan_lookback_fast_kernel<TIn, C, RL>;
+                const uint32_t fsmem = mavg::scan_fast_smem_bytes<TIn, C, RL>();
                 e = cudaFuncSetAttribute(fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
                 if (e == cudaSuccess) {
-                    fast<<<(unsigned)whole, mavg::kScanThreads, fsmem, st>>>((const int16_t*)d_in, (long long*)d_out,
+                    fast<<<(unsigned)whole, mavg::kScanThreads, fsmem, st>>>((const TIn*)d_in, (TAcc*)d_out,
                                                                             (ulonglong2*)(scratch + 256));
                     e = cudaGetLastError();
                     first_tile = (uint32_t)whole;

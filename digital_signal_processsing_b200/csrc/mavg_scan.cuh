@@ -380,61 +380,106 @@ __device__ __forceinline__ int scan_dp2a(uint32_t a, uint32_t b, int c)
     return d;
 }
 
-template <int C, int R>
+// Traits of the fast kernel per input type: chunk-local / accumulator types, padding (TLoc elements per 32), the
+// vector that holds two chunk-local prefixes.
+template <typename TIn> struct ScanFast;
+template <> struct ScanFast<int16_t> {
+    typedef int TLoc;
+    typedef long long TAcc;
+    typedef int2 Pair;                 // two prefixes of the output pair (LDS.64)
+    static constexpr int kPad = 4;     // 16 bytes of padding per 128
+};
+template <> struct ScanFast<float> {
+    typedef double TLoc;
+    typedef double TAcc;
+    typedef double2 Pair;              // LDS.128
+    static constexpr int kPad = 2;     // 16 bytes of padding per 256
+};
+
+template <typename TIn, int C, int R>
 __global__ void __launch_bounds__(kScanThreads)
-    scan_lookback_i16_kernel(const int16_t* __restrict__ in, long long* __restrict__ out, ulonglong2* __restrict__ desc)
+    scan_lookback_fast_kernel(const TIn* __restrict__ in, typename ScanFast<TIn>::TAcc* __restrict__ out,
+                              ulonglong2* __restrict__ desc)
 {
-    constexpr int NT = kScanThreads, NW = NT / 32, E = NT * R;   // 8192 (R = 32) or 4096 (R = 16) elements per chunk
-    constexpr int LV = R / 8;                          // load vectors per thread
+    typedef typename ScanFast<TIn>::TLoc TLoc;
+    typedef typename ScanFast<TIn>::TAcc TAcc;
+    typedef typename ScanFast<TIn>::Pair Pair;
+    constexpr bool I16 = sizeof(TIn) == 2;
+    constexpr int NT = kScanThreads, NW = NT / 32, E = NT * R;   // elements per chunk
+    constexpr int VE = 16 / (int)sizeof(TIn);                     // elements per 16-byte global load: 8 or 4
+    constexpr int LV = R / VE;                                    // load vectors per thread
+    constexpr int EV = 16 / (int)sizeof(TLoc);                    // chunk-local prefixes per 16-byte shared access: 4 or 2
+    constexpr int PAD = ScanFast<TIn>::kPad;
+    static_assert(C == 1 || C == 2 || C == 4 || (C == 8 && I16), "channel of a loaded element known at compile time");
     static_assert(R == 32 || R == 16, "run length");
-    static_assert(C == 1 || C == 2 || C == 4 || C == 8, "channel of a word half known at compile time");
-    constexpr int LOC = E + E / 8;                     // padded ints
+    constexpr int LOC = E + E / 32 * PAD;              // padded TLoc elements
     extern __shared__ __align__(16) uint8_t scan_smem[];
-    int* loc = reinterpret_cast<int*>(scan_smem);      // [LOC]
-    int* toff = loc + LOC;                             // [NT][C] exclusive offset of each run inside the chunk
-    int* s_warp = toff + NT * C;                       // [NW][C]
-    int* s_part = s_warp + NW * C;                     // [NW][C]
-    __shared__ __align__(16) long long s_excl[C < 2 ? 2 : C];
-    __shared__ long long s_tot[C];
+    TLoc* loc = reinterpret_cast<TLoc*>(scan_smem);    // [LOC]
+    TLoc* toff = loc + LOC;                            // [NT][C] exclusive offset of each run inside the chunk
+    TLoc* s_warp = toff + NT * C;                      // [NW][C]
+    TLoc* s_part = s_warp + NW * C;                    // [NW][C]
+    __shared__ __align__(16) TAcc s_excl[C < 2 ? 2 : C];
+    __shared__ TAcc s_tot[C];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t tile = blockIdx.x;
-    const int16_t* cin = in + (uint64_t)tile * E;
-    long long* cout = out + (uint64_t)tile * E;
+    const TIn* cin = in + (uint64_t)tile * E;
+    TAcc* cout = out + (uint64_t)tile * E;
 
-    // ---- 1. load: thread handles vectors q = tid + 256 * it (8 elements each), it < 4
-    int csum[C];
+    // ---- 1. load: thread handles vectors q = tid + 256 * it (VE elements each), it < LV
+    TLoc csum[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) csum[c] = 0;
     {
         uint4 raw[LV];
 #pragma unroll
         for (int it = 0; it < LV; ++it) raw[it] = __ldg(reinterpret_cast<const uint4*>(cin) + tid + NT * it);
-        int* dst = loc + 8 * tid + 4 * (tid >> 2);     // pad(8 q), q = tid; + it * (2048 + 256)
+        // pad(VE q) for q = tid, then + it * pad(VE * 256)
+        TLoc* dst = loc + VE * tid + PAD * ((VE * tid) >> 5);
 #pragma unroll
         for (int it = 0; it < LV; ++it) {
             const uint32_t w[4] = {raw[it].x, raw[it].y, raw[it].z, raw[it].w};
-            int v[8];
+            TLoc v[VE];
+            if constexpr (I16) {
+                int cs[C];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                v[2 * j] = (int)(short)(w[j] & 0xffffu);
-                v[2 * j + 1] = (int)w[j] >> 16;
-                if constexpr (C == 1) {
-                    csum[0] = scan_dp2a(w[j], 0x0101u, csum[0]);
-                } else {
-                    csum[(2 * j) % C] = scan_dp2a(w[j], 0x0001u, csum[(2 * j) % C]);
-                    csum[(2 * j + 1) % C] = scan_dp2a(w[j], 0x0100u, csum[(2 * j + 1) % C]);
+                for (int c = 0; c < C; ++c) cs[c] = (int)csum[c];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    v[2 * j] = (TLoc)(int)(short)(w[j] & 0xffffu);
+                    v[2 * j + 1] = (TLoc)((int)w[j] >> 16);
+                    if constexpr (C == 1) {
+                        cs[0] = scan_dp2a(w[j], 0x0101u, cs[0]);
+                    } else {
+                        cs[(2 * j) % C] = scan_dp2a(w[j], 0x0001u, cs[(2 * j) % C]);
+                        cs[(2 * j + 1) % C] = scan_dp2a(w[j], 0x0100u, cs[(2 * j + 1) % C]);
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < C; ++c) csum[c] = (TLoc)cs[c];
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    v[j] = (TLoc)__uint_as_float(w[j]);
+                    csum[j % C] += v[j];
                 }
             }
-            int4* d4 = reinterpret_cast<int4*>(dst + it * (8 * NT + NT));
-            d4[0] = make_int4(v[0], v[1], v[2], v[3]);
-            d4[1] = make_int4(v[4], v[5], v[6], v[7]);
+            TLoc* d = dst + it * (VE * NT + PAD * (VE * NT / 32));
+            if constexpr (I16) {
+                int4* d4 = reinterpret_cast<int4*>(d);
+                d4[0] = make_int4((int)v[0], (int)v[1], (int)v[2], (int)v[3]);
+                d4[1] = make_int4((int)v[4], (int)v[5], (int)v[6], (int)v[7]);
+            } else {
+                double2* d2 = reinterpret_cast<double2*>(d);
+                d2[0] = make_double2((double)v[0], (double)v[1]);
+                d2[1] = make_double2((double)v[2], (double)v[3]);
+            }
         }
     }
 #pragma unroll
     for (int c = 0; c < C; ++c) {
 #pragma unroll
-        for (int d = 16; d >= 1; d >>= 1) csum[c] += __shfl_xor_sync(0xffffffffu, csum[c], d);
+        for (int d = 16; d >= 1; d >>= 1) csum[c] += shfl_xor_t<TLoc>(csum[c], d);
     }
     if (lane == 0) {
 #pragma unroll
@@ -443,39 +488,46 @@ __global__ void __launch_bounds__(kScanThreads)
     __syncthreads();
     ulonglong2* my_desc = desc + (uint64_t)tile * C;
     if (tid < C) {   // fixed order over the warps
-        int t = 0;
+        TLoc t = 0;
 #pragma unroll
         for (int w2 = 0; w2 < NW; ++w2) t += s_part[w2 * C + tid];
-        s_tot[tid] = (long long)t;
-        st_desc(my_desc + tid, tile == 0 ? kScanPrefix : kScanAggregate, (unsigned long long)(long long)t);
+        s_tot[tid] = (TAcc)t;
+        st_desc(my_desc + tid, tile == 0 ? kScanPrefix : kScanAggregate, (unsigned long long)acc_bits<TAcc>((TAcc)t));
     }
 
-    // ---- 2. in-place scan of the own run: R contiguous ints at pad(R tid)
-    int carry[C];
+    // ---- 2. in-place scan of the own run: R contiguous prefixes at pad(R tid)
+    TLoc carry[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) carry[c] = 0;
     {
-        int4* run = reinterpret_cast<int4*>(loc + R * tid + 4 * ((R * tid) >> 5));
+        TLoc* run = loc + R * tid + PAD * ((R * tid) >> 5);
 #pragma unroll
-        for (int b = 0; b < R / 4; ++b) {
-            int4 t = run[b];
-            int v[4] = {t.x, t.y, t.z, t.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                carry[(4 * b + i) % C] += v[i];
-                v[i] = carry[(4 * b + i) % C];
+        for (int b = 0; b < R / EV; ++b) {
+            TLoc v[EV];
+            if constexpr (I16) {
+                const int4 t = reinterpret_cast<const int4*>(run)[b];
+                v[0] = t.x, v[1] = t.y, v[2] = t.z, v[3] = t.w;
+            } else {
+                const double2 t = reinterpret_cast<const double2*>(run)[b];
+                v[0] = t.x, v[1] = t.y;
             }
-            run[b] = make_int4(v[0], v[1], v[2], v[3]);
+#pragma unroll
+            for (int i = 0; i < EV; ++i) {
+                carry[(EV * b + i) % C] += v[i];
+                v[i] = carry[(EV * b + i) % C];
+            }
+            if constexpr (I16) reinterpret_cast<int4*>(run)[b] = make_int4((int)v[0], (int)v[1], (int)v[2], (int)v[3]);
+            else reinterpret_cast<double2*>(run)[b] = make_double2((double)v[0], (double)v[1]);
         }
     }
-    int inc[C];
+    TLoc inc[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) inc[c] = carry[c];
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
 #pragma unroll
         for (int c = 0; c < C; ++c) {
-            const int up = __shfl_up_sync(0xffffffffu, inc[c], d);
+            const TLoc up = shfl_up_t<TLoc>(inc[c], d);
             if (lane >= d) inc[c] += up;
         }
     }
@@ -486,7 +538,7 @@ __global__ void __launch_bounds__(kScanThreads)
     __syncthreads();
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-        int a = 0;
+        TLoc a = 0;
 #pragma unroll
         for (int w2 = 0; w2 < NW; ++w2)
             if (w2 < warp) a += s_warp[w2 * C + c];
@@ -494,45 +546,47 @@ __global__ void __launch_bounds__(kScanThreads)
     }
 
     // ---- 3. look-back (warp 0)
-    if (warp == 0) scan_look_back<long long, C>(desc, tile, lane, s_excl, s_tot);
+    if (warp == 0) scan_look_back<TAcc, C>(desc, tile, lane, s_excl, s_tot);
     __syncthreads();
 
     // ---- 4. output: pair q = tid + 256 * it, it < R / 2: elements e = 2 q, e + 1 of run e / R
     {
-        const int2* lp = reinterpret_cast<const int2*>(loc + 2 * tid + 4 * (tid >> 4));    // pad(2 q); + it * (512 + 64) ints
-        longlong2* op = reinterpret_cast<longlong2*>(cout) + tid;                          // + it * 256
-        constexpr int CP = C < 2 ? 1 : 2;                                                  // channels of a pair
-        const int c0 = (2 * tid) % C;                                                      // 2 q mod C does not depend on it (512 % C == 0)
-        const int* tp = toff + ((2 * tid) / R) * C + c0;                                   // + it * (512 / R) * C
-        long long b0, b1;
+        const Pair* lp = reinterpret_cast<const Pair*>(loc + 2 * tid + PAD * ((2 * tid) >> 5));   // pad(2 q); + it * pad(512)
+        constexpr int kPairStep = (512 + PAD * 16) / 2;                                         // in Pair units
+        longlong2* op = reinterpret_cast<longlong2*>(cout) + tid;                               // + it * 256 (16-byte units)
+        const int c0 = (2 * tid) % C;                                                           // 2 q mod C does not depend on it
+        const TLoc* tp = toff + ((2 * tid) / R) * C + c0;                                       // + it * (512 / R) * C
+        TAcc b0, b1;
         if constexpr (C == 1) {
             b0 = b1 = s_excl[0];
         } else {
-            const longlong2 bb = *reinterpret_cast<const longlong2*>(s_excl + c0);
-            b0 = bb.x, b1 = bb.y;
+            b0 = s_excl[c0], b1 = s_excl[c0 + 1];
         }
 #pragma unroll
         for (int it = 0; it < R / 2; ++it) {
-            const int2 l = lp[it * 288];
-            int t0, t1;
-            if constexpr (CP == 1) {
+            const Pair l = lp[it * kPairStep];
+            TLoc t0, t1;
+            if constexpr (C == 1) {
                 t0 = t1 = tp[it * (512 / R) * C];
             } else {
-                const int2 tt = *reinterpret_cast<const int2*>(tp + it * (512 / R) * C);
-                t0 = tt.x, t1 = tt.y;
+                t0 = tp[it * (512 / R) * C], t1 = tp[it * (512 / R) * C + 1];
             }
+            const TAcc r0 = b0 + (TAcc)(t0 + (TLoc)l.x);
+            const TAcc r1 = b1 + (TAcc)(t1 + (TLoc)l.y);
             longlong2 r;
-            r.x = b0 + (long long)(t0 + l.x);
-            r.y = b1 + (long long)(t1 + l.y);
+            r.x = acc_bits<TAcc>(r0);
+            r.y = acc_bits<TAcc>(r1);
             op[it * NT] = r;
         }
     }
 }
 
-template <int C, int R>
-constexpr uint32_t scan_i16_smem_bytes()
+template <typename TIn, int C, int R>
+constexpr uint32_t scan_fast_smem_bytes()
 {
-    return (uint32_t)((kScanThreads * R + kScanThreads * R / 8) * 4 + kScanThreads * C * 4 + 2 * (kScanThreads / 32) * C * 4 + 64);
+    typedef typename ScanFast<TIn>::TLoc TLoc;
+    return (uint32_t)((kScanThreads * R + kScanThreads * R / 32 * ScanFast<TIn>::kPad) * sizeof(TLoc) +
+                      kScanThreads * C * sizeof(TLoc) + 2 * (kScanThreads / 32) * C * sizeof(TLoc) + 64);
 }
 
 // bytes of dynamic shared memory scan_lookback_kernel needs

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, call K: whole GPU suite + bench + generic-shape timings after the RMS template change
-O=gpurun_out/r2k; mkdir -p $O
+O=gpurun_out/r2k2; mkdir -p $O
 ( time timeout 1200 python -m pytest tests -m gpu -x -q ) > $O/pytest.log 2>&1; echo "rc=$?" >> $O/pytest.log
 timeout 300 python tests/perf/bench_configs.py --config gen > $O/cfg_gen.json 2> $O/cfg_gen.err
 timeout 300 python tests/perf/bench_configs.py --config g6i > $O/cfg_g6i.json 2> $O/cfg_g6i.err
