@@ -84,7 +84,7 @@ int get_encoder(EncodeTiledFn* out)
 // One signal batch as a [signals][rows][128 bytes] tensor (32 floats or 64 int16 per row), boxes of
 // [1][tile_rows][row], 128B swizzle.
 int make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t signals, uint64_t signal_stride_bytes,
-             uint32_t tile_rows, uint32_t elem_bytes, bool swizzle = true)
+             uint32_t tile_rows, uint32_t elem_bytes, int swizzle = 128)
 {
     EncodeTiledFn enc = nullptr;
     MAVG_TRY(get_encoder(&enc));
@@ -95,7 +95,11 @@ int make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t signals
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(map, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT16, 3,
                      const_cast<void*>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     swizzle == 128  ? CU_TENSOR_MAP_SWIZZLE_128B
+                     : swizzle == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                     : swizzle == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                     : CU_TENSOR_MAP_SWIZZLE_NONE,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
         return fail(MAVG_ERR_DRIVER, "cuTensorMapEncodeTiled failed (%d) rows=%llu signals=%llu stride=%llu", (int)r,
@@ -144,6 +148,18 @@ StreamGeom plan_stream_i16(uint32_t k, uint32_t C, const mavg_tuning& tu)
     StreamGeom g;
     g.NT = tu.threads == 256 ? 256 : 512;
     g.R = 32;    // 16-sample runs with two CTAs per SM were measured 10-20 % slower (per-run overheads dominate)
+    // 3 / 4 / 6 / 8 interleaved channels (multichannel PCM) run on the same flat-stream kernel: a run holds whole
+    // frames (24 samples for 3 and 6 channels), so the channel of run element r is r % C at compile time.  The scan of
+    // C channel deltas per run is what these shapes pay for, so by default they run with half the threads and runs
+    // twice as long (one CTA of 256 threads per SM; 2^27 samples, k = 64: 8 channels 0.108 -> 0.096 ms, 4 channels
+    // 0.095 -> 0.091 ms); tuning.threads = 512 selects the 512-thread shape
+    if (C == 4 || C == 8) {
+        g.NT = tu.threads == 512 ? 512 : 256;
+        g.R = g.NT == 256 ? 64 : 32;
+    } else if (C == 3 || C == 6) {                     // runs of an odd number of 16-byte chunks: dense tiles, no swizzle
+        g.NT = tu.threads == 512 ? 512 : 224;
+        g.R = g.NT == 224 ? 72 : 24;
+    }
     g.elem = 2;
     g.C = C;
     // Window sums |w| <= 32768 k fit int32 for k <= 32768, and C's truncating w / k is computed exactly as
@@ -153,7 +169,7 @@ StreamGeom plan_stream_i16(uint32_t k, uint32_t C, const mavg_tuning& tu)
     // so its floor is trunc(w / k) - 1 and the sign bit adds the 1 back.  M < 2^31 needs k >= 3; k == 2 runs with
     // every dp2a weight doubled (sums 2 w) and the constants of k = 4.  k == 1 (identity) and longer windows are
     // left to the generic kernel.
-    if (k < 2 || k > 32768u || !(C == 1 || C == 2)) return g;
+    if (k < 2 || k > 32768u || !(C == 1 || C == 2 || C == 3 || C == 4 || C == 6 || C == 8)) return g;
     const uint64_t L = (uint64_t)k * C;
     const uint32_t R = (uint32_t)g.R;
     const uint32_t s = (uint32_t)((R - L % R) % R);
@@ -165,6 +181,7 @@ StreamGeom plan_stream_i16(uint32_t k, uint32_t C, const mavg_tuning& tu)
     const uint64_t T = (uint64_t)g.NT * R;
     g.H = (int)(((uint64_t)(g.n_full + 1) * R + T - 1) / T);
     g.ctas_per_sm = tu.ctas_per_sm ? (int)tu.ctas_per_sm : (g.NT == 256 ? 2 : 1);
+    if (g.R > 32) g.ctas_per_sm = 1;
     g.P = tu.prefetch ? (int)tu.prefetch : 2;
     for (;;) {
         g.S = g.H + 1 + g.P;
@@ -432,6 +449,7 @@ StreamKernel pick_kernel(const StreamGeom& g, uint32_t k, bool rms)
     return pick_variant<512, 16>(g.MIS, g.mode, k);
 }
 
+// lag misalignment MIS = (-k C) mod 8 samples: any value for odd C, even for C = 2 and 6, 0 / 4 for C = 4, 0 for C = 8
 template <int NT, int R, int C>
 StreamKernel pick_i16(int mis)
 {
@@ -440,12 +458,22 @@ StreamKernel pick_i16(int mis)
     case M: return (StreamKernel)stream_i16_kernel<NT, R, C, M>;
     switch (mis) {
         MAVG_I16_CASE(0)
-        MAVG_I16_CASE(2)
-        MAVG_I16_CASE(4)
-        MAVG_I16_CASE(6)
     default: break;
     }
-    if constexpr (C == 1) {
+    if constexpr (C != 8) {
+        switch (mis) {
+            MAVG_I16_CASE(4)
+        default: break;
+        }
+    }
+    if constexpr (C != 8 && C != 4) {
+        switch (mis) {
+            MAVG_I16_CASE(2)
+            MAVG_I16_CASE(6)
+        default: break;
+        }
+    }
+    if constexpr (C % 2 == 1) {
         switch (mis) {
             MAVG_I16_CASE(1)
             MAVG_I16_CASE(3)
@@ -456,6 +484,19 @@ StreamKernel pick_i16(int mis)
     }
 #undef MAVG_I16_CASE
     return nullptr;
+}
+
+StreamKernel pick_i16_kernel(const StreamGeom& g)
+{
+    switch (g.C) {
+    case 1: return g.NT == 256 ? pick_i16<256, 32, 1>(g.MIS) : pick_i16<512, 32, 1>(g.MIS);
+    case 2: return g.NT == 256 ? pick_i16<256, 32, 2>(g.MIS) : pick_i16<512, 32, 2>(g.MIS);
+    case 3: return g.NT == 224 ? pick_i16<224, 72, 3>(g.MIS) : pick_i16<512, 24, 3>(g.MIS);
+    case 4: return g.NT == 256 ? pick_i16<256, 64, 4>(g.MIS) : pick_i16<512, 32, 4>(g.MIS);
+    case 6: return g.NT == 224 ? pick_i16<224, 72, 6>(g.MIS) : pick_i16<512, 24, 6>(g.MIS);
+    case 8: return g.NT == 256 ? pick_i16<256, 64, 8>(g.MIS) : pick_i16<512, 32, 8>(g.MIS);
+    default: return nullptr;
+    }
 }
 
 // ---------------------------------------------------------------------------------
@@ -1030,10 +1071,12 @@ int launch_shard(mavg_plan* p, DevCtx& d, const void* in, void* out, const void*
     const uint64_t T = (uint64_t)g.NT * g.R;
 
     CUtensorMap in_map, out_map, halo_map;
-    MAVG_TRY(make_map(&in_map, in, rows, signals, stride * g.elem, tile_rows, g.elem));
-    MAVG_TRY(make_map(&out_map, out, rows, signals, stride * g.elem, tile_rows, g.elem));
+    // int16: the swizzle under which a warp's 128-bit accesses to consecutive runs of R samples do not collide
+    const int swz = g.elem == 2 ? mavg::i16_swizzle_bytes(g.R) : 128;
+    MAVG_TRY(make_map(&in_map, in, rows, signals, stride * g.elem, tile_rows, g.elem, swz));
+    MAVG_TRY(make_map(&out_map, out, rows, signals, stride * g.elem, tile_rows, g.elem, swz));
     const uint64_t halo_rows = (uint64_t)g.H * tile_rows;
-    if (halo) MAVG_TRY(make_map(&halo_map, halo, halo_rows, 1, halo_rows * 128, tile_rows, g.elem));
+    if (halo) MAVG_TRY(make_map(&halo_map, halo, halo_rows, 1, halo_rows * 128, tile_rows, g.elem, swz));
     else halo_map = in_map;
 
     mavg::StreamParams sp;
@@ -1064,9 +1107,7 @@ int launch_shard(mavg_plan* p, DevCtx& d, const void* in, void* out, const void*
     sp.has_halo = halo ? 1 : 0;
     sp.pdl = pdl_mode(p->desc.tuning);
 
-    StreamKernel kern = g.elem == 4 ? pick_kernel(g, p->desc.window, p->desc.op == MAVG_OP_RMS)
-                        : g.NT == 256 ? (g.C == 1 ? pick_i16<256, 32, 1>(g.MIS) : pick_i16<256, 32, 2>(g.MIS))
-                                      : (g.C == 1 ? pick_i16<512, 32, 1>(g.MIS) : pick_i16<512, 32, 2>(g.MIS));
+    StreamKernel kern = g.elem == 4 ? pick_kernel(g, p->desc.window, p->desc.op == MAVG_OP_RMS) : pick_i16_kernel(g);
     if (!kern) return fail(MAVG_ERR_UNSUPPORTED, "no stream kernel variant for this window");
     MAVG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
     const unsigned grid = (unsigned)std::min<uint64_t>(ctas, (uint64_t)sp.total_chunks);
@@ -1330,8 +1371,12 @@ int mavg_plan_create(const mavg_desc* desc, mavg_plan** out)
             p->geom = plan_cols(desc->window, desc->channels, desc->tuning, true);
             stream_shape = p->geom.ok;
         } else if (!planar && desc->channels >= 3) {
-            p->geom = plan_fewc(desc->window, desc->channels, desc->tuning, 2);
+            // 3 / 4 / 6 / 8 channels: the flat-stream kernel while the window fits its ring, else the few-channel kernels
             stream_shape = p->geom.ok;
+            if (!p->geom.ok) {
+                p->geom = plan_fewc(desc->window, desc->channels, desc->tuning, 2);
+                stream_shape = p->geom.ok;
+            }
         }
     }
     if (desc->path == MAVG_PATH_STREAM && !(stream_shape && p->geom.ok)) {

@@ -907,7 +907,24 @@ __host__ __device__ inline uint32_t stream_i16_smem_bytes(int NT, int R, int S, 
 {
     (void)H;
     const uint32_t TB = (uint32_t)NT * R * 2;
-    return 1024u + (uint32_t)S * TB + 2u * TB + 2u * 32 * C * 4 + (uint32_t)S * 8;
+    const uint32_t NW = (uint32_t)NT / 32, G = 32 / NW;          // warps; channel groups of the cross-warp scan
+    return 1024u + (uint32_t)S * TB + 2u * TB + 2u * 32 * ((C + G - 1) / G) * 4 + (uint32_t)S * 8;
+}
+
+// TMA swizzle (bytes: 0 / 32 / 64 / 128) under which the 128-bit shared-memory accesses of a warp whose threads own
+// consecutive runs of R int16 samples (R / 8 chunks of 16 bytes) are free of bank conflicts
+__host__ __device__ constexpr int i16_swizzle_bytes(int R)
+{
+    const int chunks = R / 8;
+    return chunks % 2 == 1 ? 0 : 128;   // (strides of 6 / 12 chunks would need the 32- / 64-byte modes, whose boxes are narrower than a row)
+}
+// offset inside a 1024-byte aligned tile under the TMA swizzle of SWZ bytes: address bits [4, 4 + log2(SWZ / 16)) are
+// XORed with the bits starting at 7
+template <int SWZ>
+__device__ __forceinline__ int pre_swz_n(int x)
+{
+    if constexpr (SWZ == 0) return x;
+    else return x ^ ((x >> 3) & (SWZ == 128 ? 0x70 : SWZ == 64 ? 0x30 : 0x10));
 }
 
 __device__ __forceinline__ uint4 lds128u(uint32_t addr)
@@ -967,7 +984,7 @@ __device__ __forceinline__ uint32_t div_trunc_mulhi(int w, int mul, uint32_t sh)
 }
 
 template <int NT, int R, int C, int MIS>
-__global__ void __launch_bounds__(NT, (NT == 256 ? 2 : 1))
+__global__ void __launch_bounds__(NT, (NT == 256 && R <= 32 ? 2 : 1))
     stream_i16_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map,
                       const __grid_constant__ CUtensorMap halo_map, const StreamParams p)
 {
@@ -978,25 +995,38 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : 1))
     constexpr int NW = NT / 32;
     constexpr int CH_OWN = R / 8;
     constexpr int CH_LAG = CH_OWN + (MIS ? 1 : 0);
-    static_assert(R % C == 0 && R % 8 == 0 && NW <= 16 && MIS >= 0 && MIS < 8 && MIS % C == 0, "shape");
+    // 64-byte runs (R = 32) need the 128-byte XOR swizzle for conflict-free 128-bit accesses; runs of an odd number of
+    // 16-byte chunks (R = 24, 40: 3 / 5 / 6 interleaved channels) are conflict-free in the dense layout and collide in
+    // the swizzled one, so their tensor maps are encoded without swizzle
+    // (brute-forced over every quarter-warp: strides of 3 / 5 / 9 chunks: dense; 4 / 8: 128-byte swizzle; 6: 2-way
+    // conflicts either way, which is why 3 / 6 channels run as 224 threads x 72 samples and not 256 x 48)
+    constexpr int SWZ = i16_swizzle_bytes(R);
+    static_assert(R % C == 0 && R % 8 == 0 && NW <= 16 && MIS >= 0 && MIS < 8 && T % 64 == 0 && ROWS <= 256, "shape");
 
     extern __shared__ uint8_t smem_raw[];
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
     TileRing<TB, ROWS> tr;
-    const uint32_t wraw = tr.setup(smem_u32(smem_raw), p, &in_map, &out_map, &halo_map);   // int [2][32][C] warp totals
+    // Cross-warp scan of the warp totals, once per warp with the lanes working in parallel: lane = (warp w' = lane % NW,
+    // channel group g = lane / NW) owns the totals of warp w' for channels g, g + G, g + 2 G ...; the array is laid out
+    // [parity][channel][NW] so that the j-th load of a warp is one dense row of 32 words
+    constexpr int G = 32 / NW;                // channel groups
+    constexpr int CJ = (C + G - 1) / G;       // channels per lane
+    const uint32_t wraw = tr.setup(smem_u32(smem_raw), p, &in_map, &out_map, &halo_map);   // uint32 [2][CJ * G][NW]
     const int H = tr.H;
-    tr.init_barriers(wraw + 2u * 32 * C * 4);
+    tr.init_barriers(wraw + 2u * 32 * CJ * 4);
+    const int wq = lane % NW;                 // the warp whose totals this lane scans
+    const int wlast = lane - wq + NW - 1;     // the lane of this group that ends up with the inclusive total
     // dp2a byte weights (+w / -w on the low or the high half; w = 2 when k == 2, see plan_stream_i16)
     const uint32_t w_lo = p.wscale, w_hi = p.wscale << 8;
     const uint32_t n_lo = (0u - p.wscale) & 0xffu, n_hi = n_lo << 8;
     const int L = (int)(p.k * (uint32_t)C);              // lag distance in flat samples
     int xo[CH_OWN], xg[CH_LAG];                          // pre-swizzled chunk offsets: own run, lag run
 #pragma unroll
-    for (int c = 0; c < CH_OWN; ++c) xo[c] = pre_swz(tid * (R * 2) + 16 * c);
+    for (int c = 0; c < CH_OWN; ++c) xo[c] = pre_swz_n<SWZ>(tid * (R * 2) + 16 * c);
 #pragma unroll
-    for (int c = 0; c < CH_LAG; ++c) xg[c] = pre_swz((tid * CH_OWN - (int)p.lag_chunks + c) * 16);
+    for (int c = 0; c < CH_LAG; ++c) xg[c] = pre_swz_n<SWZ>((tid * CH_OWN - (int)p.lag_chunks + c) * 16);
     const int mul = (int)p.div_mul;
     const uint32_t sh = p.div_shift;
 
@@ -1006,9 +1036,9 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : 1))
         const int first = t0 - H;
         const int ntl = t1 - first;
         tr.prologue(first, ntl, sig);
-        uint32_t W[C];                                   // window sum (per channel) at the first sample of the tile
-#pragma unroll
-        for (int c = 0; c < C; ++c) W[c] = 0u;
+        uint32_t Wl[CJ];                                 // window sum at the first sample of the tile, channels g + j G,
+#pragma unroll                                           // kept by the lanes that scan warp 0 (wq == 0)
+        for (int j = 0; j < CJ; ++j) Wl[j] = 0u;
 
         for (int j = 0; j < ntl; ++j) {
             const int tile = first + j;
@@ -1059,8 +1089,8 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : 1))
                     if constexpr (C == 1) {
                         a[0] = dp2a_s(xw[q], m0 | m1, a[0]);
                     } else {
-                        a[0] = dp2a_s(xw[q], m0, a[0]);
-                        a[1] = dp2a_s(xw[q], m1, a[1]);
+                        a[(2 * q) % C] = dp2a_s(xw[q], m0, a[(2 * q) % C]);
+                        a[(2 * q + 1) % C] = dp2a_s(xw[q], m1, a[(2 * q + 1) % C]);
                     }
                 }
 #pragma unroll
@@ -1081,29 +1111,35 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : 1))
                     if (lane >= dd) incl[c] += up;
                 }
             }
+            const uint32_t wbase = wraw + (it & 1u) * (32u * CJ * 4u);
             if (lane == 31) {
 #pragma unroll
-                for (int c = 0; c < C; ++c) sts32u(wraw + (((it & 1u) * 32u + warp) * C + c) * 4u, incl[c]);
+                for (int c = 0; c < C; ++c) sts32u(wbase + (uint32_t)((c / G) * 32 + (c % G) * NW + warp) * 4u, incl[c]);
             }
+#pragma unroll
+            for (int c = 0; c < C; ++c) incl[c] -= d[c];   // exclusive inside the warp
 
             tr.before_sync();
             __syncthreads();
             tr.after_sync(j, ntl, first, sig);
 
-            uint32_t start[C], total[C];
+            uint32_t excl[CJ];                           // W + totals of the warps in front of warp wq
 #pragma unroll
-            for (int c = 0; c < C; ++c) {
-                const uint32_t v = (lane < NW) ? lds32u(wraw + (((it & 1u) * 32u + lane) * C + c) * 4u) : 0u;
-                uint32_t wi = v;
+            for (int jj = 0; jj < CJ; ++jj) {
+                const uint32_t v = lds32u(wbase + (uint32_t)(jj * 32 + lane) * 4u);
+                uint32_t wi = v + (wq == 0 ? Wl[jj] : 0u);
 #pragma unroll
                 for (int dd = 1; dd < NW; dd <<= 1) {
                     const uint32_t up = __shfl_up_sync(0xffffffffu, wi, dd);
-                    if (lane >= dd) wi += up;
+                    if (wq >= dd) wi += up;
                 }
-                const uint32_t own_off = __shfl_sync(0xffffffffu, wi - v, warp);   // totals of the warps in front
-                total[c] = __shfl_sync(0xffffffffu, wi, NW - 1);
-                start[c] = W[c] + own_off + (incl[c] - d[c]);
+                Wl[jj] = __shfl_sync(0xffffffffu, wi, wlast);   // next tile's W (used where wq == 0)
+                excl[jj] = wi - v;
             }
+            uint32_t start[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+                start[c] = __shfl_sync(0xffffffffu, excl[c / G], (c % G) * NW + warp) + incl[c];
 
             if (is_out) {
                 const uint32_t ob = tr.out_tile();
@@ -1124,8 +1160,6 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : 1))
                 }
                 tr.staged(tile, sig);
             }
-#pragma unroll
-            for (int c = 0; c < C; ++c) W[c] += total[c];
             tr.advance();
         }
 

@@ -167,7 +167,7 @@ def test_single_process_multi_device_plan(mavg, oracle_mod):
     xi6 = oracle_mod.fill_i16(6 * (50 * 1280 + 17), 13)
     for k in (100, 1500):
         with mavg.Plan(50 * 1280 + 17, k, channels=6, dtype="i16", devices=devs) as plan:
-            assert plan.info.mode == 4
+            assert plan.info.mode == 6          # the flat-stream int16 kernel (3 / 4 / 6 / 8 channels)
             assert np.array_equal(plan.run_host(xi6), oracle_mod.mavg_i16(xi6, k, 6)), k
     xp = oracle_mod.fill_f32(6 * 8192 * 3, 6)
     with mavg.Plan(8192 * 3, 64, channels=6, layout="planar", devices=devs) as plan:

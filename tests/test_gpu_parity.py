@@ -568,46 +568,82 @@ def _fewc_runs(ch):
     return runs
 
 
-@pytest.mark.parametrize("ch", [3, 5, 6, 7, 8, 12, 24, 31])
+FLAT_I16_CH = (3, 4, 6, 8)      # channel counts the flat-stream int16 kernel takes (info.mode 6), runs of whole frames
+
+
+@pytest.mark.parametrize("ch", [3, 4, 5, 6, 7, 8, 10, 12, 24, 31])
 @pytest.mark.parametrize("k", [1, 2, 3, 7, 8, 31, 32, 33, 64, 100, 255, 256, 300])
 def test_few_channel_interleaved_i16_bit_exact(mavg, oracle_mod, ch, k):
-    """Odd channel counts: 2-byte accesses, 32-frame runs.  Even counts: channel pairs as 32-bit words, 16-frame runs."""
+    """3 / 4 / 6 / 8 channels: the stereo kernel's delta scan over the flat stream (runs of whole frames).  Other odd
+    channel counts: 2-byte accesses, 32-frame runs.  Other even counts: channel pairs as 32-bit words, 16-frame runs."""
     pair = ch % 2 == 0
     runs = _fewc_runs(ch // 2 if pair else ch)
     rf = 16 if pair else 32
     frames = 3 * runs * rf + 41                    # several tiles, ragged tail (flat length not a multiple of 64)
+    if ch in FLAT_I16_CH:
+        frames = 3 * (224 * 72 if ch % 3 == 0 else 256 * 64) // ch + 41
     x = oracle_mod.fill_i16(frames * ch, 26000 + k + ch)
     with mavg.Plan(frames, k, channels=ch, dtype="i16") as plan:
         y = plan.run_host(x)
         i = plan.info
-        if 2 <= k <= 256 and (k + rf - 1) // rf <= runs:
+        if ch in FLAT_I16_CH:
+            if k >= 2:      # default shape: 224 threads x runs of 72 samples / 256 x 64
+                assert i.path == 1 and i.mode == 6 and i.run == (72 if ch % 3 == 0 else 64), "expected the flat-stream int16 kernel"
+        elif 2 <= k <= 256 and (k + rf - 1) // rf <= runs:
             assert i.path == 1 and i.mode == 4 and i.run == rf, "expected the few-channel int16 kernel"
     assert np.array_equal(y, oracle_mod.mavg_i16(x, k, ch))
+    if ch in FLAT_I16_CH and k >= 2:                  # the 512-thread shape (runs of 24 / 32 samples)
+        with mavg.Plan(frames, k, channels=ch, dtype="i16", threads=512) as plan:
+            assert plan.info.mode == 6 and plan.info.run == (24 if ch % 3 == 0 else 32)
+            assert np.array_equal(plan.run_host(x), oracle_mod.mavg_i16(x, k, ch))
+
+
+@pytest.mark.parametrize("ch", FLAT_I16_CH)
+def test_flat_multichannel_i16_every_lag_alignment_and_ring_depth(mavg, oracle_mod, ch):
+    """Every lag misalignment (k C mod 8 samples), windows of one to several tiles of history, the longest window of the
+    ring and the first one beyond it (which has to leave the kernel and still be exact)."""
+    tile_frames = (224 * 72 if ch % 3 == 0 else 256 * 64) // ch      # the default shape's tile (the 512-thread one: 512 x 24 / 32)
+    frames = 9 * tile_frames + 77
+    x = oracle_mod.fill_i16(frames * ch, 26500 + ch)
+    ks = list(range(2, 19)) + [tile_frames - 1, tile_frames, tile_frames + 1, 2 * tile_frames + 3, 3 * tile_frames - 5]
+    for k in ks:
+        e = oracle_mod.mavg_i16(x, k, ch)
+        for threads in (0, 512):
+            with mavg.Plan(frames, k, channels=ch, dtype="i16", threads=threads) as plan:
+                assert plan.info.path == 1 and plan.info.mode == 6, (ch, k)
+                assert np.array_equal(plan.run_host(x), e), (ch, k, threads)
+    # beyond the ring: any other path, same result
+    with mavg.Plan(1 << 20, 32768, channels=ch, dtype="i16") as plan:
+        assert plan.info.mode != 6
+    k = 7 * tile_frames + 1
+    if k <= 32768:
+        with mavg.Plan(frames, k, channels=ch, dtype="i16") as plan:
+            assert np.array_equal(plan.run_host(x), oracle_mod.mavg_i16(x, k, ch)), (ch, k)
 
 
 def test_few_channel_i16_extremes_and_negative_truncation(mavg, oracle_mod):
     """Saturated inputs (window sums up to 256 * 32768 in magnitude) and sign-alternating ramps whose sums straddle
     zero: the multiply-high division has to truncate toward zero exactly as C's `/` does."""
-    for ch in (6, 5):                              # pair kernel, scalar kernel
+    for ch in (6, 3, 8, 10, 5):                    # flat-stream kernel (6, 3, 8), pair kernel, scalar kernel
         frames = 4 * 80 * 32 + 5
         for val in (-32768, 32767, -1, 1):
             x = np.full(frames * ch, val, dtype=np.int16)
             for k in (2, 3, 7, 100, 255, 256):
                 with mavg.Plan(frames, k, channels=ch, dtype="i16") as plan:
-                    assert plan.info.mode == 4
+                    assert plan.info.mode == (6 if ch in FLAT_I16_CH else 4)
                     assert np.array_equal(plan.run_host(x), oracle_mod.mavg_i16(x, k, ch)), (ch, val, k)
         x = ((np.arange(frames * ch) % 11 - 5) * 997).astype(np.int16)
         for k in (2, 3, 5, 6, 7, 9, 10, 11, 12, 13, 100):
             assert np.array_equal(mavg.moving_average(x, k, channels=ch), oracle_mod.mavg_i16(x, k, ch)), (ch, k)
 
 
-@pytest.mark.parametrize("case", [(6, 64), (3, 5), (7, 200), (8, 256), (4, 2)])
+@pytest.mark.parametrize("case", [(6, 64), (3, 5), (7, 200), (8, 256), (4, 2), (12, 64), (6, 3000), (4, 9000), (3, 4097)])
 def test_few_channel_i16_shard_with_halo_bit_exact(mavg, oracle_mod, torch_cuda, case):
     torch = torch_cuda
     ch, k = case
     with mavg.Plan(100_000, k, channels=ch, dtype="i16") as probe:
         tf = int(probe.info.halo_frames)
-        assert probe.info.mode == 4 and tf >= k
+        assert probe.info.mode == (6 if ch in FLAT_I16_CH else 4) and tf >= k
     frames, cut = 37 * tf + 123, 9 * tf
     x = oracle_mod.fill_i16(frames * ch, 27000 + k)
     dx = torch.from_numpy(x).cuda()
@@ -636,7 +672,9 @@ def test_few_channel_long_windows(mavg, oracle_mod, ch, k, dtype):
     with mavg.Plan(frames, k, channels=ch, dtype=dtype) as plan:
         y = plan.run_host(x)
         i = plan.info
-        if ch <= 8 and k <= 1024:
+        if dtype == "i16" and ch in FLAT_I16_CH:
+            assert i.path == 1 and i.mode == 6, "expected the flat-stream int16 kernel"
+        elif ch <= 8 and k <= 1024:
             assert i.path == 1 and i.mode == 4, "expected a few-channel streaming kernel"
     if dtype == "f32":
         assert _rel(y, oracle_mod.mavg_f64(x, k, ch)) < TOL
@@ -658,7 +696,7 @@ def test_few_channel_long_window_conditioning(mavg, oracle_mod, dist):
     assert np.max(np.abs(y - e) / np.maximum(scale, 1e-30)) < TOL
 
 
-@pytest.mark.parametrize("case", [("f32", 6, 1000), ("f32", 3, 4096), ("i16", 6, 1000), ("i16", 5, 2048)])
+@pytest.mark.parametrize("case", [("f32", 6, 1000), ("f32", 3, 4096), ("i16", 6, 1000), ("i16", 5, 2048), ("i16", 10, 1000)])
 def test_few_channel_long_window_shard_with_halo(mavg, oracle_mod, torch_cuda, case):
     torch = torch_cuda
     dtype, ch, k = case
@@ -667,7 +705,7 @@ def test_few_channel_long_window_shard_with_halo(mavg, oracle_mod, torch_cuda, c
     with mavg.Plan(1_000_000, k, channels=ch, dtype=dtype) as probe:
         halo = int(probe.info.halo_frames)
         tiles_back = int(probe.info.history_tiles)
-        assert probe.info.mode == 4 and halo >= k and tiles_back >= 1
+        assert probe.info.mode == (6 if dtype == "i16" and ch in FLAT_I16_CH else 4) and halo >= k and tiles_back >= 1
     tf = halo // tiles_back
     frames, cut = 23 * tf + 123, 7 * tf
     x = (oracle_mod.fill_f32 if dtype == "f32" else oracle_mod.fill_i16)(frames * ch, 30000 + k)
@@ -694,7 +732,8 @@ def test_few_channel_long_window_shard_with_halo(mavg, oracle_mod, torch_cuda, c
 
 
 @pytest.mark.parametrize("case", [("f32", 3, 1 << 24, 1000), ("f32", 6, 1 << 23, 64), ("i16", 6, 1 << 23, 700),
-                                  ("i16", 5, 1 << 23, 48)])
+                                  ("i16", 5, 1 << 23, 48), ("i16", 10, 1 << 22, 200), ("i16", 8, 1 << 23, 4000),
+                                  ("i16", 3, 1 << 24, 77), ("i16", 4, 1 << 23, 1)])
 def test_few_channel_many_tiles_per_cta(mavg, oracle_mod, case):
     """Tens of tiles per persistent CTA (ring wrap-around, staging double buffer, chunk boundaries with history
     replay) on 50 M samples; every output checked."""
@@ -704,7 +743,8 @@ def test_few_channel_many_tiles_per_cta(mavg, oracle_mod, case):
     else:
         x = oracle_mod.fill_i16(frames * ch, 31000 + k)
     with mavg.Plan(frames, k, channels=ch, dtype=dtype) as plan:
-        assert plan.info.mode == 4
+        if k >= 2:
+            assert plan.info.mode == (6 if dtype == "i16" and ch in FLAT_I16_CH else 4)
         y = plan.run_host(x)
     if dtype == "f32":
         assert _rel(y, oracle_mod.mavg_f64(x, k, ch)) < TOL
@@ -951,7 +991,7 @@ def test_far_lag_kernel_with_context_in_another_allocation(mavg, oracle_mod, tor
     assert _rel(d_out2.cpu().numpy(), e[:short * ch]) < TOL
 
 
-@pytest.mark.parametrize("dtype,ch,k", [("i16", 2, 40_000), ("i16", 1, 70_000), ("i16", 6, 9_000), ("f32", 3, 20_000),
+@pytest.mark.parametrize("dtype,ch,k", [("i16", 2, 40_000), ("i16", 1, 70_000), ("i16", 6, 12_000), ("f32", 3, 20_000),
                                         ("i16", 2, 3_000_000)])
 def test_prefix_difference_path_far_windows(mavg, oracle_mod, torch_cuda, dtype, ch, k):
     """Far windows that no streaming kernel takes run as single-pass prefix sum + difference (info.mode 7): whole
