@@ -143,7 +143,22 @@ void i16_mulhi_consts(uint32_t k, uint32_t* mul, uint32_t* shift, uint32_t* wsca
     *shift = lg - 2;
 }
 
+StreamGeom plan_stream_i16_shape(uint32_t k, uint32_t C, const mavg_tuning& tu);
+
+// 3+ channels: CTAs of 128 threads, two per SM (their latency phases overlap: 2^27 samples, 6 channels 0.108 -> 0.103 ms,
+// 8 channels 0.095 -> 0.093 ms), while the window leaves them two tiles of prefetch; one larger CTA per SM beyond
 StreamGeom plan_stream_i16(uint32_t k, uint32_t C, const mavg_tuning& tu)
+{
+    if (C > 2 && tu.threads == 0 && tu.ctas_per_sm == 0 && tu.prefetch == 0) {
+        mavg_tuning t2 = tu;
+        t2.threads = 128;
+        const StreamGeom g = plan_stream_i16_shape(k, C, t2);
+        if (g.ok && g.ctas_per_sm == 2 && g.P == 2) return g;
+    }
+    return plan_stream_i16_shape(k, C, tu);
+}
+
+StreamGeom plan_stream_i16_shape(uint32_t k, uint32_t C, const mavg_tuning& tu)
 {
     StreamGeom g;
     g.NT = tu.threads == 256 ? 256 : 512;
@@ -154,11 +169,11 @@ StreamGeom plan_stream_i16(uint32_t k, uint32_t C, const mavg_tuning& tu)
     // twice as long (one CTA of 256 threads per SM; 2^27 samples, k = 64: 8 channels 0.108 -> 0.096 ms, 4 channels
     // 0.095 -> 0.091 ms); tuning.threads = 512 selects the 512-thread shape
     if (C == 4 || C == 8) {
-        g.NT = tu.threads == 512 ? 512 : 256;
-        g.R = g.NT == 256 ? 64 : 32;
+        g.NT = tu.threads == 512 ? 512 : tu.threads == 128 ? 128 : 256;
+        g.R = g.NT == 512 ? 32 : 64;
     } else if (C == 3 || C == 6) {                     // runs of an odd number of 16-byte chunks: dense tiles, no swizzle
-        g.NT = tu.threads == 512 ? 512 : 224;
-        g.R = g.NT == 224 ? 72 : 24;
+        g.NT = tu.threads == 512 ? 512 : tu.threads == 128 ? 128 : 224;
+        g.R = g.NT == 512 ? 24 : 72;
     }
     g.elem = 2;
     g.C = C;
@@ -180,8 +195,8 @@ StreamGeom plan_stream_i16(uint32_t k, uint32_t C, const mavg_tuning& tu)
     g.mode = 6;                                        // one arithmetic for every window: exclusive scan of run deltas
     const uint64_t T = (uint64_t)g.NT * R;
     g.H = (int)(((uint64_t)(g.n_full + 1) * R + T - 1) / T);
-    g.ctas_per_sm = tu.ctas_per_sm ? (int)tu.ctas_per_sm : (g.NT == 256 ? 2 : 1);
-    if (g.R > 32) g.ctas_per_sm = 1;
+    g.ctas_per_sm = tu.ctas_per_sm ? (int)tu.ctas_per_sm : (g.NT * g.R * 2 <= 18432 ? 2 : 1);
+    if (g.NT * g.R * 2 > 18432) g.ctas_per_sm = 1;
     g.P = tu.prefetch ? (int)tu.prefetch : 2;
     for (;;) {
         g.S = g.H + 1 + g.P;
@@ -491,10 +506,10 @@ StreamKernel pick_i16_kernel(const StreamGeom& g)
     switch (g.C) {
     case 1: return g.NT == 256 ? pick_i16<256, 32, 1>(g.MIS) : pick_i16<512, 32, 1>(g.MIS);
     case 2: return g.NT == 256 ? pick_i16<256, 32, 2>(g.MIS) : pick_i16<512, 32, 2>(g.MIS);
-    case 3: return g.NT == 224 ? pick_i16<224, 72, 3>(g.MIS) : pick_i16<512, 24, 3>(g.MIS);
-    case 4: return g.NT == 256 ? pick_i16<256, 64, 4>(g.MIS) : pick_i16<512, 32, 4>(g.MIS);
-    case 6: return g.NT == 224 ? pick_i16<224, 72, 6>(g.MIS) : pick_i16<512, 24, 6>(g.MIS);
-    case 8: return g.NT == 256 ? pick_i16<256, 64, 8>(g.MIS) : pick_i16<512, 32, 8>(g.MIS);
+    case 3: return g.NT == 224 ? pick_i16<224, 72, 3>(g.MIS) : g.NT == 128 ? pick_i16<128, 72, 3>(g.MIS) : pick_i16<512, 24, 3>(g.MIS);
+    case 4: return g.NT == 256 ? pick_i16<256, 64, 4>(g.MIS) : g.NT == 128 ? pick_i16<128, 64, 4>(g.MIS) : pick_i16<512, 32, 4>(g.MIS);
+    case 6: return g.NT == 224 ? pick_i16<224, 72, 6>(g.MIS) : g.NT == 128 ? pick_i16<128, 72, 6>(g.MIS) : pick_i16<512, 24, 6>(g.MIS);
+    case 8: return g.NT == 256 ? pick_i16<256, 64, 8>(g.MIS) : g.NT == 128 ? pick_i16<128, 64, 8>(g.MIS) : pick_i16<512, 32, 8>(g.MIS);
     default: return nullptr;
     }
 }

@@ -984,7 +984,7 @@ __device__ __forceinline__ uint32_t div_trunc_mulhi(int w, int mul, uint32_t sh)
 }
 
 template <int NT, int R, int C, int MIS>
-__global__ void __launch_bounds__(NT, (NT == 256 && R <= 32 ? 2 : 1))
+__global__ void __launch_bounds__(NT, (NT * R * 2 <= 18432 ? 2 : 1))   // tiles of 16 / 18 KB: two CTAs per SM
     stream_i16_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map,
                       const __grid_constant__ CUtensorMap halo_map, const StreamParams p)
 {

@@ -608,7 +608,7 @@ def test_flat_multichannel_i16_every_lag_alignment_and_ring_depth(mavg, oracle_m
     ks = list(range(2, 19)) + [tile_frames - 1, tile_frames, tile_frames + 1, 2 * tile_frames + 3, 3 * tile_frames - 5]
     for k in ks:
         e = oracle_mod.mavg_i16(x, k, ch)
-        for threads in (0, 512):
+        for threads in (0, 256, 512):      # auto (two 128-thread CTAs per SM while the window allows), one CTA of 256 / 224, of 512
             with mavg.Plan(frames, k, channels=ch, dtype="i16", threads=threads) as plan:
                 assert plan.info.path == 1 and plan.info.mode == 6, (ch, k)
                 assert np.array_equal(plan.run_host(x), e), (ch, k, threads)

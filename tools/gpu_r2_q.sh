@@ -3,6 +3,4 @@
 O=gpurun_out/r2q; mkdir -p $O
 ( time timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_dropin.py tests/test_gpu_random.py -m gpu -x -q -k "i16 or few_channel or flat_multichannel or random or multi_device" ) > $O/pytest.log 2>&1; echo "rc=$?" >> $O/pytest.log
 timeout 300 python tests/perf/bench_configs.py --config mci > $O/cfg_mci.json 2> $O/cfg_mci.err
-timeout 300 python tests/perf/bench_configs.py --config mci --tune threads=512 > $O/cfg_mci_512.json 2> $O/cfg_mci_512.err
-timeout 300 python tests/perf/bench_configs.py --config i16 > $O/cfg_i16.json 2> $O/cfg_i16.err
 ls -la $O; tail -5 $O/pytest.log
