@@ -174,6 +174,18 @@ StreamGeom plan_stream_i16_shape(uint32_t k, uint32_t C, const mavg_tuning& tu)
     } else if (C == 3 || C == 6) {                     // runs of an odd number of 16-byte chunks: dense tiles, no swizzle
         g.NT = tu.threads == 512 ? 512 : tu.threads == 128 ? 128 : 224;
         g.R = g.NT == 512 ? 24 : 72;
+    } else if (C == 12) {
+        g.NT = tu.threads == 128 ? 128 : 224;
+        g.R = 72;
+    } else if (C == 16) {
+        g.NT = tu.threads == 128 ? 128 : 256;
+        g.R = 64;
+    } else if (C == 5) {                               // runs of lcm(C, 8) samples: 5 / 7 chunks, dense tiles
+        g.NT = 384;
+        g.R = 40;
+    } else if (C == 7) {
+        g.NT = 256;
+        g.R = 56;
     }
     g.elem = 2;
     g.C = C;
@@ -184,7 +196,7 @@ StreamGeom plan_stream_i16_shape(uint32_t k, uint32_t C, const mavg_tuning& tu)
     // so its floor is trunc(w / k) - 1 and the sign bit adds the 1 back.  M < 2^31 needs k >= 3; k == 2 runs with
     // every dp2a weight doubled (sums 2 w) and the constants of k = 4.  k == 1 (identity) and longer windows are
     // left to the generic kernel.
-    if (k < 2 || k > 32768u || !(C == 1 || C == 2 || C == 3 || C == 4 || C == 6 || C == 8)) return g;
+    if (k < 2 || k > 32768u || !(C <= 8 || C == 12 || C == 16)) return g;
     const uint64_t L = (uint64_t)k * C;
     const uint32_t R = (uint32_t)g.R;
     const uint32_t s = (uint32_t)((R - L % R) % R);
@@ -464,7 +476,7 @@ StreamKernel pick_kernel(const StreamGeom& g, uint32_t k, bool rms)
     return pick_variant<512, 16>(g.MIS, g.mode, k);
 }
 
-// lag misalignment MIS = (-k C) mod 8 samples: any value for odd C, even for C = 2 and 6, 0 / 4 for C = 4, 0 for C = 8
+// lag misalignment MIS = (-k C) mod 8 samples: any value for odd C, even for C = 2 and 6, 0 / 4 for C = 4 and 12, 0 for C = 8 and 16
 template <int NT, int R, int C>
 StreamKernel pick_i16(int mis)
 {
@@ -475,13 +487,13 @@ StreamKernel pick_i16(int mis)
         MAVG_I16_CASE(0)
     default: break;
     }
-    if constexpr (C != 8) {
+    if constexpr (C % 8 != 0) {
         switch (mis) {
             MAVG_I16_CASE(4)
         default: break;
         }
     }
-    if constexpr (C != 8 && C != 4) {
+    if constexpr (C % 4 != 0) {
         switch (mis) {
             MAVG_I16_CASE(2)
             MAVG_I16_CASE(6)
@@ -510,6 +522,10 @@ StreamKernel pick_i16_kernel(const StreamGeom& g)
     case 4: return g.NT == 256 ? pick_i16<256, 64, 4>(g.MIS) : g.NT == 128 ? pick_i16<128, 64, 4>(g.MIS) : pick_i16<512, 32, 4>(g.MIS);
     case 6: return g.NT == 224 ? pick_i16<224, 72, 6>(g.MIS) : g.NT == 128 ? pick_i16<128, 72, 6>(g.MIS) : pick_i16<512, 24, 6>(g.MIS);
     case 8: return g.NT == 256 ? pick_i16<256, 64, 8>(g.MIS) : g.NT == 128 ? pick_i16<128, 64, 8>(g.MIS) : pick_i16<512, 32, 8>(g.MIS);
+    case 5: return pick_i16<384, 40, 5>(g.MIS);
+    case 7: return pick_i16<256, 56, 7>(g.MIS);
+    case 12: return g.NT == 128 ? pick_i16<128, 72, 12>(g.MIS) : pick_i16<224, 72, 12>(g.MIS);
+    case 16: return g.NT == 128 ? pick_i16<128, 64, 16>(g.MIS) : pick_i16<256, 64, 16>(g.MIS);
     default: return nullptr;
     }
 }

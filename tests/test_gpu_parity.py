@@ -568,31 +568,35 @@ def _fewc_runs(ch):
     return runs
 
 
-FLAT_I16_CH = (3, 4, 6, 8)      # channel counts the flat-stream int16 kernel takes (info.mode 6), runs of whole frames
+# channel counts the flat-stream int16 kernel takes (info.mode 6) with runs of whole frames: (threads, run) of the shape
+# with one CTA per SM; 3 / 4 / 6 / 8 channels also have a 512-thread shape (tuning.threads = 512)
+FLAT_I16_SHAPE = {3: (224, 72), 6: (224, 72), 12: (224, 72), 4: (256, 64), 8: (256, 64), 16: (256, 64), 5: (384, 40),
+                  7: (256, 56)}
+FLAT_I16_CH = tuple(sorted(FLAT_I16_SHAPE))
 
 
-@pytest.mark.parametrize("ch", [3, 4, 5, 6, 7, 8, 10, 12, 24, 31])
+@pytest.mark.parametrize("ch", [3, 4, 5, 6, 7, 8, 9, 10, 12, 16, 24, 31])
 @pytest.mark.parametrize("k", [1, 2, 3, 7, 8, 31, 32, 33, 64, 100, 255, 256, 300])
 def test_few_channel_interleaved_i16_bit_exact(mavg, oracle_mod, ch, k):
-    """3 / 4 / 6 / 8 channels: the stereo kernel's delta scan over the flat stream (runs of whole frames).  Other odd
+    """3 ... 8, 12, 16 channels: the stereo kernel's delta scan over the flat stream (runs of whole frames).  Other odd
     channel counts: 2-byte accesses, 32-frame runs.  Other even counts: channel pairs as 32-bit words, 16-frame runs."""
     pair = ch % 2 == 0
     runs = _fewc_runs(ch // 2 if pair else ch)
     rf = 16 if pair else 32
     frames = 3 * runs * rf + 41                    # several tiles, ragged tail (flat length not a multiple of 64)
     if ch in FLAT_I16_CH:
-        frames = 3 * (224 * 72 if ch % 3 == 0 else 256 * 64) // ch + 41
+        frames = 3 * FLAT_I16_SHAPE[ch][0] * FLAT_I16_SHAPE[ch][1] // ch + 41
     x = oracle_mod.fill_i16(frames * ch, 26000 + k + ch)
     with mavg.Plan(frames, k, channels=ch, dtype="i16") as plan:
         y = plan.run_host(x)
         i = plan.info
         if ch in FLAT_I16_CH:
-            if k >= 2:      # default shape: 224 threads x runs of 72 samples / 256 x 64
-                assert i.path == 1 and i.mode == 6 and i.run == (72 if ch % 3 == 0 else 64), "expected the flat-stream int16 kernel"
+            if k >= 2:
+                assert i.path == 1 and i.mode == 6 and i.run == FLAT_I16_SHAPE[ch][1], "expected the flat-stream int16 kernel"
         elif 2 <= k <= 256 and (k + rf - 1) // rf <= runs:
             assert i.path == 1 and i.mode == 4 and i.run == rf, "expected the few-channel int16 kernel"
     assert np.array_equal(y, oracle_mod.mavg_i16(x, k, ch))
-    if ch in FLAT_I16_CH and k >= 2:                  # the 512-thread shape (runs of 24 / 32 samples)
+    if ch in (3, 4, 6, 8) and k >= 2:                 # the 512-thread shape (runs of 24 / 32 samples)
         with mavg.Plan(frames, k, channels=ch, dtype="i16", threads=512) as plan:
             assert plan.info.mode == 6 and plan.info.run == (24 if ch % 3 == 0 else 32)
             assert np.array_equal(plan.run_host(x), oracle_mod.mavg_i16(x, k, ch))
@@ -602,7 +606,7 @@ def test_few_channel_interleaved_i16_bit_exact(mavg, oracle_mod, ch, k):
 def test_flat_multichannel_i16_every_lag_alignment_and_ring_depth(mavg, oracle_mod, ch):
     """Every lag misalignment (k C mod 8 samples), windows of one to several tiles of history, the longest window of the
     ring and the first one beyond it (which has to leave the kernel and still be exact)."""
-    tile_frames = (224 * 72 if ch % 3 == 0 else 256 * 64) // ch      # the default shape's tile (the 512-thread one: 512 x 24 / 32)
+    tile_frames = FLAT_I16_SHAPE[ch][0] * FLAT_I16_SHAPE[ch][1] // ch   # tile of the one-CTA shape (the 512-thread one: 512 x 24 / 32)
     frames = 9 * tile_frames + 77
     x = oracle_mod.fill_i16(frames * ch, 26500 + ch)
     ks = list(range(2, 19)) + [tile_frames - 1, tile_frames, tile_frames + 1, 2 * tile_frames + 3, 3 * tile_frames - 5]
@@ -624,7 +628,7 @@ def test_flat_multichannel_i16_every_lag_alignment_and_ring_depth(mavg, oracle_m
 def test_few_channel_i16_extremes_and_negative_truncation(mavg, oracle_mod):
     """Saturated inputs (window sums up to 256 * 32768 in magnitude) and sign-alternating ramps whose sums straddle
     zero: the multiply-high division has to truncate toward zero exactly as C's `/` does."""
-    for ch in (6, 3, 8, 10, 5):                    # flat-stream kernel (6, 3, 8), pair kernel, scalar kernel
+    for ch in (6, 3, 8, 5, 10, 9):                 # flat-stream kernel (6, 3, 8, 5), pair kernel, scalar kernel
         frames = 4 * 80 * 32 + 5
         for val in (-32768, 32767, -1, 1):
             x = np.full(frames * ch, val, dtype=np.int16)
@@ -637,7 +641,8 @@ def test_few_channel_i16_extremes_and_negative_truncation(mavg, oracle_mod):
             assert np.array_equal(mavg.moving_average(x, k, channels=ch), oracle_mod.mavg_i16(x, k, ch)), (ch, k)
 
 
-@pytest.mark.parametrize("case", [(6, 64), (3, 5), (7, 200), (8, 256), (4, 2), (12, 64), (6, 3000), (4, 9000), (3, 4097)])
+@pytest.mark.parametrize("case", [(6, 64), (3, 5), (7, 200), (8, 256), (4, 2), (12, 64), (6, 3000), (4, 9000), (3, 4097),
+                                  (10, 64), (9, 100), (5, 3001), (16, 1500)])
 def test_few_channel_i16_shard_with_halo_bit_exact(mavg, oracle_mod, torch_cuda, case):
     torch = torch_cuda
     ch, k = case
@@ -672,7 +677,7 @@ def test_few_channel_long_windows(mavg, oracle_mod, ch, k, dtype):
     with mavg.Plan(frames, k, channels=ch, dtype=dtype) as plan:
         y = plan.run_host(x)
         i = plan.info
-        if dtype == "i16" and ch in FLAT_I16_CH:
+        if dtype == "i16" and ch in FLAT_I16_CH and ch <= 8:
             assert i.path == 1 and i.mode == 6, "expected the flat-stream int16 kernel"
         elif ch <= 8 and k <= 1024:
             assert i.path == 1 and i.mode == 4, "expected a few-channel streaming kernel"
