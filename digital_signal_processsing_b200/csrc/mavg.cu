@@ -127,6 +127,7 @@ struct StreamGeom {
     bool pair = false;          // few-channel int16 with an even channel count: the kernel works on channel-pair words
     int cww = 1;              // column kernel: 32-channel column-warps side by side in one tile
     int runs = 0;             // few-channel kernel: 16-frame runs per tile
+    bool tmast = false;       // int16 column kernel: results leave through staging tiles and TMA stores
 };
 
 constexpr uint32_t kMaxSmem = 232448;  // 227 KB opt-in limit per CTA on sm_100
@@ -275,6 +276,9 @@ StreamGeom plan_cols(uint32_t k, uint32_t C, const mavg_tuning& tu, bool i16 = f
     g.C = C;
     g.mode = 3;
     if (i16) {
+        // int16: 8 warps x 32 frames by default (same tiles; half the threads with runs twice as long pay the per-run
+        // work -- barrier, delta exchange, addressing -- half as often); tuning.threads = 512: 16 warps x 16 frames
+        if (tu.threads != 512) { g.NT = 8 * 32; g.R = 32; }
         if (C % 8 != 0 || k < 2 || k > 32768u) return g;
         C /= 2;
         g.C = C;
@@ -283,28 +287,32 @@ StreamGeom plan_cols(uint32_t k, uint32_t C, const mavg_tuning& tu, bool i16 = f
         i16_mulhi_consts(k, &g.div_mul, &g.div_shift, &g.wscale);
     }
     if (C < 32 || C % 4 != 0) return g;
-    const uint32_t R = kColsRF;
+    const uint32_t R = (uint32_t)g.R;
     const uint32_t s = (R - k % R) % R;
     g.m_part = R - s;
     g.n_full = (k + s) / R - 1;
     g.ctas_per_sm = 1;
-    // widest tile (most contiguous bytes per row) whose history still leaves two tiles of prefetch
-    for (int cww = 8; cww >= 1; cww >>= 1) {
-        if (32u * cww > C && cww > 1) continue;
-        const uint32_t FT = (kColsNW / cww) * kColsRF;
-        g.cww = cww;
-        g.H = (int)(((uint64_t)(g.n_full + 1) * R + FT - 1) / FT);
-        g.P = tu.prefetch ? (int)tu.prefetch : 2;
-        bool fits = false;
-        for (;;) {
-            g.S = g.H + 1 + g.P;
-            g.smem = i16 ? mavg::cols_i16_smem_bytes(kColsNW, kColsRF, g.S)
-                         : mavg::cols_smem_bytes(kColsNW, kColsRF, g.S, g.H, 4u);
-            if (g.smem <= kMaxSmem) { fits = true; break; }
-            if (cww == 1 && g.P > 1) { --g.P; continue; }   // only the narrowest shape trades prefetch for history
-            break;
+    // widest tile (most contiguous bytes per row) whose history still leaves two tiles of prefetch; int16: with the
+    // staging tiles of the TMA store while they fit (tuning.direct_max_k = 1 forces the stores from registers)
+    for (int tmast = (i16 && tu.direct_max_k != 1) ? 1 : 0; tmast >= 0; --tmast) {
+        g.tmast = tmast != 0;
+        for (int cww = 8; cww >= 1; cww >>= 1) {
+            if (32u * cww > C && cww > 1) continue;
+            const uint32_t FT = (kColsNW / cww) * kColsRF;
+            g.cww = cww;
+            g.H = (int)(((uint64_t)(g.n_full + 1) * R + FT - 1) / FT);
+            g.P = tu.prefetch ? (int)tu.prefetch : 2;
+            bool fits = false;
+            for (;;) {
+                g.S = g.H + 1 + g.P;
+                g.smem = i16 ? mavg::cols_i16_smem_bytes(g.NT / 32, g.R, g.S, g.tmast)
+                             : mavg::cols_smem_bytes(kColsNW, kColsRF, g.S, g.H, 4u);
+                if (g.smem <= kMaxSmem) { fits = true; break; }
+                if (cww == 1 && g.P > 1) { --g.P; continue; }   // only the narrowest shape trades prefetch for history
+                break;
+            }
+            if (fits) { g.ok = true; return g; }
         }
-        if (fits) { g.ok = true; return g; }
     }
     return g;
 }
@@ -848,14 +856,20 @@ int launch_cols(mavg_plan* p, DevCtx& d, const void* in, void* out, const void* 
     cp.has_halo = halo ? 1 : 0;
     const unsigned grid = (unsigned)std::min<uint64_t>(ctas, (uint64_t)cp.total_chunks);
     if (g.pair) {
-        void (*kern16)(const CUtensorMap, const CUtensorMap, uint32_t*, const mavg::ColsParams, const uint32_t, const uint32_t,
-                       const uint32_t) =
-            g.cww == 8   ? mavg::stream_cols_i16x2_kernel<kColsNW, kColsRF, 8>
-            : g.cww == 4 ? mavg::stream_cols_i16x2_kernel<kColsNW, kColsRF, 4>
-            : g.cww == 2 ? mavg::stream_cols_i16x2_kernel<kColsNW, kColsRF, 2>
-                         : mavg::stream_cols_i16x2_kernel<kColsNW, kColsRF, 1>;
+        typedef void (*Kern16)(const CUtensorMap, const CUtensorMap, const CUtensorMap, uint32_t*, const mavg::ColsParams,
+                               const uint32_t, const uint32_t, const uint32_t);
+#define MAVG_COLS16(NW_, RF_, TM_)                                                 \
+    (g.cww == 8   ? (Kern16)mavg::stream_cols_i16x2_kernel<NW_, RF_, 8, TM_>       \
+     : g.cww == 4 ? (Kern16)mavg::stream_cols_i16x2_kernel<NW_, RF_, 4, TM_>       \
+     : g.cww == 2 ? (Kern16)mavg::stream_cols_i16x2_kernel<NW_, RF_, 2, TM_>       \
+                  : (Kern16)mavg::stream_cols_i16x2_kernel<NW_, RF_, 1, TM_>)
+        Kern16 kern16 = g.NT == 256 ? (g.tmast ? MAVG_COLS16(8, 32, true) : MAVG_COLS16(8, 32, false))
+                                    : (g.tmast ? MAVG_COLS16(kColsNW, kColsRF, true) : MAVG_COLS16(kColsNW, kColsRF, false));
+#undef MAVG_COLS16
+        CUtensorMap out_map = in_map;
+        if (g.tmast) MAVG_TRY(make_map_2d(&out_map, out, C, frames, FT, CW));
         MAVG_CUDA(cudaFuncSetAttribute(kern16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
-        kern16<<<grid, kColsNW * 32, g.smem, d.stream>>>(in_map, halo_map, (uint32_t*)out, cp, g.div_mul, g.div_shift, g.wscale);
+        kern16<<<grid, g.NT, g.smem, d.stream>>>(in_map, halo_map, out_map, (uint32_t*)out, cp, g.div_mul, g.div_shift, g.wscale);
         MAVG_CUDA(cudaGetLastError());
         ++*launches;
         return MAVG_OK;

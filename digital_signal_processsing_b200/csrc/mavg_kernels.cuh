@@ -1444,6 +1444,14 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         : "memory");
 }
 
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(map)),
+                 "r"(src), "r"(c0), "r"(c1)
+                 : "memory");
+}
+
 // NWT warps per CTA arranged as CWW column-warps (32 channels each, side by side) x NW = NWT / CWW
 // frame-warps (RF frames each).  Wider tiles (CWW > 1) read longer contiguous row pieces from HBM but
 // hold fewer frames of history, so the host picks the widest shape whose window still fits.
@@ -1678,16 +1686,21 @@ __global__ void __launch_bounds__(NWT * 32)
 //     chunk start - k, the first tile masked).
 // p.channels = C/2 (words per frame).  Bit-identical to profilable_cpu_computations.  4 B/sample.
 // ----------------------------------------------------------------------------------
-__host__ __device__ inline uint32_t cols_i16_smem_bytes(int NWT, int RF, int S)
+// TMAST: results leave through a double-buffered staging tile and one TMA store per tile (which also clips the rows
+// and columns past the end of the signal) instead of one 32-bit global store per word: a store from registers cost
+// 8 of 23 instructions per word (64-bit row addressing, bounds checks), and bursts of them slowed the kernel down
+// further (measured: all stores of a run back to back, 0.125 -> 0.163 ms on 2^27 samples).  The staging tiles take two
+// ring stages, so the longest windows of a channel count run with TMAST = false.
+__host__ __device__ inline uint32_t cols_i16_smem_bytes(int NWT, int RF, int S, bool tmast = false)
 {
-    return 1024u + (uint32_t)S * NWT * RF * 128u + 2u * NWT * 32 * 8u + (uint32_t)S * 8;
+    return 1024u + (uint32_t)(S + (tmast ? 2 : 0)) * NWT * RF * 128u + 2u * NWT * 32 * 8u + (uint32_t)S * 8;
 }
 
-template <int NWT, int RF, int CWW>
+template <int NWT, int RF, int CWW, bool TMAST = false>
 __global__ void __launch_bounds__(NWT * 32)
     stream_cols_i16x2_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap halo_map,
-                             uint32_t* __restrict__ out, const ColsParams p, const uint32_t div_mul,
-                             const uint32_t div_shift, const uint32_t wscale)
+                             const __grid_constant__ CUtensorMap out_map, uint32_t* __restrict__ out, const ColsParams p,
+                             const uint32_t div_mul, const uint32_t div_shift, const uint32_t wscale)
 {
     constexpr int NW = NWT / CWW;            // frame-warps
     constexpr int CW = 32 * CWW;             // words per tile row
@@ -1707,7 +1720,8 @@ __global__ void __launch_bounds__(NWT * 32)
 
     const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t ring_bytes = (uint32_t)S * TB;
-    const uint32_t dsum = ring + ring_bytes;                    // int2 [2][NW][CW]: run deltas (low / high channel), by tile parity
+    const uint32_t outb = ring + ring_bytes;                    // TMAST: two staging tiles
+    const uint32_t dsum = outb + (TMAST ? 2u * TB : 0u);        // int2 [2][NW][CW]: run deltas (low / high channel), by tile parity
     const uint32_t bars = dsum + 2u * NW * GROW;
     const uint32_t w_lo = wscale, w_hi = wscale << 8;
     const uint32_t n_lo = (0u - wscale) & 0xffu, n_hi = n_lo << 8;
@@ -1716,6 +1730,7 @@ __global__ void __launch_bounds__(NWT * 32)
     if (tid == 0) {
         prefetch_tmap(&in_map);
         if (p.has_halo) prefetch_tmap(&halo_map);
+        if (TMAST) prefetch_tmap(&out_map);
         for (int s = 0; s < S; ++s) mbar_init(bars + 8u * s, 1);
         fence_mbar_init();
     }
@@ -1732,6 +1747,20 @@ __global__ void __launch_bounds__(NWT * 32)
 
     uint32_t it = 0;
     int st = 0;
+    // TMAST, thread 0: the store of a staged tile is issued one iteration late (behind the next barrier) and its
+    // staging buffer is reused two tiles later, after cp.async.bulk.wait_group.read
+    uint32_t otiles = 0;
+    bool st_pending = false, st_inflight = false;
+    int st_tile = 0, st_cb = 0;
+    uint32_t st_buf = 0;
+    auto flush_store = [&]() {
+        if (st_pending) {
+            tma_store_2d(&out_map, st_buf, st_cb * CW, st_tile * FT);
+            tma_commit();
+            st_pending = false;
+            st_inflight = true;
+        }
+    };
 
     for (int chunk = blockIdx.x; chunk < p.total_chunks; chunk += gridDim.x) {
         const int rng = chunk / p.col_blocks;
@@ -1744,6 +1773,7 @@ __global__ void __launch_bounds__(NWT * 32)
         const int ntl = t1 - first;
         const uint32_t ch = (uint32_t)cb * CW + lane;
         const bool ch_ok = ch < p.channels;
+        (void)ch_ok;
 
         if (tid == 0) {
             int s2 = st;
@@ -1805,12 +1835,19 @@ __global__ void __launch_bounds__(NWT * 32)
             const uint32_t dbase = dsum + (it & 1u) * NW * GROW + (uint32_t)lane * 8u;
             sts64i(dbase + (uint32_t)warp * GROW, a0, a1);
 
+            if (TMAST && tid == 0 && st_inflight) {      // the staging buffer about to be rewritten is free again
+                tma_wait_read0();
+                st_inflight = false;
+            }
             __syncthreads();
 
-            if (tid == 0 && j + P < ntl) {
-                int s2 = st + P;
-                if (s2 >= S) s2 -= S;
-                issue_load(first + j + P, cb, s2);
+            if (tid == 0) {
+                if (j + P < ntl) {
+                    int s2 = st + P;
+                    if (s2 >= S) s2 -= S;
+                    issue_load(first + j + P, cb, s2);
+                }
+                if (TMAST) flush_store();
             }
 
             uint32_t e0 = 0u, e1 = 0u, tt0 = 0u, tt1 = 0u;   // deltas of the frame-warps in front / of all of them
@@ -1823,16 +1860,32 @@ __global__ void __launch_bounds__(NWT * 32)
 
             if (is_out) {
                 const uint32_t b0 = W0 + e0, b1 = W1 + e1;
-                const uint64_t f_base = (uint64_t)tile * FT + (uint64_t)warp * RF;
-                uint32_t* dst = out + f_base * p.channels + ch;
-                int nvalid = 0;
-                if (ch_ok && f_base < p.frames) nvalid = (p.frames - f_base < (uint64_t)RF) ? (int)(p.frames - f_base) : RF;
-                const uint32_t cstride = p.channels;
+                if constexpr (TMAST) {
+                    const uint32_t ob = outb + (otiles & 1u) * TB + ((uint32_t)(warp * RF) * CW + lane) * 4u;
 #pragma unroll
-                for (int r = 0; r < RF; ++r) {
-                    const uint32_t y = __byte_perm(div_trunc_mulhi((int)(b0 + s0[r]), mul, div_shift),
-                                                   div_trunc_mulhi((int)(b1 + s1[r]), mul, div_shift), 0x5410);
-                    if (r < nvalid) dst[(uint32_t)r * cstride] = y;
+                    for (int r = 0; r < RF; ++r)
+                        sts32u(ob + (uint32_t)r * ROWB, __byte_perm(div_trunc_mulhi((int)(b0 + s0[r]), mul, div_shift),
+                                                                    div_trunc_mulhi((int)(b1 + s1[r]), mul, div_shift), 0x5410));
+                    fence_proxy_async_smem();
+                    if (tid == 0) {
+                        st_pending = true;
+                        st_tile = tile;
+                        st_cb = cb;
+                        st_buf = outb + (otiles & 1u) * TB;
+                    }
+                    ++otiles;
+                } else {
+                    const uint64_t f_base = (uint64_t)tile * FT + (uint64_t)warp * RF;
+                    uint32_t* dst = out + f_base * p.channels + ch;
+                    int nvalid = 0;
+                    if (ch_ok && f_base < p.frames) nvalid = (p.frames - f_base < (uint64_t)RF) ? (int)(p.frames - f_base) : RF;
+                    const uint32_t cstride = p.channels;
+#pragma unroll
+                    for (int r = 0; r < RF; ++r) {
+                        const uint32_t y = __byte_perm(div_trunc_mulhi((int)(b0 + s0[r]), mul, div_shift),
+                                                       div_trunc_mulhi((int)(b1 + s1[r]), mul, div_shift), 0x5410);
+                        if (r < nvalid) dst[(uint32_t)r * cstride] = y;
+                    }
                 }
             }
             W0 += tt0, W1 += tt1;
@@ -1841,7 +1894,9 @@ __global__ void __launch_bounds__(NWT * 32)
             st = (st + 1 == S) ? 0 : st + 1;
         }
         __syncthreads();   // ring stages may be refilled by the next chunk's prologue
+        if (TMAST && tid == 0) flush_store();
     }
+    if (TMAST && tid == 0) tma_wait_all0();
 }
 
 // ----------------------------------------------------------------------------------

@@ -63,7 +63,7 @@ def timed(fn, stream, iters, warmup, world):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--config", required=True, choices=["4", "5p", "5i", "i16", "g3", "g6i", "mci", "gen", "s2", "scan"])
+    ap.add_argument("--config", required=True, choices=["4", "5p", "5i", "i16", "g3", "g6i", "mci", "ci", "gen", "s2", "scan"])
     ap.add_argument("--log2", type=int, default=32, help="total samples (log2) for configs 4/5")
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
@@ -269,6 +269,29 @@ def main():
                            "launches": int(plan.info.launches_per_run)}
             plan.close()
         out.update(workload="6-channel interleaved int16, 6 x 2^25 samples, k sweep", per_k=res)
+
+    elif args.config == "ci":  # many-channel interleaved int16 (column kernel), 2^27 samples
+        res = {}
+        for C, k in ((64, 8), (64, 64), (64, 1000), (128, 64), (256, 8), (256, 64), (1024, 64), (72, 64), (32, 64)):
+            n_frames = (1 << 27) // C
+            n = n_frames * C
+            d_in, d_out = alloc(2 * n), alloc(2 * n)
+            mavg.fill_synthetic_device(d_in.value, "i16", n, 0, SEED, 0, stream.cuda_stream)
+            stream.synchronize()
+            plan = mavg.Plan(n_frames, k, channels=C, dtype="i16", **tune)
+            plan.set_stream(stream.cuda_stream)
+            plan.enable_timing(False)
+            ms = timed(lambda: plan.run_device([d_in.value], [d_out.value]), stream, 5, 2, world)
+            y = torch.as_tensor(_Arr(d_out.value, n, "<i2"), device="cuda")
+            m = C * 3000
+            ok = bool(np.array_equal(y[:m].cpu().numpy(), oracle.mavg_i16(oracle.fill_i16(m, SEED), k, C)))
+            res[f"c{C}_k{k}"] = {"ms": round(ms, 4), "gsamples_s": round(n / ms / 1e6, 1), "hbm_gbs": round(4 * n / ms / 1e6, 1),
+                                 "bit_exact_head": ok, "mode": int(plan.info.mode), "threads": int(plan.info.threads),
+                                 "path": "stream" if plan.info.path == 1 else "generic"}
+            plan.close()
+            lib.mavg_device_free(d_in)
+            lib.mavg_device_free(d_out)
+        out.update(workload="C-channel interleaved int16 (C >= 32), 2^27 samples", per_k=res)
 
     elif args.config == "mci":  # multichannel PCM: 3 / 4 / 6 / 8 (flat-stream kernel) and 5 / 12 (few-channel kernels) int16 channels
         res = {}

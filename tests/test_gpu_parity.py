@@ -816,7 +816,13 @@ def test_many_channel_interleaved_i16_bit_exact(mavg, oracle_mod, ch, k):
         y = plan.run_host(x)
         if 2 <= k <= 96:
             assert plan.info.path == 1 and plan.info.mode == 3, "expected the int16 column kernel"
-    assert np.array_equal(y, oracle_mod.mavg_i16(x, k, ch))
+            assert plan.info.threads == 256 and plan.info.run == 32      # 8 warps x 32 frames
+    e = oracle_mod.mavg_i16(x, k, ch)
+    assert np.array_equal(y, e)
+    for tune in (dict(threads=512), dict(direct_max_k=1), dict(threads=512, direct_max_k=1)):
+        # 16 warps x 16 frames; stores from registers instead of staging tiles + TMA stores
+        with mavg.Plan(frames, k, channels=ch, dtype="i16", **tune) as plan:
+            assert np.array_equal(plan.run_host(x), e), tune
 
 
 def test_many_channel_i16_extremes_shards_and_odd_counts(mavg, oracle_mod, torch_cuda):
