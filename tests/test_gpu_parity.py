@@ -825,6 +825,19 @@ def test_many_channel_interleaved_i16_bit_exact(mavg, oracle_mod, ch, k):
             assert np.array_equal(plan.run_host(x), e), tune
 
 
+@pytest.mark.parametrize("case", [(64, (1 << 18) + 77, 64, {}), (256, (1 << 16) + 5, 8, {}), (128, (1 << 17) + 33, 200, dict(chunks_per_cta=3)),
+                                  (64, (1 << 18) + 77, 700, dict(direct_max_k=1)), (1024, (1 << 14) + 3, 64, dict(threads=512))])
+def test_many_channel_i16_many_tiles_per_cta(mavg, oracle_mod, case):
+    """Several tiles per persistent CTA (ring wrap-around, staging double buffer, history replay at every range
+    boundary, carried window sums) on 16 M samples; every output checked."""
+    ch, frames, k, tune = case
+    x = oracle_mod.fill_i16(frames * ch, 32500 + k + ch)
+    with mavg.Plan(frames, k, channels=ch, dtype="i16", **tune) as plan:
+        assert plan.info.path == 1 and plan.info.mode == 3
+        y = plan.run_host(x)
+    assert np.array_equal(y, oracle_mod.mavg_i16_mt(x, k, ch, 8))
+
+
 def test_many_channel_i16_extremes_shards_and_odd_counts(mavg, oracle_mod, torch_cuda):
     torch = torch_cuda
     ch, frames = 64, 3000
