@@ -380,19 +380,21 @@ StreamGeom plan_fewc(uint32_t k, uint32_t C, const mavg_tuning& tu, uint32_t ele
 StreamGeom plan_far(uint32_t k, uint32_t C, const mavg_tuning& tu)
 {
     StreamGeom g;
-    g.NT = 512;
+    // Tiles of 384 x 16 samples (24 KB; the lag samples of a tile are one 193-row box): results are written over the own
+    // tile and stored from its ring stage, so 227 KB hold four own stages (two loading, one computing, one storing)
+    // and three lag stages (two loading) -- twice the bytes in flight of the round-1 shape (512 x 16, staging tiles,
+    // one own tile and one lag tile in flight), which was latency-bound.  tuning.threads = 512: tiles of 512 x 16.
+    g.NT = tu.threads == 512 ? 512 : 384;
     g.R = 16;
     g.C = C;
     g.mode = 5;
-    const uint64_t T = 8192;
+    const uint64_t T = (uint64_t)g.NT * g.R;
     const uint64_t L = (uint64_t)k * C;               // lag distance in flat samples
     if (L < T || L > 0x40000000u || C > 2) return g;
     g.H = (int)((L + T - 1) / T);
-    // 227 KB hold either one own tile in flight and a two-stage lag ring (default: 0.249 ms on 2^27 samples at
-    // k = 60 000) or two and one (tuning.prefetch = 2: 0.289 ms -- the lag box is the exposed latency)
-    g.P = tu.prefetch == 2 ? 2 : 1;
-    g.S = 1 + g.P;
-    g.lag_stages = g.P == 2 ? 1 : 2;
+    g.P = tu.prefetch ? (int)std::min<uint32_t>(tu.prefetch, 3u) : 2;
+    g.S = g.P + 2;
+    g.lag_stages = g.NT == 512 ? 2 : g.P + 1;         // lag boxes in flight: lag_stages - 1 (at least one)
     g.MIS = (int)((4 - L % 4) % 4);
     g.ctas_per_sm = 1;
     g.smem = mavg::far_smem_bytes(g.NT, g.R, g.S, g.lag_stages);
@@ -954,13 +956,14 @@ int launch_far(mavg_plan* p, DevCtx& d, const void* in, void* out, const void* h
     uint64_t n, signals, stride;
     shard_signals(p, d, frames, &n, &signals, &stride);
     const uint64_t rows = n / 32;
-    const uint32_t tile_rows = 256;
-    const uint64_t T = 8192;
+    const uint64_t T = (uint64_t)g.NT * g.R;
+    const uint32_t tile_rows = (uint32_t)(T / 32);
     const uint64_t row_base = halo ? (uint64_t)g.H * tile_rows : 0;
     const void* base = halo ? halo : in;
     CUtensorMap in_map, out_map, lag_map;
     MAVG_TRY(make_map(&in_map, base, rows + row_base, signals, stride * 4, tile_rows, 4));
-    MAVG_TRY(make_map(&lag_map, base, rows + row_base, signals, stride * 4, 129, 4));
+    MAVG_TRY(make_map(&lag_map, base, rows + row_base, signals, stride * 4,
+                      tile_rows / mavg::far_lag_boxes((int)tile_rows) + 1, 4));
     MAVG_TRY(make_map(&out_map, out, rows, signals, stride * 4, tile_rows, 4));
     mavg::FarParams fp;
     memset(&fp, 0, sizeof fp);
@@ -988,7 +991,7 @@ int launch_far(mavg_plan* p, DevCtx& d, const void* in, void* out, const void* h
     fp.koff = (32 - k % 32) % 32;
     fp.lag_rows = (int32_t)((k + fp.koff) / 32);
     fp.lag_stages = g.lag_stages;
-    fp.lag_prefetch = g.lag_stages;
+    fp.lag_prefetch = std::max(1, g.lag_stages - 1);
     {
         static const int hints = [] {
             const char* e = getenv("MAVG_FAR_HINTS");
@@ -997,12 +1000,15 @@ int launch_far(mavg_plan* p, DevCtx& d, const void* in, void* out, const void* h
         }();
         fp.hints = hints;   // measured at k = 60 000 (2^27 samples): DRAM reads 899 -> 645 -> 643 MB for 537 MB of input
     }
-    void (*kern)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const mavg::FarParams) =
-        g.C == 2 ? (g.MIS == 0 ? mavg::stream_far_f32_kernel<512, 16, 0, 2> : mavg::stream_far_f32_kernel<512, 16, 2, 2>)
-        : g.MIS == 0 ? mavg::stream_far_f32_kernel<512, 16, 0>
-        : g.MIS == 1 ? mavg::stream_far_f32_kernel<512, 16, 1>
-        : g.MIS == 2 ? mavg::stream_far_f32_kernel<512, 16, 2>
-                     : mavg::stream_far_f32_kernel<512, 16, 3>;
+    typedef void (*FarKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const mavg::FarParams);
+#define MAVG_FAR(NT_)                                                                                                     \
+    (g.C == 2 ? (g.MIS == 0 ? (FarKernel)mavg::stream_far_f32_kernel<NT_, 16, 0, 2> : (FarKernel)mavg::stream_far_f32_kernel<NT_, 16, 2, 2>) \
+     : g.MIS == 0 ? (FarKernel)mavg::stream_far_f32_kernel<NT_, 16, 0>                                                    \
+     : g.MIS == 1 ? (FarKernel)mavg::stream_far_f32_kernel<NT_, 16, 1>                                                    \
+     : g.MIS == 2 ? (FarKernel)mavg::stream_far_f32_kernel<NT_, 16, 2>                                                    \
+                  : (FarKernel)mavg::stream_far_f32_kernel<NT_, 16, 3>)
+    FarKernel kern = g.NT == 512 ? MAVG_FAR(512) : MAVG_FAR(384);
+#undef MAVG_FAR
     MAVG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
     const unsigned grid = (unsigned)std::min<uint64_t>(ctas, (uint64_t)sp.total_chunks);
     kern<<<grid, g.NT, g.smem, d.stream>>>(in_map, out_map, lag_map, fp);
@@ -1071,7 +1077,7 @@ int launch_shard(mavg_plan* p, DevCtx& d, const void* in, void* out, const void*
         // a context somewhere else (a peer's tail) is served by the generic kernel
         const size_t hb = (size_t)p->halo_frames * (planar_batch(p) ? 1 : p->desc.channels) * sizeof(float);
         const bool contiguous = halo == nullptr || (const char*)halo + hb == (const char*)in;
-        const uint64_t rows_all = (planar_batch(p) ? p->desc.frames : frames * p->desc.channels) / 32 + (uint64_t)p->geom.H * 256;
+        const uint64_t rows_all = (planar_batch(p) ? p->desc.frames : frames * p->desc.channels) / 32 + (uint64_t)p->geom.H * (p->geom.NT * p->geom.R / 32);
         if (contiguous && stream_eligible(p, d, in, out, halo, frames) && rows_all < 0x7fffffffull - 65536)
             return launch_far(p, d, in, out, halo, frames, launches);
         if (!contiguous && !planar_batch(p) && stream_eligible(p, d, in, out, halo, frames) &&

@@ -433,7 +433,10 @@ __host__ __device__ inline uint32_t stream_smem_bytes(int NT, int R, int S, int 
 // ----------------------------------------------------------------------------------
 // TB_ / ROWS_ = tile bytes / 128-byte rows per tile as compile-time constants, or 0 for run-time values passed to
 // setup() (the few-channel kernel's tile depends on the channel count).
-template <uint32_t TB_, int ROWS_>
+// INPLACE_: no staging tiles -- a kernel that reads nothing but its own run from the current tile writes the results
+// over it and the TMA store leaves from the ring stage itself (stages: P loading, 1 computing, 1 storing; S >= P + 2).
+// The refill of a stage waits until the store issued one iteration earlier has read it (wait_group.read 1).
+template <uint32_t TB_, int ROWS_, bool INPLACE_ = false>
 struct TileRing {
     uint32_t tb_rt;
     int rows_rt;
@@ -479,7 +482,7 @@ struct TileRing {
         }
         pdl_wait_loads = p.pdl == 1;
         row_base = 0; load_hint = kEvictFirst; store_hint = 0;
-        return outb + 2u * tbv();
+        return INPLACE_ ? outb : outb + 2u * tbv();
     }
     __device__ __forceinline__ void init_barriers(uint32_t bars_addr)
     {
@@ -523,7 +526,7 @@ struct TileRing {
     }
     __device__ __forceinline__ void before_sync()
     {
-        if (threadIdx.x == 0 && st_inflight) {  // the staging buffer about to be rewritten is free again
+        if (!INPLACE_ && threadIdx.x == 0 && st_inflight) {  // the staging buffer about to be rewritten is free again
             tma_wait_read0();
             st_inflight = false;
         }
@@ -533,12 +536,24 @@ struct TileRing {
     __device__ __forceinline__ void after_sync(int j, int ntl, int first, int sig)
     {
         if (threadIdx.x == 0) {
-            if (j + P < ntl) {
-                int s2 = st + P;
-                if (s2 >= S) s2 -= S;
-                issue_load(first + j + P, sig, s2);
+            if constexpr (INPLACE_) {
+                flush_store();                   // the previous tile's results leave from their ring stage
+                if (j + P < ntl) {
+                    int s2 = st + P;
+                    if (s2 >= S) s2 -= S;
+                    // stage s2 held tile j + P - S <= j - 2, whose store was committed at least one group before the
+                    // one just issued
+                    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    issue_load(first + j + P, sig, s2);
+                }
+            } else {
+                if (j + P < ntl) {
+                    int s2 = st + P;
+                    if (s2 >= S) s2 -= S;
+                    issue_load(first + j + P, sig, s2);
+                }
+                flush_store();
             }
-            flush_store();
         }
     }
     __device__ __forceinline__ void flush_store()
@@ -555,7 +570,10 @@ struct TileRing {
             st_inflight = true;
         }
     }
-    __device__ __forceinline__ uint32_t out_tile() const { return outb + (otiles & 1u) * tbv(); }
+    __device__ __forceinline__ uint32_t out_tile() const
+    {
+        return INPLACE_ ? ring + (uint32_t)st * tbv() : outb + (otiles & 1u) * tbv();
+    }
     // all threads, after writing their part of the staging tile
     __device__ __forceinline__ void staged(int tile, int sig)
     {
@@ -578,7 +596,10 @@ struct TileRing {
     __device__ __forceinline__ void epilogue()
     {
         __syncthreads();
-        if (threadIdx.x == 0) flush_store();
+        if (threadIdx.x == 0) {
+            flush_store();
+            if (INPLACE_) tma_wait_read0();     // the next chunk's prologue refills stages without further checks
+        }
     }
     __device__ __forceinline__ void finish() const
     {
@@ -1197,13 +1218,22 @@ struct FarParams {
                             // is dead once read, the output is never read back: neither should push the own tiles that
                             // come back as lag boxes out of L2); 2 = 1 + own tiles evict-last
 };
-constexpr uint32_t kFarLagHalf = 17408;   // one 129-row box, padded to whole 1024-byte swizzle atoms
+// The lag samples of a tile of ROWS 128-byte rows span ROWS + 1 rows: one TMA box, or two boxes of ROWS / 2 + 1 rows
+// when that exceeds the 256 rows a box can hold; each box is padded to whole 1024-byte swizzle atoms.
+__host__ __device__ constexpr int far_lag_boxes(int rows) { return rows + 1 > 256 ? 2 : 1; }
+__host__ __device__ constexpr uint32_t far_lag_box_bytes(int rows)
+{
+    return ((uint32_t)(rows / far_lag_boxes(rows) + 1) * 128u + 1023u) & ~1023u;
+}
 
+// Results are written over the own tile (the kernel reads nothing but the thread's own run from it) and stored from
+// the ring stage: S = P + 2 own stages and no staging tiles.
 __host__ __device__ inline uint32_t far_smem_bytes(int NT, int R, int S, int SL)
 {
     const uint32_t TB = (uint32_t)NT * R * 4;
-    return 1024u + (uint32_t)S * TB + 2u * TB + (uint32_t)SL * 2u * kFarLagHalf + 2u * 32 * 2 * 4 + (uint32_t)SL * 8 +
-           (uint32_t)S * 8 + 64;
+    const int rows = NT * R / 32;
+    return 1024u + (uint32_t)S * TB + (uint32_t)SL * far_lag_boxes(rows) * far_lag_box_bytes(rows) + 2u * 32 * 2 * 4 +
+           (uint32_t)SL * 8 + (uint32_t)S * 8 + 64;
 }
 
 template <int NT, int R, int MIS, int C = 1>
@@ -1220,21 +1250,25 @@ __global__ void __launch_bounds__(NT)
     constexpr int NW = NT / 32;
     constexpr int CH_OWN = R / 4;
     constexpr int CH_LAG = CH_OWN + (MIS ? 1 : 0);
+    constexpr int NBOX = far_lag_boxes(ROWS);                 // lag boxes per tile
+    constexpr int BOXROWS = ROWS / NBOX + 1;
+    constexpr uint32_t LAGBOX = far_lag_box_bytes(ROWS);
+    constexpr int TPB = NT / NBOX;                            // threads whose lag runs live in one box
     const int SL = fp.lag_stages;
-    static_assert(NT == 512 && R == 16 && MIS >= 0 && MIS < 4, "two 129-row lag boxes cover exactly one 256-row tile");
+    static_assert(R == 16 && MIS >= 0 && MIS < 4 && ROWS % NBOX == 0 && NT % NBOX == 0 && ROWS <= 256, "shape");
     static_assert((C == 1 || C == 2) && MIS % C == 0, "mono or interleaved stereo");
 
     extern __shared__ uint8_t smem_raw[];
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    TileRing<TB, ROWS> tr;
-    const uint32_t lagbuf = tr.setup(smem_u32(smem_raw), p, &in_map, &out_map, &in_map);   // 1024-aligned: ring + whole tiles
+    TileRing<TB, ROWS, true> tr;
+    const uint32_t lagbuf = tr.setup(smem_u32(smem_raw), p, &in_map, &out_map, &in_map);   // 1024-aligned: ring of whole tiles
     tr.row_base = fp.row_base;
     tr.load_hint = fp.hints == 2 ? kEvictLast : kEvictNormal;
     tr.store_hint = fp.hints ? kEvictFirst : 0;
     const uint64_t lag_hint = fp.hints ? kEvictFirst : kEvictNormal;
-    const uint32_t wraw = lagbuf + (uint32_t)SL * 2u * kFarLagHalf;   // float [2][32][2]
+    const uint32_t wraw = lagbuf + (uint32_t)SL * NBOX * LAGBOX;      // float [2][32][2]
     const uint32_t lbars = wraw + 2u * 32 * 2 * 4;                    // u64 [SL]
     if (tid == 0) {
         prefetch_tmap(&lag_map);
@@ -1246,19 +1280,19 @@ __global__ void __launch_bounds__(NT)
 #pragma unroll
     for (int c = 0; c < CH_OWN; ++c) xo[c] = pre_swz(tid * (R * 4) + 16 * c);
     {
-        const int half = tid >> 8;
-        const int c0 = (int)(fp.koff >> 2) + CH_OWN * (tid & 255);
+        const int half = tid / TPB;
+        const int c0 = (int)(fp.koff >> 2) + CH_OWN * (tid % TPB);
 #pragma unroll
-        for (int c = 0; c < CH_LAG; ++c) xg[c] = pre_swz((c0 + c) * 16) + half * (int)kFarLagHalf;
+        for (int c = 0; c < CH_LAG; ++c) xg[c] = pre_swz((c0 + c) * 16) + half * (int)LAGBOX;
     }
     const int PL = fp.lag_prefetch;
     auto issue_lag = [&](int tile, int sig, int stage) {              // thread 0
         const uint32_t bar = lbars + 8u * (uint32_t)stage;
-        mbar_arrive_expect_tx(bar, 2u * 129u * 128u);
+        mbar_arrive_expect_tx(bar, (uint32_t)NBOX * BOXROWS * 128u);
         const int r0 = tile * ROWS - fp.lag_rows + fp.row_base;
-        const uint32_t dst = lagbuf + (uint32_t)stage * 2u * kFarLagHalf;
+        const uint32_t dst = lagbuf + (uint32_t)stage * NBOX * LAGBOX;
         tma_load_3d(dst, &lag_map, bar, 0, r0, sig, lag_hint);
-        tma_load_3d(dst + kFarLagHalf, &lag_map, bar, 0, r0 + 128, sig, lag_hint);
+        if constexpr (NBOX == 2) tma_load_3d(dst + LAGBOX, &lag_map, bar, 0, r0 + ROWS / 2, sig, lag_hint);
     };
     uint32_t lagit = 0;   // lag boxes consumed so far by this CTA, never reset
     int lst = 0;          // lagit % SL
@@ -1297,7 +1331,7 @@ __global__ void __launch_bounds__(NT)
             float d[C];
             if (is_out) {
                 mbar_wait(lbars + 8u * (uint32_t)lst, (lagit / (uint32_t)SL) & 1u);
-                const uint32_t lb = lagbuf + (uint32_t)lst * 2u * kFarLagHalf;
+                const uint32_t lb = lagbuf + (uint32_t)lst * NBOX * LAGBOX;
 #pragma unroll
                 for (int c = 0; c < CH_LAG; ++c) {
                     const float4 v = lds128(lb + (uint32_t)xg[c]);

@@ -158,12 +158,12 @@ def stream_model(x: np.ndarray, k: int, NT: int = 256, R: int = 16, direct_max: 
     return y[:n]
 
 
-def far_lag_model(x: np.ndarray, L: int, chunk_tiles: int = 4) -> np.ndarray:
+def far_lag_model(x: np.ndarray, L: int, chunk_tiles: int = 4, NT: int = 384) -> np.ndarray:
     """stream_far_f32_kernel (mono), operation for operation in fp32 / fp64: per chunk of `chunk_tiles` tiles the
     window sum W in front of the tile is built by ceil(L / T) masked warm-up tiles and carried in fp64; inside a
     tile every thread forms d = (own run total) - (lag run total) pairwise in fp32, the tile scans d (warp-level
-    Hillis-Steele, then the 16 warp totals), a run starts from float(W + exclusive prefix) and slides in fp32."""
-    NT, R, NW = 512, 16, 16
+    Hillis-Steele, then the NT / 32 warp totals), a run starts from float(W + exclusive prefix) and slides in fp32."""
+    R, NW = 16, NT // 32            # tiles of NT x 16 samples: 384 threads by default, 512 with tuning.threads = 512
     T = NT * R
     x = np.asarray(x, dtype=f32)
     n = x.size

@@ -967,17 +967,20 @@ def test_far_lag_kernel_stereo(mavg, oracle_mod, k):
     assert _rel(y, oracle_mod.mavg_f64(x, k, 2)) < TOL
 
 
+@pytest.mark.parametrize("threads", [384, 512])
 @pytest.mark.parametrize("L", [60_013, 100_003])
-def test_far_lag_kernel_matches_numpy_model_bitwise(mavg, oracle_mod, L):
+def test_far_lag_kernel_matches_numpy_model_bitwise(mavg, oracle_mod, L, threads):
     """The far-lag kernel performs exactly the operations of tests/algo_model.far_lag_model (one tile per chunk here:
-    fewer tiles than SMs), so the two agree bit for bit on every sample the streaming kernel produces."""
+    fewer tiles than SMs), so the two agree bit for bit on every sample the streaming kernel produces.  Tiles of
+    384 x 16 samples by default, 512 x 16 with tuning.threads = 512."""
     from algo_model import far_lag_model
     n = 23 * 8192 + 123
     x = oracle_mod.fill_f32(n, 777)
-    with mavg.Plan(n, L, path="stream") as plan:
+    with mavg.Plan(n, L, path="stream", threads=threads) as plan:
         assert plan.info.mode == 5, "windows of 60 000 samples and more are beyond the ring of the ordinary kernel"
+        assert plan.info.threads == threads
         y = plan.run_host(x)
-    m = far_lag_model(x, L, chunk_tiles=1)
+    m = far_lag_model(x, L, chunk_tiles=1, NT=threads)
     whole_rows = n // 32 * 32                  # the last partial row belongs to tail_kernel
     assert np.array_equal(y[:whole_rows], m[:whole_rows])
 
