@@ -65,7 +65,7 @@ def parse_args(argv=None):
                          "under the previous kernel's tail (the input buffer is never written), 1 = wait before the first "
                          "load, 3 = off")
     ap.add_argument("--no-graph", action="store_true", help="plain stream launches instead of replaying a CUDA graph of one step")
-    ap.add_argument("--skip", default="", help="comma list of evidence blocks to skip: parity,dense_k,i16,configs,e2e,steps")
+    ap.add_argument("--skip", default="", help="comma list of evidence blocks to skip: parity,dense_k,i16,configs,shapes,e2e,steps")
     ap.add_argument("--configs-log2", type=int, default=32, help="total samples (log2) of BASELINE configs 4 and 5")
     ap.add_argument("--ref-samples-log2", type=int, default=0,
                     help="reference arm: samples per k and step (log2); 0 = the GPU arm's --samples-log2")
@@ -596,6 +596,79 @@ def block_configs(cx, total_log2, peak, reps=10):
     return out
 
 
+def block_shapes(cx, peak, reps=10):
+    """The other kernels of the library on the shapes they exist for, 2^27 samples each, every rank the same signal:
+    multichannel int16 (flat-stream kernel: 4 / 6 / 8 channels; column kernel: 64 / 256 channels), every output sample
+    compared with the CPU oracle; a far window (float32, k = 60 000, far-lag kernel), spot-checked against the fp64
+    oracle; the prefix-sum primitive (int16 -> int64, 2^28 samples), head compared with an int64 cumsum."""
+    import numpy as np
+    import oracle
+    torch = cx.torch
+    threads = max(1, (os.cpu_count() or 1) // max(1, cx.world))
+    res = {}
+    for name, C, k in (("i16_c4_k1024", 4, 1024), ("i16_c6_k64", 6, 64), ("i16_c8_k64", 8, 64), ("i16_c64_k64", 64, 64),
+                       ("i16_c256_k64", 256, 64)):
+        frames = (1 << 27) // C
+        n = frames * C
+        d_in, d_out = cx.alloc(2 * n), cx.alloc(2 * n)
+        cx.mavg.fill_synthetic_device(d_in.value, "i16", n, 0, SEED, 0, cx.stream.cuda_stream)
+        cx.stream.synchronize()
+        p = cx.plan(frames, k, channels=C, dtype="i16")
+        ms = cx.time_launches(lambda: p.run_device([d_in.value], [d_out.value]), reps)
+        cx.stream.synchronize()
+        got = torch.as_tensor(_Arr(d_out.value, n, "<i2"), device="cuda").cpu().numpy()
+        x = oracle.fill_i16(n, SEED)
+        exp = oracle.mavg_i16_mt(x, k, C, threads) if threads > 1 else oracle.mavg_i16(x, k, C)
+        mism = int(_allsum(cx, int(np.count_nonzero(got != exp))))
+        info = p.info
+        res[name] = {"ms": round(ms, 4), "hbm_gbs": round(4 * n / (ms * 1e-3) / 1e9, 1),
+                     "frac_measured": round(4 * n / (ms * 1e-3) / 1e9 / peak, 4), "mismatches": mism,
+                     "compared_samples": n, "mode": int(info.mode), "threads": int(info.threads), "run": int(info.run)}
+        p.close()
+        cx.free(d_in)
+        cx.free(d_out)
+    # far window, float32 mono
+    n, k = 1 << 27, 60_000
+    d_in, d_out = cx.alloc(4 * n), cx.alloc(4 * n)
+    cx.mavg.fill_synthetic_device(d_in.value, "f32", n, 0, SEED, cx.mavg.DIST_U01, cx.stream.cuda_stream)
+    cx.stream.synchronize()
+    p = cx.plan(n, k)
+    ms = cx.time_launches(lambda: p.run_device([d_in.value], [d_out.value]), reps)
+    cx.stream.synchronize()
+    worst, cnt = spot_check_f32(cx, d_out.value, n, 0, k, np.random.default_rng(99), npoints=150)
+    worst = cx.allmax([worst])[0]
+    info = p.info
+    res["f32_c1_k60000"] = {"ms": round(ms, 4), "hbm_gbs": round(8 * n / (ms * 1e-3) / 1e9, 1),
+                            "frac_measured": round(8 * n / (ms * 1e-3) / 1e9 / peak, 4), "max_rel_err_spot": worst,
+                            "ok": bool(worst <= 1e-5), "mode": int(info.mode), "threads": int(info.threads)}
+    p.close()
+    cx.free(d_in)
+    cx.free(d_out)
+    # prefix-sum primitive
+    n = 1 << 28
+    d_in, d_out = cx.alloc(2 * n), cx.alloc(8 * n)
+    cx.mavg.fill_synthetic_device(d_in.value, "i16", n, 0, SEED, 0, cx.stream.cuda_stream)
+    cx.stream.synchronize()
+    ms = cx.time_launches(lambda: cx.mavg.prefix_sum_device(d_in.value, d_out.value, "i16", n, 1, cx.stream.cuda_stream), reps)
+    cx.stream.synchronize()
+    m = 1 << 22
+    got = torch.as_tensor(_Arr(d_out.value, n, "<i8"), device="cuda")
+    head_ok = bool(np.array_equal(got[:m].cpu().numpy(), np.cumsum(oracle.fill_i16(m, SEED).astype(np.int64))))
+    # the last prefix equals the sum of all samples: a checksum over the whole look-back chain
+    total = int(torch.as_tensor(_Arr(d_in.value, n, "<i2"), device="cuda").to(torch.int64).sum().item())
+    last_ok = int(got[n - 1].item()) == total
+    res["prefix_sum_i16_2^28"] = {"ms": round(ms, 4), "hbm_gbs": round(10 * n / (ms * 1e-3) / 1e9, 1),
+                                  "frac_measured": round(10 * n / (ms * 1e-3) / 1e9 / peak, 4),
+                                  "ok": bool(_allsum(cx, int(not (head_ok and last_ok))) == 0),
+                                  "what": "int16 -> int64, 2 + 8 bytes per sample; head of 2^22 prefixes == cumsum, last prefix == sum of all samples"}
+    cx.free(d_in)
+    cx.free(d_out)
+    ok = all(v.get("mismatches", 0) == 0 and v.get("ok", True) for v in res.values())
+    return {"ok": bool(ok), "per_shape": res,
+            "note": "%d back-to-back launches per shape on the bench stream (launch gaps included), max over ranks; int16 "
+                    "shapes: 4 bytes per sample, every output sample compared with the CPU oracle" % reps}
+
+
 def host_copy_ceiling(cx, nbytes, reps=3):
     """What the host side can deliver with NO kernel in the way: pinned H2D and D2H copies of `nbytes` each running
     at the same time on two streams, all ranks at once (so that shared PCIe uplinks / one NUMA node show up)."""
@@ -672,6 +745,12 @@ def block_e2e(cx, ks, samples_log2, steps):
             p.close()
         return res
 
+    # the copy probe runs before and after the legs and the better pass is reported: PCIe throughput of a shared box
+    # drifts by tens of percent within seconds, and a probe taken in a slow moment would sit below the pipeline it bounds
+    try:
+        ceil0 = host_copy_ceiling(cx, 4 * n)
+    except Exception:  # pragma: no cover
+        ceil0 = None
     out = leg("f32", torch.float32, 4, 1)
     try:
         out["i16"] = leg("i16", torch.int16, 2, 2)
@@ -679,7 +758,12 @@ def block_e2e(cx, ks, samples_log2, steps):
     except Exception as e:  # pragma: no cover
         out["i16"] = {"error": str(e)}
     try:
-        out["host_ceiling"] = host_copy_ceiling(cx, 4 * n)
+        ceil1 = host_copy_ceiling(cx, 4 * n)
+        if ceil0 and ceil0["gbs_each_way_per_gpu"] > ceil1["gbs_each_way_per_gpu"]:
+            ceil0, ceil1 = ceil1, ceil0
+        if ceil0:
+            ceil1["other_pass_gbs_each_way_per_gpu"] = ceil0["gbs_each_way_per_gpu"]
+        out["host_ceiling"] = ceil1
     except Exception as e:  # pragma: no cover
         out["host_ceiling"] = {"error": str(e)}
     return out
@@ -881,6 +965,7 @@ def main():
 
     guarded("i16", lambda: block_i16(cx, ks, args.samples_log2, peak))
     guarded("configs", lambda: block_configs(cx, args.configs_log2, peak))
+    guarded("shapes", lambda: block_shapes(cx, peak))
 
     # ---------------- end to end through the C ABI with HOST buffers (pinned), copies inside the timing
     e2e = None
