@@ -1057,3 +1057,66 @@ def test_prefix_difference_path_far_windows(mavg, oracle_mod, torch_cuda, dtype,
         plan.run_device_halo(d_in.data_ptr(), d_out.data_ptr(), d_ctx.data_ptr())
         plan.synchronize()
     check(d_out.cpu().numpy(), e[cut * ch:])
+
+
+# ------------------------------------------------------------------ size-independent properties at full size, no oracle in the loop
+@pytest.mark.parametrize("case", [("i16", 2, 1 << 27, 4096, 12_345), ("i16", 6, (1 << 27) // 6, 64, 1_001), ("i16", 8, 1 << 24, 1000, 77),
+                                  ("i16", 64, 1 << 21, 64, 333), ("i16", 256, 1 << 19, 8, 50), ("i16", 5, (1 << 26) // 5, 300, 4_097),
+                                  ("i16", 1, 1 << 27, 32768, 9)])
+def test_full_size_shift_invariance_and_impulse_response_i16(mavg, torch_cuda, case):
+    """A causal filter commutes with a delay: filtering the signal delayed by d frames (zeros shifted in) gives the
+    output delayed by d frames -- bit for bit for int16, whatever tile, run or tile-range boundary the delay moves the
+    samples across (d is never a multiple of a tile).  And the response to a single full-scale impulse is
+    trunc(32767 / k) for exactly k frames.  Both checked on the device over the whole 2^27-sample signal."""
+    torch = torch_cuda
+    dtype, ch, frames, k, d = case
+    n = frames * ch
+    x = torch.empty(n, dtype=torch.int16, device="cuda")
+    mavg.fill_synthetic_device(x.data_ptr(), "i16", n, 0, 4242 + k)
+    x2 = torch.zeros(n, dtype=torch.int16, device="cuda")
+    x2[d * ch:] = x[:n - d * ch]
+    y, y2 = torch.empty_like(x), torch.empty_like(x)
+    torch.cuda.synchronize()
+    with mavg.Plan(frames, k, channels=ch, dtype="i16") as plan:
+        assert plan.info.path == 1
+        plan.run_device([x.data_ptr()], [y.data_ptr()])
+        plan.run_device([x2.data_ptr()], [y2.data_ptr()])
+        plan.synchronize()
+        assert int(torch.count_nonzero(y2[:d * ch])) == 0
+        assert torch.equal(y2[d * ch:], y[:n - d * ch])
+        # impulse of 32767 in channel c at frame f0 = c * 1000 + 123_457 (mod frames)
+        x2.zero_()
+        pos = [((c * 1000 + 123_457) % (frames - k - 1), c) for c in range(ch)]
+        for f0, c in pos:
+            x2[f0 * ch + c] = 32767
+        plan.run_device([x2.data_ptr()], [y2.data_ptr()])
+        plan.synchronize()
+    yv = y2.view(frames, ch)
+    for f0, c in pos:
+        col = yv[:, c]
+        assert int(torch.count_nonzero(col)) == (k if 32767 // k else 0)
+        assert bool(torch.all(col[f0:f0 + k] == 32767 // k))
+
+
+@pytest.mark.parametrize("case", [(1, 1 << 27, 4096, 12_345), (2, 1 << 26, 100, 7), (1, 1 << 27, 60_000, 1_001), (6, (1 << 26) // 6, 64, 99),
+                                  (256, 1 << 18, 64, 11)])
+def test_full_size_shift_invariance_f32(mavg, torch_cuda, case):
+    """The same delay property for float32, where a delay that is not a multiple of a tile changes the order of the
+    additions: the two outputs agree to 1e-5 relative (inputs in [0.5, 1.5), so every window sum is far from zero)."""
+    torch = torch_cuda
+    ch, frames, k, d = case
+    n = frames * ch
+    x = torch.empty(n, dtype=torch.float32, device="cuda")
+    mavg.fill_synthetic_device(x.data_ptr(), "f32", n, 0, 4343 + k)
+    x += 0.5
+    x2 = torch.zeros(n, dtype=torch.float32, device="cuda")
+    x2[d * ch:] = x[:n - d * ch]
+    y, y2 = torch.empty_like(x), torch.empty_like(x)
+    torch.cuda.synchronize()
+    with mavg.Plan(frames, k, channels=ch) as plan:
+        plan.run_device([x.data_ptr()], [y.data_ptr()])
+        plan.run_device([x2.data_ptr()], [y2.data_ptr()])
+        plan.synchronize()
+    assert float(y2[:d * ch].abs().max()) == 0.0
+    a, b = y2[d * ch:], y[:n - d * ch]
+    assert float(((a - b).abs() / b.abs().clamp_min(1e-30)).max()) < TOL
