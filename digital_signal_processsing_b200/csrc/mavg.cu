@@ -169,7 +169,10 @@ StreamGeom plan_stream_i16_shape(uint32_t k, uint32_t C, const mavg_tuning& tu)
     // C channel deltas per run is what these shapes pay for, so by default they run with half the threads and runs
     // twice as long (one CTA of 256 threads per SM; 2^27 samples, k = 64: 8 channels 0.108 -> 0.096 ms, 4 channels
     // 0.095 -> 0.091 ms); tuning.threads = 512 selects the 512-thread shape
-    if (C == 4 || C == 8) {
+    if ((C == 4 || C == 8) && tu.run == 72) {          // experiment: the dense 72-sample shape on 4 / 8 channels
+        g.NT = tu.threads == 128 ? 128 : 224;
+        g.R = 72;
+    } else if (C == 4 || C == 8) {
         g.NT = tu.threads == 512 ? 512 : tu.threads == 128 ? 128 : 256;
         g.R = g.NT == 512 ? 32 : 64;
     } else if (C == 3 || C == 6) {                     // runs of an odd number of 16-byte chunks: dense tiles, no swizzle
@@ -529,9 +532,13 @@ StreamKernel pick_i16_kernel(const StreamGeom& g)
     case 1: return g.NT == 256 ? pick_i16<256, 32, 1>(g.MIS) : pick_i16<512, 32, 1>(g.MIS);
     case 2: return g.NT == 256 ? pick_i16<256, 32, 2>(g.MIS) : pick_i16<512, 32, 2>(g.MIS);
     case 3: return g.NT == 224 ? pick_i16<224, 72, 3>(g.MIS) : g.NT == 128 ? pick_i16<128, 72, 3>(g.MIS) : pick_i16<512, 24, 3>(g.MIS);
-    case 4: return g.NT == 256 ? pick_i16<256, 64, 4>(g.MIS) : g.NT == 128 ? pick_i16<128, 64, 4>(g.MIS) : pick_i16<512, 32, 4>(g.MIS);
+    case 4:
+        if (g.R == 72) return g.NT == 128 ? pick_i16<128, 72, 4>(g.MIS) : pick_i16<224, 72, 4>(g.MIS);
+        return g.NT == 256 ? pick_i16<256, 64, 4>(g.MIS) : g.NT == 128 ? pick_i16<128, 64, 4>(g.MIS) : pick_i16<512, 32, 4>(g.MIS);
     case 6: return g.NT == 224 ? pick_i16<224, 72, 6>(g.MIS) : g.NT == 128 ? pick_i16<128, 72, 6>(g.MIS) : pick_i16<512, 24, 6>(g.MIS);
-    case 8: return g.NT == 256 ? pick_i16<256, 64, 8>(g.MIS) : g.NT == 128 ? pick_i16<128, 64, 8>(g.MIS) : pick_i16<512, 32, 8>(g.MIS);
+    case 8:
+        if (g.R == 72) return g.NT == 128 ? pick_i16<128, 72, 8>(g.MIS) : pick_i16<224, 72, 8>(g.MIS);
+        return g.NT == 256 ? pick_i16<256, 64, 8>(g.MIS) : g.NT == 128 ? pick_i16<128, 64, 8>(g.MIS) : pick_i16<512, 32, 8>(g.MIS);
     case 5: return pick_i16<384, 40, 5>(g.MIS);
     case 7: return pick_i16<256, 56, 7>(g.MIS);
     case 12: return g.NT == 128 ? pick_i16<128, 72, 12>(g.MIS) : pick_i16<224, 72, 12>(g.MIS);
@@ -569,6 +576,11 @@ struct DevCtx {
     bool timed = false;
     // run_host pipeline: copies on their own streams so H2D, kernels and D2H overlap
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    // the few frames past the last whole 128-byte row run on a side stream, forked in front of the streaming kernel and
+    // joined behind it (they depend on the input only): serialised behind the kernel they cost ~10 us per call
+    cudaStream_t s_tail = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool tail_forked = false;
     std::vector<cudaEvent_t> pool;  // untimed events ordering slices across the three streams
 };
 
@@ -788,6 +800,47 @@ int launch_generic(const mavg_plan* p, DevCtx& d, const void* in, void* out, con
                                      out_begin, out_end, launches);
 }
 
+// Tail of a streamed shard (frames [out_begin, frames): less than one 128-byte row): enqueued on the device's side
+// stream BEFORE the streaming kernel is launched, so the two run concurrently; tail_join() makes the main stream wait
+// for it.  Capture-safe (fork and join by events).  Longer remainders stay on the main stream (launch_tail).
+int tail_fork(const mavg_plan* p, DevCtx& d, const void* in, void* out, const void* halo, uint64_t frames,
+              uint64_t out_begin, uint32_t* launches)
+{
+    d.tail_forked = false;
+    if (out_begin >= frames) return MAVG_OK;
+    if (frames - out_begin > 128) return MAVG_OK;        // tail_join launches it behind the kernel
+    // A frame that straddles the last whole row is written by both kernels: the same bits for int16 (exact), but a
+    // float32 tail rounds differently from the streaming kernel, so there the tail keeps running behind it (its value wins)
+    if (p->desc.dtype == MAVG_F32 && !planar_batch(p) && (frames * p->desc.channels / 32 * 32) % p->desc.channels != 0)
+        return MAVG_OK;
+    if (!d.s_tail) {
+        MAVG_CUDA(cudaStreamCreateWithFlags(&d.s_tail, cudaStreamNonBlocking));
+        MAVG_CUDA(cudaEventCreateWithFlags(&d.ev_fork, cudaEventDisableTiming));
+        MAVG_CUDA(cudaEventCreateWithFlags(&d.ev_join, cudaEventDisableTiming));
+    }
+    MAVG_CUDA(cudaEventRecord(d.ev_fork, d.stream));
+    MAVG_CUDA(cudaStreamWaitEvent(d.s_tail, d.ev_fork, 0));
+    cudaStream_t main_stream = d.stream;
+    d.stream = d.s_tail;
+    const int rc = launch_tail(p, d, in, out, halo, frames, out_begin, frames, launches);
+    d.stream = main_stream;
+    MAVG_TRY(rc);
+    MAVG_CUDA(cudaEventRecord(d.ev_join, d.s_tail));
+    d.tail_forked = true;
+    return MAVG_OK;
+}
+
+int tail_join(const mavg_plan* p, DevCtx& d, const void* in, void* out, const void* halo, uint64_t frames,
+              uint64_t out_begin, uint32_t* launches)
+{
+    if (d.tail_forked) {
+        d.tail_forked = false;
+        MAVG_CUDA(cudaStreamWaitEvent(d.stream, d.ev_join, 0));
+        return MAVG_OK;
+    }
+    return launch_tail(p, d, in, out, halo, frames, out_begin, frames, launches);
+}
+
 bool stream_eligible(const mavg_plan* p, const DevCtx& d, const void* in, const void* out, const void* halo,
                      uint64_t frames)
 {
@@ -942,10 +995,11 @@ int launch_fewc(mavg_plan* p, DevCtx& d, const void* in, void* out, const void* 
                : g.elem == 4 ? mavg::stream_fewc_f32_kernel<16> : mavg::stream_fewc_i16_kernel<32>;
     MAVG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
     const unsigned grid = (unsigned)std::min<uint64_t>(ctas, cps);
+    // flat samples past the last whole 128-byte row: the frames that touch them go to the tail kernel (side stream)
+    if (rows * row < n) MAVG_TRY(tail_fork(p, d, in, out, halo, frames, rows * row / C, launches));
     MAVG_CUDA(launch_ring(kern, grid, 512, g.smem, d.stream, sp.pdl, in_map, out_map, halo_map, fp));
     ++*launches;
-    // flat samples past the last whole 128-byte row: the frames that touch them go to the generic kernel
-    if (rows * row < n) MAVG_TRY(launch_tail(p, d, in, out, halo, frames, rows * row / C, frames, launches));
+    if (rows * row < n) MAVG_TRY(tail_join(p, d, in, out, halo, frames, rows * row / C, launches));
     return MAVG_OK;
 }
 
@@ -1011,10 +1065,11 @@ int launch_far(mavg_plan* p, DevCtx& d, const void* in, void* out, const void* h
 #undef MAVG_FAR
     MAVG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
     const unsigned grid = (unsigned)std::min<uint64_t>(ctas, (uint64_t)sp.total_chunks);
+    if (rows * 32 < n) MAVG_TRY(tail_fork(p, d, in, out, halo, frames, rows * 32 / g.C, launches));
     kern<<<grid, g.NT, g.smem, d.stream>>>(in_map, out_map, lag_map, fp);
     MAVG_CUDA(cudaGetLastError());
     ++*launches;
-    if (rows * 32 < n) MAVG_TRY(launch_tail(p, d, in, out, halo, frames, rows * 32 / g.C, frames, launches));
+    if (rows * 32 < n) MAVG_TRY(tail_join(p, d, in, out, halo, frames, rows * 32 / g.C, launches));
     return MAVG_OK;
 }
 
@@ -1168,13 +1223,11 @@ int launch_shard(mavg_plan* p, DevCtx& d, const void* in, void* out, const void*
     if (!kern) return fail(MAVG_ERR_UNSUPPORTED, "no stream kernel variant for this window");
     MAVG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
     const unsigned grid = (unsigned)std::min<uint64_t>(ctas, (uint64_t)sp.total_chunks);
+    // samples past the last whole 128-byte row (per signal): tail kernel, forked onto the side stream
+    if (rows * row < n) MAVG_TRY(tail_fork(p, d, in, out, halo, frames, rows * row / g.C, launches));
     MAVG_CUDA(launch_ring(kern, grid, (unsigned)g.NT, g.smem, d.stream, sp.pdl, in_map, out_map, halo_map, sp));
     ++*launches;
-
-    // samples past the last whole 128-byte row (per signal): generic kernel
-    if (rows * row < n) {
-        MAVG_TRY(launch_tail(p, d, in, out, halo, frames, rows * row / g.C, frames, launches));
-    }
+    if (rows * row < n) MAVG_TRY(tail_join(p, d, in, out, halo, frames, rows * row / g.C, launches));
     return MAVG_OK;
 }
 
@@ -1530,6 +1583,9 @@ int mavg_plan_destroy(mavg_plan* p)
         if (d.d_far_stage) cudaFree(d.d_far_stage);
         if (d.d_prefix) cudaFree(d.d_prefix);
         if (d.ev_pass) cudaEventDestroy(d.ev_pass);
+        if (d.s_tail) { cudaStreamSynchronize(d.s_tail); cudaStreamDestroy(d.s_tail); }
+        if (d.ev_fork) cudaEventDestroy(d.ev_fork);
+        if (d.ev_join) cudaEventDestroy(d.ev_join);
         if (d.s_h2d) { cudaStreamSynchronize(d.s_h2d); cudaStreamDestroy(d.s_h2d); }
         if (d.s_d2h) { cudaStreamSynchronize(d.s_d2h); cudaStreamDestroy(d.s_d2h); }
         for (cudaEvent_t e : d.pool) cudaEventDestroy(e);
