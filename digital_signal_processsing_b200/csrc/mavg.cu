@@ -169,10 +169,7 @@ StreamGeom plan_stream_i16_shape(uint32_t k, uint32_t C, const mavg_tuning& tu)
     // C channel deltas per run is what these shapes pay for, so by default they run with half the threads and runs
     // twice as long (one CTA of 256 threads per SM; 2^27 samples, k = 64: 8 channels 0.108 -> 0.096 ms, 4 channels
     // 0.095 -> 0.091 ms); tuning.threads = 512 selects the 512-thread shape
-    if ((C == 4 || C == 8) && tu.run == 72) {          // experiment: the dense 72-sample shape on 4 / 8 channels
-        g.NT = tu.threads == 128 ? 128 : 224;
-        g.R = 72;
-    } else if (C == 4 || C == 8) {
+    if (C == 4 || C == 8) {
         g.NT = tu.threads == 512 ? 512 : tu.threads == 128 ? 128 : 256;
         g.R = g.NT == 512 ? 32 : 64;
     } else if (C == 3 || C == 6) {                     // runs of an odd number of 16-byte chunks: dense tiles, no swizzle
@@ -533,11 +530,9 @@ StreamKernel pick_i16_kernel(const StreamGeom& g)
     case 2: return g.NT == 256 ? pick_i16<256, 32, 2>(g.MIS) : pick_i16<512, 32, 2>(g.MIS);
     case 3: return g.NT == 224 ? pick_i16<224, 72, 3>(g.MIS) : g.NT == 128 ? pick_i16<128, 72, 3>(g.MIS) : pick_i16<512, 24, 3>(g.MIS);
     case 4:
-        if (g.R == 72) return g.NT == 128 ? pick_i16<128, 72, 4>(g.MIS) : pick_i16<224, 72, 4>(g.MIS);
         return g.NT == 256 ? pick_i16<256, 64, 4>(g.MIS) : g.NT == 128 ? pick_i16<128, 64, 4>(g.MIS) : pick_i16<512, 32, 4>(g.MIS);
     case 6: return g.NT == 224 ? pick_i16<224, 72, 6>(g.MIS) : g.NT == 128 ? pick_i16<128, 72, 6>(g.MIS) : pick_i16<512, 24, 6>(g.MIS);
     case 8:
-        if (g.R == 72) return g.NT == 128 ? pick_i16<128, 72, 8>(g.MIS) : pick_i16<224, 72, 8>(g.MIS);
         return g.NT == 256 ? pick_i16<256, 64, 8>(g.MIS) : g.NT == 128 ? pick_i16<128, 64, 8>(g.MIS) : pick_i16<512, 32, 8>(g.MIS);
     case 5: return pick_i16<384, 40, 5>(g.MIS);
     case 7: return pick_i16<256, 56, 7>(g.MIS);

@@ -99,12 +99,17 @@ typedef enum mavg_op {
 
 /* Optional tuning overrides; 0 = library default. */
 typedef struct mavg_tuning {
-    uint32_t threads;        /* threads per CTA of the float32 stream kernel: 256 or 512   */
-    uint32_t run;            /* samples per thread run: 16 or 32                           */
+    uint32_t threads;        /* threads per CTA.  float32 stream kernel: 256 or 512.  int16 with 3+ interleaved
+                                channels: 128 (two CTAs per SM), 256 (one CTA of 224 / 256 / 384 threads with the
+                                long runs), 512 (short runs; 3 / 4 / 6 / 8 channels).  int16 column kernel
+                                (64+ channels): 512 = 16 warps x 16 frames instead of 8 x 32.  Far-lag kernel: 512 =
+                                tiles of 512 x 16 samples instead of 384 x 16                                   */
+    uint32_t run;            /* samples per thread run of the float32 stream kernel: 16 or 32                  */
     uint32_t prefetch;       /* tiles in flight ahead of the one being filtered            */
     uint32_t ctas_per_sm;    /* resident CTAs per SM the grid is sized for                 */
     uint32_t chunks_per_cta; /* contiguous tile ranges each CTA walks (>=1)                */
-    uint32_t direct_max_k;   /* largest k*channels served by direct group sums (default 256) */
+    uint32_t direct_max_k;   /* largest k*channels served by direct group sums (default 256); int16 column
+                                kernel: 1 = results stored from registers instead of staging tiles + TMA stores */
     uint32_t slice_bytes;    /* mavg_run_host: bytes per pipelined H2D/kernel/D2H slice (default 16 MiB) */
     uint32_t overlap;        /* programmatic dependent launch of the streaming kernels (the next launch's prologue
                                 runs under the previous kernel's tail; nothing is written before the previous
