@@ -150,14 +150,20 @@ def test_pre_swizzled_offsets_equal_swizzled_addresses():
 
 
 # ---------------------------------------------------------------- far-lag kernel (stream_far_f32_kernel) geometry
-def test_far_lag_boxes_and_warm_up_cover_exactly_the_window():
-    """Index algebra of the far-lag kernel with its real constants (tiles of 8192 samples = 256 rows of 32, two
-    129-row lag boxes per tile, koff / lag_rows / MIS from launch_far): every thread's lag run is x[i - L .. i - L + 16)
-    for its own run start i, and the masked warm-up tiles in front of a chunk sum exactly the L samples in front of
-    it.  Integer data, so equality is exact."""
-    T, ROW, NT, R = 8192, 32, 512, 16
+@pytest.mark.parametrize("NT", [384, 512])
+def test_far_lag_boxes_and_warm_up_cover_exactly_the_window(NT):
+    """Index algebra of the far-lag kernel with its real constants (tiles of NT x 16 samples: 384 threads = 192 rows of
+    32 with ONE 193-row lag box per tile, 512 threads = 256 rows with two 129-row boxes; koff / lag_rows / MIS from
+    launch_far): every thread's lag run is x[i - L .. i - L + 16) for its own run start i, and the masked warm-up tiles
+    in front of a chunk sum exactly the L samples in front of it.  Integer data, so equality is exact."""
+    ROW, R = 32, 16
+    T = NT * R
+    ROWS = T // ROW
+    NBOX = 2 if ROWS + 1 > 256 else 1                                   # far_lag_boxes()
+    BOXROWS = ROWS // NBOX + 1
+    TPB = NT // NBOX
     rng = np.random.default_rng(9)
-    for L in (8192, 8193, 9001, 12_346, 16_384, 20_007, 40_000):       # lag distance in flat samples (k, or 2k stereo)
+    for L in (T, T + 1, 9001, 12_346, 16_384, 20_007, 40_000):         # lag distance in flat samples (k, or 2k stereo)
         n = 7 * T
         x = rng.integers(-1000, 1000, size=n).astype(np.int64)
         koff = (ROW - L % ROW) % ROW
@@ -177,15 +183,15 @@ def test_far_lag_boxes_and_warm_up_cover_exactly_the_window():
 
         for j in (0, 1, 3, 6):
             r0 = j * (T // ROW) - lag_rows
-            halves = [box(r0, 129), box(r0 + 128, 129)]
-            for t in (0, 1, 255, 256, 300, 511):
-                c0 = koff // 4 + 4 * (t & 255)                          # first 16-byte chunk the thread loads
-                chunks = halves[t >> 8][4 * c0: 4 * (c0 + 5)]
+            halves = [box(r0 + b * (ROWS // 2), BOXROWS) for b in range(NBOX)]
+            for t in (0, 1, TPB - 1, TPB % NT, 300, NT - 1):
+                c0 = koff // 4 + 4 * (t % TPB)                          # first 16-byte chunk the thread loads
+                chunks = halves[t // TPB][4 * c0: 4 * (c0 + 5)]
                 lag_run = chunks[mis: mis + R]
                 i = j * T + R * t
                 want = np.array([x[i - L + r] if i - L + r >= 0 else 0 for r in range(R)])
                 assert np.array_equal(lag_run, want), (L, j, t)
-                assert 4 * (c0 + 4 + (1 if mis else 0)) <= 129 * ROW    # the chunks stay inside the 129-row box
+                assert 4 * (c0 + 4 + (1 if mis else 0)) <= BOXROWS * ROW   # the chunks stay inside the lag box
         # warm-up in front of a chunk that starts at tile t0: HT tiles, the first one masked from m0 on
         for t0 in (0, 2, 5):
             W = 0
@@ -196,3 +202,99 @@ def test_far_lag_boxes_and_warm_up_cover_exactly_the_window():
                 W += int(tile[m0:].sum())
             lo = t0 * T - L
             assert W == int(x[max(lo, 0): t0 * T].sum()), (L, t0)
+
+
+# ---------------------------------------------------------------- flat-stream int16 kernel (stream_i16_kernel), any channel count
+FLAT_SHAPES = [(512, 32, 1), (512, 32, 2), (128, 72, 3), (224, 72, 3), (512, 24, 3), (256, 64, 4), (384, 40, 5), (128, 72, 6),
+               (224, 72, 6), (256, 56, 7), (128, 64, 8), (256, 64, 8), (224, 72, 12), (256, 64, 16)]
+
+
+@pytest.mark.parametrize("NT,R,C", FLAT_SHAPES)
+def test_flat_i16_delta_scan_matches_exact_window_sums(NT, R, C):
+    """stream_i16_kernel's arithmetic restated on integers: a run of R flat samples holds whole frames (channel of
+    element r = r % C); s[r] = running sum of x[i] - x[i - L] per channel inside the run, d = its last value per
+    channel, start(t) = W + exclusive scan of d over the tile, W carried from tile to tile and built by masked warm-up
+    tiles in front of a tile range.  The result has to equal the exact causal window sums for every lag distance,
+    including lags that are not whole runs or whole tiles, and ranges that start anywhere."""
+    assert R % C == 0 and R % 8 == 0
+    T = NT * R
+    rng = np.random.default_rng(100 + NT + R + C)
+    ntiles = 5
+    n = ntiles * T
+    x = rng.integers(-32768, 32768, size=n).astype(np.int64)
+    xp = np.concatenate([np.zeros(4 * T, dtype=np.int64), x])          # zero padding in front (TMA out-of-bounds fill)
+    base = 4 * T
+    for k in (2, 3, R // C, R // C + 1, T // C - 1, T // C, T // C + 5, 2 * T // C + 7):
+        L = k * C
+        H = (L + R - 1) // R * R                                        # (n_full + 1) * R of plan_stream_i16
+        H = (H + T - 1) // T
+        exact = np.zeros(n, dtype=np.int64)                             # exact window sums per flat sample
+        for c in range(C):
+            col = xp[c::C].cumsum()
+            colp = np.concatenate([np.zeros(k, dtype=np.int64), col])
+            win = colp[k:] - colp[:-k]
+            exact_c = win[(base + c) // C if (base % C) == 0 else 0:]
+            exact[c::C] = exact_c[:len(exact[c::C])]
+        for t0 in (0, 2):                                               # a tile range that starts at tile t0
+            W = np.zeros(C, dtype=np.int64)
+            for j in range(H):                                          # warm-up tiles, the first one masked
+                u = t0 - H + j
+                tile = xp[base + u * T: base + (u + 1) * T]
+                idx = np.arange(T)
+                rel = (t0 - u) * T - L                                  # samples at or behind (range start - L) count
+                m = np.where(idx >= rel, tile, 0)
+                for c in range(C):
+                    W[c] += m[c::C].sum()
+            for t in range(t0, ntiles):
+                own = xp[base + t * T: base + (t + 1) * T].reshape(NT, R)
+                lag = xp[base + t * T - L: base + (t + 1) * T - L].reshape(NT, R)
+                delta = own - lag
+                s_run = np.zeros((NT, R), dtype=np.int64)
+                for c in range(C):
+                    s_run[:, c::C] = delta[:, c::C].cumsum(axis=1)
+                d = np.stack([s_run[:, R - C + c] for c in range(C)], axis=1)     # last value per channel = run delta
+                excl = np.cumsum(d, axis=0) - d
+                for c in range(C):
+                    y = W[c] + excl[:, c][:, None] + s_run[:, c::C]
+                    got = y.reshape(-1)
+                    want = exact[t * T: (t + 1) * T].reshape(NT, R)[:, c::C].reshape(-1)
+                    assert np.array_equal(got, want), (NT, R, C, k, t0, t, c)
+                W += d.sum(axis=0)
+
+
+@pytest.mark.parametrize("NT,R,C", FLAT_SHAPES)
+def test_flat_i16_cross_warp_layout_and_lag_alignment(NT, R, C):
+    """(i) The [channel][warp] array of the cross-warp scan: lane = (warp w' = lane % NW, group g = lane // NW) reads
+    word j * 32 + lane, which has to be the total that warp w' wrote for channel g + j * G -- every (warp, channel) pair
+    exactly once, inside the 32 * CJ words the kernel reserves.  (ii) plan_stream_i16's lag addressing: lag_chunks
+    16-byte chunks back from the own run plus MIS samples is exactly L samples back, for every window."""
+    NW = NT // 32
+    G = 32 // NW
+    CJ = (C + G - 1) // G
+    seen = {}
+    for warp in range(NW):
+        for c in range(C):
+            w = (c // G) * 32 + (c % G) * NW + warp                    # where lane 31 of `warp` stores channel c
+            assert 0 <= w < 32 * CJ and w not in seen
+            seen[w] = (warp, c)
+    for lane in range(G * NW):
+        wq, g = lane % NW, lane // NW
+        for j in range(CJ):
+            c = g + j * G
+            if c < C:
+                assert seen[j * 32 + lane] == (wq, c)
+    for c in range(C):                                                  # the lane a thread of `warp` fetches channel c from
+        for warp in range(NW):
+            src = (c % G) * NW + warp
+            assert src < 32 and src % NW == warp and src // NW == c % G
+    for k in range(2, 200):
+        L = k * C
+        lag_chunks = (L + 7) // 8
+        mis = 8 * lag_chunks - L
+        assert 0 <= mis < 8 and lag_chunks * 8 - mis == L
+        if C % 8 == 0:
+            assert mis == 0
+        elif C % 4 == 0:
+            assert mis in (0, 4)
+        elif C % 2 == 0:
+            assert mis % 2 == 0
