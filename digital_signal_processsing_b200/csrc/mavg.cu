@@ -377,6 +377,42 @@ StreamGeom plan_fewc(uint32_t k, uint32_t C, const mavg_tuning& tu, uint32_t ele
 
 // float32 mono / planar with a window too long for the ring of plan_stream: the lag samples come back through a
 // second TMA stream (stream_far_f32_kernel).  H = warm-up tiles = left context in whole tiles.
+// int16 twin (stream_far_i16_kernel): mono / stereo / 4 / 6 / 8 interleaved channels, exact int32 window sums, so
+// k * k < 2^31 (k <= 46 340; the multiply-high division is exact while 32768 k e < 2^(30 + ceil(log2 k)) with
+// e <= k, i.e. while 2^15 k^2 <= 2^46).  Shapes: 384 x 32 for mono / stereo, 192 x 64 for 4 / 8 channels (24 KB tiles,
+// one lag box, three lag stages), 224 x 72 for 6 channels (31.5 KB tiles, two lag stages).
+StreamGeom plan_far_i16(uint32_t k, uint32_t C, const mavg_tuning& tu)
+{
+    StreamGeom g;
+    g.mode = 5;
+    g.elem = 2;
+    g.C = C;
+    if (k < 3 || (uint64_t)k * k >= (1ull << 31)) return g;
+    if (C <= 2) { g.NT = 384; g.R = 32; }
+    else if (C == 4 || C == 8) { g.NT = 192; g.R = 64; }   // 24 KB tiles, one lag box: two lag boxes in flight (8 ch, k = 19 200: 0.158 -> 0.136 ms against 256 x 64)
+    else if (C == 6) { g.NT = 224; g.R = 72; }
+    else return g;
+    const uint64_t T = (uint64_t)g.NT * g.R;
+    const uint64_t L = (uint64_t)k * C;
+    if (L < T) return g;
+    g.H = (int)((L + T - 1) / T);
+    g.P = 2;
+    g.S = g.P + 2;
+    g.lag_stages = 3;                                  // two lag boxes in flight where 227 KB allow it (24 KB tiles)
+    g.lag_chunks = (uint32_t)((L + 7) / 8);
+    g.MIS = (int)(8ull * g.lag_chunks - L);
+    g.ctas_per_sm = 1;
+    for (;;) {
+        g.smem = mavg::far_i16_smem_bytes(g.NT, g.R, g.S, g.lag_stages, (int)C);
+        if (g.smem <= kMaxSmem) break;
+        if (g.lag_stages > 2) { --g.lag_stages; continue; }
+        return g;
+    }
+    i16_mulhi_consts(k, &g.div_mul, &g.div_shift, &g.wscale);
+    g.ok = true;
+    return g;
+}
+
 StreamGeom plan_far(uint32_t k, uint32_t C, const mavg_tuning& tu)
 {
     StreamGeom g;
@@ -1004,23 +1040,29 @@ int launch_far(mavg_plan* p, DevCtx& d, const void* in, void* out, const void* h
     const StreamGeom& g = p->geom;
     uint64_t n, signals, stride;
     shard_signals(p, d, frames, &n, &signals, &stride);
-    const uint64_t rows = n / 32;
+    const uint32_t es = g.elem;                         // 4: float32 kernel, 2: int16 twin
+    const uint32_t row = 128 / es;                      // samples per 128-byte row
+    const uint64_t rows = n / row;
     const uint64_t T = (uint64_t)g.NT * g.R;
-    const uint32_t tile_rows = (uint32_t)(T / 32);
+    const uint32_t tile_rows = (uint32_t)(T / row);
     const uint64_t row_base = halo ? (uint64_t)g.H * tile_rows : 0;
     const void* base = halo ? halo : in;
+    const int swz = es == 2 ? mavg::i16_swizzle_bytes(g.R) : 128;
     CUtensorMap in_map, out_map, lag_map;
-    MAVG_TRY(make_map(&in_map, base, rows + row_base, signals, stride * 4, tile_rows, 4));
-    MAVG_TRY(make_map(&lag_map, base, rows + row_base, signals, stride * 4,
-                      tile_rows / mavg::far_lag_boxes((int)tile_rows) + 1, 4));
-    MAVG_TRY(make_map(&out_map, out, rows, signals, stride * 4, tile_rows, 4));
+    MAVG_TRY(make_map(&in_map, base, rows + row_base, signals, stride * es, tile_rows, es, swz));
+    MAVG_TRY(make_map(&lag_map, base, rows + row_base, signals, stride * es,
+                      tile_rows / mavg::far_lag_boxes((int)tile_rows) + 1, es, swz));
+    MAVG_TRY(make_map(&out_map, out, rows, signals, stride * es, tile_rows, es, swz));
     mavg::FarParams fp;
     memset(&fp, 0, sizeof fp);
     mavg::StreamParams& sp = fp.sp;
     const uint32_t k = (uint32_t)((uint64_t)p->desc.window * g.C);   // lag distance in flat samples
     sp.inv_k = 1.0f / (float)p->desc.window;
-    sp.k = k;
-    const uint64_t tiles = (rows * 32 + T - 1) / T;
+    sp.k = es == 2 ? p->desc.window : k;                // the int16 kernel multiplies by its channel count itself
+    sp.div_mul = g.div_mul;
+    sp.div_shift = g.div_shift;
+    sp.wscale = g.wscale;
+    const uint64_t tiles = (rows * row + T - 1) / T;
     sp.tiles_per_signal = (int32_t)tiles;
     const uint64_t ctas = (uint64_t)d.sm_count;
     uint64_t cps = std::max<uint64_t>(1, ctas * std::max<uint32_t>(1u, p->desc.tuning.chunks_per_cta) / signals);
@@ -1037,8 +1079,8 @@ int launch_far(mavg_plan* p, DevCtx& d, const void* in, void* out, const void* h
     sp.has_halo = 0;
     fp.warm_tiles = g.H;
     fp.row_base = (int32_t)row_base;
-    fp.koff = (32 - k % 32) % 32;
-    fp.lag_rows = (int32_t)((k + fp.koff) / 32);
+    fp.koff = (row - k % row) % row;
+    fp.lag_rows = (int32_t)((k + fp.koff) / row);
     fp.lag_stages = g.lag_stages;
     fp.lag_prefetch = std::max(1, g.lag_stages - 1);
     {
@@ -1058,13 +1100,26 @@ int launch_far(mavg_plan* p, DevCtx& d, const void* in, void* out, const void* h
                   : (FarKernel)mavg::stream_far_f32_kernel<NT_, 16, 3>)
     FarKernel kern = g.NT == 512 ? MAVG_FAR(512) : MAVG_FAR(384);
 #undef MAVG_FAR
+    if (es == 2) {
+        kern = nullptr;
+#define MAVG_FAR16(NT_, R_, C_, M_) \
+    if (g.C == C_ && g.MIS == M_ && g.NT == NT_) kern = (FarKernel)mavg::stream_far_i16_kernel<NT_, R_, C_, M_>;
+        MAVG_FAR16(384, 32, 1, 0) MAVG_FAR16(384, 32, 1, 1) MAVG_FAR16(384, 32, 1, 2) MAVG_FAR16(384, 32, 1, 3)
+        MAVG_FAR16(384, 32, 1, 4) MAVG_FAR16(384, 32, 1, 5) MAVG_FAR16(384, 32, 1, 6) MAVG_FAR16(384, 32, 1, 7)
+        MAVG_FAR16(384, 32, 2, 0) MAVG_FAR16(384, 32, 2, 2) MAVG_FAR16(384, 32, 2, 4) MAVG_FAR16(384, 32, 2, 6)
+        MAVG_FAR16(192, 64, 4, 0) MAVG_FAR16(192, 64, 4, 4)
+        MAVG_FAR16(224, 72, 6, 0) MAVG_FAR16(224, 72, 6, 2) MAVG_FAR16(224, 72, 6, 4) MAVG_FAR16(224, 72, 6, 6)
+        MAVG_FAR16(192, 64, 8, 0)
+#undef MAVG_FAR16
+        if (!kern) return fail(MAVG_ERR_UNSUPPORTED, "no far-lag int16 kernel for %u channels, misalignment %d", g.C, g.MIS);
+    }
     MAVG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
     const unsigned grid = (unsigned)std::min<uint64_t>(ctas, (uint64_t)sp.total_chunks);
-    if (rows * 32 < n) MAVG_TRY(tail_fork(p, d, in, out, halo, frames, rows * 32 / g.C, launches));
+    if (rows * row < n) MAVG_TRY(tail_fork(p, d, in, out, halo, frames, rows * row / g.C, launches));
     kern<<<grid, g.NT, g.smem, d.stream>>>(in_map, out_map, lag_map, fp);
     MAVG_CUDA(cudaGetLastError());
     ++*launches;
-    if (rows * 32 < n) MAVG_TRY(tail_join(p, d, in, out, halo, frames, rows * 32 / g.C, launches));
+    if (rows * row < n) MAVG_TRY(tail_join(p, d, in, out, halo, frames, rows * row / g.C, launches));
     return MAVG_OK;
 }
 
@@ -1125,9 +1180,12 @@ int launch_shard(mavg_plan* p, DevCtx& d, const void* in, void* out, const void*
     if (p->path == MAVG_PATH_STREAM && p->geom.ok && p->geom.mode == 5) {
         // the left context has to sit directly in front of the shard (run_host slices, contiguous callers);
         // a context somewhere else (a peer's tail) is served by the generic kernel
-        const size_t hb = (size_t)p->halo_frames * (planar_batch(p) ? 1 : p->desc.channels) * sizeof(float);
+        const size_t fes = p->geom.elem;                  // 4: float32, 2: int16 twin
+        const size_t hb = (size_t)p->halo_frames * (planar_batch(p) ? 1 : p->desc.channels) * fes;
         const bool contiguous = halo == nullptr || (const char*)halo + hb == (const char*)in;
-        const uint64_t rows_all = (planar_batch(p) ? p->desc.frames : frames * p->desc.channels) / 32 + (uint64_t)p->geom.H * (p->geom.NT * p->geom.R / 32);
+        const uint64_t frow = 128 / fes;
+        const uint64_t rows_all = (planar_batch(p) ? p->desc.frames : frames * p->desc.channels) / frow +
+                                  (uint64_t)p->geom.H * (p->geom.NT * p->geom.R / frow);
         if (contiguous && stream_eligible(p, d, in, out, halo, frames) && rows_all < 0x7fffffffull - 65536)
             return launch_far(p, d, in, out, halo, frames, launches);
         if (!contiguous && !planar_batch(p) && stream_eligible(p, d, in, out, halo, frames) &&
@@ -1136,7 +1194,7 @@ int launch_shard(mavg_plan* p, DevCtx& d, const void* in, void* out, const void*
             // halo_frames frames of the shard can see it: [context | those frames] is copied into a small plan-owned
             // buffer (two times the window, a few MB) where the context IS contiguous, and filtered from there straight
             // into the output; the rest of the shard finds its context inside the shard itself.
-            const size_t fb = (size_t)p->desc.channels * sizeof(float);
+            const size_t fb = (size_t)p->desc.channels * fes;
             const uint64_t fa = std::min<uint64_t>(frames, p->halo_frames);
             const size_t need = hb + fa * fb;
             if (d.far_stage_bytes < need) {
@@ -1475,10 +1533,19 @@ int mavg_plan_create(const mavg_desc* desc, mavg_plan** out)
         if (!planar && desc->channels >= 32) {
             p->geom = plan_cols(desc->window, desc->channels, desc->tuning, true);
             stream_shape = p->geom.ok;
-        } else if (!planar && desc->channels >= 3) {
-            // 3 / 4 / 6 / 8 channels: the flat-stream kernel while the window fits its ring, else the few-channel kernels
-            stream_shape = p->geom.ok;
+        } else {
+            // 3+ channels: the flat-stream kernel while the window fits its ring (stream_shape follows the plan)
+            if (!planar && desc->channels >= 3) stream_shape = p->geom.ok;
+            // beyond the ring: the far-lag int16 kernel (mono / stereo / planar, 4 / 6 / 8 channels, k <= 46 340) ...
             if (!p->geom.ok) {
+                const StreamGeom gf = plan_far_i16(desc->window, planar ? 1u : desc->channels, desc->tuning);
+                if (gf.ok) {
+                    p->geom = gf;
+                    stream_shape = true;
+                }
+            }
+            // ... then the few-channel kernels
+            if (!p->geom.ok && !planar && desc->channels >= 3) {
                 p->geom = plan_fewc(desc->window, desc->channels, desc->tuning, 2);
                 stream_shape = p->geom.ok;
             }

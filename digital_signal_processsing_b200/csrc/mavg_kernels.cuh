@@ -1434,6 +1434,245 @@ __global__ void __launch_bounds__(NT)
 }
 
 // ----------------------------------------------------------------------------------
+// Far-lag int16 kernel -- stream_i16_kernel's exact delta-scan arithmetic with stream_far_f32_kernel's data movement:
+// interleaved int16 with C channels whose lag distance L = k C no longer fits the ring (stereo beyond k = 24 576,
+// 8 channels beyond k = 6 144 ...).  The lag run x[i - L .. i - L + R) of every thread comes back through a second TMA
+// stream (one or two lag boxes per tile, normally still in L2: the same CTA read those bytes as its own tile L samples
+// earlier), the results are written over the own tile and stored from its ring stage (TileRing<..., INPLACE>), the
+// window sum W at the first sample of the tile is carried in int32 (|W| <= 32768 k < 2^31 for k <= 46 340, exact, so
+// -- unlike the float32 far-lag kernel -- sliced, sharded and whole runs agree bit for bit), a tile range builds its
+// first W from the ceil(L / T) masked warm-up tiles in front of it.  fp.sp.k = k (frames); fp.koff / fp.lag_rows
+// describe L in int16 samples and 64-sample rows.
+// ----------------------------------------------------------------------------------
+__host__ __device__ inline uint32_t far_i16_smem_bytes(int NT, int R, int S, int SL, int C)
+{
+    const uint32_t TB = (uint32_t)NT * R * 2;
+    const int rows = NT * R / 64;
+    const uint32_t NW = (uint32_t)NT / 32, G = 32 / NW;
+    return 2048u + (uint32_t)S * TB + (uint32_t)SL * far_lag_boxes(rows) * far_lag_box_bytes(rows) +
+           2u * 32 * ((C + G - 1) / G) * 4 + (uint32_t)SL * 8 + (uint32_t)S * 8 + 64;
+}
+
+template <int NT, int R, int C, int MIS>
+__global__ void __launch_bounds__(NT)
+    stream_far_i16_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map,
+                          const __grid_constant__ CUtensorMap lag_map, const FarParams fp)
+{
+    const StreamParams& p = fp.sp;
+    constexpr int T = NT * R;
+    constexpr uint32_t TB = T * 2;
+    constexpr int ROWS = T / 64;
+    constexpr int NW = NT / 32;
+    constexpr int CH_OWN = R / 8;
+    constexpr int CH_LAG = CH_OWN + (MIS ? 1 : 0);
+    constexpr int SWZ = i16_swizzle_bytes(R);
+    constexpr int NBOX = far_lag_boxes(ROWS);
+    constexpr int BOXROWS = ROWS / NBOX + 1;
+    constexpr uint32_t LAGBOX = far_lag_box_bytes(ROWS);
+    constexpr int TPB = NT / NBOX;
+    constexpr int G = 32 / NW;
+    constexpr int CJ = (C + G - 1) / G;
+    static_assert(R % C == 0 && R % 8 == 0 && NW <= 16 && MIS >= 0 && MIS < 8 && T % 64 == 0 && ROWS <= 256 &&
+                      ROWS % NBOX == 0 && NT % NBOX == 0 && (SWZ == 0 || TB % 1024 == 0),
+                  "shape");
+    const int SL = fp.lag_stages;
+
+    extern __shared__ uint8_t smem_raw[];
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    TileRing<TB, ROWS, true> tr;
+    uint32_t lagbuf = tr.setup(smem_u32(smem_raw), p, &in_map, &out_map, &in_map);
+    lagbuf = (lagbuf + 1023u) & ~1023u;       // (dense shapes: the ring is not a whole number of 1024-byte atoms)
+    tr.row_base = fp.row_base;
+    tr.load_hint = fp.hints == 2 ? kEvictLast : kEvictNormal;
+    tr.store_hint = fp.hints ? kEvictFirst : 0;
+    const uint64_t lag_hint = fp.hints ? kEvictFirst : kEvictNormal;
+    const uint32_t wraw = lagbuf + (uint32_t)SL * NBOX * LAGBOX;      // uint32 [2][CJ * G][NW] warp totals
+    const uint32_t lbars = wraw + 2u * 32 * CJ * 4;                   // u64 [SL]
+    if (tid == 0) {
+        prefetch_tmap(&lag_map);
+        for (int s2 = 0; s2 < SL; ++s2) mbar_init(lbars + 8u * s2, 1);
+    }
+    tr.init_barriers(lbars + (uint32_t)SL * 8);
+    const int wq = lane % NW;
+    const int wlast = lane - wq + NW - 1;
+    const uint32_t w_lo = p.wscale, w_hi = p.wscale << 8;
+    const uint32_t n_lo = (0u - p.wscale) & 0xffu, n_hi = n_lo << 8;
+    const int L = (int)(p.k * (uint32_t)C);
+    int xo[CH_OWN], xg[CH_LAG];
+#pragma unroll
+    for (int c = 0; c < CH_OWN; ++c) xo[c] = pre_swz_n<SWZ>(tid * (R * 2) + 16 * c);
+    {
+        const int half = tid / TPB;
+        const int c0 = (int)(fp.koff >> 3) + CH_OWN * (tid % TPB);
+#pragma unroll
+        for (int c = 0; c < CH_LAG; ++c) xg[c] = pre_swz_n<SWZ>((c0 + c) * 16) + half * (int)LAGBOX;
+    }
+    const int mul = (int)p.div_mul;
+    const uint32_t sh = p.div_shift;
+    const int PL = fp.lag_prefetch;
+    auto issue_lag = [&](int tile, int sig, int stage) {              // thread 0
+        const uint32_t bar = lbars + 8u * (uint32_t)stage;
+        mbar_arrive_expect_tx(bar, (uint32_t)NBOX * BOXROWS * 128u);
+        const int r0 = tile * ROWS - fp.lag_rows + fp.row_base;
+        const uint32_t dst = lagbuf + (uint32_t)stage * NBOX * LAGBOX;
+        tma_load_3d(dst, &lag_map, bar, 0, r0, sig, lag_hint);
+        if constexpr (NBOX == 2) tma_load_3d(dst + LAGBOX, &lag_map, bar, 0, r0 + ROWS / 2, sig, lag_hint);
+    };
+    uint32_t lagit = 0;
+    int lst = 0;
+
+    for (int chunk = blockIdx.x; chunk < p.total_chunks; chunk += gridDim.x) {
+        int sig, t0, t1;
+        if (!chunk_range(p, chunk, sig, t0, t1)) continue;
+        const int HT = fp.warm_tiles;
+        const int first = t0 - HT;
+        const int ntl = t1 - first;
+        tr.prologue(first, ntl, sig);
+        if (tid == 0) {
+            int s2 = lst;
+            for (int i = 0; i < PL && t0 + i < t1; ++i) {
+                issue_lag(t0 + i, sig, s2);
+                s2 = (s2 + 1 == SL) ? 0 : s2 + 1;
+            }
+        }
+        uint32_t Wl[CJ];
+#pragma unroll
+        for (int j = 0; j < CJ; ++j) Wl[j] = 0u;
+
+        for (int j = 0; j < ntl; ++j) {
+            const int tile = first + j;
+            const bool is_out = (j >= HT);
+            const uint32_t cur = tr.wait_tile();
+            const uint32_t it = tr.it;
+
+            uint32_t xw[R / 2];
+#pragma unroll
+            for (int c = 0; c < CH_OWN; ++c) {
+                const uint4 v = lds128u(cur + (uint32_t)xo[c]);
+                xw[4 * c] = v.x, xw[4 * c + 1] = v.y, xw[4 * c + 2] = v.z, xw[4 * c + 3] = v.w;
+            }
+            uint32_t s[R];
+            uint32_t d[C];
+            if (is_out) {
+                mbar_wait(lbars + 8u * (uint32_t)lst, (lagit / (uint32_t)SL) & 1u);
+                const uint32_t lb = lagbuf + (uint32_t)lst * NBOX * LAGBOX;
+                uint32_t xlw[CH_LAG * 4];
+#pragma unroll
+                for (int c = 0; c < CH_LAG; ++c) {
+                    const uint4 v = lds128u(lb + (uint32_t)xg[c]);
+                    xlw[4 * c] = v.x, xlw[4 * c + 1] = v.y, xlw[4 * c + 2] = v.z, xlw[4 * c + 3] = v.w;
+                }
+                int a[C];
+#pragma unroll
+                for (int c = 0; c < C; ++c) a[c] = 0;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int e = MIS + r;
+                    int a2 = dp2a_s(xw[r >> 1], (r & 1) ? w_hi : w_lo, a[r % C]);
+                    a2 = dp2a_s(xlw[e >> 1], (e & 1) ? n_hi : n_lo, a2);
+                    a[r % C] = a2;
+                    s[r] = (uint32_t)a2;
+                }
+#pragma unroll
+                for (int c = 0; c < C; ++c) d[c] = (uint32_t)a[c];
+            } else {
+                const int rel = (t0 - tile) * T - L - tid * R;       // leading run elements in front of the first window
+                int a[C];
+#pragma unroll
+                for (int c = 0; c < C; ++c) a[c] = 0;
+#pragma unroll
+                for (int q = 0; q < R / 2; ++q) {
+                    const uint32_t m0 = (2 * q >= rel) ? w_lo : 0u, m1 = (2 * q + 1 >= rel) ? w_hi : 0u;
+                    if constexpr (C == 1) {
+                        a[0] = dp2a_s(xw[q], m0 | m1, a[0]);
+                    } else {
+                        a[(2 * q) % C] = dp2a_s(xw[q], m0, a[(2 * q) % C]);
+                        a[(2 * q + 1) % C] = dp2a_s(xw[q], m1, a[(2 * q + 1) % C]);
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < C; ++c) d[c] = (uint32_t)a[c];
+#pragma unroll
+                for (int r = 0; r < R; ++r) s[r] = 0u;
+            }
+
+            uint32_t incl[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) incl[c] = d[c];
+#pragma unroll
+            for (int dd = 1; dd < 32; dd <<= 1) {
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const uint32_t up = __shfl_up_sync(0xffffffffu, incl[c], dd);
+                    if (lane >= dd) incl[c] += up;
+                }
+            }
+            const uint32_t wbase = wraw + (it & 1u) * (32u * CJ * 4u);
+            if (lane == 31) {
+#pragma unroll
+                for (int c = 0; c < C; ++c) sts32u(wbase + (uint32_t)((c / G) * 32 + (c % G) * NW + warp) * 4u, incl[c]);
+            }
+#pragma unroll
+            for (int c = 0; c < C; ++c) incl[c] -= d[c];
+
+            tr.before_sync();
+            __syncthreads();
+            tr.after_sync(j, ntl, first, sig);
+            if (tid == 0 && is_out && tile + PL < t1) {
+                int s2 = lst + PL;
+                if (s2 >= SL) s2 -= SL;
+                issue_lag(tile + PL, sig, s2);       // that stage was read into registers before the barrier
+            }
+
+            uint32_t excl[CJ];
+#pragma unroll
+            for (int jj = 0; jj < CJ; ++jj) {
+                const uint32_t v = lds32u(wbase + (uint32_t)(jj * 32 + lane) * 4u);
+                uint32_t wi = v + (wq == 0 ? Wl[jj] : 0u);
+#pragma unroll
+                for (int dd = 1; dd < NW; dd <<= 1) {
+                    const uint32_t up = __shfl_up_sync(0xffffffffu, wi, dd);
+                    if (wq >= dd) wi += up;
+                }
+                Wl[jj] = __shfl_sync(0xffffffffu, wi, wlast);
+                excl[jj] = wi - v;
+            }
+            uint32_t start[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+                start[c] = __shfl_sync(0xffffffffu, excl[c / G], (c % G) * NW + warp) + incl[c];
+
+            if (is_out) {
+                const uint32_t ob = tr.out_tile();   // = cur: the results replace the own tile
+#pragma unroll
+                for (int c = 0; c < CH_OWN; ++c) {
+                    uint32_t wds[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        uint32_t y[2];
+#pragma unroll
+                        for (int hh = 0; hh < 2; ++hh) {
+                            const int r = 8 * c + 2 * q + hh;
+                            y[hh] = div_trunc_mulhi((int)(start[r % C] + s[r]), mul, sh);
+                        }
+                        wds[q] = __byte_perm(y[0], y[1], 0x5410);
+                    }
+                    sts128u(ob + (uint32_t)xo[c], wds[0], wds[1], wds[2], wds[3]);
+                }
+                tr.staged(tile, sig);
+                ++lagit;
+                lst = (lst + 1 == SL) ? 0 : lst + 1;
+            }
+            tr.advance();
+        }
+        tr.epilogue();
+    }
+    tr.finish();
+}
+
+// ----------------------------------------------------------------------------------
 // Column kernel -- many-channel interleaved float32 ([frame][channel], C >= 32), e.g.
 // BASELINE config 5's 256-channel batch in the reference layout.
 // One CTA streams [FT frames x 32 channels] tiles of one 32-channel column block down the

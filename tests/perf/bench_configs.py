@@ -213,7 +213,9 @@ def main():
         res = {}
         for name, dtype, C, frames, k in (("i16_c64_k64", "i16", 64, 1 << 21, 64), ("i16_c256_k64", "i16", 256, 1 << 19, 64), ("i16_c256_k8", "i16", 256, 1 << 19, 8), ("i16_c64_k1000", "i16", 64, 1 << 21, 1000), ("f32_c40_k20000", "f32", 40, 1 << 21, 20000), ("i16_c256_k8", "i16", 256, 1 << 19, 8), ("i16_c64_k1000", "i16", 64, 1 << 21, 1000),
                                           ("f32_c34_k64", "f32", 34, 1 << 22, 64), ("f32_c64_k2048", "f32", 64, 1 << 21, 2048),
-                                          ("f32_c1_k60000", "f32", 1, 1 << 27, 60000), ("f32_c1_k300000", "f32", 1, 1 << 27, 300000), ("f32_c2_k30000", "f32", 2, 1 << 26, 30000), ("f32_c1_k4096_tail", "f32", 1, (1 << 27) + 5, 4096), ("f32_c1_k4096", "f32", 1, 1 << 27, 4096), ("i16_c2_k40000", "i16", 2, 1 << 26, 40000)):
+                                          ("f32_c1_k60000", "f32", 1, 1 << 27, 60000), ("f32_c1_k300000", "f32", 1, 1 << 27, 300000), ("f32_c2_k30000", "f32", 2, 1 << 26, 30000), ("f32_c1_k4096_tail", "f32", 1, (1 << 27) + 5, 4096), ("f32_c1_k4096", "f32", 1, 1 << 27, 4096), ("i16_c2_k40000", "i16", 2, 1 << 26, 40000), ("i16_c1_k46000", "i16", 1, 1 << 27, 46000),
+                                          ("i16_c8_k19200", "i16", 8, 1 << 24, 19200), ("i16_c6_k19200", "i16", 6, (1 << 27) // 6, 19200),
+                                          ("i16_c4_k19200", "i16", 4, 1 << 25, 19200), ("i16_c2_k50000", "i16", 2, 1 << 26, 50000)):
             es = 4 if dtype == "f32" else 2
             n = frames * C
             d_in, d_out = alloc(es * n), alloc(es * n)

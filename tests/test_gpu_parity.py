@@ -878,7 +878,8 @@ def test_very_long_windows_on_the_generic_kernel(mavg, oracle_mod, case):
     n = frames * ch
     x = oracle_mod.fill_f32(n, 35000 + k) if dtype == "f32" else oracle_mod.fill_i16(n, 35000 + k)
     with mavg.Plan(frames, k, channels=ch, dtype=dtype, layout=layout) as plan:
-        far = dtype == "f32" and (ch == 1 or layout == "planar")      # mono / planar float32: far-lag streaming kernel
+        # mono / planar float32: far-lag streaming kernel; int16 mono / stereo / 4 / 6 / 8 channels up to k = 46 340: its twin
+        far = (dtype == "f32" and (ch == 1 or layout == "planar")) or (dtype == "i16" and k <= 46_340 and ch in (1, 2, 4, 6, 8))
         assert (plan.info.path, plan.info.mode) == ((1, 5) if far else (2, plan.info.mode))
         y = plan.run_host(x)
     if layout == "planar":
@@ -1018,7 +1019,71 @@ def test_far_lag_kernel_with_context_in_another_allocation(mavg, oracle_mod, tor
     assert _rel(d_out2.cpu().numpy(), e[:short * ch]) < TOL
 
 
-@pytest.mark.parametrize("dtype,ch,k", [("i16", 2, 40_000), ("i16", 1, 70_000), ("i16", 6, 12_000), ("f32", 3, 20_000),
+# ------------------------------------------------------------------ far-lag int16 kernel (windows beyond the ring, exact)
+@pytest.mark.parametrize("ch,k", [(1, 32_769), (1, 32_770), (1, 32_771), (1, 32_772), (1, 32_773), (1, 32_774), (1, 32_775),
+                                  (1, 32_776), (1, 46_340), (2, 24_577), (2, 24_578), (2, 24_579), (2, 24_580), (2, 40_000),
+                                  (2, 46_340), (4, 12_289), (4, 12_290), (4, 20_001), (4, 46_340), (6, 8_065), (6, 8_066),
+                                  (6, 8_067), (6, 8_068), (6, 19_200), (6, 30_001), (8, 6_145), (8, 19_200), (8, 40_000)])
+def test_far_lag_i16_kernel_bit_exact(mavg, oracle_mod, ch, k):
+    """stream_far_i16_kernel: every lag misalignment a channel count can have, the first windows beyond the ring of the
+    flat-stream kernel, the longest exact window (k = 46 340), several tiles per CTA, a ragged end -- bit-identical to
+    the reference CPU function."""
+    frames = ((148 * 3 + 5) * 16384 + 77 * ch) // ch
+    x = oracle_mod.fill_i16(frames * ch, 43_000 + k % 1000 + ch)
+    with mavg.Plan(frames, k, channels=ch, dtype="i16") as plan:
+        assert plan.info.path == 1 and plan.info.mode == 5
+        y = plan.run_host(x)
+    assert np.array_equal(y, oracle_mod.mavg_i16_mt(x, k, ch, 8))
+
+
+def test_far_lag_i16_slices_shards_and_planar_bit_identical(mavg, oracle_mod, torch_cuda):
+    """int32 window sums are exact, so -- unlike the float32 far-lag kernel -- sliced host runs, shards with their
+    context in front of them or in another allocation, and the whole run agree bit for bit."""
+    torch = torch_cuda
+    ch, k = 2, 30_000
+    frames = (1 << 22) + 333
+    x = oracle_mod.fill_i16(frames * ch, 44_000)
+    e = oracle_mod.mavg_i16_mt(x, k, ch, 8)
+    with mavg.Plan(frames, k, channels=ch, dtype="i16", slice_bytes=1 << 20) as plan:
+        assert plan.info.mode == 5
+        assert np.array_equal(plan.run_host(x), e)
+        assert plan.info.launches_per_run >= 4
+        halo = int(plan.info.halo_frames)
+    assert halo >= k
+    dx = torch.from_numpy(x).cuda()
+    cut = halo + 5 * 8192 + 1000                         # not a multiple of a tile: the shard has its own tile grid
+    dz = torch.zeros((frames - cut) * ch, dtype=torch.int16, device="cuda")
+    torch.cuda.synchronize()
+    with mavg.Plan(frames - cut, k, channels=ch, dtype="i16", first_frame=cut) as plan:
+        plan.run_device_halo(dx.data_ptr() + 2 * cut * ch, dz.data_ptr(), dx.data_ptr() + 2 * (cut - halo) * ch)
+        plan.synchronize()
+        assert np.array_equal(dz.cpu().numpy(), e[cut * ch:])
+        d_ctx = torch.from_numpy(x[(cut - halo) * ch:cut * ch].copy()).cuda()      # context in its own allocation
+        d_in = torch.from_numpy(x[cut * ch:].copy()).cuda()
+        dz.zero_()
+        torch.cuda.synchronize()
+        plan.run_device_halo(d_in.data_ptr(), dz.data_ptr(), d_ctx.data_ptr())
+        plan.synchronize()
+        assert plan.info.launches_per_run >= 2
+        assert np.array_equal(dz.cpu().numpy(), e[cut * ch:])
+    # saturated input: window sums of 32768 k in magnitude
+    for val in (-32768, 32767):
+        xs = np.full(300_000 * 4, val, dtype=np.int16)
+        for kk in (20_000, 46_340):
+            assert np.array_equal(mavg.moving_average(xs, kk, channels=4), oracle_mod.mavg_i16(xs, kk, 4)), (val, kk)
+    # window longer than the signal, and a planar batch of three mono signals
+    xs = oracle_mod.fill_i16(70_000, 44_001)
+    assert np.array_equal(mavg.moving_average(xs, 45_000), oracle_mod.mavg_i16(xs, 45_000))
+    xp = oracle_mod.fill_i16(3 * 200_000, 44_002)
+    with mavg.Plan(200_000, 40_000, channels=3, layout="planar", dtype="i16") as plan:
+        assert plan.info.mode == 5
+        yp = plan.run_host(xp)
+    for c in range(3):
+        seg = slice(c * 200_000, (c + 1) * 200_000)
+        assert np.array_equal(yp[seg], oracle_mod.mavg_i16(xp[seg], 40_000))
+
+
+@pytest.mark.parametrize("dtype,ch,k", [("i16", 2, 50_000), ("i16", 1, 70_000), ("i16", 5, 12_000), ("f32", 3, 20_000),
                                         ("i16", 2, 3_000_000)])
 def test_prefix_difference_path_far_windows(mavg, oracle_mod, torch_cuda, dtype, ch, k):
     """Far windows that no streaming kernel takes run as single-pass prefix sum + difference (info.mode 7): whole
