@@ -741,6 +741,30 @@ def block_e2e(cx, ks, samples_log2, steps):
                "last_call_phases_ms": {"h2d": round(tm.h2d_ms, 3), "compute": round(tm.compute_ms, 3),
                                        "d2h": round(tm.d2h_ms, 3)}}
         res["check"] = e2e_check(cx, h_out, dtype, channels, first_frame, ks[-1])
+        # the same sweep through mavg_run_host_sweep: the step's input crosses the host link ONCE, every window's result
+        # comes back (one pinned output buffer per window)
+        try:
+            outs = [torch.empty(n, dtype=tdtype, pin_memory=True) for _ in ks]
+            plist = [hplans[k] for k in ks]
+            optrs = [o.data_ptr() for o in outs]
+            mavg.run_host_sweep_ptr(plist, in_ptr, optrs)      # warm-up: allocates the sweep's device input buffer
+            cx.barrier()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                mavg.run_host_sweep_ptr(plist, in_ptr, optrs)
+            dts = cx.allmax([time.perf_counter() - t0])[0]
+            tms = hplans[ks[0]].timing()
+            res["sweep"] = {"value": cx.world * n * len(ks) * steps / dts / 1e9, "unit": "Gsamples/s",
+                            "h2d_bytes_per_step": es * (n + halo_elems), "d2h_bytes_per_step": es * n * len(ks),
+                            "steps": steps, "api": "mavg_run_host_sweep (one upload of the signal per step, one pinned "
+                                                   "output per window; results bit-identical to the per-window calls)",
+                            "phases_ms": {"h2d": round(tms.h2d_ms, 3), "compute": round(tms.compute_ms, 3),
+                                          "d2h": round(tms.d2h_ms, 3)},
+                            "check_first_k": e2e_check(cx, outs[0], dtype, channels, first_frame, ks[0]),
+                            "check_last_k": e2e_check(cx, outs[-1], dtype, channels, first_frame, ks[-1])}
+            del outs
+        except Exception as e:  # pragma: no cover
+            res["sweep"] = {"error": "%s: %s" % (type(e).__name__, e)}
         for p in hplans.values():
             p.close()
         return res

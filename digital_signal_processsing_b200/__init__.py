@@ -8,5 +8,5 @@ no CPU fallback.
 from . import _lib  # noqa: F401
 from ._lib import (DIST_DC1E4, DIST_I16, DIST_U01, DIST_USYM, MavgError)  # noqa: F401
 from .plan import (PinnedArray, Plan, device_count, fill_synthetic_device, moving_average, moving_rms, pinned,  # noqa: F401
-                   prefix_sum_device, version)
+                   prefix_sum_device, run_host_sweep, run_host_sweep_ptr, version)
 from . import wav  # noqa: F401

@@ -85,6 +85,7 @@ SYMBOLS = [
     ("mavg_plan_destroy", _i, [_vp]),
     ("mavg_plan_info", _i, [_vp, ctypes.POINTER(Info)]),
     ("mavg_run_host", _i, [_vp, _vp, _vp]),
+    ("mavg_run_host_sweep", _i, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_uint32, _vp, ctypes.POINTER(ctypes.c_void_p)]),
     ("mavg_run_device", _i, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_vp)]),
     ("mavg_run_cascade", _i, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.c_uint32]),
     ("mavg_run_device_halo", _i, [_vp, _vp, _vp, _vp]),

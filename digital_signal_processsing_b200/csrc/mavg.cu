@@ -597,6 +597,8 @@ struct DevCtx {
     void* d_halo = nullptr;     // halo_frames * channels elements of left context (frame sharding)
     void* d_bsum = nullptr;     // generic path, long windows: 64-frame block sums
     void* d_scratch = nullptr;  // mavg_run_cascade intermediates
+    void* d_sweep_in = nullptr;    // mavg_run_host_sweep: [largest halo of the sweep | shard], uploaded once
+    size_t sweep_in_bytes = 0;
     void* d_far_stage = nullptr;   // far-lag kernel, context not contiguous with the shard: [context | first frames]
     size_t far_stage_bytes = 0;
     void* d_prefix = nullptr;      // prefix-difference path: 8-byte prefixes of the shard and of its left context
@@ -1643,6 +1645,7 @@ int mavg_plan_destroy(mavg_plan* p)
         if (d.d_bsum) cudaFree(d.d_bsum);
         if (d.d_scratch) cudaFree(d.d_scratch);
         if (d.d_far_stage) cudaFree(d.d_far_stage);
+        if (d.d_sweep_in) cudaFree(d.d_sweep_in);
         if (d.d_prefix) cudaFree(d.d_prefix);
         if (d.ev_pass) cudaEventDestroy(d.ev_pass);
         if (d.s_tail) { cudaStreamSynchronize(d.s_tail); cudaStreamDestroy(d.s_tail); }
@@ -2114,6 +2117,166 @@ int run_host_impl(mavg_plan* p, const void* h_in, void* h_out)
     return mavg_synchronize(p);
 }
 }  // namespace
+
+namespace {
+uint64_t gcd_u64(uint64_t a, uint64_t b)
+{
+    while (b) { const uint64_t t = a % b; a = b; b = t; }
+    return a;
+}
+
+// true when the sweep pipeline can serve these plans; otherwise mavg_run_host is called once per plan
+bool sweep_compatible(mavg_plan* const* plans, uint32_t count, void* const* h_out)
+{
+    const mavg_plan* p0 = plans[0];
+    if (planar_batch(p0) || p0->dev.size() != 1 || p0->desc.frames == 0) return false;
+    for (uint32_t i = 0; i < count; ++i) {
+        const mavg_plan* p = plans[i];
+        if (p->dev.size() != 1 || p->dev[0].device != p0->dev[0].device) return false;
+        if (p->desc.dtype != p0->desc.dtype || p->desc.layout != p0->desc.layout || p->desc.channels != p0->desc.channels ||
+            p->desc.frames != p0->desc.frames || p->desc.first_frame != p0->desc.first_frame)
+            return false;
+        if (is_pageable(h_out[i])) return false;
+    }
+    return true;
+}
+
+int run_host_sweep_impl(mavg_plan* const* plans, uint32_t count, const void* h_in, void* const* h_out)
+{
+    mavg_plan* p0 = plans[0];
+    DevCtx& d0 = p0->dev[0];
+    const size_t es = elem_size(p0->desc.dtype);
+    const uint64_t C = p0->desc.channels;
+    const uint64_t frames = d0.frames;
+    const bool has_halo = p0->desc.first_frame > 0;
+    MAVG_CUDA(cudaSetDevice(d0.device));
+    // slices: whole tiles of every plan (least common multiple of the plans' units), at least the longest left context
+    uint64_t unit = 1, max_halo = 0;
+    for (uint32_t i = 0; i < count; ++i) {
+        const uint64_t u = plans[i]->path == MAVG_PATH_STREAM ? tile_frames(plans[i]) : 1024;
+        unit = unit / gcd_u64(unit, u) * u;
+        max_halo = std::max<uint64_t>(max_halo, plans[i]->halo_frames);
+        if (unit > (1ull << 26)) return fail(MAVG_ERR_UNSUPPORTED, "sweep: the plans' tile sizes have no common slice size");
+    }
+    const uint64_t halo0 = has_halo ? max_halo : 0;
+    uint64_t slice_bytes = p0->desc.tuning.slice_bytes;
+    if (!slice_bytes) {
+        slice_bytes = 4ull << 20;
+        while (slice_bytes < (64ull << 20) && slice_bytes * slice_bytes < ((frames * C * es) << 20)) slice_bytes <<= 1;
+    }
+    uint64_t slice_frames = std::max<uint64_t>(slice_bytes / (C * es), max_halo);
+    slice_frames = (slice_frames + unit - 1) / unit * unit;
+    if (slice_frames * 2 > frames) slice_frames = frames;
+    const uint64_t nslices = (frames + slice_frames - 1) / slice_frames;
+
+    // device buffers: the input once (with the longest halo in front of it), one output per plan
+    const size_t halo_pad = ((size_t)halo0 * C * es + 255) / 256 * 256;   // the shard starts 256-byte aligned on the device
+    const size_t in_bytes = halo_pad + (size_t)frames * C * es;
+    if (d0.sweep_in_bytes < in_bytes) {
+        if (d0.d_sweep_in) MAVG_CUDA(cudaFree(d0.d_sweep_in));
+        d0.d_sweep_in = nullptr;
+        d0.sweep_in_bytes = 0;
+        if (cudaMalloc(&d0.d_sweep_in, std::max<size_t>(in_bytes, 256)) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(MAVG_ERR_ALLOC, "cudaMalloc of %zu sweep input bytes failed on device %d", in_bytes, d0.device);
+        }
+        d0.sweep_in_bytes = in_bytes;
+    }
+    for (uint32_t i = 0; i < count; ++i) {
+        DevCtx& d = plans[i]->dev[0];
+        if (!d.d_out) {
+            const size_t bytes = std::max<size_t>((size_t)frames * C * es, 256);
+            if (cudaMalloc(&d.d_out, bytes) != cudaSuccess) {
+                cudaGetLastError();
+                return fail(MAVG_ERR_ALLOC, "cudaMalloc of %zu output bytes failed on device %d", bytes, d.device);
+            }
+        }
+    }
+    if (!d0.s_h2d) MAVG_CUDA(cudaStreamCreateWithFlags(&d0.s_h2d, cudaStreamNonBlocking));
+    if (!d0.s_d2h) MAVG_CUDA(cudaStreamCreateWithFlags(&d0.s_d2h, cudaStreamNonBlocking));
+    const size_t nev = 1 + (size_t)nslices * (1 + count);
+    while (d0.pool.size() < nev) {
+        cudaEvent_t e;
+        MAVG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        d0.pool.push_back(e);
+    }
+    // the copy streams start behind whatever the plans' compute streams were doing before this call
+    for (uint32_t i = 0; i < count; ++i) {
+        MAVG_CUDA(cudaEventRecord(d0.pool[0], plans[i]->dev[0].stream));
+        MAVG_CUDA(cudaStreamWaitEvent(d0.s_h2d, d0.pool[0], 0));
+        MAVG_CUDA(cudaStreamWaitEvent(d0.s_d2h, d0.pool[0], 0));
+    }
+    if (p0->timing_on) cudaEventRecord(d0.ev[0], d0.s_h2d);
+    char* const dev_in = (char*)d0.d_sweep_in + halo_pad;             // first frame of the shard
+    if (has_halo)
+        MAVG_CUDA(cudaMemcpyAsync(dev_in - halo0 * C * es, (const char*)h_in - halo0 * C * es, halo0 * C * es,
+                                  cudaMemcpyHostToDevice, d0.s_h2d));
+    std::vector<uint32_t> launches(count, 0);
+    for (uint64_t i = 0; i < nslices; ++i) {
+        const uint64_t f0 = i * slice_frames;
+        const uint64_t fcount = std::min<uint64_t>(slice_frames, frames - f0);
+        const size_t off = (size_t)f0 * C * es, bytes = (size_t)fcount * C * es;
+        cudaEvent_t e_in = d0.pool[1 + i * (1 + count)];
+        MAVG_CUDA(cudaMemcpyAsync(dev_in + off, (const char*)h_in + off, bytes, cudaMemcpyHostToDevice, d0.s_h2d));
+        MAVG_CUDA(cudaEventRecord(e_in, d0.s_h2d));
+        if (i + 1 == nslices && p0->timing_on) cudaEventRecord(d0.ev[1], d0.s_h2d);
+        for (uint32_t j = 0; j < count; ++j) {
+            mavg_plan* p = plans[j];
+            DevCtx& d = p->dev[0];
+            cudaEvent_t e_k = d0.pool[2 + i * (1 + count) + j];
+            MAVG_CUDA(cudaStreamWaitEvent(d.stream, e_in, 0));
+            const void* halo = (i == 0) ? (has_halo ? dev_in - p->halo_frames * C * es : nullptr)
+                                        : dev_in + off - p->halo_frames * C * es;
+            MAVG_TRY(launch_shard(p, d, dev_in + off, (char*)d.d_out + off, halo, fcount, &launches[j]));
+            MAVG_CUDA(cudaEventRecord(e_k, d.stream));
+            if (i + 1 == nslices && j + 1 == count && p0->timing_on) cudaEventRecord(d0.ev[2], d.stream);
+            MAVG_CUDA(cudaStreamWaitEvent(d0.s_d2h, e_k, 0));
+            MAVG_CUDA(cudaMemcpyAsync((char*)h_out[j] + off, (char*)d.d_out + off, bytes, cudaMemcpyDeviceToHost, d0.s_d2h));
+        }
+    }
+    if (p0->timing_on) cudaEventRecord(d0.ev[3], d0.s_d2h);
+    d0.timed = p0->timing_on;
+    for (uint32_t j = 0; j < count; ++j) {
+        plans[j]->launches_last_run = launches[j];
+        if (j > 0) plans[j]->dev[0].timed = false;
+        MAVG_CUDA(cudaStreamSynchronize(plans[j]->dev[0].stream));
+    }
+    MAVG_CUDA(cudaStreamSynchronize(d0.s_h2d));
+    MAVG_CUDA(cudaStreamSynchronize(d0.s_d2h));
+    return gather_timing(p0);
+}
+}  // namespace
+
+int mavg_run_host_sweep(mavg_plan* const* plans, uint32_t count, const void* h_in, void* const* h_out)
+{
+    if (!plans || !h_in || !h_out || count == 0) return fail(MAVG_ERR_INVALID_ARG, "null argument or empty sweep");
+    for (uint32_t i = 0; i < count; ++i) {
+        if (!plans[i] || !h_out[i]) return fail(MAVG_ERR_INVALID_ARG, "plan or output %u is null", i);
+        if (h_out[i] == h_in) return fail(MAVG_ERR_INVALID_ARG, "output must not alias input");
+        for (uint32_t j = 0; j < i; ++j)
+            if (plans[j] == plans[i] || h_out[j] == h_out[i])
+                return fail(MAVG_ERR_INVALID_ARG, "plans and outputs of a sweep must be distinct");
+    }
+    DeviceGuard guard;
+    if (count == 1 || !sweep_compatible(plans, count, h_out)) {
+        for (uint32_t i = 0; i < count; ++i) MAVG_TRY(mavg_run_host(plans[i], h_in, h_out[i]));
+        return MAVG_OK;
+    }
+    const int rc = run_host_sweep_impl(plans, count, h_in, h_out);
+    if (rc != MAVG_OK) {
+        // drain what is queued on the caller's buffers before they are handed back; the first error stays the one reported
+        const std::string first = g_last_error;
+        DevCtx& d0 = plans[0]->dev[0];
+        if (cudaSetDevice(d0.device) == cudaSuccess) {
+            if (d0.s_h2d) cudaStreamSynchronize(d0.s_h2d);
+            for (uint32_t i = 0; i < count; ++i) cudaStreamSynchronize(plans[i]->dev[0].stream);
+            if (d0.s_d2h) cudaStreamSynchronize(d0.s_d2h);
+        }
+        cudaGetLastError();
+        g_last_error = first;
+    }
+    return rc;
+}
 
 int mavg_fill_synthetic_device(void* d_dst, int dtype, uint64_t n, uint64_t first_index, uint64_t seed, int dist,
                                void* cuda_stream)

@@ -238,6 +238,34 @@ def prefix_sum_device(in_ptr: int, out_ptr: int, dtype: str, frames: int, channe
                                       channels, ctypes.c_void_p(stream)))
 
 
+def run_host_sweep_ptr(plans: Sequence["Plan"], in_ptr: int, out_ptrs: Sequence[int]) -> None:
+    """mavg_run_host_sweep on raw host addresses (pinned buffers): one upload of the input, every plan's result
+    downloaded to its own buffer."""
+    n = len(plans)
+    if n == 0 or n != len(out_ptrs):
+        raise ValueError("one output per plan")
+    handles = (ctypes.c_void_p * n)(*[p._h.value for p in plans])
+    outs = (ctypes.c_void_p * n)(*[int(o) for o in out_ptrs])
+    check(_lib.load().mavg_run_host_sweep(handles, n, ctypes.c_void_p(in_ptr), outs))
+
+
+def run_host_sweep(plans: Sequence["Plan"], x: np.ndarray, outs: Optional[Sequence[np.ndarray]] = None) -> list:
+    """Several plans over the SAME host signal (a sweep over windows): the input crosses the host link once, the
+    results are bit-identical to one `Plan.run_host` per plan."""
+    if not plans:
+        return []
+    x = np.ascontiguousarray(x, dtype=plans[0].np_dtype).reshape(-1)
+    if x.size != plans[0].samples:
+        raise ValueError(f"expected {plans[0].samples} samples, got {x.size}")
+    if outs is None:
+        outs = [np.empty_like(x) for _ in plans]
+    for o in outs:
+        if o.dtype != x.dtype or o.size != x.size or not o.flags.c_contiguous:
+            raise ValueError("outputs must be contiguous arrays of the plans' dtype and size")
+    run_host_sweep_ptr(plans, x.ctypes.data, [o.ctypes.data for o in outs])
+    return list(outs)
+
+
 def moving_rms(x: np.ndarray, window: int, channels: int = 1, layout: str = "interleaved") -> np.ndarray:
     """One-shot convenience: moving RMS (sqrt of the windowed mean of squares) of a host array on the GPU."""
     return moving_average(x, window, channels, layout, op="rms")

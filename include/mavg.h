@@ -208,6 +208,18 @@ int mavg_plan_info(const mavg_plan *plan, mavg_info *info);
  * h_in (h_in points into a [halo | shard] buffer). */
 int mavg_run_host(mavg_plan *plan, const void *h_in, void *h_out);
 
+/* One upload, many windows -- what a sweep over grades does with one WAV file
+ * (basics/run_benchmarks.py:21-47 runs the binaries once per grade on the same input): `count` plans that
+ * describe the SAME signal (dtype, layout, channels, frames, first_frame, one and the same device) and differ in
+ * window / op / tuning are run over h_in; plan i's output goes to h_out[i].  The input crosses the host link once
+ * instead of `count` times: slices of it are uploaded, every plan's kernel runs on the slice as soon as it has
+ * arrived, and the `count` results of the slice go back while the next slice arrives.  Results are bit-identical
+ * to `count` calls of mavg_run_host.  Interleaved / mono single-device plans; other plans (planar batches,
+ * multi-device plans, pageable outputs) are served by calling mavg_run_host once per plan.  Timing of the whole
+ * sweep (exposed phase times) is reported through plans[0] (mavg_get_timing).  For shard plans the largest
+ * info.halo_frames of the plans must sit in host memory in front of h_in.  Blocks until every output is in place. */
+int mavg_run_host_sweep(mavg_plan *const *plans, uint32_t count, const void *h_in, void *const *h_out);
+
 /* Kernel(s) only, on device-resident data: d_in[r] / d_out[r] are device r's shard
  * (info.shard_frames[r] frames; for one device simply the whole signal).  Pointers must
  * be 16-byte aligned for the stream path (otherwise the generic path runs).

@@ -245,3 +245,66 @@ def test_box_filter_cascade(mavg, oracle_mod):
     with mavg.Plan(1000, 5) as plan:
         with pytest.raises(Exception):
             plan.run_cascade([dx.data_ptr()], [dx.data_ptr() + 4096], 0)
+
+
+# ------------------------------------------------------------------ mavg_run_host_sweep: one upload, many windows
+@pytest.mark.parametrize("case", [("f32", 1, (1 << 22) + 37, [3, 16, 64, 256, 1024, 4096]),
+                                  ("i16", 2, (1 << 21) + 5, [3, 64, 4096, 30_000]),          # 30 000: far-lag int16 kernel
+                                  ("i16", 6, 300_000, [2, 64, 1000, 9000]),
+                                  ("f32", 3, 200_000, [5, 300, 20_000]),                      # 20 000: prefix sum + difference
+                                  ("f32", 1, 1 << 21, [64, 60_000])])                         # 60 000: far-lag float32 kernel
+def test_run_host_sweep_matches_one_call_per_window(mavg, oracle_mod, case):
+    """The sweep call uploads the input once and runs every plan on each slice; its outputs have to be bit-identical
+    to one mavg_run_host per plan (the slices start on tile boundaries of every plan) -- except for the float32 far-lag
+    kernel, whose carried window sum starts from a different warm-up in every slice (1e-6)."""
+    dtype, ch, frames, ks = case
+    n = frames * ch
+    x = oracle_mod.fill_f32(n, 51_000 + frames % 1000) if dtype == "f32" else oracle_mod.fill_i16(n, 51_000 + frames % 1000)
+    plans = [mavg.Plan(frames, k, channels=ch, dtype=dtype, slice_bytes=1 << 20) for k in ks]
+    try:
+        single = [p.run_host(x).copy() for p in plans]
+        xin = mavg.PinnedArray(n, x.dtype)
+        xin.array[:] = x
+        outs = [mavg.PinnedArray(n, x.dtype) for _ in ks]
+        mavg.run_host_sweep_ptr(plans, xin.array.ctypes.data, [o.array.ctypes.data for o in outs])
+        for k, p, s, o in zip(ks, plans, single, outs):
+            if dtype == "f32" and int(p.info.mode) == 5:
+                e = oracle_mod.mavg_f64(x, k, ch)
+                assert float(np.max(np.abs(o.array - s) / np.abs(e))) < 1e-6, k
+            else:
+                assert np.array_equal(o.array, s), k
+        # pageable outputs take the per-plan route and give the same result
+        got = mavg.run_host_sweep(plans, x)
+        for k, p, s, g in zip(ks, plans, single, got):
+            if not (dtype == "f32" and int(p.info.mode) == 5):
+                assert np.array_equal(g, s), k
+        t = plans[0].timing()
+        assert t.total_ms > 0
+    finally:
+        for p in plans:
+            p.close()
+
+
+def test_run_host_sweep_shard_plans_and_argument_checks(mavg, oracle_mod):
+    """Shard plans (first_frame > 0): the longest halo of the sweep sits in front of h_in; every plan finds its own
+    shorter halo right in front of the shard.  Bad arguments are refused with a status code."""
+    frames, cut, ch = (1 << 20) + 11, 300_000, 2
+    ks = [5, 300, 4096]
+    x = oracle_mod.fill_i16(frames * ch, 52_000)
+    plans = [mavg.Plan(frames - cut, k, channels=ch, dtype="i16", first_frame=cut, slice_bytes=1 << 19) for k in ks]
+    try:
+        halo = max(int(p.info.halo_frames) for p in plans)
+        assert halo <= cut
+        buf = mavg.PinnedArray((frames - cut + halo) * ch, np.int16)
+        buf.array[:] = x[(cut - halo) * ch:]
+        outs = [mavg.PinnedArray((frames - cut) * ch, np.int16) for _ in ks]
+        mavg.run_host_sweep_ptr(plans, buf.array.ctypes.data + 2 * halo * ch, [o.array.ctypes.data for o in outs])
+        for k, o in zip(ks, outs):
+            assert np.array_equal(o.array, oracle_mod.mavg_i16(x, k, ch)[cut * ch:]), k
+        with pytest.raises(mavg.MavgError):
+            mavg.run_host_sweep_ptr([plans[0], plans[0]], buf.array.ctypes.data, [outs[0].array.ctypes.data, outs[1].array.ctypes.data])
+        with pytest.raises(mavg.MavgError):
+            mavg.run_host_sweep_ptr(plans[:2], buf.array.ctypes.data, [outs[0].array.ctypes.data, outs[0].array.ctypes.data])
+    finally:
+        for p in plans:
+            p.close()
