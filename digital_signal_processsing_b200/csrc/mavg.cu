@@ -182,10 +182,10 @@ StreamGeom plan_stream_i16_shape(uint32_t k, uint32_t C, const mavg_tuning& tu)
         g.NT = tu.threads == 128 ? 128 : 256;
         g.R = 64;
     } else if (C == 5) {                               // runs of lcm(C, 8) samples: 5 / 7 chunks, dense tiles
-        g.NT = 384;
+        g.NT = tu.threads == 128 ? 192 : 384;          // "128": the two-CTAs-per-SM shape (192 x 40 = 15 KB tiles)
         g.R = 40;
     } else if (C == 7) {
-        g.NT = 256;
+        g.NT = tu.threads == 128 ? 128 : 256;          // 128 x 56 = 14 KB tiles, two CTAs per SM
         g.R = 56;
     }
     g.elem = 2;
@@ -570,8 +570,8 @@ StreamKernel pick_i16_kernel(const StreamGeom& g)
     case 6: return g.NT == 224 ? pick_i16<224, 72, 6>(g.MIS) : g.NT == 128 ? pick_i16<128, 72, 6>(g.MIS) : pick_i16<512, 24, 6>(g.MIS);
     case 8:
         return g.NT == 256 ? pick_i16<256, 64, 8>(g.MIS) : g.NT == 128 ? pick_i16<128, 64, 8>(g.MIS) : pick_i16<512, 32, 8>(g.MIS);
-    case 5: return pick_i16<384, 40, 5>(g.MIS);
-    case 7: return pick_i16<256, 56, 7>(g.MIS);
+    case 5: return g.NT == 192 ? pick_i16<192, 40, 5>(g.MIS) : pick_i16<384, 40, 5>(g.MIS);
+    case 7: return g.NT == 128 ? pick_i16<128, 56, 7>(g.MIS) : pick_i16<256, 56, 7>(g.MIS);
     case 12: return g.NT == 128 ? pick_i16<128, 72, 12>(g.MIS) : pick_i16<224, 72, 12>(g.MIS);
     case 16: return g.NT == 128 ? pick_i16<128, 64, 16>(g.MIS) : pick_i16<256, 64, 16>(g.MIS);
     default: return nullptr;

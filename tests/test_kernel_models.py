@@ -205,8 +205,8 @@ def test_far_lag_boxes_and_warm_up_cover_exactly_the_window(NT):
 
 
 # ---------------------------------------------------------------- flat-stream int16 kernel (stream_i16_kernel), any channel count
-FLAT_SHAPES = [(512, 32, 1), (512, 32, 2), (128, 72, 3), (224, 72, 3), (512, 24, 3), (256, 64, 4), (384, 40, 5), (128, 72, 6),
-               (224, 72, 6), (256, 56, 7), (128, 64, 8), (256, 64, 8), (224, 72, 12), (256, 64, 16)]
+FLAT_SHAPES = [(512, 32, 1), (512, 32, 2), (128, 72, 3), (224, 72, 3), (512, 24, 3), (256, 64, 4), (384, 40, 5), (192, 40, 5), (128, 72, 6),
+               (224, 72, 6), (256, 56, 7), (128, 56, 7), (128, 64, 8), (256, 64, 8), (224, 72, 12), (256, 64, 16), (384, 32, 2), (192, 64, 8)]
 
 
 @pytest.mark.parametrize("NT,R,C", FLAT_SHAPES)
