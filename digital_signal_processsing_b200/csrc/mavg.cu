@@ -175,9 +175,12 @@ StreamGeom plan_stream_i16_shape(uint32_t k, uint32_t C, const mavg_tuning& tu)
     } else if (C == 3 || C == 6) {                     // runs of an odd number of 16-byte chunks: dense tiles, no swizzle
         g.NT = tu.threads == 512 ? 512 : tu.threads == 128 ? 128 : 224;
         g.R = g.NT == 512 ? 24 : 72;
-    } else if (C == 12) {
+    } else if (C == 12 || C == 9) {
         g.NT = tu.threads == 128 ? 128 : 224;
         g.R = 72;
+    } else if (C == 10) {
+        g.NT = tu.threads == 128 ? 192 : 384;
+        g.R = 40;
     } else if (C == 16) {
         g.NT = tu.threads == 128 ? 128 : 256;
         g.R = 64;
@@ -197,7 +200,7 @@ StreamGeom plan_stream_i16_shape(uint32_t k, uint32_t C, const mavg_tuning& tu)
     // so its floor is trunc(w / k) - 1 and the sign bit adds the 1 back.  M < 2^31 needs k >= 3; k == 2 runs with
     // every dp2a weight doubled (sums 2 w) and the constants of k = 4.  k == 1 (identity) and longer windows are
     // left to the generic kernel.
-    if (k < 2 || k > 32768u || !(C <= 8 || C == 12 || C == 16)) return g;
+    if (k < 2 || k > 32768u || !(C <= 10 || C == 12 || C == 16)) return g;
     const uint64_t L = (uint64_t)k * C;
     const uint32_t R = (uint32_t)g.R;
     const uint32_t s = (uint32_t)((R - L % R) % R);
@@ -572,6 +575,8 @@ StreamKernel pick_i16_kernel(const StreamGeom& g)
         return g.NT == 256 ? pick_i16<256, 64, 8>(g.MIS) : g.NT == 128 ? pick_i16<128, 64, 8>(g.MIS) : pick_i16<512, 32, 8>(g.MIS);
     case 5: return g.NT == 192 ? pick_i16<192, 40, 5>(g.MIS) : pick_i16<384, 40, 5>(g.MIS);
     case 7: return g.NT == 128 ? pick_i16<128, 56, 7>(g.MIS) : pick_i16<256, 56, 7>(g.MIS);
+    case 9: return g.NT == 128 ? pick_i16<128, 72, 9>(g.MIS) : pick_i16<224, 72, 9>(g.MIS);
+    case 10: return g.NT == 192 ? pick_i16<192, 40, 10>(g.MIS) : pick_i16<384, 40, 10>(g.MIS);
     case 12: return g.NT == 128 ? pick_i16<128, 72, 12>(g.MIS) : pick_i16<224, 72, 12>(g.MIS);
     case 16: return g.NT == 128 ? pick_i16<128, 64, 16>(g.MIS) : pick_i16<256, 64, 16>(g.MIS);
     default: return nullptr;

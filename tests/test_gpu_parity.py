@@ -570,12 +570,12 @@ def _fewc_runs(ch):
 
 # channel counts the flat-stream int16 kernel takes (info.mode 6) with runs of whole frames: (threads, run) of the shape
 # with one CTA per SM; 3 / 4 / 6 / 8 channels also have a 512-thread shape (tuning.threads = 512)
-FLAT_I16_SHAPE = {3: (224, 72), 6: (224, 72), 12: (224, 72), 4: (256, 64), 8: (256, 64), 16: (256, 64), 5: (384, 40),
-                  7: (256, 56)}
+FLAT_I16_SHAPE = {3: (224, 72), 6: (224, 72), 9: (224, 72), 12: (224, 72), 4: (256, 64), 8: (256, 64), 16: (256, 64),
+                  5: (384, 40), 10: (384, 40), 7: (256, 56)}
 FLAT_I16_CH = tuple(sorted(FLAT_I16_SHAPE))
 
 
-@pytest.mark.parametrize("ch", [3, 4, 5, 6, 7, 8, 9, 10, 12, 16, 24, 31])
+@pytest.mark.parametrize("ch", [3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 14, 16, 24, 31])
 @pytest.mark.parametrize("k", [1, 2, 3, 7, 8, 31, 32, 33, 64, 100, 255, 256, 300])
 def test_few_channel_interleaved_i16_bit_exact(mavg, oracle_mod, ch, k):
     """3 ... 8, 12, 16 channels: the stereo kernel's delta scan over the flat stream (runs of whole frames).  Other odd
@@ -628,7 +628,7 @@ def test_flat_multichannel_i16_every_lag_alignment_and_ring_depth(mavg, oracle_m
 def test_few_channel_i16_extremes_and_negative_truncation(mavg, oracle_mod):
     """Saturated inputs (window sums up to 256 * 32768 in magnitude) and sign-alternating ramps whose sums straddle
     zero: the multiply-high division has to truncate toward zero exactly as C's `/` does."""
-    for ch in (6, 3, 8, 5, 10, 9):                 # flat-stream kernel (6, 3, 8, 5), pair kernel, scalar kernel
+    for ch in (6, 3, 8, 5, 9, 14, 11):             # flat-stream kernel (6, 3, 8, 5, 9), pair kernel (14), scalar kernel (11)
         frames = 4 * 80 * 32 + 5
         for val in (-32768, 32767, -1, 1):
             x = np.full(frames * ch, val, dtype=np.int16)
@@ -642,7 +642,7 @@ def test_few_channel_i16_extremes_and_negative_truncation(mavg, oracle_mod):
 
 
 @pytest.mark.parametrize("case", [(6, 64), (3, 5), (7, 200), (8, 256), (4, 2), (12, 64), (6, 3000), (4, 9000), (3, 4097),
-                                  (10, 64), (9, 100), (5, 3001), (16, 1500)])
+                                  (10, 64), (9, 100), (14, 64), (11, 100), (5, 3001), (16, 1500)])
 def test_few_channel_i16_shard_with_halo_bit_exact(mavg, oracle_mod, torch_cuda, case):
     torch = torch_cuda
     ch, k = case
@@ -701,7 +701,7 @@ def test_few_channel_long_window_conditioning(mavg, oracle_mod, dist):
     assert np.max(np.abs(y - e) / np.maximum(scale, 1e-30)) < TOL
 
 
-@pytest.mark.parametrize("case", [("f32", 6, 1000), ("f32", 3, 4096), ("i16", 6, 1000), ("i16", 5, 2048), ("i16", 10, 1000)])
+@pytest.mark.parametrize("case", [("f32", 6, 1000), ("f32", 3, 4096), ("i16", 6, 1000), ("i16", 5, 2048), ("i16", 14, 1000)])
 def test_few_channel_long_window_shard_with_halo(mavg, oracle_mod, torch_cuda, case):
     torch = torch_cuda
     dtype, ch, k = case
@@ -737,7 +737,7 @@ def test_few_channel_long_window_shard_with_halo(mavg, oracle_mod, torch_cuda, c
 
 
 @pytest.mark.parametrize("case", [("f32", 3, 1 << 24, 1000), ("f32", 6, 1 << 23, 64), ("i16", 6, 1 << 23, 700),
-                                  ("i16", 5, 1 << 23, 48), ("i16", 10, 1 << 22, 200), ("i16", 8, 1 << 23, 4000),
+                                  ("i16", 5, 1 << 23, 48), ("i16", 14, 1 << 22, 200), ("i16", 10, 1 << 22, 200), ("i16", 9, 1 << 22, 77), ("i16", 8, 1 << 23, 4000),
                                   ("i16", 3, 1 << 24, 77), ("i16", 4, 1 << 23, 1)])
 def test_few_channel_many_tiles_per_cta(mavg, oracle_mod, case):
     """Tens of tiles per persistent CTA (ring wrap-around, staging double buffer, chunk boundaries with history
