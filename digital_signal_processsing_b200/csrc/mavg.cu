@@ -380,7 +380,7 @@ StreamGeom plan_fewc(uint32_t k, uint32_t C, const mavg_tuning& tu, uint32_t ele
 
 // float32 mono / planar with a window too long for the ring of plan_stream: the lag samples come back through a
 // second TMA stream (stream_far_f32_kernel).  H = warm-up tiles = left context in whole tiles.
-// int16 twin (stream_far_i16_kernel): mono / stereo / 4 / 6 / 8 interleaved channels, exact int32 window sums, so
+// int16 twin (stream_far_i16_kernel): mono / stereo / 4 / 6 / 8 / 12 / 16 interleaved channels, exact int32 window sums, so
 // k * k < 2^31 (k <= 46 340; the multiply-high division is exact while 32768 k e < 2^(30 + ceil(log2 k)) with
 // e <= k, i.e. while 2^15 k^2 <= 2^46).  Shapes: 384 x 32 for mono / stereo, 192 x 64 for 4 / 8 channels (24 KB tiles,
 // one lag box, three lag stages), 224 x 72 for 6 channels (31.5 KB tiles, two lag stages).
@@ -392,8 +392,8 @@ StreamGeom plan_far_i16(uint32_t k, uint32_t C, const mavg_tuning& tu)
     g.C = C;
     if (k < 3 || (uint64_t)k * k >= (1ull << 31)) return g;
     if (C <= 2) { g.NT = 384; g.R = 32; }
-    else if (C == 4 || C == 8) { g.NT = 192; g.R = 64; }   // 24 KB tiles, one lag box: two lag boxes in flight (8 ch, k = 19 200: 0.158 -> 0.136 ms against 256 x 64)
-    else if (C == 6) { g.NT = 224; g.R = 72; }
+    else if (C == 4 || C == 8 || C == 16) { g.NT = 192; g.R = 64; }   // 24 KB tiles, one lag box: two lag boxes in flight (8 ch, k = 19 200: 0.158 -> 0.136 ms against 256 x 64)
+    else if (C == 6 || C == 12) { g.NT = 224; g.R = 72; }
     else return g;
     const uint64_t T = (uint64_t)g.NT * g.R;
     const uint64_t L = (uint64_t)k * C;
@@ -1117,6 +1117,7 @@ int launch_far(mavg_plan* p, DevCtx& d, const void* in, void* out, const void* h
         MAVG_FAR16(192, 64, 4, 0) MAVG_FAR16(192, 64, 4, 4)
         MAVG_FAR16(224, 72, 6, 0) MAVG_FAR16(224, 72, 6, 2) MAVG_FAR16(224, 72, 6, 4) MAVG_FAR16(224, 72, 6, 6)
         MAVG_FAR16(192, 64, 8, 0)
+        MAVG_FAR16(224, 72, 12, 0) MAVG_FAR16(224, 72, 12, 4) MAVG_FAR16(192, 64, 16, 0)
 #undef MAVG_FAR16
         if (!kern) return fail(MAVG_ERR_UNSUPPORTED, "no far-lag int16 kernel for %u channels, misalignment %d", g.C, g.MIS);
     }
@@ -1543,7 +1544,7 @@ int mavg_plan_create(const mavg_desc* desc, mavg_plan** out)
         } else {
             // 3+ channels: the flat-stream kernel while the window fits its ring (stream_shape follows the plan)
             if (!planar && desc->channels >= 3) stream_shape = p->geom.ok;
-            // beyond the ring: the far-lag int16 kernel (mono / stereo / planar, 4 / 6 / 8 channels, k <= 46 340) ...
+            // beyond the ring: the far-lag int16 kernel (mono / stereo / planar, 4 / 6 / 8 / 12 / 16 channels, k <= 46 340) ...
             if (!p->geom.ok) {
                 const StreamGeom gf = plan_far_i16(desc->window, planar ? 1u : desc->channels, desc->tuning);
                 if (gf.ok) {

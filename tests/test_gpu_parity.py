@@ -879,7 +879,7 @@ def test_very_long_windows_on_the_generic_kernel(mavg, oracle_mod, case):
     x = oracle_mod.fill_f32(n, 35000 + k) if dtype == "f32" else oracle_mod.fill_i16(n, 35000 + k)
     with mavg.Plan(frames, k, channels=ch, dtype=dtype, layout=layout) as plan:
         # mono / planar float32: far-lag streaming kernel; int16 mono / stereo / 4 / 6 / 8 channels up to k = 46 340: its twin
-        far = (dtype == "f32" and (ch == 1 or layout == "planar")) or (dtype == "i16" and k <= 46_340 and ch in (1, 2, 4, 6, 8))
+        far = (dtype == "f32" and (ch == 1 or layout == "planar")) or (dtype == "i16" and k <= 46_340 and ch in (1, 2, 4, 6, 8, 12, 16))
         assert (plan.info.path, plan.info.mode) == ((1, 5) if far else (2, plan.info.mode))
         y = plan.run_host(x)
     if layout == "planar":
@@ -1023,7 +1023,8 @@ def test_far_lag_kernel_with_context_in_another_allocation(mavg, oracle_mod, tor
 @pytest.mark.parametrize("ch,k", [(1, 32_769), (1, 32_770), (1, 32_771), (1, 32_772), (1, 32_773), (1, 32_774), (1, 32_775),
                                   (1, 32_776), (1, 46_340), (2, 24_577), (2, 24_578), (2, 24_579), (2, 24_580), (2, 40_000),
                                   (2, 46_340), (4, 12_289), (4, 12_290), (4, 20_001), (4, 46_340), (6, 8_065), (6, 8_066),
-                                  (6, 8_067), (6, 8_068), (6, 19_200), (6, 30_001), (8, 6_145), (8, 19_200), (8, 40_000)])
+                                  (6, 8_067), (6, 8_068), (6, 19_200), (6, 30_001), (8, 6_145), (8, 19_200), (8, 40_000),
+                                  (12, 4_033), (12, 4_034), (12, 20_000), (16, 3_073), (16, 12_000)])
 def test_far_lag_i16_kernel_bit_exact(mavg, oracle_mod, ch, k):
     """stream_far_i16_kernel: every lag misalignment a channel count can have, the first windows beyond the ring of the
     flat-stream kernel, the longest exact window (k = 46 340), several tiles per CTA, a ragged end -- bit-identical to
