@@ -1,8 +1,9 @@
 #!/bin/bash
-# round 2, call AD: prefix sum with two chunks per CTA against one
+# round 2, call AD: float32 prefix sum, chunk size x chunks per CTA
 O=gpurun_out/r2ad; mkdir -p $O
-( time timeout 600 python -m pytest tests/test_gpu_scan.py tests/test_gpu_parity.py -m gpu -x -q -k "scan or prefix" ) > $O/pytest.log 2>&1; echo "rc=$?" >> $O/pytest.log
-for nch in 2 1 2 1; do
-  MAVG_SCAN_NCH=$nch timeout 300 python tests/perf/bench_configs.py --config scan >> $O/cfg_scan_nch$nch.json 2> $O/cfg_scan_nch$nch.err
+for cfg in "32 2" "64 2" "64 1" "32 2" "64 1"; do
+  set -- $cfg
+  echo "chunk_kb=$1 nch=$2" >> $O/f32.log
+  MAVG_SCAN_CHUNK_KB=$1 MAVG_SCAN_NCH=$2 timeout 300 python tests/perf/bench_configs.py --config scan >> $O/f32.log 2>> $O/f32.err
 done
-tail -3 $O/pytest.log; cat $O/cfg_scan_nch2.json; cat $O/cfg_scan_nch1.json
+cat $O/f32.log | cut -c1-400
