@@ -40,6 +40,18 @@ xf = oracle.fill_f32(12 * 8192 + 45, 11)                          # far-lag kern
 assert rel(mavg.moving_average(xf, 60001), oracle.mavg_f64(xf, 60001)) < 1e-5
 xf2 = oracle.fill_f32(2 * (12 * 4096 + 21), 12)
 assert rel(mavg.moving_average(xf2, 30001, channels=2), oracle.mavg_f64(xf2, 30001, 2)) < 1e-5
+for ch in (3, 4, 5, 7, 8, 9, 10, 12, 16):                         # flat-stream int16 kernel, every channel count it takes
+    xm = oracle.fill_i16(ch * 40001, 20 + ch)
+    for k in (3, 500):
+        assert np.array_equal(mavg.moving_average(xm, k, channels=ch), oracle.mavg_i16(xm, k, ch)), (ch, k)
+for ch, k in ((11, 64), (14, 64), (24, 300)):                     # the older few-channel int16 kernels
+    xm = oracle.fill_i16(ch * 20001, 40 + ch)
+    assert np.array_equal(mavg.moving_average(xm, k, channels=ch), oracle.mavg_i16(xm, k, ch)), (ch, k)
+for ch, k in ((2, 30001), (1, 46340), (8, 7000), (6, 9001), (16, 3500)):   # far-lag int16 kernel
+    xm = oracle.fill_i16(ch * (900_000 // ch + 7), 60 + ch)
+    assert np.array_equal(mavg.moving_average(xm, k, channels=ch), oracle.mavg_i16(xm, k, ch)), (ch, k)
+x256 = oracle.fill_i16(256 * 2001, 70)                            # int16 column kernel, four column warps per row
+assert np.array_equal(mavg.moving_average(x256, 8, channels=256), oracle.mavg_i16(x256, 8, 256))
 d = torch.from_numpy(oracle.fill_i16(2 * 50001, 7)).cuda()
 o = torch.zeros(2 * 50001, dtype=torch.int64, device="cuda")
 torch.cuda.synchronize()
