@@ -400,7 +400,7 @@ template <> struct ScanFast<float> {
 // first goes through its phases, and only the first chunk of a CTA looks back -- the next one knows its exclusive
 // prefix (the predecessor is local) and publishes a full PREFIX descriptor right behind its load barrier.
 template <typename TIn, int C, int R, int NCH = 1>
-__global__ void __launch_bounds__(kScanThreads)
+__global__ void __launch_bounds__(kScanThreads, (sizeof(TIn) == 2 && NCH == 2 && C == 1 ? 5 : 0))   // mono int16: 48 registers, five resident CTAs (0.463 -> 0.445 ms); stereo loses with the cap (0.451 -> 0.497)
     scan_lookback_fast_kernel(const TIn* __restrict__ in, typename ScanFast<TIn>::TAcc* __restrict__ out,
                               ulonglong2* __restrict__ desc)
 {

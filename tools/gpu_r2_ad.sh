@@ -1,9 +1,6 @@
 #!/bin/bash
-# round 2, call AD: float32 prefix sum, chunk size x chunks per CTA
+# round 2, call AD: int16 prefix sum, two chunks per CTA, registers capped for five resident CTAs
 O=gpurun_out/r2ad; mkdir -p $O
-for cfg in "32 2" "64 2" "64 1" "32 2" "64 1"; do
-  set -- $cfg
-  echo "chunk_kb=$1 nch=$2" >> $O/f32.log
-  MAVG_SCAN_CHUNK_KB=$1 MAVG_SCAN_NCH=$2 timeout 300 python tests/perf/bench_configs.py --config scan >> $O/f32.log 2>> $O/f32.err
-done
-cat $O/f32.log | cut -c1-400
+( timeout 300 python -m pytest tests/test_gpu_scan.py tests/test_gpu_parity.py -m gpu -x -q -k "scan or prefix" ) > $O/pytest.log 2>&1; echo "rc=$?" >> $O/pytest.log
+for i in 1 2 3; do timeout 300 python tests/perf/bench_configs.py --config scan >> $O/scan.log 2>> $O/scan.err; done
+tail -2 $O/pytest.log; cat $O/scan.log | cut -c100-420
