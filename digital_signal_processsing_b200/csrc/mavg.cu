@@ -1405,7 +1405,8 @@ int launch_scan_cb(const void* d_in, void* d_out, uint64_t n, cudaStream_t st)
                     const char* ev = getenv("MAVG_SCAN_NCH");
                     return ev ? atoi(ev) : 0;
                 }();
-                const int nch = nch_env == 1 ? 1 : nch_env == 2 ? 2 : (std::is_same<TIn, int16_t>::value ? 2 : 1);
+                // (4 / 8 channels keep one chunk per CTA: the second chunk's load registers would cost them resident CTAs)
+                const int nch = nch_env == 1 ? 1 : nch_env == 2 ? 2 : (std::is_same<TIn, int16_t>::value && C <= 2 ? 2 : 1);
                 const uint32_t fsmem = mavg::scan_fast_smem_bytes<TIn, C, RL>();
                 if (nch == 2 && whole >= 2) {
                     auto fast = mavg::scan_lookback_fast_kernel<TIn, C, RL, 2>;
