@@ -298,3 +298,77 @@ def test_flat_i16_cross_warp_layout_and_lag_alignment(NT, R, C):
             assert mis in (0, 4)
         elif C % 2 == 0:
             assert mis % 2 == 0
+
+
+# ---------------------------------------------------------------- far-lag int16 kernel (stream_far_i16_kernel) geometry
+@pytest.mark.parametrize("NT,R,C", [(384, 32, 1), (384, 32, 2), (192, 64, 4), (224, 72, 6), (192, 64, 8), (224, 72, 12), (192, 64, 16)])
+def test_far_lag_i16_boxes_lag_runs_and_exact_range(NT, R, C):
+    """Index algebra of launch_far / stream_far_i16_kernel in int16 samples and 64-sample rows: the lag box of a tile
+    starts lag_rows rows in front of it, a thread's lag run starts koff / 8 + (R / 8) * (t % TPB) chunks into its box plus
+    MIS samples, which has to be exactly x[i - L .. i - L + R); the warm-up tiles cover exactly the L samples in front
+    of a tile range; and the int32 carry / multiply-high division are exact up to k = 46 340 (plan_far_i16)."""
+    ROW = 64
+    T = NT * R
+    ROWS = T // ROW
+    NBOX = 2 if ROWS + 1 > 256 else 1
+    BOXROWS = ROWS // NBOX + 1
+    TPB = NT // NBOX
+    CH_OWN = R // 8
+    rng = np.random.default_rng(17 + NT + C)
+    n = 6 * T
+    x = rng.integers(-32768, 32768, size=n).astype(np.int64)
+    xr = x.reshape(n // ROW, ROW)
+
+    def box(r0, nrows):
+        out = np.zeros((nrows, ROW), dtype=np.int64)
+        lo, hi = max(r0, 0), min(r0 + nrows, n // ROW)
+        if lo < hi:
+            out[lo - r0:hi - r0] = xr[lo:hi]
+        return out.reshape(-1)
+
+    for k in (T // C + 1, T // C + 3, (2 * T + 5 * C) // C, 3 * T // C + 7):
+        L = k * C
+        koff = (ROW - L % ROW) % ROW
+        lag_rows = (L + koff) // ROW
+        lag_chunks = (L + 7) // 8
+        mis = 8 * lag_chunks - L
+        assert koff % 8 == mis and (L + koff) % ROW == 0
+        for j in (0, 2, 5):
+            r0 = j * ROWS - lag_rows
+            boxes = [box(r0 + b * (ROWS // 2), BOXROWS) for b in range(NBOX)]
+            for t in (0, 1, TPB - 1, TPB % NT, NT // 3, NT - 1):
+                c0 = koff // 8 + CH_OWN * (t % TPB)
+                chunks = boxes[t // TPB][8 * c0: 8 * (c0 + CH_OWN + 1)]
+                lag_run = chunks[mis: mis + R]
+                i = j * T + R * t
+                want = np.array([x[i - L + r] if i - L + r >= 0 else 0 for r in range(R)])
+                assert np.array_equal(lag_run, want), (k, j, t)
+                assert 8 * (c0 + CH_OWN + (1 if mis else 0)) <= BOXROWS * ROW
+        HT = (L + T - 1) // T
+        for t0 in (1, 4):
+            W = np.zeros(C, dtype=np.int64)
+            for jj in range(HT):
+                u = t0 - HT + jj
+                tile = box(u * ROWS, ROWS)
+                rel = (t0 - u) * T - L
+                m = np.where(np.arange(T) >= rel, tile, 0)
+                for c in range(C):
+                    W[c] += m[c::C].sum()
+            lo = t0 * T - L
+            seg = x[max(lo, 0): t0 * T]
+            off = (max(lo, 0)) % C
+            for c in range(C):
+                assert W[c] == int(seg[(c - off) % C::C].sum()), (k, t0, c)
+    # exact range of the int32 carry and of the multiply-high division (i16_mulhi_consts): every k with k * k < 2^31
+    for k in (32_769, 40_000, 46_340):
+        assert k * k < 2 ** 31 and 32768 * k < 2 ** 31
+        lg = (k - 1).bit_length()
+        M = (1 << (30 + lg)) // k + 1
+        assert M < 2 ** 31
+        e = M * k - (1 << (30 + lg))
+        assert 0 < e <= k and 32768 * k * e < (1 << (30 + lg))
+        for w in (0, 1, k - 1, k, k + 1, 32768 * k - 1, 32768 * k, 12345 * k + 7, -1, -k, -k - 1, -32768 * k, -(32767 * k + 5)):
+            t = (w * M) >> 32                                  # mulhi_s32 (arithmetic shift of the 64-bit product)
+            y = (t >> (lg - 2)) + (1 if t < 0 else 0)
+            want = abs(w) // k * (1 if w >= 0 else -1)         # C's truncating division
+            assert y == want, (k, w)
