@@ -85,6 +85,9 @@ def test_argument_validation_without_gpu(mavg):
     assert lib.mavg_plan_destroy(None) == 0
     assert lib.mavg_run_host(None, None, None) == _lib.ERR_INVALID_ARG
     assert lib.mavg_run_device(None, None, None) == _lib.ERR_INVALID_ARG
+    assert lib.mavg_run_host_sweep(None, 0, None, None) == _lib.ERR_INVALID_ARG
+    one = (ctypes.c_void_p * 1)(None)
+    assert lib.mavg_run_host_sweep(one, 1, ctypes.c_void_p(8), one) == _lib.ERR_INVALID_ARG    # a null plan in the list
     assert lib.mavg_run_cascade(None, None, None, None, 3) == _lib.ERR_INVALID_ARG
     assert lib.mavg_host_register(None, 64) == _lib.ERR_INVALID_ARG
     assert lib.mavg_host_unregister(None) == 0
